@@ -1,0 +1,367 @@
+// bmo_detector.cu -- Photodetector: coherent superposition of Gaussian beamlet fields (K4).
+//
+// Restates interact3d(::Photodetector, ::GaussianBeamlet, ray_id) (Photodetector.jl:69-107) ->
+// electric_field(gauss, r, z) (Gaussian.jl:381-392) -> point_on_beam (Beam.jl:177-205) +
+// gauss_parameters (Gaussian.jl:298-353) -> electric_field(r, z, E0, w0, w, k, psi, R)
+// (OpticUtils.jl:87-89), one thread per pixel, beamlet records staged through shared memory.
+// Per-beamlet constants (lengths, OPL, reference phase, projection) are hoisted into the records;
+// everything that depends on the pixel keeps the reference's operation order (k*z is O(1e7) rad).
+#include "bmo_host.cuh"
+#include "bmo_interact.cuh"
+
+namespace bmo {
+
+// segment table rows (must match bmo_trace.cu)
+enum { S_PX = 0, S_PY, S_PZ, S_DX, S_DY, S_DZ, S_N, S_T, S_NX, S_NY, S_NZ };
+
+// One leaf beamlet that ends on the detector.  Plain doubles so a tile can be copied to smem as words.
+struct PdRec {
+    double p0[3], d0[3];      // chief ray of the last segment (ray_id)
+    double wp[3], wd[3];      // waist ray
+    double dp[3], dd[3];      // divergence ray
+    double cn;                // refractive index of the chief segment
+    double l0;                // length(gauss) - length(ray)              (Photodetector.jl:74)
+    double temp;              // cumulative length before the last segment (Beam.jl:179-199, parent-first sum)
+    double plen;              // length(parent)
+    double lambda, k;         // wavelength, 2pi/lambda                   (Gaussian.jl:384)
+    double w0b, e0r, e0i;     // beam_waist(gauss), electric_field(gauss)
+    double cr, ci;            // exp(im * ref_phi), ref_phi = (OPL - L)/lambda * 2pi   (Gaussian.jl:388-391)
+    double sq;                // sqrt(|d0 . n_hit|)                       (Photodetector.jl:84,103)
+    double first_row;         // first chief row of this beam in the segment table (as double; slow path)
+    double nseg;
+    double pose;
+    double pad;
+};
+static_assert(sizeof(PdRec) % 8 == 0, "PdRec must be a whole number of doubles");
+
+struct ResView {
+    const double* seg_d; const int32_t* seg_part; int64_t rows;
+    const int32_t *nseg, *status, *lam, *pose;
+    const long long* first_seg;
+    const double *w0, *e0, *plen, *popl;
+    int64_t n_beams;
+};
+
+// flags[b] = 1 if beam b ended on detector `pd` after a full interaction (all three rays on the PD shape)
+__global__ void pd_flag(ResView R, SysView S, int pd_object, int pose_filter, int32_t* flags) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= R.n_beams) return;
+    int f = 0;
+    if (R.status[b] == BMO_ST_ABSORBED && R.nseg[b] > 0 && (pose_filter < 0 || R.pose[b] == pose_filter)) {
+        const int64_t row = (R.first_seg[b] + R.nseg[b] - 1) * 3;
+        const int part = R.seg_part[row];
+        if (part >= 0 && S.parts[part].object == pd_object) f = 1;
+    }
+    flags[b] = f;
+}
+__global__ void pd_build(ResView R, SysView S, const int32_t* flags, const long long* offs, PdRec* recs) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= R.n_beams || !flags[b]) return;
+    PdRec rc;
+    const int n = R.nseg[b];
+    const int64_t f = R.first_seg[b];
+    const int64_t rows = R.rows;
+    const double plen = R.plen[b], popl = R.popl[b];
+    // running sums with the reference's association (Beam.jl:125-205)
+    double lsum = 0.0, lpar = plen, opl = popl;
+    for (int s = 0; s < n - 1; s++) {
+        const int64_t row = (f + s) * 3;
+        const double t = R.seg_d[S_T * rows + row], nn = R.seg_d[S_N * rows + row];
+        lsum += t; lpar += t; opl += t * nn;
+    }
+    const int64_t rc_ = (f + n - 1) * 3, rw = rc_ + 1, rd = rc_ + 2;
+    const double* d = R.seg_d;
+    const double t_last = d[S_T * rows + rc_];
+    rc.cn = d[S_N * rows + rc_];
+    for (int k = 0; k < 3; k++) {
+        rc.p0[k] = d[(S_PX + k) * rows + rc_]; rc.d0[k] = d[(S_DX + k) * rows + rc_];
+        rc.wp[k] = d[(S_PX + k) * rows + rw]; rc.wd[k] = d[(S_DX + k) * rows + rw];
+        rc.dp[k] = d[(S_PX + k) * rows + rd]; rc.dd[k] = d[(S_DX + k) * rows + rd];
+    }
+    const double L = (lsum + t_last) + plen;          // length(gauss) = l + l0
+    const double OPL = opl + t_last * rc.cn;           // optical_path_length(gauss)
+    rc.l0 = L - t_last;
+    rc.temp = lpar;
+    rc.plen = plen;
+    rc.lambda = S.lambdas[R.lam[b]];
+    rc.k = kTwoPi / rc.lambda;
+    rc.w0b = R.w0[b]; rc.e0r = R.e0[2 * b]; rc.e0i = R.e0[2 * b + 1];
+    const double dl = OPL - L;
+    const double ref_phi = dl / rc.lambda * kTwoPi;
+    Cx c = cis(ref_phi);
+    rc.cr = c.re; rc.ci = c.im;
+    V3 nrm = mk3(d[S_NX * rows + rc_], d[S_NY * rows + rc_], d[S_NZ * rows + rc_]);
+    rc.sq = sqrt(fabs(dot(mk3(rc.d0[0], rc.d0[1], rc.d0[2]), nrm)));
+    rc.first_row = (double)f; rc.nseg = (double)n; rc.pose = (double)R.pose[b]; rc.pad = 0;
+    recs[offs[b]] = rc;
+}
+
+constexpr int PD_TILE = 16;   // 16 x 16 pixels per block
+constexpr int PD_BATCH = 32;  // beamlet records staged per smem tile
+
+struct PdParams {
+    const PdRec* recs; int64_t n_recs;
+    ResView R;
+    double* field;            // [n_fields][n*n*2] column-major [i + n*j], re/im interleaved
+    const double* det_pose;   // [n_poses][n_objects][12]
+    const long long* pose_off;// NULL (single field) or [n_fields+1] record ranges per pose
+    int32_t n, pd_object, n_objects, pose0;
+    double lo, hi;
+};
+
+// LinRange getindex: lerpi(i, n-1, lo, hi) = (1 - t)*lo + t*hi, t = i/(n-1)
+BMO_D double lin_coord(int i, int n, double lo, double hi) {
+    const double t = (n == 1) ? 0.0 : (double)i / (double)(n - 1);
+    return (1 - t) * lo + t * hi;
+}
+
+__global__ void __launch_bounds__(PD_TILE* PD_TILE) pd_field(const PdParams P) {
+    __shared__ PdRec s_rec[PD_BATCH];
+    const int i = blockIdx.x * PD_TILE + threadIdx.x, j = blockIdx.y * PD_TILE + threadIdx.y;
+    const int tid = threadIdx.y * PD_TILE + threadIdx.x;
+    const int fld = blockIdx.z;
+    const int pose = P.pose0 + fld;
+    const bool inside = i < P.n && j < P.n;
+    // pixel -> world: p1 = dir' * (x, 0, y) + pos   (Photodetector.jl:78,92-96 -- transposed orientation)
+    const double* dp = P.det_pose + 12 * ((int64_t)pose * P.n_objects + P.pd_object);
+    const double x = lin_coord(min(i, P.n - 1), P.n, P.lo, P.hi), y = lin_coord(min(j, P.n - 1), P.n, P.lo, P.hi);
+    // T = transpose(dir): T[r][c] = dir[c][r]; dir row-major at dp[3 + 3*r + c]
+    const V3 p1 = mk3(dp[3 + 0] * x + dp[3 + 6] * y + dp[0],      // T[1,1]*x + T[1,3]*y + p[1]
+                      dp[3 + 1] * x + dp[3 + 7] * y + dp[1],      // T[2,1]*x + T[2,3]*y + p[2]
+                      dp[3 + 2] * x + dp[3 + 8] * y + dp[2]);     // T[3,1]*x + T[3,3]*y + p[3]
+    int64_t rb = 0, re = P.n_recs;
+    if (P.pose_off) { rb = P.pose_off[fld]; re = P.pose_off[fld + 1]; }
+    Cx acc = mkc(0, 0);
+    for (int64_t base = rb; base < re; base += PD_BATCH) {
+        const int nb = (int)min((int64_t)PD_BATCH, re - base);
+        __syncthreads();
+        {
+            const int nw = nb * (int)(sizeof(PdRec) / 8);
+            const double* src = reinterpret_cast<const double*>(P.recs + base);
+            double* dst = reinterpret_cast<double*>(s_rec);
+            for (int k = tid; k < nw; k += PD_TILE * PD_TILE) dst[k] = src[k];
+        }
+        __syncthreads();
+        if (!inside) continue;
+        for (int q = 0; q < nb; q++) {
+            const PdRec& rc = s_rec[q];
+            const V3 p0 = mk3(rc.p0[0], rc.p0[1], rc.p0[2]), d0 = mk3(rc.d0[0], rc.d0[1], rc.d0[2]);
+            // projection of the pixel onto the beamlet axis (Photodetector.jl:98-101)
+            const double l1 = dot(p1 - p0, d0);
+            const V3 p2 = p0 + l1 * d0;
+            const double r = norm(p1 - p2);
+            const double z = rc.l0 + l1;
+            // point_on_beam(gauss, z) (Beam.jl:177-205)
+            V3 point, c_dir = d0, w_pos = mk3(rc.wp[0], rc.wp[1], rc.wp[2]), w_dir = mk3(rc.wd[0], rc.wd[1], rc.wd[2]),
+                      d_pos = mk3(rc.dp[0], rc.dp[1], rc.dp[2]), d_dir = mk3(rc.dd[0], rc.dd[1], rc.dd[2]);
+            double c_n = rc.cn;
+            bool found = false;
+            if (rc.nseg > 1.0 && z < rc.temp) {   // an earlier segment: replay the reference's loop
+                const int ns = (int)rc.nseg;
+                const int64_t f = (int64_t)rc.first_row, rows = P.R.rows;
+                const double* d = P.R.seg_d;
+                double temp = rc.plen;
+                for (int s = 0; s < ns - 1; s++) {
+                    const int64_t row = (f + s) * 3;
+                    const double len = d[S_T * rows + row];
+                    temp += len;
+                    if (z < temp) {
+                        const double b = temp - z;
+                        const V3 sp = mk3(d[S_PX * rows + row], d[S_PY * rows + row], d[S_PZ * rows + row]);
+                        c_dir = mk3(d[S_DX * rows + row], d[S_DY * rows + row], d[S_DZ * rows + row]);
+                        point = sp + (len - b) * c_dir;
+                        c_n = d[S_N * rows + row];
+                        w_pos = mk3(d[S_PX * rows + row + 1], d[S_PY * rows + row + 1], d[S_PZ * rows + row + 1]);
+                        w_dir = mk3(d[S_DX * rows + row + 1], d[S_DY * rows + row + 1], d[S_DZ * rows + row + 1]);
+                        d_pos = mk3(d[S_PX * rows + row + 2], d[S_PY * rows + row + 2], d[S_PZ * rows + row + 2]);
+                        d_dir = mk3(d[S_DX * rows + row + 2], d[S_DY * rows + row + 2], d[S_DZ * rows + row + 2]);
+                        found = true;
+                        break;
+                    }
+                }
+            }
+            if (!found) point = p0 + (z - rc.temp) * d0;
+            double w, Rc, psi, w0;
+            gauss_parameters(point, c_dir, c_n, w_pos, w_dir, d_pos, d_dir, rc.lambda, w, Rc, psi, w0);
+            // electric_field(gauss, r, z) (Gaussian.jl:381-392, OpticUtils.jl:87-89)
+            const Cx E0 = mkc(rc.e0r, rc.e0i) * (rc.w0b / w0);
+            Cx e = ((E0 * w0) / w) * exp(-(r * r) / (w * w));
+            e = e * cis(rc.k * z + psi + (rc.k * (r * r) * Rc) / 2);
+            e = e * mkc(rc.cr, rc.ci);
+            e = e * rc.sq;
+            acc = acc + e;
+        }
+    }
+    if (inside) {
+        double* f = P.field + ((int64_t)fld * P.n * P.n + (int64_t)i + (int64_t)P.n * j) * 2;
+        f[0] += acc.re;
+        f[1] += acc.im;
+    }
+}
+
+// optical_power = trapz((x, y), |E|^2 / (2 Z0)) (Photodetector.jl:109-116, Trapz.jl), one block per field
+__global__ void pd_power_kernel(const double* fields, int n, double lo, double hi, double* power) {
+    extern __shared__ double s_col[];
+    const double* f = fields + (int64_t)blockIdx.x * n * n * 2;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        double s = 0;
+        for (int i = 0; i + 1 < n; i++) {
+            const double* a = f + ((int64_t)i + (int64_t)n * j) * 2;
+            const double ia = (a[0] * a[0] + a[1] * a[1]) / (2 * kZvac), ib = (a[2] * a[2] + a[3] * a[3]) / (2 * kZvac);
+            s += (lin_coord(i + 1, n, lo, hi) - lin_coord(i, n, lo, hi)) * (ia + ib) / 2;
+        }
+        s_col[j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double p = 0;
+        for (int j = 0; j + 1 < n; j++) p += (lin_coord(j + 1, n, lo, hi) - lin_coord(j, n, lo, hi)) * (s_col[j] + s_col[j + 1]) / 2;
+        power[blockIdx.x] = p;
+    }
+}
+
+__global__ void scan_flags(const int32_t* in, int64_t n, long long* out, long long* total);
+
+}  // namespace bmo
+
+using namespace bmo;
+
+// single-block chunked exclusive scan (same scheme as scan_counts in bmo_trace.cu)
+__global__ void __launch_bounds__(1024) bmo::scan_flags(const int32_t* in, int64_t n, long long* out, long long* total) {
+    __shared__ long long s_sum[1024];
+    const int T = blockDim.x;
+    const int64_t chunk = (n + T - 1) / T;
+    const int64_t b = (int64_t)threadIdx.x * chunk, e = min(b + chunk, n);
+    long long s = 0;
+    for (int64_t i = b; i < e; i++) s += in[i];
+    s_sum[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 1; o < T; o <<= 1) {
+        long long v = threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0;
+        __syncthreads();
+        s_sum[threadIdx.x] += v;
+        __syncthreads();
+    }
+    long long run = threadIdx.x == 0 ? 0 : s_sum[threadIdx.x - 1];
+    for (int64_t i = b; i < e; i++) { out[i] = run; run += in[i]; }
+    if (threadIdx.x == T - 1) *total = s_sum[T - 1];
+}
+
+static ResView res_view(bmo_result* r) {
+    ResView v;
+    v.seg_d = r->seg_d; v.seg_part = r->seg_part; v.rows = r->seg_rows; v.nseg = r->nseg; v.status = r->status; v.lam = r->lam;
+    v.pose = r->pose; v.first_seg = r->first_seg; v.w0 = r->w0; v.e0 = r->e0; v.plen = r->plen; v.popl = r->popl; v.n_beams = r->n_beams;
+    return v;
+}
+
+static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t pose0, int32_t n_fields, double* fields, uint32_t flags,
+                      bool per_pose) {
+    if (!sys || !r || !fields) return fail(BMO_EINVAL, "bmo_pd_accumulate: NULL argument");
+    if (r->mode != 2) return fail(BMO_EINVAL, "bmo_pd_accumulate: result does not hold Gaussian beamlets (Photodetector.jl:57-60)");
+    if (pd_object < 0 || pd_object >= (int)sys->objects.size() || sys->objects[pd_object].kind != BMO_OBJ_PHOTODETECTOR)
+        return fail(BMO_EINVAL, "bmo_pd_accumulate: object is not a Photodetector");
+    if (pose0 < 0 || pose0 + n_fields > sys->view.n_poses) return fail(BMO_EINVAL, "bmo_pd_accumulate: pose out of range");
+    bmo_ctx* ctx = sys->ctx;
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bmo_object& ob = sys->objects[pd_object];
+    const int n = ob.pd_n;
+    const size_t fbytes = (size_t)n_fields * n * n * 2 * sizeof(double);
+    const bool on_dev = flags & BMO_INPUT_DEVICE;
+    BMO_CUDA(cudaEventRecord(ctx->ev0, st));
+    double* d_field = fields;
+    if (!on_dev) {
+        BMO_CUDA(dev_alloc(&d_field, (size_t)n_fields * n * n * 2, st));
+        BMO_CUDA(cudaMemcpyAsync(d_field, fields, fbytes, cudaMemcpyHostToDevice, st));
+    }
+    int32_t* d_flags = nullptr; long long* d_offs = nullptr; PdRec* d_recs = nullptr; long long* d_pose_off = nullptr;
+    const int64_t nb = r->n_beams;
+    BMO_CUDA(dev_alloc(&d_flags, (size_t)nb, st));
+    BMO_CUDA(dev_alloc(&d_offs, (size_t)nb, st));
+    ResView rv = res_view(r);
+    pd_flag<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(rv, sys->view, pd_object, per_pose ? -1 : pose0, d_flags);
+    ctx->launches++;
+    scan_flags<<<1, 1024, 0, st>>>(d_flags, nb, d_offs, ctx->d_totals);
+    ctx->launches++;
+    BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    const int64_t m = ctx->h_totals[0];
+    if (m > 0) {
+        BMO_CUDA(dev_alloc(&d_recs, (size_t)m, st));
+        pd_build<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(rv, sys->view, d_flags, d_offs, d_recs);
+        ctx->launches++;
+        if (per_pose) {
+            // group the records by pose (stable): tiny host round trip (m records)
+            std::vector<PdRec> h((size_t)m);
+            BMO_CUDA(cudaMemcpyAsync(h.data(), d_recs, (size_t)m * sizeof(PdRec), cudaMemcpyDeviceToHost, st));
+            BMO_CUDA(cudaStreamSynchronize(st));
+            std::stable_sort(h.begin(), h.end(), [](const PdRec& a, const PdRec& b) { return a.pose < b.pose; });
+            std::vector<long long> off((size_t)n_fields + 1, 0);
+            size_t q = 0;
+            for (int p = 0; p < n_fields; p++) {
+                while (q < h.size() && (int)h[q].pose < pose0 + p) q++;
+                off[p] = (long long)q;
+            }
+            while (q < h.size() && (int)h[q].pose < pose0 + n_fields) q++;
+            off[n_fields] = (long long)q;
+            BMO_CUDA(cudaMemcpyAsync(d_recs, h.data(), (size_t)m * sizeof(PdRec), cudaMemcpyHostToDevice, st));
+            BMO_CUDA(dev_alloc(&d_pose_off, off.size(), st));
+            BMO_CUDA(cudaMemcpyAsync(d_pose_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
+            BMO_CUDA(cudaStreamSynchronize(st));
+        }
+        PdParams pp{};
+        pp.recs = d_recs; pp.n_recs = m; pp.R = rv; pp.field = d_field; pp.det_pose = sys->view.det_pose; pp.pose_off = d_pose_off;
+        pp.n = n; pp.pd_object = pd_object; pp.n_objects = sys->view.n_objects; pp.pose0 = pose0; pp.lo = ob.pd_lo; pp.hi = ob.pd_hi;
+        dim3 grid((n + PD_TILE - 1) / PD_TILE, (n + PD_TILE - 1) / PD_TILE, n_fields), block(PD_TILE, PD_TILE);
+        pd_field<<<grid, block, 0, st>>>(pp);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return fail(BMO_ECUDA, std::string("pd_field: ") + cudaGetErrorString(e));
+        ctx->px_beamlets += m * (int64_t)n * n;
+    }
+    if (!on_dev) {
+        BMO_CUDA(cudaMemcpyAsync(fields, d_field, fbytes, cudaMemcpyDeviceToHost, st));
+    }
+    BMO_CUDA(cudaEventRecord(ctx->ev1, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    BMO_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->pd_ms = ms;
+    if (!on_dev) dev_free(d_field, st);
+    dev_free(d_flags, st); dev_free(d_offs, st); dev_free(d_recs, st); dev_free(d_pose_off, st);
+    return BMO_OK;
+}
+
+int32_t bmo_pd_accumulate(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t pose, double* field, uint32_t flags) {
+    return pd_run(sys, r, pd_object, pose, 1, field, flags, false);
+}
+int32_t bmo_pd_accumulate_poses(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_poses, double* fields, uint32_t flags) {
+    return pd_run(sys, r, pd_object, 0, n_poses, fields, flags, true);
+}
+int32_t bmo_pd_power(bmo_sys* sys, int32_t pd_object, int32_t n_fields, const double* fields, double* power, uint32_t flags) {
+    if (!sys || !fields || !power) return fail(BMO_EINVAL, "bmo_pd_power: NULL argument");
+    if (pd_object < 0 || pd_object >= (int)sys->objects.size() || sys->objects[pd_object].kind != BMO_OBJ_PHOTODETECTOR)
+        return fail(BMO_EINVAL, "bmo_pd_power: object is not a Photodetector");
+    bmo_ctx* ctx = sys->ctx;
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bmo_object& ob = sys->objects[pd_object];
+    const int n = ob.pd_n;
+    const bool on_dev = flags & BMO_INPUT_DEVICE;
+    const double* d_f = fields;
+    double* d_tmp = nullptr; double* d_p = nullptr;
+    if (!on_dev) {
+        BMO_CUDA(dev_alloc(&d_tmp, (size_t)n_fields * n * n * 2, st));
+        BMO_CUDA(cudaMemcpyAsync(d_tmp, fields, (size_t)n_fields * n * n * 2 * sizeof(double), cudaMemcpyHostToDevice, st));
+        d_f = d_tmp;
+        BMO_CUDA(dev_alloc(&d_p, (size_t)n_fields, st));
+    } else d_p = power;
+    pd_power_kernel<<<n_fields, 256, n * sizeof(double), st>>>(d_f, n, ob.pd_lo, ob.pd_hi, d_p);
+    ctx->launches++;
+    if (!on_dev) {
+        BMO_CUDA(cudaMemcpyAsync(power, d_p, (size_t)n_fields * sizeof(double), cudaMemcpyDeviceToHost, st));
+        BMO_CUDA(cudaStreamSynchronize(st));
+        dev_free(d_tmp, st); dev_free(d_p, st);
+    }
+    return BMO_OK;
+}

@@ -1,0 +1,163 @@
+// bmo_host.cuh -- host-side state of libbmo.so: context, uploaded system, result tables, error
+// handling and the BVH builder.  Shared by bmo_trace.cu and bmo_detector.cu.
+#pragma once
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include "bmo_geom.cuh"
+
+namespace bmo {
+
+extern thread_local std::string g_last_error;
+inline int32_t fail(int32_t code, const std::string& msg) { g_last_error = msg; return code; }
+
+#define BMO_CUDA(call)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (call);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(BMO_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
+    } while (0)
+
+struct DevCounters { unsigned long long interactions, sdf, tri; };
+
+}  // namespace bmo
+
+struct bmo_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bmo::DevCounters* d_counters = nullptr;
+    long long* d_totals = nullptr;   // [4] scratch for scans
+    long long* h_totals = nullptr;   // pinned
+    int64_t waves = 0, launches = 0, px_beamlets = 0;
+    double trace_ms = 0, pd_ms = 0;
+    int sm_count = 148;
+};
+
+struct bmo_sys {
+    bmo_ctx* ctx = nullptr;
+    bmo::SysView view{};         // device pointers
+    // host copies (needed for pose updates and detector metadata)
+    std::vector<bmo_prim> prims;
+    std::vector<bmo_part> parts;
+    std::vector<bmo_object> objects;
+    std::vector<bmo::MeshView> meshes;
+    std::vector<double> lambdas;
+    int64_t n_vertices = 0, n_faces = 0;
+    // owned device buffers
+    bmo_prim* d_prims = nullptr; bmo_part* d_parts = nullptr; bmo_object* d_objects = nullptr;
+    bmo::MeshView* d_meshes = nullptr; double* d_vertices = nullptr; int32_t* d_faces = nullptr;
+    bmo::BvhNode* d_nodes = nullptr; int32_t* d_bvh_faces = nullptr; double* d_ntable = nullptr;
+    double* d_bounds = nullptr; double* d_detpose = nullptr; double* d_lambdas = nullptr;
+    // pose-0 copies to restore after a sweep
+    std::vector<double> h_vertices, h_bounds, h_detpose;
+};
+
+// One wave of segment records (wave-major), gathered into beam-major order at the end of a trace.
+struct WaveBuf {
+    double* d = nullptr;    // [nsd][count]
+    int32_t* part = nullptr;
+    int32_t* beam = nullptr;
+    int32_t* seg = nullptr;
+    int64_t count = 0;      // rays in this wave
+};
+
+struct bmo_result {
+    bmo_sys* sys = nullptr;
+    int mode = 0;           // 0 ray, 1 polarized ray, 2 gaussian beamlet
+    int R = 1;              // rays per beam
+    int nsd = 12;           // doubles per segment record
+    int64_t n_roots = 0, n_beams = 0, n_segments = 0, interactions = 0;
+    int32_t waves = 0;
+    bool keep = false;
+    // per-beam tables (device), capacity cap_beams
+    int64_t cap_beams = 0;
+    int32_t *parent = nullptr, *slot = nullptr, *nseg = nullptr, *status = nullptr, *lam = nullptr, *pose = nullptr;
+    double *w0 = nullptr, *e0 = nullptr, *plen = nullptr, *popl = nullptr;
+    int32_t* spot_obj = nullptr;  // [cap_beams * R]
+    double* spot_xz = nullptr;    // [cap_beams * R * 2]
+    long long* first_seg = nullptr;  // [n_beams + 1] after finalisation
+    // beam-major segment table (device): rows = n_segments * R
+    double* seg_d = nullptr;      // [nsd][rows]
+    int32_t* seg_part = nullptr;  // [rows]
+    int64_t seg_rows = 0;
+    std::vector<WaveBuf> wavebufs;
+};
+
+namespace bmo {
+
+// ---- BVH (host build, median split on the longest centroid axis, <= 4 faces per leaf) ---------
+struct BvhBuild {
+    std::vector<BvhNode> nodes;
+    std::vector<int32_t> order;
+};
+inline void bvh_build(const double* verts, const int32_t* faces, int64_t nf, BvhBuild& out) {
+    out.nodes.clear();
+    out.order.resize(nf);
+    for (int64_t i = 0; i < nf; i++) out.order[i] = (int32_t)i;
+    std::vector<double> cen(3 * nf), lo(3 * nf), hi(3 * nf);
+    double glo[3] = {1e300, 1e300, 1e300}, ghi[3] = {-1e300, -1e300, -1e300};
+    for (int64_t f = 0; f < nf; f++)
+        for (int k = 0; k < 3; k++) {
+            double a = verts[3 * faces[3 * f] + k], b = verts[3 * faces[3 * f + 1] + k], c = verts[3 * faces[3 * f + 2] + k];
+            lo[3 * f + k] = std::min(a, std::min(b, c));
+            hi[3 * f + k] = std::max(a, std::max(b, c));
+            cen[3 * f + k] = (a + b + c) / 3;
+            glo[k] = std::min(glo[k], lo[3 * f + k]);
+            ghi[k] = std::max(ghi[k], hi[3 * f + k]);
+        }
+    // Moeller-Trumbore accepts (u, v) up to 1e-9 outside the triangle and the slab test rounds:
+    // inflate every box by a margin far above both (SURVEY hard part 11).
+    double diag = 0;
+    for (int k = 0; k < 3; k++) diag = std::max(diag, ghi[k] - glo[k]);
+    const double pad = 1e-6 * diag + 1e-12;
+    struct Item { int64_t b, e; int32_t node; };
+    std::vector<Item> stack;
+    out.nodes.push_back(BvhNode{});
+    stack.push_back({0, nf, 0});
+    while (!stack.empty()) {
+        Item it = stack.back(); stack.pop_back();
+        BvhNode nd{};
+        double clo[3] = {1e300, 1e300, 1e300}, chi[3] = {-1e300, -1e300, -1e300};
+        for (int k = 0; k < 3; k++) { nd.lo[k] = 1e300; nd.hi[k] = -1e300; }
+        for (int64_t i = it.b; i < it.e; i++) {
+            int32_t f = out.order[i];
+            for (int k = 0; k < 3; k++) {
+                nd.lo[k] = std::min(nd.lo[k], lo[3 * f + k]); nd.hi[k] = std::max(nd.hi[k], hi[3 * f + k]);
+                clo[k] = std::min(clo[k], cen[3 * f + k]); chi[k] = std::max(chi[k], cen[3 * f + k]);
+            }
+        }
+        for (int k = 0; k < 3; k++) { nd.lo[k] -= pad; nd.hi[k] += pad; }
+        int64_t cnt = it.e - it.b;
+        int ax = 0;
+        for (int k = 1; k < 3; k++) if (chi[k] - clo[k] > chi[ax] - clo[ax]) ax = k;
+        if (cnt <= 4 || !(chi[ax] - clo[ax] > 0)) {
+            nd.first = (int32_t)it.b; nd.count = (int32_t)cnt; nd.left = nd.right = -1;
+            // keep the reference's face order inside a leaf
+            std::sort(out.order.begin() + it.b, out.order.begin() + it.e);
+            out.nodes[it.node] = nd;
+            continue;
+        }
+        int64_t mid = (it.b + it.e) / 2;
+        std::nth_element(out.order.begin() + it.b, out.order.begin() + mid, out.order.begin() + it.e,
+                         [&](int32_t a, int32_t b) { return cen[3 * a + ax] < cen[3 * b + ax]; });
+        nd.count = 0; nd.first = 0;
+        nd.left = (int32_t)out.nodes.size(); out.nodes.push_back(BvhNode{});
+        nd.right = (int32_t)out.nodes.size(); out.nodes.push_back(BvhNode{});
+        out.nodes[it.node] = nd;
+        stack.push_back({it.b, mid, nd.left});
+        stack.push_back({mid, it.e, nd.right});
+    }
+}
+
+template <class T> inline cudaError_t dev_alloc(T** p, size_t n, cudaStream_t s) {
+    return cudaMallocAsync((void**)p, std::max<size_t>(n, 1) * sizeof(T), s);
+}
+template <class T> inline void dev_free(T*& p, cudaStream_t s) {
+    if (p) cudaFreeAsync((void*)p, s);
+    p = nullptr;
+}
+
+}  // namespace bmo

@@ -1,0 +1,1058 @@
+// bmo_trace.cu -- wavefront tracer (sm_100a) and the C ABI around it.
+//
+// One wave = one `tracing_step!` + `interact3d` of every live beam (System.jl:100-154, 274-318).
+// Kernels per wave:
+//   K1 trace_step<MODE>   one thread per ray (Gaussian beamlets: chief/waist/divergence in adjacent
+//                         lanes, 10 triples per warp): intersect -> interact -> block-local queue
+//                         compaction with warp ballots + prefix sums, successors written to scratch.
+//   K2 scan_counts        exclusive scan of the per-block successor / spawn counts.
+//   K3 scatter_queue      HBM-bound copy of the compacted successors into the next queue and
+//                         numbering of beamsplitter children (deterministic: queue order).
+// With BMO_KEEP_SEGMENTS the segment records are written wave-major by K1 and gathered into
+// beam-major order at the end (K4 gather_segments).
+#include "bmo_host.cuh"
+#include "bmo_interact.cuh"
+
+namespace bmo {
+thread_local std::string g_last_error;
+
+// ---- queue layout -------------------------------------------------------------------------------
+// double fields (SoA, stride = capacity): px py pz dx dy dz n | E0 re/im x3 (polarized) |
+//                                         lsum lpar oplpar (gaussian chief accumulators)
+enum { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_N, F_X0 };
+// int fields: lambda id, hinted part, beam, segment index, pose | scratch: child slot, local spawn index
+enum { I_LAM = 0, I_HINT, I_BEAM, I_SEG, I_POSE, NI_Q, I_SLOT = NI_Q, I_LSPAWN, NI_S };
+// segment record rows
+enum { S_PX = 0, S_PY, S_PZ, S_DX, S_DY, S_DZ, S_N, S_T, S_NX, S_NY, S_NZ, S_E0 };
+
+struct Queue {
+    double* d = nullptr;
+    int32_t* i = nullptr;
+    int64_t cap = 0;  // rays
+};
+
+inline int nf_queue(int mode) { return mode == 1 ? 13 : (mode == 2 ? 10 : 7); }
+inline int nf_scratch(int mode) { return mode == 2 ? 15 : nf_queue(mode); }
+inline int nf_seg(int mode) { return mode == 1 ? 17 : 11; }
+
+struct BeamTab {
+    int32_t *parent, *slot, *nseg, *status, *lam, *pose, *spot_obj;
+    double *w0, *e0, *plen, *popl, *spot_xz;
+};
+
+struct StepParams {
+    SysView S;
+    Queue cur, scr;
+    int64_t count;       // beams in the current queue
+    int32_t r_max, use_smem, keep, pad;
+    WaveBuf wave;
+    BeamTab B;
+    int32_t* blk_cnt;    // [nblocks][2] successors, spawns
+    DevCounters* counters;
+};
+
+template <int MODE> struct Cfg {
+    static constexpr int R = MODE == 2 ? 3 : 1;
+    static constexpr int BLOCK = 128;
+    static constexpr int NWARP = BLOCK / 32;
+    static constexpr int UNITS = MODE == 2 ? NWARP * 10 : BLOCK;  // beams per block
+};
+
+BMO_D unsigned lanemask_lt() { unsigned m; asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m)); return m; }
+BMO_D V3 shfl3(V3 v, int l) {
+    return mk3(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l), __shfl_sync(0xffffffffu, v.z, l));
+}
+
+// ---- K1 ---------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams P) {
+    constexpr int R = Cfg<MODE>::R;
+    constexpr int UNITS = Cfg<MODE>::UNITS;
+    constexpr int NWARP = Cfg<MODE>::NWARP;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
+    __shared__ int s_wcnt[NWARP][2];
+    __shared__ int s_woff[NWARP][2];
+
+    const SysView& S = P.S;
+    if (P.use_smem) {
+        const int nwords = S.n_prims * (int)(sizeof(bmo_prim) / 8);
+        const double* src = reinterpret_cast<const double*>(S.prims);
+        double* dst = reinterpret_cast<double*>(s_prims);
+        for (int k = threadIdx.x; k < nwords; k += blockDim.x) dst[k] = src[k];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int uib, r;
+    bool lane_ok = true;
+    if (MODE == 2) { uib = warp * 10 + lane / 3; r = lane % 3; lane_ok = lane < 30; }
+    else { uib = threadIdx.x; r = 0; }
+    const int64_t unit = (int64_t)blockIdx.x * UNITS + uib;
+    const bool active = lane_ok && unit < P.count;
+    const bool leader = active && r == 0;
+    const int64_t ri = unit * R + r;
+    const int64_t qs = P.cur.cap;
+
+    V3 pos = mk3(0, 0, 0), dir = mk3(0, 1, 0);
+    double rn = 1.0;
+    int lam = 0, hint = -1, beam = 0, seg = 0, pose = 0;
+    Cx E0[3];
+    E0[0] = E0[1] = E0[2] = mkc(0, 0);
+    double acc_lsum = 0, acc_lpar = 0, acc_opl = 0;
+    if (active) {
+        const double* q = P.cur.d;
+        pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
+        dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
+        rn = q[F_N * qs + ri];
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) E0[k] = mkc(q[(F_X0 + 2 * k) * qs + ri], q[(F_X0 + 2 * k + 1) * qs + ri]);
+        }
+        if (MODE == 2) { acc_lsum = q[F_X0 * qs + ri]; acc_lpar = q[(F_X0 + 1) * qs + ri]; acc_opl = q[(F_X0 + 2) * qs + ri]; }
+        const int32_t* qi = P.cur.i;
+        lam = qi[I_LAM * qs + ri]; hint = qi[I_HINT * qs + ri]; beam = qi[I_BEAM * qs + ri];
+        seg = qi[I_SEG * qs + ri]; pose = qi[I_POSE * qs + ri];
+    }
+
+    Stats st; st.sdf = 0; st.tri = 0;
+    TraceCtx C;
+    C.S = &S;
+    C.pose = pose;
+    C.prims = P.use_smem ? s_prims : (S.prims + (int64_t)pose * S.n_prims);
+
+    // ---- intersect (System.jl:100-110) ----
+    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+    int status = BMO_ST_ACTIVE;
+    if (active) {
+        if (seg + 1 >= P.r_max) status = BMO_ST_RMAX;          // `while length(rays) < r_max`, System.jl:133 / :281
+        else {
+            h = tracing_step(C, pos, dir, hint, st);
+            if (h.part < 0) status = BMO_ST_MISS;
+        }
+    }
+    double seg_t = h.t;       // t stored in this lane's segment record (Inf <=> intersection === nothing)
+    int hit_part = h.part;    // part the interaction dispatches on (Gaussian: the chief's)
+
+    // ---- Gaussian triple rules (System.jl:283-304) ----
+    V3 c_pos = pos, c_dir = dir, c_nrm = h.n, w_pos = pos, w_dir = dir, d_pos = pos, d_dir = dir;
+    double c_t = h.t, c_n = rn;
+    int base = lane, lw = lane, ld = lane;
+    if (MODE == 2) {
+        __syncwarp();
+        base = lane - r; lw = min(base + 1, 31); ld = min(base + 2, 31);
+        const unsigned full = 0xffffffffu;
+        const int pc = __shfl_sync(full, h.part, base), pw = __shfl_sync(full, h.part, lw), pd = __shfl_sync(full, h.part, ld);
+        const int stc = __shfl_sync(full, status, base);
+        c_pos = shfl3(pos, base); c_dir = shfl3(dir, base); c_nrm = shfl3(h.n, base);
+        w_pos = shfl3(pos, lw); w_dir = shfl3(dir, lw);
+        d_pos = shfl3(pos, ld); d_dir = shfl3(dir, ld);
+        c_t = __shfl_sync(full, h.t, base);
+        c_n = __shfl_sync(full, rn, base);
+        hit_part = pc;
+        if (active) {
+            if (stc == BMO_ST_RMAX) { status = BMO_ST_RMAX; seg_t = INFINITY; }
+            else if (pc < 0) { status = BMO_ST_MISS; seg_t = INFINITY; }                 // chief missed: the others are not traced
+            else if (pw < 0) { status = BMO_ST_CLIPPED; if (r != 0) seg_t = INFINITY; }  // chief keeps its intersection (:288-291)
+            else if (pd < 0) { status = BMO_ST_CLIPPED; if (r == 2) seg_t = INFINITY; }  // (:292-296)
+            else if (!(pc == pw && pw == pd)) { status = BMO_ST_TORN; seg_t = INFINITY; }  // (:298-304)
+            else status = BMO_ST_ACTIVE;
+        }
+    }
+
+    // ---- interact (dispatch on the object kind / part role) ----
+    int nsucc = 0;
+    RayOut o1, o2;                 // continuing ray, or (transmitted, reflected) children
+    o1.valid = o2.valid = false; o1.err = o2.err = false;
+    o1.hint = o2.hint = -1;
+    bool interacted = false;
+    if (active && status == BMO_ST_ACTIVE && hit_part >= 0) {
+        interacted = true;
+        const bmo_part& pt = S.parts[hit_part];
+        const bmo_object& ob = S.objects[pt.object];
+        const bool pol = MODE == 1;
+        const double t = h.t;
+        bool split = false;
+        switch (ob.kind) {
+            case BMO_OBJ_REFRACTIVE:
+                interact_refractive(pos, dir, rn, E0, pol, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                break;
+            case BMO_OBJ_DOUBLET:      // DoubletLenses.jl:66-76 (Ray only; a PolarizedRay has no method -> nothing)
+                if (pol) break;
+                interact_refractive(pos, dir, rn, E0, false, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                o1.hint = ob.first_part + (1 - (hit_part - ob.first_part));
+                break;
+            case BMO_OBJ_MIRROR:
+                interact_mirror(pos, dir, rn, E0, pol, t, h.n, o1);
+                break;
+            case BMO_OBJ_CUBE_BS:      // CubeBeamsplitter.jl:63-121
+                if (pt.role == BMO_ROLE_COATING) split = true;
+                else {
+                    interact_refractive(pos, dir, rn, E0, pol, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                    o1.hint = ob.first_part + 2;
+                }
+                break;
+            case BMO_OBJ_PLATE_BS:     // PlateBeamsplitter.jl:189-275
+                if (pt.role == BMO_ROLE_COATING) split = true;
+                else {
+                    interact_refractive(pos, dir, rn, E0, pol, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                    o1.hint = ob.first_part + 1;
+                }
+                break;
+            case BMO_OBJ_THIN_BS:
+                split = true;
+                break;
+            case BMO_OBJ_SPOTDETECTOR: {  // Spotdetector.jl:50-61
+                const double* dp = S.det_pose + 12 * ((int64_t)pose * S.n_objects + pt.object);
+                V3 hp = pos + t * dir;
+                V3 loc = hp - mk3(dp[0], dp[1], dp[2]);
+                const int64_t bi = (int64_t)beam * R + r;
+                P.B.spot_obj[bi] = pt.object;
+                P.B.spot_xz[2 * bi] = dot(loc, mk3(dp[3], dp[6], dp[9]));        // orientation[:,1]
+                P.B.spot_xz[2 * bi + 1] = dot(loc, mk3(dp[5], dp[8], dp[11]));   // orientation[:,3]
+                break;
+            }
+            default: break;  // Photodetector (field added by bmo_pd_accumulate), IntersectableObject
+        }
+        if (split) {
+            bs_children(pos, dir, E0, pol, t, h.n, pt.reflectance, pt.transmittance, o1, o2);
+            if (ob.kind == BMO_OBJ_CUBE_BS) {          // CubeBeamsplitter.jl:80-82,110-112
+                const double ng = S.n_table[S.parts[ob.first_part].n_row * S.n_lambda + lam];
+                o1.n = ng; o2.n = ng;
+            } else if (ob.kind == BMO_OBJ_PLATE_BS) {  // PlateBeamsplitter.jl:207-223,247-270
+                const double n_opt = S.n_table[S.parts[ob.first_part].n_row * S.n_lambda + lam];
+                const bool entering = (MODE == 2) ? (dot(c_dir, c_nrm) < 0) : (dot(dir, h.n) < 0);
+                const double n2 = entering ? n_opt : S.n_system;
+                bool tir, err = false;
+                V3 nd = refraction3d_ray(dir, h.n, rn, n2, tir, err);
+                o1.n = entering ? n_opt : S.n_system;
+                o2.n = entering ? S.n_system : n_opt;
+                o1.dir = normalize(nd);
+                if (err) o1.err = true;
+            }
+            nsucc = 2;
+            status = BMO_ST_SPLIT;
+        } else if (o1.valid) {
+            nsucc = 1;
+        } else {
+            status = BMO_ST_ABSORBED;
+        }
+        if ((o1.valid && o1.err) || (o2.valid && o2.err)) { status = BMO_ST_ERROR; nsucc = 0; }
+    }
+
+    // ---- Gaussian: triple-level agreement, chief hint, child beamlet parameters ----
+    double g_w0 = 0, g_plen = 0, g_popl = 0;
+    Cx g_et = mkc(0, 0), g_er = mkc(0, 0);
+    double n_lsum = 0, n_lpar = 0, n_opl = 0;  // accumulators of the continuing / child rays
+    if (MODE == 2) {
+        __syncwarp();
+        const unsigned full = 0xffffffffu;
+        const int n0 = __shfl_sync(full, nsucc, base), n1 = __shfl_sync(full, nsucc, lw), n2 = __shfl_sync(full, nsucc, ld);
+        const int s0 = __shfl_sync(full, status, base), s1 = __shfl_sync(full, status, lw), s2 = __shfl_sync(full, status, ld);
+        const int hc = __shfl_sync(full, o1.hint, base);
+        const double accl = __shfl_sync(full, acc_lsum, base), accp = __shfl_sync(full, acc_lpar, base),
+                     acco = __shfl_sync(full, acc_opl, base);
+        if (interacted) {
+            int nm = min(n0, min(n1, n2));
+            if (s0 == BMO_ST_ERROR || s1 == BMO_ST_ERROR || s2 == BMO_ST_ERROR) { status = BMO_ST_ERROR; nm = 0; }
+            else if (nm == 0) status = BMO_ST_ABSORBED;   // any(isnothing, (i_c, i_w, i_d)) -> nothing (Gaussian.jl:131-133)
+            nsucc = nm;
+            o1.hint = hc;                                  // hint(i::GaussianBeamletInteraction) = hint(i.chief), Gaussian.jl:80
+            if (nm == 1) {                                 // Beam.jl:125-205 running sums (association kept)
+                n_lsum = accl + c_t; n_lpar = accp + c_t; n_opl = acco + c_t * c_n;
+            } else if (nm == 2) {                          // ThinBeamsplitter.jl:117-168
+                const bmo_part& pt = S.parts[hit_part];
+                const double plen_parent = P.B.plen[beam];
+                const double L = (accl + c_t) + plen_parent;              // length(gauss) = l + l0
+                V3 p0 = c_pos + (L - accp) * c_dir;                        // point_on_beam(gauss, length(gauss)), Beam.jl:201-204
+                double w, Rc, psi, w0n;
+                gauss_parameters(p0, c_dir, c_n, w_pos, w_dir, d_pos, d_dir, S.lambdas[lam], w, Rc, psi, w0n);
+                const double w0b = P.B.w0[beam];
+                const Cx e0b = mkc(P.B.e0[2 * beam], P.B.e0[2 * beam + 1]);
+                g_w0 = w0n;
+                g_et = (pt.transmittance * e0b) * (w0b / w0n);
+                g_er = (pt.reflectance * e0b) * (w0b / w0n);
+                const double phi = (dot(c_dir, c_nrm) < 0) ? kPi : 0.0;  // reflection phase jump, :151-158
+                g_er = g_er * cis(phi);
+                g_plen = L;
+                g_popl = acco + c_t * c_n;
+                n_lsum = 0.0; n_lpar = L; n_opl = g_popl;
+            }
+        }
+    }
+
+    // ---- bookkeeping: counters, segment record, per-beam state ----
+    if (P.keep && active) {
+        const int64_t ws = P.wave.count;
+        double* w = P.wave.d;
+        w[S_PX * ws + ri] = pos.x; w[S_PY * ws + ri] = pos.y; w[S_PZ * ws + ri] = pos.z;
+        w[S_DX * ws + ri] = dir.x; w[S_DY * ws + ri] = dir.y; w[S_DZ * ws + ri] = dir.z;
+        w[S_N * ws + ri] = rn; w[S_T * ws + ri] = seg_t;
+        w[S_NX * ws + ri] = h.n.x; w[S_NY * ws + ri] = h.n.y; w[S_NZ * ws + ri] = h.n.z;
+        if (MODE == 1) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { w[(S_E0 + 2 * k) * ws + ri] = E0[k].re; w[(S_E0 + 2 * k + 1) * ws + ri] = E0[k].im; }
+        }
+        P.wave.part[ri] = isinf(seg_t) ? -1 : h.part;
+        P.wave.beam[ri] = beam;
+        P.wave.seg[ri] = seg;
+    }
+    if (leader) {
+        P.B.nseg[beam] = seg + 1;
+        if (nsucc != 1) P.B.status[beam] = status;
+    }
+
+    // ---- block-local compaction: warp ballots + prefix sums ----
+    const unsigned full = 0xffffffffu;
+    const unsigned b1 = __ballot_sync(full, leader && nsucc >= 1);
+    const unsigned b2 = __ballot_sync(full, leader && nsucc == 2);
+    const unsigned lt = lanemask_lt();
+    int woff = __popc(b1 & lt) + __popc(b2 & lt);   // successors of lower lanes in this warp
+    int wsoff = __popc(b2 & lt);                     // spawn events of lower lanes
+    if (lane == 0) { s_wcnt[warp][0] = __popc(b1) + __popc(b2); s_wcnt[warp][1] = __popc(b2); }
+    // statistics ride on the same barrier
+    unsigned long long ia = interacted ? 1ull : 0ull;
+    unsigned sd = st.sdf, tr = st.tri;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        ia += __shfl_xor_sync(full, ia, o);
+        sd += __shfl_xor_sync(full, sd, o);
+        tr += __shfl_xor_sync(full, tr, o);
+    }
+    if (lane == 0) {
+        if (ia) atomicAdd(&P.counters->interactions, ia);
+        if (sd) atomicAdd(&P.counters->sdf, (unsigned long long)sd);
+        if (tr) atomicAdd(&P.counters->tri, (unsigned long long)tr);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0, b = 0;
+        for (int k = 0; k < NWARP; k++) { s_woff[k][0] = a; s_woff[k][1] = b; a += s_wcnt[k][0]; b += s_wcnt[k][1]; }
+        P.blk_cnt[2 * blockIdx.x] = a;
+        P.blk_cnt[2 * blockIdx.x + 1] = b;
+    }
+    __syncthreads();
+    if (MODE == 2) { woff = __shfl_sync(full, woff, base); wsoff = __shfl_sync(full, wsoff, base); }
+    if (active && nsucc > 0) {
+        const int64_t ss = P.scr.cap;
+        const int64_t su0 = (int64_t)blockIdx.x * (2 * UNITS) + s_woff[warp][0] + woff;
+        const int lspawn = s_woff[warp][1] + wsoff;
+        for (int k = 0; k < nsucc; k++) {
+            const RayOut& o = (k == 0) ? o1 : o2;
+            const int64_t si = (su0 + k) * R + r;
+            double* d = P.scr.d;
+            d[F_PX * ss + si] = o.pos.x; d[F_PY * ss + si] = o.pos.y; d[F_PZ * ss + si] = o.pos.z;
+            d[F_DX * ss + si] = o.dir.x; d[F_DY * ss + si] = o.dir.y; d[F_DZ * ss + si] = o.dir.z;
+            d[F_N * ss + si] = o.n;
+            if (MODE == 1) {
+#pragma unroll
+                for (int c = 0; c < 3; c++) { d[(F_X0 + 2 * c) * ss + si] = o.E0[c].re; d[(F_X0 + 2 * c + 1) * ss + si] = o.E0[c].im; }
+            }
+            if (MODE == 2) {
+                d[F_X0 * ss + si] = n_lsum; d[(F_X0 + 1) * ss + si] = n_lpar; d[(F_X0 + 2) * ss + si] = n_opl;
+                const Cx e = (k == 0) ? g_et : g_er;
+                d[(F_X0 + 3) * ss + si] = g_w0; d[(F_X0 + 4) * ss + si] = e.re; d[(F_X0 + 5) * ss + si] = e.im;
+                d[(F_X0 + 6) * ss + si] = g_plen; d[(F_X0 + 7) * ss + si] = g_popl;
+            }
+            int32_t* iq = P.scr.i;
+            iq[I_LAM * ss + si] = lam;
+            iq[I_HINT * ss + si] = (nsucc == 2) ? -1 : o1.hint;
+            iq[I_BEAM * ss + si] = beam;
+            iq[I_SEG * ss + si] = (nsucc == 2) ? 0 : seg + 1;
+            iq[I_POSE * ss + si] = pose;
+            iq[I_SLOT * ss + si] = (nsucc == 2) ? k : -1;
+            iq[I_LSPAWN * ss + si] = lspawn;
+        }
+    }
+}
+
+// ---- K2: exclusive scan of int32 counts with stride (single block, chunked) -----------------------
+// in[i*stride + which] for which in [0, nwhich) -> out (long long), totals[which]
+__global__ void __launch_bounds__(1024) scan_counts(const int32_t* in, int64_t n, int stride, int nwhich, long long* out,
+                                                    long long* totals) {
+    __shared__ long long s_sum[1024];
+    const int T = blockDim.x;
+    const int64_t chunk = (n + T - 1) / T;
+    const int64_t b = (int64_t)threadIdx.x * chunk, e = min(b + chunk, n);
+    for (int w = 0; w < nwhich; w++) {
+        long long s = 0;
+        for (int64_t i = b; i < e; i++) s += in[i * stride + w];
+        s_sum[threadIdx.x] = s;
+        __syncthreads();
+        // Hillis-Steele inclusive scan over T partial sums
+        for (int o = 1; o < T; o <<= 1) {
+            long long v = threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0;
+            __syncthreads();
+            s_sum[threadIdx.x] += v;
+            __syncthreads();
+        }
+        long long run = threadIdx.x == 0 ? 0 : s_sum[threadIdx.x - 1];
+        for (int64_t i = b; i < e; i++) { out[i * nwhich + w] = run; run += in[i * stride + w]; }
+        if (threadIdx.x == T - 1) totals[w] = s_sum[T - 1];
+        __syncthreads();
+    }
+}
+
+// ---- K3: scatter compacted successors into the next queue (HBM-bound) ----------------------------
+struct ScatterParams {
+    Queue scr, next;
+    const int32_t* blk_cnt;
+    const long long* blk_off;  // [nblocks][2]
+    BeamTab B;
+    int64_t n_beams;           // beams that exist before this wave's spawns
+    int32_t nf, mode, units, R;
+};
+__global__ void __launch_bounds__(256) scatter_queue(const ScatterParams P) {
+    const int b = blockIdx.x;
+    const int cnt = P.blk_cnt[2 * b];
+    if (cnt == 0) return;
+    const long long off = P.blk_off[2 * b], spoff = P.blk_off[2 * b + 1];
+    const int64_t ss = P.scr.cap, ns = P.next.cap;
+    const int R = P.R;
+    for (int j = threadIdx.x; j < cnt * R; j += blockDim.x) {
+        const int64_t si = ((int64_t)b * (2 * P.units)) * R + j;
+        const int64_t di = off * R + j;
+        const int r = j % R;
+        for (int f = 0; f < P.nf; f++) P.next.d[f * ns + di] = P.scr.d[f * ss + si];
+        const int32_t* iq = P.scr.i;
+        int beam = iq[I_BEAM * ss + si];
+        const int slot = iq[I_SLOT * ss + si];
+        const int lam = iq[I_LAM * ss + si], pose = iq[I_POSE * ss + si];
+        if (slot >= 0) {
+            const int parent = beam;
+            beam = (int)(P.n_beams + 2 * (spoff + iq[I_LSPAWN * ss + si]) + slot);
+            if (r == 0) {
+                P.B.parent[beam] = parent; P.B.slot[beam] = slot; P.B.nseg[beam] = 0; P.B.status[beam] = BMO_ST_ACTIVE;
+                P.B.lam[beam] = lam; P.B.pose[beam] = pose;
+                if (P.mode == 2) {
+                    P.B.w0[beam] = P.scr.d[(F_X0 + 3) * ss + si];
+                    P.B.e0[2 * beam] = P.scr.d[(F_X0 + 4) * ss + si];
+                    P.B.e0[2 * beam + 1] = P.scr.d[(F_X0 + 5) * ss + si];
+                    P.B.plen[beam] = P.scr.d[(F_X0 + 6) * ss + si];
+                    P.B.popl[beam] = P.scr.d[(F_X0 + 7) * ss + si];
+                }
+            }
+            P.B.spot_obj[(int64_t)beam * R + r] = -1;
+        }
+        int32_t* nq = P.next.i;
+        nq[I_LAM * ns + di] = lam;
+        nq[I_HINT * ns + di] = iq[I_HINT * ss + si];
+        nq[I_BEAM * ns + di] = beam;
+        nq[I_SEG * ns + di] = iq[I_SEG * ss + si];
+        nq[I_POSE * ns + di] = pose;
+    }
+}
+
+// ---- init / gather ---------------------------------------------------------------------------------
+struct InitParams {
+    Queue q;
+    int64_t n;
+    int mode;
+    const double *pos, *dir, *E0, *grays, *w0, *ge0;
+    const int32_t *lam, *pose;
+    BeamTab B;
+};
+__global__ void init_queue(const InitParams P) {
+    const int R = P.mode == 2 ? 3 : 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n * R) return;
+    const int64_t u = i / R;
+    const int r = (int)(i % R);
+    const int64_t s = P.q.cap;
+    double* d = P.q.d;
+    if (P.mode == 2) {
+        const double* g = P.grays + (u * 3 + r) * 6;
+        d[F_PX * s + i] = g[0]; d[F_PY * s + i] = g[1]; d[F_PZ * s + i] = g[2];
+        d[F_DX * s + i] = g[3]; d[F_DY * s + i] = g[4]; d[F_DZ * s + i] = g[5];
+        d[F_X0 * s + i] = 0; d[(F_X0 + 1) * s + i] = 0; d[(F_X0 + 2) * s + i] = 0;
+    } else {
+        d[F_PX * s + i] = P.pos[3 * u]; d[F_PY * s + i] = P.pos[3 * u + 1]; d[F_PZ * s + i] = P.pos[3 * u + 2];
+        d[F_DX * s + i] = P.dir[3 * u]; d[F_DY * s + i] = P.dir[3 * u + 1]; d[F_DZ * s + i] = P.dir[3 * u + 2];
+        if (P.mode == 1)
+            for (int k = 0; k < 6; k++) d[(F_X0 + k) * s + i] = P.E0[6 * u + k];
+    }
+    d[F_N * s + i] = 1.0;  // Ray(pos, dir, lambda): n = 1 (Rays.jl:32-42)
+    int32_t* q = P.q.i;
+    const int lam = P.lam ? P.lam[u] : 0, pose = P.pose ? P.pose[u] : 0;
+    q[I_LAM * s + i] = lam; q[I_HINT * s + i] = -1; q[I_BEAM * s + i] = (int)u; q[I_SEG * s + i] = 0; q[I_POSE * s + i] = pose;
+    P.B.spot_obj[i] = -1;
+    if (r == 0) {
+        P.B.parent[u] = -1; P.B.slot[u] = -1; P.B.nseg[u] = 0; P.B.status[u] = BMO_ST_ACTIVE; P.B.lam[u] = lam; P.B.pose[u] = pose;
+        if (P.mode == 2) { P.B.w0[u] = P.w0[u]; P.B.e0[2 * u] = P.ge0[2 * u]; P.B.e0[2 * u + 1] = P.ge0[2 * u + 1]; P.B.plen[u] = 0; P.B.popl[u] = 0; }
+    }
+}
+__global__ void gather_segments(WaveBuf w, int R, int nsd, const long long* first_seg, double* seg_d, int32_t* seg_part, int64_t rows) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= w.count) return;
+    const int r = (int)(i % R);
+    const int64_t row = (first_seg[w.beam[i]] + w.seg[i]) * R + r;
+    for (int f = 0; f < nsd; f++) seg_d[f * rows + row] = w.d[f * w.count + i];
+    seg_part[row] = w.part[i];
+}
+
+}  // namespace bmo
+
+using namespace bmo;
+
+// =================================================================================================
+// host side
+// =================================================================================================
+static int32_t launch_check(bmo_ctx* ctx, const char* what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(BMO_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
+    return BMO_OK;
+}
+#define BMO_LAUNCH(ctx, what) do { int32_t rc_ = launch_check(ctx, what); if (rc_) return rc_; } while (0)
+
+// (exported functions get C linkage from their declarations in include/bmo.h)
+
+const char* bmo_last_error(void) { return g_last_error.c_str(); }
+
+int32_t bmo_init(int32_t device, bmo_ctx** out) {
+    if (!out) return fail(BMO_EINVAL, "bmo_init: ctx is NULL");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(BMO_ECUDA, std::string("bmo_init: no CUDA device (") + cudaGetErrorString(e) + "); libbmo has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(BMO_EINVAL, "bmo_init: bad device index");
+    BMO_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BMO_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) return fail(BMO_ECUDA, std::string("bmo_init: ") + prop.name + " is not an sm_100-class device");
+    bmo_ctx* c = new bmo_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    BMO_CUDA(cudaEventCreate(&c->ev0));
+    BMO_CUDA(cudaEventCreate(&c->ev1));
+    BMO_CUDA(cudaMalloc((void**)&c->d_counters, sizeof(DevCounters)));
+    BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+    BMO_CUDA(cudaMalloc((void**)&c->d_totals, 4 * sizeof(long long)));
+    BMO_CUDA(cudaMallocHost((void**)&c->h_totals, 4 * sizeof(long long)));
+    cudaMemPool_t pool;
+    BMO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;  // keep freed blocks cached: the wave loop reuses them every call
+    BMO_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    *out = c;
+    return BMO_OK;
+}
+int32_t bmo_shutdown(bmo_ctx* c) {
+    if (!c) return BMO_OK;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFreeHost(c->h_totals);
+    cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
+    delete c;
+    return BMO_OK;
+}
+int32_t bmo_set_stream(bmo_ctx* c, void* s) { if (!c) return fail(BMO_EINVAL, "ctx NULL"); c->stream = (cudaStream_t)s; return BMO_OK; }
+int32_t bmo_counters_get(bmo_ctx* c, bmo_counters* o) {
+    if (!c || !o) return fail(BMO_EINVAL, "bmo_counters_get: NULL");
+    BMO_CUDA(cudaSetDevice(c->device));
+    DevCounters h;
+    BMO_CUDA(cudaStreamSynchronize(c->stream));
+    BMO_CUDA(cudaMemcpy(&h, c->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+    o->interactions = (int64_t)h.interactions; o->sdf_evals = (int64_t)h.sdf; o->tri_tests = (int64_t)h.tri;
+    o->waves = c->waves; o->kernel_launches = c->launches; o->px_beamlets = c->px_beamlets;
+    o->trace_ms = c->trace_ms; o->pd_ms = c->pd_ms;
+    return BMO_OK;
+}
+int32_t bmo_counters_reset(bmo_ctx* c) {
+    if (!c) return fail(BMO_EINVAL, "ctx NULL");
+    BMO_CUDA(cudaSetDevice(c->device));
+    BMO_CUDA(cudaStreamSynchronize(c->stream));
+    BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
+    c->waves = c->launches = c->px_beamlets = 0;
+    return BMO_OK;
+}
+
+// ---- system upload ------------------------------------------------------------------------------
+static int32_t validate_tables(const bmo_tables* t) {
+    if (!t) return fail(BMO_EINVAL, "tables NULL");
+    if (t->n_objects <= 0 || t->n_parts <= 0) return fail(BMO_EINVAL, "system has no objects");
+    if (t->n_lambda <= 0 || !t->lambdas) return fail(BMO_EINVAL, "n_lambda must be >= 1");
+    for (int p = 0; p < t->n_parts; p++) {
+        const bmo_part& pt = t->parts[p];
+        if (pt.object < 0 || pt.object >= t->n_objects) return fail(BMO_EINVAL, "part.object out of range");
+        if (pt.shape_kind == BMO_SHAPE_SDF) {
+            if (pt.first < 0 || pt.count <= 0 || pt.first + pt.count > t->n_prims) return fail(BMO_EINVAL, "part prim range out of bounds");
+        } else if (pt.shape_kind == BMO_SHAPE_MESH) {
+            if (pt.first < 0 || pt.first >= t->n_meshes) return fail(BMO_EINVAL, "part mesh index out of range");
+        } else return fail(BMO_EINVAL, "unknown shape kind");
+        if (pt.n_row >= t->n_rows) return fail(BMO_EINVAL, "part.n_row out of range");
+    }
+    for (int o = 0; o < t->n_objects; o++) {
+        const bmo_object& ob = t->objects[o];
+        if (ob.first_part < 0 || ob.n_parts <= 0 || ob.first_part + ob.n_parts > t->n_parts) return fail(BMO_EINVAL, "object part range out of bounds");
+        const int need = ob.kind == BMO_OBJ_CUBE_BS ? 3 : ((ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_DOUBLET) ? 2 : 1);
+        if (ob.n_parts != need) return fail(BMO_EINVAL, "object has the wrong number of parts for its kind");
+        if ((ob.kind == BMO_OBJ_REFRACTIVE) && t->parts[ob.first_part].n_row < 0) return fail(BMO_EINVAL, "refractive object without n_row");
+    }
+    for (int m = 0; m < t->n_meshes; m++) {
+        const bmo_mesh& me = t->meshes[m];
+        if (me.first_vertex < 0 || me.first_vertex + me.n_vertices > t->n_vertices || me.first_face < 0 || me.first_face + me.n_faces > t->n_faces)
+            return fail(BMO_EINVAL, "mesh range out of bounds");
+        for (int64_t f = 3 * me.first_face; f < 3 * (me.first_face + me.n_faces); f++)
+            if (t->faces[f] < 0 || t->faces[f] >= me.n_vertices) return fail(BMO_EINVAL, "face vertex index out of range");
+    }
+    return BMO_OK;
+}
+
+template <class T> static int32_t upload(T** dptr, const T* h, size_t n) {
+    BMO_CUDA(cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T)));
+    if (n) BMO_CUDA(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
+    return BMO_OK;
+}
+
+int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
+    if (!ctx || !out) return fail(BMO_EINVAL, "bmo_system_upload: NULL argument");
+    int32_t rc = validate_tables(t);
+    if (rc) return rc;
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    bmo_sys* s = new bmo_sys();
+    s->ctx = ctx;
+    s->prims.assign(t->prims, t->prims + t->n_prims);
+    s->parts.assign(t->parts, t->parts + t->n_parts);
+    s->objects.assign(t->objects, t->objects + t->n_objects);
+    s->lambdas.assign(t->lambdas, t->lambdas + t->n_lambda);
+    s->n_vertices = t->n_vertices; s->n_faces = t->n_faces;
+    s->h_vertices.assign(t->vertices, t->vertices + 3 * t->n_vertices);
+    // meshes + BVH
+    std::vector<BvhNode> nodes;
+    std::vector<int32_t> order(std::max<int64_t>(t->n_faces, 1), 0);
+    for (int m = 0; m < t->n_meshes; m++) {
+        const bmo_mesh& me = t->meshes[m];
+        MeshView mv{};
+        mv.first_vertex = me.first_vertex; mv.n_vertices = me.n_vertices; mv.first_face = me.first_face; mv.n_faces = me.n_faces;
+        mv.f32 = me.f32;
+        mv.first_node = (int64_t)nodes.size(); mv.n_nodes = 0;
+        if (me.n_faces > 16) {
+            BvhBuild bb;
+            bvh_build(t->vertices + 3 * me.first_vertex, t->faces + 3 * me.first_face, me.n_faces, bb);
+            mv.n_nodes = (int64_t)bb.nodes.size();
+            nodes.insert(nodes.end(), bb.nodes.begin(), bb.nodes.end());
+            std::copy(bb.order.begin(), bb.order.end(), order.begin() + me.first_face);
+        }
+        s->meshes.push_back(mv);
+    }
+    // detector poses + bounds (pose 0)
+    s->h_detpose.assign((size_t)12 * t->n_objects, 0.0);
+    for (int o = 0; o < t->n_objects; o++) {
+        for (int k = 0; k < 3; k++) s->h_detpose[12 * o + k] = t->objects[o].pos[k];
+        for (int k = 0; k < 9; k++) s->h_detpose[12 * o + 3 + k] = t->objects[o].dir[k];
+    }
+    s->h_bounds.assign((size_t)4 * t->n_parts, 0.0);
+    for (int p = 0; p < t->n_parts; p++)
+        for (int k = 0; k < 4; k++) s->h_bounds[4 * p + k] = t->parts[p].bound[k];
+    std::vector<double> ntab(t->n_table, t->n_table + (size_t)std::max(t->n_rows, 0) * t->n_lambda);
+    if ((rc = upload(&s->d_prims, s->prims.data(), s->prims.size()))) return rc;
+    if ((rc = upload(&s->d_parts, s->parts.data(), s->parts.size()))) return rc;
+    if ((rc = upload(&s->d_objects, s->objects.data(), s->objects.size()))) return rc;
+    if ((rc = upload(&s->d_meshes, s->meshes.data(), s->meshes.size()))) return rc;
+    if ((rc = upload(&s->d_vertices, s->h_vertices.data(), s->h_vertices.size()))) return rc;
+    if ((rc = upload(&s->d_faces, t->faces, (size_t)3 * t->n_faces))) return rc;
+    if ((rc = upload(&s->d_nodes, nodes.data(), nodes.size()))) return rc;
+    if ((rc = upload(&s->d_bvh_faces, order.data(), (size_t)t->n_faces))) return rc;
+    if ((rc = upload(&s->d_ntable, ntab.data(), ntab.size()))) return rc;
+    if ((rc = upload(&s->d_bounds, s->h_bounds.data(), s->h_bounds.size()))) return rc;
+    if ((rc = upload(&s->d_detpose, s->h_detpose.data(), s->h_detpose.size()))) return rc;
+    if ((rc = upload(&s->d_lambdas, s->lambdas.data(), s->lambdas.size()))) return rc;
+    SysView& v = s->view;
+    v.prims = s->d_prims; v.parts = s->d_parts; v.objects = s->d_objects; v.meshes = s->d_meshes;
+    v.vertices = s->d_vertices; v.faces = s->d_faces; v.nodes = s->d_nodes; v.bvh_faces = s->d_bvh_faces;
+    v.n_table = s->d_ntable; v.bounds = s->d_bounds; v.det_pose = s->d_detpose; v.lambdas = s->d_lambdas;
+    v.n_prims = t->n_prims; v.n_parts = t->n_parts; v.n_objects = t->n_objects; v.n_meshes = t->n_meshes;
+    v.n_lambda = t->n_lambda; v.n_poses = 1; v.zr = t->norm_zero_rule; v.n_vertices = t->n_vertices;
+    v.n_system = t->n_system;
+    *out = s;
+    return BMO_OK;
+}
+int32_t bmo_system_free(bmo_sys* s) {
+    if (!s) return BMO_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    cudaFree(s->d_prims); cudaFree(s->d_parts); cudaFree(s->d_objects); cudaFree(s->d_meshes); cudaFree(s->d_vertices);
+    cudaFree(s->d_faces); cudaFree(s->d_nodes); cudaFree(s->d_bvh_faces); cudaFree(s->d_ntable); cudaFree(s->d_bounds);
+    cudaFree(s->d_detpose); cudaFree(s->d_lambdas);
+    delete s;
+    return BMO_OK;
+}
+int32_t bmo_system_set_poses(bmo_sys* s, int32_t n_poses, const bmo_prim* prims, const double* vertices, const double* bounds,
+                             const double* det_pos, const double* det_dir) {
+    if (!s || n_poses < 1) return fail(BMO_EINVAL, "bmo_system_set_poses: bad arguments");
+    BMO_CUDA(cudaSetDevice(s->ctx->device));
+    BMO_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    SysView& v = s->view;
+    const size_t np = (size_t)n_poses;
+    auto reup = [&](auto** dptr, const auto* h, size_t n) -> int32_t {
+        cudaFree(*dptr); *dptr = nullptr;
+        return upload(dptr, h, n);
+    };
+    int32_t rc;
+    if (n_poses == 1 && !prims) {  // restore the uploaded tables
+        if ((rc = reup(&s->d_prims, s->prims.data(), s->prims.size()))) return rc;
+        if ((rc = reup(&s->d_vertices, s->h_vertices.data(), s->h_vertices.size()))) return rc;
+        if ((rc = reup(&s->d_bounds, s->h_bounds.data(), s->h_bounds.size()))) return rc;
+        if ((rc = reup(&s->d_detpose, s->h_detpose.data(), s->h_detpose.size()))) return rc;
+    } else {
+        if (!prims || !bounds || (!vertices && s->n_vertices > 0) || !det_pos || !det_dir) return fail(BMO_EINVAL, "bmo_system_set_poses: NULL table");
+        if ((rc = reup(&s->d_prims, prims, np * s->prims.size()))) return rc;
+        if ((rc = reup(&s->d_vertices, vertices, np * 3 * (size_t)s->n_vertices))) return rc;
+        if ((rc = reup(&s->d_bounds, bounds, np * 4 * s->parts.size()))) return rc;
+        std::vector<double> dp(np * 12 * s->objects.size());
+        for (size_t i = 0; i < np * s->objects.size(); i++) {
+            for (int k = 0; k < 3; k++) dp[12 * i + k] = det_pos[3 * i + k];
+            for (int k = 0; k < 9; k++) dp[12 * i + 3 + k] = det_dir[9 * i + k];
+        }
+        if ((rc = reup(&s->d_detpose, dp.data(), dp.size()))) return rc;
+    }
+    v.prims = s->d_prims; v.vertices = s->d_vertices; v.bounds = s->d_bounds; v.det_pose = s->d_detpose;
+    v.n_poses = n_poses;
+    return BMO_OK;
+}
+
+// ---- trace driver -----------------------------------------------------------------------------------
+static int32_t alloc_queue(Queue& q, int64_t cap, int nf, int ni, cudaStream_t st) {
+    q.cap = cap;
+    BMO_CUDA(dev_alloc(&q.d, (size_t)nf * cap, st));
+    BMO_CUDA(dev_alloc(&q.i, (size_t)ni * cap, st));
+    return BMO_OK;
+}
+static void free_queue(Queue& q, cudaStream_t st) { dev_free(q.d, st); dev_free(q.i, st); q.cap = 0; }
+
+static BeamTab beamtab(bmo_result* r) {
+    BeamTab b;
+    b.parent = r->parent; b.slot = r->slot; b.nseg = r->nseg; b.status = r->status; b.lam = r->lam; b.pose = r->pose;
+    b.spot_obj = r->spot_obj; b.w0 = r->w0; b.e0 = r->e0; b.plen = r->plen; b.popl = r->popl; b.spot_xz = r->spot_xz;
+    return b;
+}
+template <class T> static int32_t grow(T*& p, int64_t old_n, int64_t new_n, cudaStream_t st) {
+    T* np_ = nullptr;
+    BMO_CUDA(dev_alloc(&np_, (size_t)new_n, st));
+    if (p && old_n) BMO_CUDA(cudaMemcpyAsync(np_, p, (size_t)old_n * sizeof(T), cudaMemcpyDeviceToDevice, st));
+    dev_free(p, st);
+    p = np_;
+    return BMO_OK;
+}
+static int32_t ensure_beams(bmo_result* r, int64_t need, cudaStream_t st) {
+    if (need <= r->cap_beams) return BMO_OK;
+    int64_t nc = std::max<int64_t>(need, r->cap_beams + r->cap_beams / 2);
+    const int64_t oc = r->cap_beams, R = r->R;
+    int32_t rc;
+    if ((rc = grow(r->parent, oc, nc, st))) return rc;
+    if ((rc = grow(r->slot, oc, nc, st))) return rc;
+    if ((rc = grow(r->nseg, oc, nc, st))) return rc;
+    if ((rc = grow(r->status, oc, nc, st))) return rc;
+    if ((rc = grow(r->lam, oc, nc, st))) return rc;
+    if ((rc = grow(r->pose, oc, nc, st))) return rc;
+    if ((rc = grow(r->spot_obj, oc * R, nc * R, st))) return rc;
+    if ((rc = grow(r->spot_xz, oc * R * 2, nc * R * 2, st))) return rc;
+    if (r->mode == 2) {
+        if ((rc = grow(r->w0, oc, nc, st))) return rc;
+        if ((rc = grow(r->e0, oc * 2, nc * 2, st))) return rc;
+        if ((rc = grow(r->plen, oc, nc, st))) return rc;
+        if ((rc = grow(r->popl, oc, nc, st))) return rc;
+    }
+    r->cap_beams = nc;
+    return BMO_OK;
+}
+
+struct TraceInputs {
+    int64_t n;
+    const double *pos, *dir, *E0, *grays, *w0, *ge0;
+    const int32_t *lam, *pose;
+};
+
+template <class T> static int32_t stage_in(const T* h, size_t n, bool on_device, cudaStream_t st, const T** out, std::vector<void*>& tmp) {
+    if (!h) { *out = nullptr; return BMO_OK; }
+    if (on_device) { *out = h; return BMO_OK; }
+    T* d = nullptr;
+    BMO_CUDA(dev_alloc(&d, n, st));
+    BMO_CUDA(cudaMemcpyAsync(d, h, n * sizeof(T), cudaMemcpyHostToDevice, st));
+    tmp.push_back((void*)d);
+    *out = d;
+    return BMO_OK;
+}
+
+static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int32_t r_max, uint32_t flags, bmo_result** out) {
+    if (!sys || !out) return fail(BMO_EINVAL, "trace: NULL argument");
+    if (in_h.n <= 0) return fail(BMO_EINVAL, "trace: n must be > 0");
+    if (r_max < 1) return fail(BMO_EINVAL, "trace: r_max must be >= 1");
+    bmo_ctx* ctx = sys->ctx;
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool on_dev = flags & BMO_INPUT_DEVICE;
+    const int R = mode == 2 ? 3 : 1;
+    const int nfq = nf_queue(mode), nfs = nf_scratch(mode), nsd = nf_seg(mode);
+    const int units = mode == 2 ? Cfg<2>::UNITS : Cfg<0>::UNITS;
+    const int64_t n = in_h.n;
+
+    bmo_result* res = new bmo_result();
+    res->sys = sys; res->mode = mode; res->R = R; res->nsd = nsd; res->n_roots = n; res->keep = flags & BMO_KEEP_SEGMENTS;
+    BMO_CUDA(cudaEventRecord(ctx->ev0, st));
+    int32_t rc;
+    std::vector<void*> tmp;
+    TraceInputs in = in_h;
+    if (mode == 2) {
+        if ((rc = stage_in(in_h.grays, (size_t)n * 18, on_dev, st, &in.grays, tmp))) return rc;
+        if ((rc = stage_in(in_h.w0, (size_t)n, on_dev, st, &in.w0, tmp))) return rc;
+        if ((rc = stage_in(in_h.ge0, (size_t)n * 2, on_dev, st, &in.ge0, tmp))) return rc;
+    } else {
+        if ((rc = stage_in(in_h.pos, (size_t)n * 3, on_dev, st, &in.pos, tmp))) return rc;
+        if ((rc = stage_in(in_h.dir, (size_t)n * 3, on_dev, st, &in.dir, tmp))) return rc;
+        if (mode == 1 && (rc = stage_in(in_h.E0, (size_t)n * 6, on_dev, st, &in.E0, tmp))) return rc;
+    }
+    if ((rc = stage_in(in_h.lam, (size_t)n, on_dev, st, &in.lam, tmp))) return rc;
+    if ((rc = stage_in(in_h.pose, (size_t)n, on_dev, st, &in.pose, tmp))) return rc;
+
+    if ((rc = ensure_beams(res, n, st))) return rc;
+    Queue cur, next, scr;
+    if ((rc = alloc_queue(cur, n * R, nfq, NI_Q, st))) return rc;
+    {
+        InitParams ip{};
+        ip.q = cur; ip.n = n; ip.mode = mode; ip.pos = in.pos; ip.dir = in.dir; ip.E0 = in.E0; ip.grays = in.grays;
+        ip.w0 = in.w0; ip.ge0 = in.ge0; ip.lam = in.lam; ip.pose = in.pose; ip.B = beamtab(res);
+        const int64_t tot = n * R;
+        init_queue<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ip);
+        BMO_LAUNCH(ctx, "init_queue");
+    }
+    const bool use_smem = sys->view.n_poses == 1 && (size_t)sys->view.n_prims * sizeof(bmo_prim) <= 40 * 1024;
+    const size_t smem = use_smem ? (size_t)sys->view.n_prims * sizeof(bmo_prim) : 0;
+
+    int64_t count = n, n_beams = n;
+    int32_t* blk_cnt = nullptr; long long* blk_off = nullptr; int64_t blk_cap = 0;
+    int wave = 0;
+    while (count > 0) {
+        const int64_t nblocks = (count + units - 1) / units;
+        const int64_t scr_cap = nblocks * 2 * units * R;
+        if (scr.cap < scr_cap) { free_queue(scr, st); if ((rc = alloc_queue(scr, scr_cap, nfs, NI_S, st))) return rc; }
+        if (next.cap < 2 * count * R) { free_queue(next, st); if ((rc = alloc_queue(next, 2 * count * R, nfq, NI_Q, st))) return rc; }
+        if (blk_cap < nblocks) {
+            dev_free(blk_cnt, st); dev_free(blk_off, st);
+            BMO_CUDA(dev_alloc(&blk_cnt, (size_t)2 * nblocks, st));
+            BMO_CUDA(dev_alloc(&blk_off, (size_t)2 * nblocks, st));
+            blk_cap = nblocks;
+        }
+        if ((rc = ensure_beams(res, n_beams + 2 * count, st))) return rc;
+        WaveBuf wb{};
+        if (res->keep) {
+            wb.count = count * R;
+            BMO_CUDA(dev_alloc(&wb.d, (size_t)nsd * wb.count, st));
+            BMO_CUDA(dev_alloc(&wb.part, (size_t)wb.count, st));
+            BMO_CUDA(dev_alloc(&wb.beam, (size_t)wb.count, st));
+            BMO_CUDA(dev_alloc(&wb.seg, (size_t)wb.count, st));
+            res->wavebufs.push_back(wb);
+        }
+        StepParams sp{};
+        sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.count = count; sp.r_max = r_max; sp.use_smem = use_smem; sp.keep = res->keep;
+        sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.counters = ctx->d_counters;
+        if (mode == 0) trace_step<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, smem, st>>>(sp);
+        else if (mode == 1) trace_step<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, smem, st>>>(sp);
+        else trace_step<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, smem, st>>>(sp);
+        BMO_LAUNCH(ctx, "trace_step");
+        scan_counts<<<1, 1024, 0, st>>>(blk_cnt, nblocks, 2, 2, blk_off, ctx->d_totals);
+        BMO_LAUNCH(ctx, "scan_counts");
+        ScatterParams cp{};
+        cp.scr = scr; cp.next = next; cp.blk_cnt = blk_cnt; cp.blk_off = blk_off; cp.B = beamtab(res); cp.n_beams = n_beams;
+        cp.nf = nfq; cp.mode = mode; cp.units = units; cp.R = R;
+        scatter_queue<<<(unsigned)nblocks, 256, 0, st>>>(cp);
+        BMO_LAUNCH(ctx, "scatter_queue");
+        BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        BMO_CUDA(cudaStreamSynchronize(st));
+        count = ctx->h_totals[0];
+        n_beams += 2 * ctx->h_totals[1];
+        std::swap(cur, next);
+        wave++;
+        ctx->waves++;
+        if (wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
+    }
+    res->n_beams = n_beams;
+    res->waves = wave;
+    free_queue(cur, st); free_queue(next, st); free_queue(scr, st);
+    dev_free(blk_cnt, st); dev_free(blk_off, st);
+    for (void* p : tmp) cudaFreeAsync(p, st);
+
+    // segment table: first_seg = exclusive scan of nseg, then gather wave-major -> beam-major
+    BMO_CUDA(dev_alloc(&res->first_seg, (size_t)n_beams + 1, st));
+    scan_counts<<<1, 1024, 0, st>>>(res->nseg, n_beams, 1, 1, res->first_seg, ctx->d_totals);
+    BMO_LAUNCH(ctx, "scan_counts(nseg)");
+    BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    res->n_segments = ctx->h_totals[0];
+    BMO_CUDA(cudaMemcpyAsync(res->first_seg + n_beams, ctx->d_totals, sizeof(long long), cudaMemcpyDeviceToDevice, st));
+    if (res->keep) {
+        res->seg_rows = res->n_segments * R;
+        BMO_CUDA(dev_alloc(&res->seg_d, (size_t)nsd * res->seg_rows, st));
+        BMO_CUDA(dev_alloc(&res->seg_part, (size_t)res->seg_rows, st));
+        for (auto& wb : res->wavebufs) {
+            gather_segments<<<(unsigned)((wb.count + 255) / 256), 256, 0, st>>>(wb, R, nsd, res->first_seg, res->seg_d, res->seg_part, res->seg_rows);
+            BMO_LAUNCH(ctx, "gather_segments");
+            dev_free(wb.d, st); dev_free(wb.part, st); dev_free(wb.beam, st); dev_free(wb.seg, st);
+        }
+        res->wavebufs.clear();
+    }
+    BMO_CUDA(cudaEventRecord(ctx->ev1, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    float ms = 0;
+    BMO_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->trace_ms = ms;
+    {
+        DevCounters h;
+        BMO_CUDA(cudaMemcpy(&h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+        static thread_local unsigned long long last = 0;
+        (void)last;
+        res->interactions = (int64_t)h.interactions;  // cumulative since reset; bmo_result_get_info reports the delta below
+    }
+    *out = res;
+    return BMO_OK;
+}
+
+int32_t bmo_trace_rays(bmo_sys* sys, int64_t n, const double* pos, const double* dir, const int32_t* lambda_id, const double* E0,
+                       const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out) {
+    if (!pos || !dir) return fail(BMO_EINVAL, "bmo_trace_rays: pos/dir NULL");
+    TraceInputs in{};
+    in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id;
+    if (!sys) return fail(BMO_EINVAL, "sys NULL");
+    DevCounters before;
+    BMO_CUDA(cudaSetDevice(sys->ctx->device));
+    BMO_CUDA(cudaStreamSynchronize(sys->ctx->stream));
+    BMO_CUDA(cudaMemcpy(&before, sys->ctx->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
+    int32_t rc = trace_common(sys, E0 ? 1 : 0, in, r_max, flags, out);
+    if (rc == BMO_OK) (*out)->interactions -= (int64_t)before.interactions;
+    return rc;
+}
+int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const int32_t* lambda_id, const double* w0, const double* E0,
+                           const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out) {
+    if (!rays || !w0 || !E0) return fail(BMO_EINVAL, "bmo_trace_beamlets: rays/w0/E0 NULL");
+    TraceInputs in{};
+    in.n = n; in.grays = rays; in.w0 = w0; in.ge0 = E0; in.lam = lambda_id; in.pose = pose_id;
+    if (!sys) return fail(BMO_EINVAL, "sys NULL");
+    DevCounters before;
+    BMO_CUDA(cudaSetDevice(sys->ctx->device));
+    BMO_CUDA(cudaStreamSynchronize(sys->ctx->stream));
+    BMO_CUDA(cudaMemcpy(&before, sys->ctx->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
+    int32_t rc = trace_common(sys, 2, in, r_max, flags | BMO_KEEP_SEGMENTS, out);
+    if (rc == BMO_OK) (*out)->interactions -= (int64_t)before.interactions;
+    return rc;
+}
+
+// ---- result access ----------------------------------------------------------------------------------
+int32_t bmo_result_get_info(bmo_result* r, bmo_result_info* info) {
+    if (!r || !info) return fail(BMO_EINVAL, "bmo_result_get_info: NULL");
+    info->n_roots = r->n_roots; info->n_beams = r->n_beams; info->n_segments = r->n_segments; info->interactions = r->interactions;
+    info->rays_per_beam = r->R; info->polarized = r->mode == 1; info->waves = r->waves; info->reserved = 0;
+    return BMO_OK;
+}
+template <class T> static int32_t d2h(T* dst, const T* src, size_t n, cudaStream_t st) {
+    if (!dst || !n) return BMO_OK;
+    BMO_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(T), cudaMemcpyDeviceToHost, st));
+    return BMO_OK;
+}
+int32_t bmo_result_beams(bmo_result* r, int32_t* parent, int32_t* child_slot, int32_t* n_seg, int32_t* status, int64_t* first_seg,
+                         double* w0, double* E0, int32_t* lambda_id) {
+    if (!r) return fail(BMO_EINVAL, "result NULL");
+    BMO_CUDA(cudaSetDevice(r->sys->ctx->device));
+    cudaStream_t st = r->sys->ctx->stream;
+    const size_t nb = (size_t)r->n_beams;
+    int32_t rc;
+    if ((rc = d2h(parent, r->parent, nb, st))) return rc;
+    if ((rc = d2h(child_slot, r->slot, nb, st))) return rc;
+    if ((rc = d2h(n_seg, r->nseg, nb, st))) return rc;
+    if ((rc = d2h(status, r->status, nb, st))) return rc;
+    if ((rc = d2h((long long*)first_seg, r->first_seg, nb, st))) return rc;
+    if ((rc = d2h(lambda_id, r->lam, nb, st))) return rc;
+    if (r->mode == 2) {
+        if ((rc = d2h(w0, r->w0, nb, st))) return rc;
+        if ((rc = d2h(E0, r->e0, 2 * nb, st))) return rc;
+    }
+    BMO_CUDA(cudaStreamSynchronize(st));
+    return BMO_OK;
+}
+int32_t bmo_result_segments(bmo_result* r, double* pos, double* dir, double* n, double* t, double* nrm, int32_t* object, int32_t* part,
+                            double* E0) {
+    if (!r) return fail(BMO_EINVAL, "result NULL");
+    if (!r->keep) return fail(BMO_ESTATE, "bmo_result_segments: trace was run without BMO_KEEP_SEGMENTS");
+    BMO_CUDA(cudaSetDevice(r->sys->ctx->device));
+    cudaStream_t st = r->sys->ctx->stream;
+    const size_t rows = (size_t)r->seg_rows;
+    if (rows == 0) return BMO_OK;
+    // device table is SoA [field][row]; the ABI hands out [row][3] arrays -> stage through a host buffer
+    std::vector<double> h((size_t)r->nsd * rows);
+    std::vector<int32_t> hp(rows);
+    BMO_CUDA(cudaMemcpyAsync(h.data(), r->seg_d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaMemcpyAsync(hp.data(), r->seg_part, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    const std::vector<bmo_part>& parts = r->sys->parts;
+    for (size_t i = 0; i < rows; i++) {
+        if (pos) { pos[3 * i] = h[S_PX * rows + i]; pos[3 * i + 1] = h[S_PY * rows + i]; pos[3 * i + 2] = h[S_PZ * rows + i]; }
+        if (dir) { dir[3 * i] = h[S_DX * rows + i]; dir[3 * i + 1] = h[S_DY * rows + i]; dir[3 * i + 2] = h[S_DZ * rows + i]; }
+        if (n) n[i] = h[S_N * rows + i];
+        if (t) t[i] = h[S_T * rows + i];
+        if (nrm) { nrm[3 * i] = h[S_NX * rows + i]; nrm[3 * i + 1] = h[S_NY * rows + i]; nrm[3 * i + 2] = h[S_NZ * rows + i]; }
+        if (part) part[i] = hp[i];
+        if (object) object[i] = hp[i] >= 0 ? parts[hp[i]].object : -1;
+        if (E0 && r->mode == 1) for (int k = 0; k < 6; k++) E0[6 * i + k] = h[(S_E0 + k) * rows + i];
+    }
+    return BMO_OK;
+}
+int32_t bmo_result_spots(bmo_result* r, int32_t* det_object, double* xz) {
+    if (!r) return fail(BMO_EINVAL, "result NULL");
+    BMO_CUDA(cudaSetDevice(r->sys->ctx->device));
+    cudaStream_t st = r->sys->ctx->stream;
+    const size_t nr = (size_t)r->n_beams * r->R;
+    int32_t rc;
+    if ((rc = d2h(det_object, r->spot_obj, nr, st))) return rc;
+    if ((rc = d2h(xz, r->spot_xz, 2 * nr, st))) return rc;
+    BMO_CUDA(cudaStreamSynchronize(st));
+    return BMO_OK;
+}
+int32_t bmo_result_spots_device(bmo_result* r, const int32_t** det_object, const double** xz) {
+    if (!r) return fail(BMO_EINVAL, "result NULL");
+    if (det_object) *det_object = r->spot_obj;
+    if (xz) *xz = r->spot_xz;
+    return BMO_OK;
+}
+int32_t bmo_result_free(bmo_result* r) {
+    if (!r) return BMO_OK;
+    cudaSetDevice(r->sys->ctx->device);
+    cudaStream_t st = r->sys->ctx->stream;
+    dev_free(r->parent, st); dev_free(r->slot, st); dev_free(r->nseg, st); dev_free(r->status, st); dev_free(r->lam, st); dev_free(r->pose, st);
+    dev_free(r->w0, st); dev_free(r->e0, st); dev_free(r->plen, st); dev_free(r->popl, st);
+    dev_free(r->spot_obj, st); dev_free(r->spot_xz, st); dev_free(r->first_seg, st);
+    dev_free(r->seg_d, st); dev_free(r->seg_part, st);
+    for (auto& wb : r->wavebufs) { dev_free(wb.d, st); dev_free(wb.part, st); dev_free(wb.beam, st); dev_free(wb.seg, st); }
+    delete r;
+    return BMO_OK;
+}
+
+// ---- FP64 peak probe (roofline denominator for the FP64-bound kernels) -------------------------------
+__global__ void dfma_probe(double* out, int iters) {
+    double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6, a7 = a0 + 7;
+    const double b = 1.0000001, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = __fma_rn(a0, b, c); a1 = __fma_rn(a1, b, c); a2 = __fma_rn(a2, b, c); a3 = __fma_rn(a3, b, c);
+        a4 = __fma_rn(a4, b, c); a5 = __fma_rn(a5, b, c); a6 = __fma_rn(a6, b, c); a7 = __fma_rn(a7, b, c);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops) {
+    if (!ctx || !tflops) return fail(BMO_EINVAL, "NULL");
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    const int blocks = ctx->sm_count * 8, threads = 256, iters = 1 << 16;
+    double* d = nullptr;
+    BMO_CUDA(cudaMalloc((void**)&d, (size_t)blocks * threads * sizeof(double)));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; rep++) {
+        BMO_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+        dfma_probe<<<blocks, threads, 0, ctx->stream>>>(d, iters);
+        BMO_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+        BMO_CUDA(cudaStreamSynchronize(ctx->stream));
+        float ms;
+        BMO_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaFree(d);
+    *tflops = 2.0 * 8 * iters * (double)blocks * threads / (best * 1e-3) / 1e12;
+    return BMO_OK;
+}
+
+

@@ -1,0 +1,296 @@
+"""`solve_system!` on the GPU (reference: src/System.jl:444-475).
+
+`solve_system_(system, beam)` flattens the system at call time (poses are static during a trace,
+docs/src/basics/elements.md), uploads the tables, runs the wavefront tracer of libbmo.so and puts
+the results where the reference puts them: `Beam.rays` / `.children`, `Spotdetector.data`,
+`Photodetector.field`.  The reference's `retrace=true` re-validates a stored path against the
+previously hit objects (System.jl:188-428); here every call is a fresh non-sequential trace, which
+gives the same result whenever the path is unchanged (see DESIGN.md "retrace").
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import beams as bm
+from . import components as co
+from .flatten import FlatSystem
+
+
+class DeviceSystem:
+    """Uploaded copy of a flattened System (bmo_sys)."""
+
+    def __init__(self, flat, device=0):
+        self.flat = flat
+        self.device = device
+        self.ctx = L.context(device)
+        h = C.c_void_p()
+        L.check(L.lib().bmo_system_upload(self.ctx, C.byref(flat.tables), C.byref(h)))
+        self.h = h
+
+    def free(self):
+        if self.h:
+            L.lib().bmo_system_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class TraceResult:
+    """Device-resident result of one trace (bmo_result) with lazy host views."""
+
+    def __init__(self, dsys, handle):
+        self.dsys, self.h = dsys, handle
+        info = L.bmo_result_info()
+        L.check(L.lib().bmo_result_get_info(handle, C.byref(info)))
+        self.n_roots, self.n_beams, self.n_segments = info.n_roots, info.n_beams, info.n_segments
+        self.interactions, self.R, self.polarized, self.waves = info.interactions, info.rays_per_beam, bool(info.polarized), info.waves
+        self._beams = self._segs = self._spots = None
+
+    def free(self):
+        if self.h:
+            L.lib().bmo_result_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def beams(self):
+        if self._beams is None:
+            nb = self.n_beams
+            d = dict(parent=np.zeros(nb, np.int32), slot=np.zeros(nb, np.int32), nseg=np.zeros(nb, np.int32),
+                     status=np.zeros(nb, np.int32), first=np.zeros(nb, np.int64), lam_id=np.zeros(nb, np.int32))
+            w0 = E0 = None
+            if self.R == 3:
+                w0, E0 = np.zeros(nb), np.zeros(2 * nb)
+            L.check(L.lib().bmo_result_beams(self.h, L.ptr(d["parent"]), L.ptr(d["slot"]), L.ptr(d["nseg"]), L.ptr(d["status"]),
+                                            L.ptr(d["first"]), L.ptr(w0), L.ptr(E0), L.ptr(d["lam_id"])))
+            if self.R == 3:
+                d["w0"], d["E0"] = w0, E0[0::2] + 1j * E0[1::2]
+            self._beams = d
+        return self._beams
+
+    def segments(self):
+        """Beam-major segment table: arrays of `n_segments * R` rows (Gaussian: chief, waist, div interleaved)."""
+        if self._segs is None:
+            rows = self.n_segments * self.R
+            d = dict(pos=np.zeros((rows, 3)), dir=np.zeros((rows, 3)), n=np.zeros(rows), t=np.zeros(rows), nrm=np.zeros((rows, 3)),
+                     obj=np.zeros(rows, np.int32), part=np.zeros(rows, np.int32))
+            E0 = np.zeros((rows, 6)) if self.polarized else None
+            L.check(L.lib().bmo_result_segments(self.h, L.ptr(d["pos"]), L.ptr(d["dir"]), L.ptr(d["n"]), L.ptr(d["t"]), L.ptr(d["nrm"]),
+                                               L.ptr(d["obj"]), L.ptr(d["part"]), L.ptr(E0)))
+            if self.polarized:
+                d["E0"] = E0[:, 0::2] + 1j * E0[:, 1::2]
+            self._segs = d
+        return self._segs
+
+    def spots(self):
+        if self._spots is None:
+            n = self.n_beams * self.R
+            obj, xz = np.zeros(n, np.int32), np.zeros((n, 2))
+            L.check(L.lib().bmo_result_spots(self.h, L.ptr(obj), L.ptr(xz)))
+            self._spots = (obj, xz)
+        return self._spots
+
+    def bfs_order(self):
+        """Beam ids in the reference's processing order: root by root, FIFO over each beam tree
+        (System.jl:444-461 = level order, children as [transmitted, reflected])."""
+        b = self.beams()
+        parent, slot = b["parent"], b["slot"]
+        nb = self.n_beams
+        if nb == self.n_roots:
+            return np.arange(nb)
+        root = np.arange(nb)
+        depth = np.zeros(nb, np.int64)
+        code = np.zeros(nb, np.int64)      # path of 0/1 choices, MSB first
+        for i in range(self.n_roots, nb):   # children always have larger ids than their parent
+            p = parent[i]
+            root[i], depth[i], code[i] = root[p], depth[p] + 1, code[p] * 2 + slot[i]
+        return np.lexsort((code, depth, root))
+
+
+def _lambda_ids(lams):
+    uniq, inv = np.unique(np.asarray(lams, dtype=np.float64), return_inverse=True)
+    return [float(x) for x in uniq], np.ascontiguousarray(inv.astype(np.int32))
+
+
+def upload_system(system, lambdas, device=0, norm_zero_rule=0):
+    return DeviceSystem(FlatSystem(system, lambdas, norm_zero_rule), device)
+
+
+def trace_rays(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100, keep_segments=True, device_inputs=False):
+    """Thin wrapper of bmo_trace_rays.  With device_inputs=True pos/dir/lam_id/E0/pose_id are integer
+    device pointers (e.g. torch tensors' data_ptr()) and `n` must be given as pos=(ptr, n)."""
+    flags = L.KEEP_SEGMENTS if keep_segments else 0
+    h = C.c_void_p()
+    if device_inputs:
+        (ppos, n) = pos
+        flags |= L.INPUT_DEVICE
+        L.check(L.lib().bmo_trace_rays(dsys.h, n, L.ptr(ppos), L.ptr(dir), L.ptr(lam_id), L.ptr(E0), L.ptr(pose_id), r_max, flags, C.byref(h)))
+    else:
+        pos = np.ascontiguousarray(pos, dtype=np.float64)
+        dir = np.ascontiguousarray(dir, dtype=np.float64)
+        lam_id = np.ascontiguousarray(lam_id, dtype=np.int32)
+        e = None
+        if E0 is not None:
+            ec = np.ascontiguousarray(E0, dtype=np.complex128)
+            e = np.ascontiguousarray(np.stack([ec.real, ec.imag], axis=-1).reshape(pos.shape[0], 6))
+        pid = None if pose_id is None else np.ascontiguousarray(pose_id, dtype=np.int32)
+        L.check(L.lib().bmo_trace_rays(dsys.h, pos.shape[0], L.ptr(pos), L.ptr(dir), L.ptr(lam_id), L.ptr(e), L.ptr(pid), r_max, flags, C.byref(h)))
+    return TraceResult(dsys, h)
+
+
+def trace_beamlets(dsys, rays, lam_id, w0, E0, pose_id=None, r_max=100):
+    rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 18)
+    lam_id = np.ascontiguousarray(lam_id, dtype=np.int32)
+    w0 = np.ascontiguousarray(w0, dtype=np.float64)
+    ec = np.ascontiguousarray(E0, dtype=np.complex128)
+    e = np.ascontiguousarray(np.stack([ec.real, ec.imag], axis=-1))
+    pid = None if pose_id is None else np.ascontiguousarray(pose_id, dtype=np.int32)
+    h = C.c_void_p()
+    L.check(L.lib().bmo_trace_beamlets(dsys.h, rays.shape[0], L.ptr(rays), L.ptr(lam_id), L.ptr(w0), L.ptr(e), L.ptr(pid), r_max, 0, C.byref(h)))
+    return TraceResult(dsys, h)
+
+
+def pd_accumulate(dsys, result, pd_index, field, pose=0):
+    """field: (n, n) complex128 Fortran-ordered host array; the beamlet fields are ADDED to it."""
+    assert field.flags["F_CONTIGUOUS"] and field.dtype == np.complex128
+    L.check(L.lib().bmo_pd_accumulate(dsys.h, result.h, int(pd_index), int(pose), L.ptr(field), 0))
+
+
+# ---- rebuilding the reference's host objects from the segment table --------------------------------
+def _mk_ray(seg, row, flat, polarized, lam):
+    if polarized:
+        r = bm.PolarizedRay.__new__(bm.PolarizedRay)
+        r.E0 = tuple(complex(x) for x in seg["E0"][row])
+    else:
+        r = bm.Ray.__new__(bm.Ray)
+    r.pos, r.dir = tuple(seg["pos"][row]), tuple(seg["dir"][row])
+    r.lam, r.n = lam, float(seg["n"][row])
+    t = float(seg["t"][row])
+    if np.isfinite(t):
+        part = int(seg["part"][row])
+        r.intersection = bm.Intersection(t, tuple(seg["nrm"][row]), flat.objects[int(seg["obj"][row])], flat.part_owner[part].shape)
+    else:
+        r.intersection = None
+    return r
+
+
+def _rebuild_beam(beam, res, flat, root=0):
+    b, seg = res.beams(), res.segments()
+    lam = beam.rays[0].lam
+    pol = res.polarized
+    objs = {root: beam}
+    beam.children = []
+    ids = [root] + [i for i in range(res.n_roots, res.n_beams)]
+    # roots of other rays are not part of this tree
+    owner = {root: True}
+    for i in ids:
+        if i != root:
+            if not owner.get(int(b["parent"][i]), False):
+                continue
+            owner[i] = True
+            nb = bm.Beam.__new__(bm.Beam)
+            nb.parent, nb.children = objs[int(b["parent"][i])], []
+            objs[i] = nb
+        tgt = objs[i]
+        f, n = int(b["first"][i]), int(b["nseg"][i])
+        tgt.rays = [_mk_ray(seg, f + k, flat, pol, lam) for k in range(n)]
+    for i in sorted(objs):
+        if i != root:
+            objs[int(b["parent"][i])].children.append(objs[i])   # slot 0 (transmitted) is numbered before slot 1
+    return objs
+
+
+def _rebuild_gauss(g, res, flat, root=0):
+    b, seg = res.beams(), res.segments()
+    objs = {root: g}
+    g.children = []
+    for i in [root] + list(range(res.n_roots, res.n_beams)):
+        if i != root:
+            p = int(b["parent"][i])
+            if p not in objs:
+                continue
+            ng = bm.GaussianBeamlet._raw(bm.Beam.__new__(bm.Beam), bm.Beam.__new__(bm.Beam), bm.Beam.__new__(bm.Beam),
+                                         g.lam, float(b["w0"][i]), complex(b["E0"][i]))
+            ng.parent = objs[p]
+            for bb in (ng.chief, ng.waist, ng.divergence):
+                bb.parent, bb.children = None, []
+            ng.chief.parent = objs[p].chief          # Gaussian.jl:107-111
+            objs[p].children.append(ng)
+            objs[i] = ng
+        tgt = objs[i]
+        f, n = int(b["first"][i]), int(b["nseg"][i])
+        for r, bb in enumerate((tgt.chief, tgt.waist, tgt.divergence)):
+            bb.rays = [_mk_ray(seg, (f + k) * 3 + r, flat, False, g.lam) for k in range(n)]
+    return objs
+
+
+def _collect_spots(system_flat, res):
+    """Append Spotdetector hits in the reference's push! order."""
+    obj, xz = res.spots()
+    if not (obj >= 0).any():
+        return
+    order = res.bfs_order()
+    R = res.R
+    idx = (order[:, None] * R + np.arange(R)[None, :]).ravel()
+    for oi, o in enumerate(system_flat.objects):
+        if isinstance(o, co.Spotdetector):
+            sel = idx[obj[idx] == oi]
+            if sel.size:
+                o.data = np.concatenate([o.data, xz[sel]])
+
+
+def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rule=0, keep_segments=True):
+    """solve_system!(system, beam; r_max, retrace) for a Beam, GaussianBeamlet, RayBundle or
+    BeamletBundle (System.jl:444-468).  Returns the TraceResult (the reference returns nothing)."""
+    if isinstance(beam, (list, tuple)):
+        return [solve_system_(system, b, r_max, retrace, device, norm_zero_rule, keep_segments) for b in beam]
+    if isinstance(beam, bm.Beam):
+        r0 = beam.rays[0]
+        lams, lam_id = _lambda_ids([r0.lam])
+        dsys = upload_system(system, lams, device, norm_zero_rule)
+        E0 = np.array([r0.E0]) if r0.polarized else None
+        res = trace_rays(dsys, np.array([r0.pos]), np.array([r0.dir]), lam_id, E0, None, r_max, True)
+        _rebuild_beam(beam, res, dsys.flat)
+        _collect_spots(dsys.flat, res)
+        return res
+    if isinstance(beam, bm.GaussianBeamlet):
+        lams, lam_id = _lambda_ids([beam.lam])
+        dsys = upload_system(system, lams, device, norm_zero_rule)
+        res = trace_beamlets(dsys, np.array([beam.rays18()]), lam_id, np.array([beam.w0]), np.array([beam.E0]), None, r_max)
+        _rebuild_gauss(beam, res, dsys.flat)
+        _collect_spots(dsys.flat, res)
+        _accumulate_pds(dsys, res)
+        return res
+    if isinstance(beam, bm.RayBundle):
+        lams, lam_id = _lambda_ids(beam.lam)
+        dsys = upload_system(system, lams, device, norm_zero_rule)
+        res = trace_rays(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max, keep_segments)
+        beam.result = res
+        _collect_spots(dsys.flat, res)
+        return res
+    if isinstance(beam, bm.BeamletBundle):
+        lams, lam_id = _lambda_ids(beam.lam)
+        dsys = upload_system(system, lams, device, norm_zero_rule)
+        res = trace_beamlets(dsys, beam.rays, lam_id, beam.w0, beam.E0, None, r_max)
+        beam.result = res
+        _collect_spots(dsys.flat, res)
+        _accumulate_pds(dsys, res)
+        return res
+    raise TypeError(f"cannot trace {type(beam).__name__}")
+
+
+def _accumulate_pds(dsys, res):
+    for oi, o in enumerate(dsys.flat.objects):
+        if isinstance(o, co.Photodetector):
+            if not o.field.flags["F_CONTIGUOUS"]:
+                o.field = np.asfortranarray(o.field)
+            pd_accumulate(dsys, res, oi, o.field)

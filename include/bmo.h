@@ -1,0 +1,222 @@
+/* bmo.h -- C ABI of libbmo.so, the B200-native (sm_100a) trace hot path behind BeamletOptics.jl's
+ * solve_system! seam.
+ *
+ * The reference (pure Julia, /root/reference) has no FFI boundary; its extension mechanism is
+ * multiple dispatch on `solve_system!(system::AbstractSystem, beam; r_max, retrace)`
+ * (src/System.jl:444-468).  A host-side `CUDASystem <: AbstractSystem` (Julia)
+ * or the Python mirror in beamletoptics.jl_b200/ flattens `Leaves(system.objects)`
+ * (src/System.jl:21) into the plain tables below and calls these entry points via ccall/ctypes.
+ * All functions return 0 on success or a negative BMO_E* code; bmo_last_error() gives the text.
+ * No exceptions cross the boundary, no torch/Julia types appear in signatures, the caller owns
+ * every input array and every output buffer it passes in.
+ *
+ * All arithmetic is FP64 (complex128 for fields / Jones vectors).
+ */
+#ifndef BMO_H
+#define BMO_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BMO_OK 0
+#define BMO_EINVAL (-1)   /* bad argument (reference: ArgumentError / ErrorException) */
+#define BMO_ECUDA (-2)    /* CUDA runtime error */
+#define BMO_ENOMEM (-3)
+#define BMO_ESTATE (-4)   /* call order / handle misuse */
+
+/* ---- SDF primitives: replaces the `sdf(shape, point)` methods of
+ * src/SDFs/SphericalLensSDF.jl:60-65,86-89,159-170,219-232, src/SDFs/PrimitiveSDF.jl:41-46,71-76,
+ * 112-124,162-166,204-210 and src/SDFs/MeniscusLensSDF.jl:42-46.  par[] per type:               */
+enum bmo_prim_type {
+    BMO_PRIM_PLANO = 0,     /* par: thickness, diameter                          */
+    BMO_PRIM_CYLINDER = 1,  /* par: radius, half height                          */
+    BMO_PRIM_SPHERE = 2,    /* par: radius                                       */
+    BMO_PRIM_CONVEX = 3,    /* par: radius, diameter, sag, height                */
+    BMO_PRIM_CONCAVE = 4,   /* par: radius, diameter, sag                        */
+    BMO_PRIM_CUTSPHERE = 5, /* par: radius, height, w                            */
+    BMO_PRIM_BOX = 6,       /* par: half extents x, y, z                         */
+    BMO_PRIM_RING = 7,      /* par: inner_radius(+hwidth), hwidth, hthickness    */
+    BMO_PRIM_RAPRISM = 8,   /* par: half extents x, y, z                         */
+    BMO_PRIM_MENISCUS = 9   /* frame only; followed by 3 child records: convex, cylinder, concave,
+                               posed relative to this frame (MeniscusLensSDF.jl:42-46)            */
+};
+typedef struct bmo_prim {
+    int32_t type;
+    int32_t reserved;
+    double pos[3];   /* position(shape)                                   (AbstractSDF.jl:35-40) */
+    double tdir[9];  /* transposed_orientation(shape), row-major: local = tdir * (P - pos)       */
+    double par[4];
+} bmo_prim;
+
+/* ---- parts: one shape each.  A part is what `shape(intersection)` / `Hint.shape` identify
+ * (src/AbstractTypes/AbstractRay.jl:13-18, AbstractSystem.jl:49-57).                             */
+enum bmo_shape_kind { BMO_SHAPE_SDF = 0, BMO_SHAPE_MESH = 1 };
+enum bmo_role {
+    BMO_ROLE_SINGLE = 0,     /* SingleShape object                                                */
+    BMO_ROLE_FRONT = 1,      /* DoubletLens.front / CubeBeamsplitter.front                        */
+    BMO_ROLE_BACK = 2,       /* DoubletLens.back  / CubeBeamsplitter.back                         */
+    BMO_ROLE_SUBSTRATE = 3,  /* AbstractPlateBeamsplitter.substrate                               */
+    BMO_ROLE_COATING = 4     /* ThinBeamsplitter coating of a plate / cube splitter               */
+};
+typedef struct bmo_part {
+    int32_t object;      /* owning object (index into objects)                                    */
+    int32_t role;
+    int32_t shape_kind;
+    int32_t first;       /* SDF: first prim record; MESH: mesh index                              */
+    int32_t count;       /* SDF: number of prim records of the union (meniscus children included) */
+    int32_t n_row;       /* row of n_table for refractive parts, else -1                          */
+    double reflectance;  /* coating amplitudes sqrt(R), sqrt(1-R^2)  (ThinBeamsplitter.jl:43-51)   */
+    double transmittance;
+    double bound[4];     /* conservative world-space bounding sphere (centre, radius); only used for
+                            result-identical early exits of guaranteed misses                     */
+} bmo_part;
+
+/* ---- objects in `Leaves(system.objects)` order (tie-break order of trace_all, System.jl:57-72).
+ * NonInteractableObject is skipped by the flattener (NonInteractable.jl:19-20).                  */
+enum bmo_obj_kind {
+    BMO_OBJ_REFRACTIVE = 0,   /* Lens, Prism            (Lenses.jl:46-126)                        */
+    BMO_OBJ_MIRROR = 1,       /* AbstractReflectiveOptic (Mirrors.jl:39-69)                       */
+    BMO_OBJ_THIN_BS = 2,      /* ThinBeamsplitter       (ThinBeamsplitter.jl:108-168)             */
+    BMO_OBJ_PLATE_BS = 3,     /* parts: substrate, coating (PlateBeamsplitter.jl:160-275)         */
+    BMO_OBJ_CUBE_BS = 4,      /* parts: front, back, coating (CubeBeamsplitter.jl:63-121)         */
+    BMO_OBJ_DOUBLET = 5,      /* parts: front, back     (DoubletLenses.jl:66-76)                  */
+    BMO_OBJ_PHOTODETECTOR = 6,/* (Photodetector.jl:69-107)                                        */
+    BMO_OBJ_SPOTDETECTOR = 7, /* (Spotdetector.jl:50-61)                                          */
+    BMO_OBJ_STOP = 8          /* IntersectableObject    (Intersectable.jl:15)                     */
+};
+typedef struct bmo_object {
+    int32_t kind;
+    int32_t first_part;
+    int32_t n_parts;
+    int32_t pd_n;        /* Photodetector: pixels per side                                        */
+    double pos[3];       /* detectors: position(shape)                                            */
+    double dir[9];       /* detectors: orientation(shape), row-major                              */
+    double pd_lo, pd_hi; /* Photodetector: x = y = LinRange(pd_lo, pd_hi, pd_n) (Photodetector.jl:52) */
+} bmo_object;
+
+typedef struct bmo_mesh {
+    int64_t first_vertex, n_vertices;  /* into vertices[] (xyz triples, WORLD coordinates, Mesh.jl:33-39) */
+    int64_t first_face, n_faces;       /* into faces[] (3 x int32 each, 0-based, mesh-local vertex ids)   */
+    int32_t f32;                       /* 1: Mesh{Float32} (STL, Mesh.jl:48-70): edge vectors and face normals
+                                          are formed in Float32 like the reference's Point3{Float32} arithmetic */
+    int32_t reserved;
+} bmo_mesh;
+
+typedef struct bmo_tables {
+    int32_t n_prims;    const bmo_prim* prims;
+    int32_t n_parts;    const bmo_part* parts;
+    int32_t n_objects;  const bmo_object* objects;
+    int32_t n_meshes;   const bmo_mesh* meshes;
+    int64_t n_vertices; const double* vertices;
+    int64_t n_faces;    const int32_t* faces;
+    int32_t n_lambda;   const double* lambdas;   /* distinct vacuum wavelengths of the beams       */
+    int32_t n_rows;     const double* n_table;   /* [n_rows][n_lambda] refractive_index(obj, lambda),
+                                                    evaluated on the host (Lenses.jl:37-38)        */
+    double n_system;                             /* refractive_index(system, lambda) = 1.0 (AbstractSystem.jl:21) */
+    int32_t norm_zero_rule;                      /* 0: zero-vector norm of duals has NaN partials (default), 1: clean zero */
+    int32_t reserved;
+} bmo_tables;
+
+typedef struct bmo_ctx bmo_ctx;        /* one per process and GPU                                  */
+typedef struct bmo_sys bmo_sys;        /* device copy of a flattened System                        */
+typedef struct bmo_result bmo_result;  /* device-resident result of one trace call                 */
+
+/* flags of bmo_trace_* */
+#define BMO_KEEP_SEGMENTS 1u  /* keep the full segment table (needed to rebuild Beam trees / run the PD kernel) */
+#define BMO_INPUT_DEVICE 2u   /* input arrays are device pointers (already resident in HBM)        */
+
+typedef struct bmo_counters {
+    int64_t interactions;   /* hits that reached interact3d (a Gaussian triple counts 3)           */
+    int64_t sdf_evals;      /* primitive-SDF evaluations (value or dual)                           */
+    int64_t tri_tests;      /* Moeller-Trumbore evaluations                                        */
+    int64_t waves;          /* wavefront iterations (bounces)                                      */
+    int64_t kernel_launches;/* CUDA kernels launched by the library since the last reset           */
+    int64_t px_beamlets;    /* pixel-beamlet pairs accumulated by bmo_pd_accumulate                */
+    double trace_ms;        /* device time of the last trace call (CUDA events on the ctx stream)  */
+    double pd_ms;           /* device time of the last bmo_pd_accumulate                           */
+} bmo_counters;
+
+int32_t bmo_init(int32_t device, bmo_ctx** ctx);
+int32_t bmo_shutdown(bmo_ctx* ctx);
+const char* bmo_last_error(void);
+int32_t bmo_set_stream(bmo_ctx* ctx, void* cuda_stream);  /* cudaStream_t; NULL = legacy default  */
+int32_t bmo_counters_get(bmo_ctx* ctx, bmo_counters* out);
+int32_t bmo_counters_reset(bmo_ctx* ctx);
+
+/* replaces: construction of System / StaticSystem + Leaves flattening (System.jl:10-45)          */
+int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* tables, bmo_sys** sys);
+int32_t bmo_system_free(bmo_sys* sys);
+/* Batched kinematic poses (replaces translate3d!/rotate3d! between solves, AbstractShape.jl:56-94,
+ * Mesh.jl:78-96): pose p uses prims[p*n_prims ...], vertices[p*n_vertices ...], bounds[p*n_parts*4 ...].
+ * Rays select their pose with pose_id.  n_poses = 1 restores the uploaded tables.                */
+int32_t bmo_system_set_poses(bmo_sys* sys, int32_t n_poses, const bmo_prim* prims, const double* vertices,
+                             const double* bounds, const double* det_pos /* [n_poses][n_objects][3] */,
+                             const double* det_dir /* [n_poses][n_objects][9] */);
+
+/* replaces: solve_system!(system, beams(bg)) for Beam{Ray} / Beam{PolarizedRay}
+ * (System.jl:130-154, 444-475).  pos/dir: [n][3]; lambda_id: [n] index into tables.lambdas;
+ * E0: NULL or [n][6] (re,im x 3) -> PolarizedRay; pose_id: NULL or [n].                          */
+int32_t bmo_trace_rays(bmo_sys* sys, int64_t n, const double* pos, const double* dir, const int32_t* lambda_id,
+                       const double* E0, const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out);
+
+/* replaces: solve_system!(system, ::GaussianBeamlet) (System.jl:274-318) for n root beamlets.
+ * rays: [n][3 (chief, waist, divergence)][6 (pos, dir)]; w0, E0 (re,im): beamlet fields
+ * (Gaussian.jl:33-42).                                                                           */
+int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const int32_t* lambda_id, const double* w0,
+                           const double* E0, const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out);
+
+/* ---- result access.  Beams are numbered roots first (0..n-1), children in spawn order.         */
+typedef struct bmo_result_info {
+    int64_t n_roots, n_beams, n_segments, interactions;
+    int32_t rays_per_beam;  /* 1 (Beam) or 3 (GaussianBeamlet: chief, waist, divergence)          */
+    int32_t polarized;
+    int32_t waves;
+    int32_t reserved;
+} bmo_result_info;
+int32_t bmo_result_get_info(bmo_result* r, bmo_result_info* info);
+/* per beam: parent beam (-1 for roots), index of the child within its parent (0 transmitted, 1 reflected),
+ * number of segments, status of the last segment (bmo_status), first segment row.
+ * Gaussian extras (NULL ok): w0, E0 (re,im), lambda_id.                                          */
+int32_t bmo_result_beams(bmo_result* r, int32_t* parent, int32_t* child_slot, int32_t* n_seg, int32_t* status,
+                         int64_t* first_seg, double* w0, double* E0, int32_t* lambda_id);
+/* segment table, beam-major; rows = n_segments * rays_per_beam (Gaussian: chief, waist, div interleaved).
+ * Any pointer may be NULL.  t = Inf <=> intersection === nothing.  E0: [rows][6].                 */
+int32_t bmo_result_segments(bmo_result* r, double* pos, double* dir, double* n, double* t, double* nrm,
+                            int32_t* object, int32_t* part, double* E0);
+/* Spotdetector hits (Spotdetector.jl:50-61): per beam the detector object index (-1: none) and local (x, z). */
+int32_t bmo_result_spots(bmo_result* r, int32_t* det_object, double* xz);
+/* same, but leaves the data on the device: returns device pointers valid until bmo_result_free   */
+int32_t bmo_result_spots_device(bmo_result* r, const int32_t** det_object, const double** xz);
+int32_t bmo_result_free(bmo_result* r);
+
+enum bmo_status {
+    BMO_ST_ACTIVE = 0,
+    BMO_ST_MISS = 1,      /* no intersection: beam leaves the system                               */
+    BMO_ST_ABSORBED = 2,  /* interact3d returned nothing (detector, stop, unsupported pairing)     */
+    BMO_ST_RMAX = 3,      /* r_max segments reached (System.jl:133)                                */
+    BMO_ST_SPLIT = 4,     /* beamsplitter: children spawned, parent stops                          */
+    BMO_ST_CLIPPED = 5,   /* Gaussian: waist or divergence ray missed (System.jl:288-296)          */
+    BMO_ST_TORN = 6,      /* Gaussian: rays hit different shapes (System.jl:298-304)               */
+    BMO_ST_ERROR = 7      /* reference would throw (non-unit vectors, E0 not orthogonal, ...)      */
+};
+
+/* replaces: interact3d(::AbstractSystem, ::Photodetector, ::GaussianBeamlet, ray_id)
+ * (Photodetector.jl:69-107) summed over every leaf beamlet of `r` whose chief ray ends on detector
+ * `pd_object`, for pose `pose`.  field: n*n complex128, column-major [i, j] (re,im interleaved),
+ * host pointer, or device pointer if flags has BMO_INPUT_DEVICE; the result is ADDED to it (the
+ * reference's `+=`).                                                                             */
+int32_t bmo_pd_accumulate(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t pose, double* field, uint32_t flags);
+/* batched form for pose sweeps: fields[pose] for pose in [0, n_poses)                             */
+int32_t bmo_pd_accumulate_poses(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_poses, double* fields, uint32_t flags);
+/* optical_power(pd) = trapz((x, y), |E|^2 / (2 Z0)) (Photodetector.jl:109-116) on the device.    */
+int32_t bmo_pd_power(bmo_sys* sys, int32_t pd_object, int32_t n_fields, const double* fields, double* power, uint32_t flags);
+
+/* FP64 DFMA micro-benchmark used as the roofline denominator of the FP64-bound kernels.          */
+int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BMO_H */

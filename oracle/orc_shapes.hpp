@@ -377,9 +377,11 @@ struct Mesh : Shape {
     void set_new_origin() { dir = M3::identity(); pos = {0, 0, 0}; }  // Mesh.jl:171-175
 
     // Mesh.jl:203-237  (k_eps = l_eps = 1e-9); returns Inf on miss
-    static double moeller_trumbore(V3 V1, V3 V2, V3 V3_, V3 rpos, V3 rdir) {
+    // For Mesh{Float32} the edges are Float32 differences (Point3{Float32} arithmetic) before promotion.
+    static double moeller_trumbore(V3 V1, V3 V2, V3 V3_, V3 rpos, V3 rdir, bool f32 = false) {
         const double ke = 1e-9, le = 1e-9;
         V3 E1 = V2 - V1, E2 = V3_ - V1;
+        if (f32) { E1 = {r32(E1.x), r32(E1.y), r32(E1.z)}; E2 = {r32(E2.x), r32(E2.y), r32(E2.z)}; }
         V3 Pv = cross(rdir, E2);
         double Det = dot(E1, Pv);
         if (std::fabs(Det) < ke) return kInf;
@@ -397,6 +399,14 @@ struct Mesh : Shape {
     // Mesh.jl:183-192
     V3 face_normal(int f) const {
         V3 a = vertices[faces[f][0]], b = vertices[faces[f][1]], c = vertices[faces[f][2]];
+        if (f32) {  // cross / normalize in Float32 (Point3{Float32})
+            float ax = (float)a.x, ay = (float)a.y, az = (float)a.z;
+            float ux = (float)b.x - ax, uy = (float)b.y - ay, uz = (float)b.z - az;
+            float vx = (float)c.x - ax, vy = (float)c.y - ay, vz = (float)c.z - az;
+            float nx = uy * vz - uz * vy, ny = uz * vx - ux * vz, nz = ux * vy - uy * vx;
+            float il = 1.0f / std::sqrt(nx * nx + ny * ny + nz * nz);
+            return V3{(double)(il * nx), (double)(il * ny), (double)(il * nz)};
+        }
         return normalize(cross(b - a, c - a));
     }
     // Mesh.jl:244-267  brute force, strict-min => lowest face index wins ties
@@ -404,7 +414,7 @@ struct Mesh : Shape {
         int fid = -1;
         double t0 = kInf;
         for (size_t i = 0; i < faces.size(); i++) {
-            double t = moeller_trumbore(vertices[faces[i][0]], vertices[faces[i][1]], vertices[faces[i][2]], rpos, rdir);
+            double t = moeller_trumbore(vertices[faces[i][0]], vertices[faces[i][1]], vertices[faces[i][2]], rpos, rdir, f32);
             if (t < t0) { t0 = t; fid = (int)i; }
         }
         if (std::isinf(t0)) return Hit{};
