@@ -54,7 +54,9 @@ class bmo_tables(C.Structure):
 
 class bmo_counters(C.Structure):
     _fields_ = [("interactions", C.c_int64), ("sdf_evals", C.c_int64), ("tri_tests", C.c_int64), ("waves", C.c_int64),
-                ("kernel_launches", C.c_int64), ("px_beamlets", C.c_int64), ("trace_ms", C.c_double), ("pd_ms", C.c_double)]
+                ("kernel_launches", C.c_int64), ("px_beamlets", C.c_int64), ("trace_ms", C.c_double), ("pd_ms", C.c_double),
+                ("trace_step_ms", C.c_double), ("trace_step_launches", C.c_int64), ("scatter_ms", C.c_double),
+                ("scatter_bytes", C.c_double), ("pd_field_ms", C.c_double)]
 
 
 class bmo_result_info(C.Structure):

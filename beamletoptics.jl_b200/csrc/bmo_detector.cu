@@ -313,7 +313,9 @@ static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t po
         pp.recs = d_recs; pp.n_recs = m; pp.R = rv; pp.field = d_field; pp.det_pose = sys->view.det_pose; pp.pose_off = d_pose_off;
         pp.n = n; pp.pd_object = pd_object; pp.n_objects = sys->view.n_objects; pp.pose0 = pose0; pp.lo = ob.pd_lo; pp.hi = ob.pd_hi;
         dim3 grid((n + PD_TILE - 1) / PD_TILE, (n + PD_TILE - 1) / PD_TILE, n_fields), block(PD_TILE, PD_TILE);
+        BMO_CUDA(cudaEventRecord(ctx->evk0, st));
         pd_field<<<grid, block, 0, st>>>(pp);
+        BMO_CUDA(cudaEventRecord(ctx->evk1, st));
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return fail(BMO_ECUDA, std::string("pd_field: ") + cudaGetErrorString(e));
@@ -327,6 +329,7 @@ static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t po
     float ms = 0;
     BMO_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     ctx->pd_ms = ms;
+    if (m > 0) { float kms = 0; BMO_CUDA(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1)); ctx->k4_ms += kms; }
     if (!on_dev) dev_free(d_field, st);
     dev_free(d_flags, st); dev_free(d_offs, st); dev_free(d_recs, st); dev_free(d_pose_off, st);
     return BMO_OK;

@@ -524,6 +524,8 @@ int32_t bmo_init(int32_t device, bmo_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     BMO_CUDA(cudaEventCreate(&c->ev0));
     BMO_CUDA(cudaEventCreate(&c->ev1));
+    BMO_CUDA(cudaEventCreate(&c->evk0)); BMO_CUDA(cudaEventCreate(&c->evk1));
+    BMO_CUDA(cudaEventCreate(&c->evs0)); BMO_CUDA(cudaEventCreate(&c->evs1));
     BMO_CUDA(cudaMalloc((void**)&c->d_counters, sizeof(DevCounters)));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     BMO_CUDA(cudaMalloc((void**)&c->d_totals, 4 * sizeof(long long)));
@@ -554,6 +556,8 @@ int32_t bmo_counters_get(bmo_ctx* c, bmo_counters* o) {
     o->interactions = (int64_t)h.interactions; o->sdf_evals = (int64_t)h.sdf; o->tri_tests = (int64_t)h.tri;
     o->waves = c->waves; o->kernel_launches = c->launches; o->px_beamlets = c->px_beamlets;
     o->trace_ms = c->trace_ms; o->pd_ms = c->pd_ms;
+    o->trace_step_ms = c->k1_ms; o->trace_step_launches = c->k1_launches; o->scatter_ms = c->k3_ms; o->scatter_bytes = c->k3_bytes;
+    o->pd_field_ms = c->k4_ms;
     return BMO_OK;
 }
 int32_t bmo_counters_reset(bmo_ctx* c) {
@@ -562,6 +566,7 @@ int32_t bmo_counters_reset(bmo_ctx* c) {
     BMO_CUDA(cudaStreamSynchronize(c->stream));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     c->waves = c->launches = c->px_beamlets = 0;
+    c->k1_ms = c->k3_ms = c->k3_bytes = c->k4_ms = 0; c->k1_launches = 0;
     return BMO_OK;
 }
 
@@ -845,19 +850,31 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         StepParams sp{};
         sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.count = count; sp.r_max = r_max; sp.use_smem = use_smem; sp.keep = res->keep;
         sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.counters = ctx->d_counters;
+        BMO_CUDA(cudaEventRecord(ctx->evk0, st));
         if (mode == 0) trace_step<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, smem, st>>>(sp);
         else if (mode == 1) trace_step<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, smem, st>>>(sp);
         else trace_step<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, smem, st>>>(sp);
         BMO_LAUNCH(ctx, "trace_step");
+        BMO_CUDA(cudaEventRecord(ctx->evk1, st));
         scan_counts<<<1, 1024, 0, st>>>(blk_cnt, nblocks, 2, 2, blk_off, ctx->d_totals);
         BMO_LAUNCH(ctx, "scan_counts");
         ScatterParams cp{};
         cp.scr = scr; cp.next = next; cp.blk_cnt = blk_cnt; cp.blk_off = blk_off; cp.B = beamtab(res); cp.n_beams = n_beams;
         cp.nf = nfq; cp.mode = mode; cp.units = units; cp.R = R;
+        BMO_CUDA(cudaEventRecord(ctx->evs0, st));
         scatter_queue<<<(unsigned)nblocks, 256, 0, st>>>(cp);
         BMO_LAUNCH(ctx, "scatter_queue");
+        BMO_CUDA(cudaEventRecord(ctx->evs1, st));
         BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
         BMO_CUDA(cudaStreamSynchronize(st));
+        {
+            float kms = 0, sms = 0;
+            BMO_CUDA(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
+            BMO_CUDA(cudaEventElapsedTime(&sms, ctx->evs0, ctx->evs1));
+            ctx->k1_ms += kms; ctx->k1_launches++;
+            ctx->k3_ms += sms;
+            ctx->k3_bytes += (double)ctx->h_totals[0] * R * (2.0 * (nfq * 8 + NI_Q * 4) + 2 * 4);
+        }
         count = ctx->h_totals[0];
         n_beams += 2 * ctx->h_totals[1];
         std::swap(cur, next);

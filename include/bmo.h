@@ -136,6 +136,11 @@ typedef struct bmo_counters {
     int64_t px_beamlets;    /* pixel-beamlet pairs accumulated by bmo_pd_accumulate                */
     double trace_ms;        /* device time of the last trace call (CUDA events on the ctx stream)  */
     double pd_ms;           /* device time of the last bmo_pd_accumulate                           */
+    double trace_step_ms;   /* accumulated device time of the trace_step kernel (K1) since the reset  */
+    int64_t trace_step_launches;
+    double scatter_ms;      /* accumulated device time of the queue scatter kernel (K3)             */
+    double scatter_bytes;   /* algorithmic bytes moved by K3 (read + write of the surviving rays)   */
+    double pd_field_ms;     /* accumulated device time of the pd_field kernel (K4)                  */
 } bmo_counters;
 
 int32_t bmo_init(int32_t device, bmo_ctx** ctx);
