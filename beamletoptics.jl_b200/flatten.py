@@ -55,7 +55,7 @@ def _emit_sdf(shape, prims):
 class FlatSystem:
     """Host tables + the bookkeeping needed to map device ids back to host objects."""
 
-    def __init__(self, system, lambdas, norm_zero_rule=0):
+    def __init__(self, system, lambdas, norm_zero_rule=1):
         self.lambdas = [float(x) for x in lambdas]
         leaves = [o for o in system.leaves() if not isinstance(o, co.NonInteractableObject)]
         if not leaves:

@@ -121,7 +121,7 @@ def _lambda_ids(lams):
     return [float(x) for x in uniq], np.ascontiguousarray(inv.astype(np.int32))
 
 
-def upload_system(system, lambdas, device=0, norm_zero_rule=0):
+def upload_system(system, lambdas, device=0, norm_zero_rule=1):
     return DeviceSystem(FlatSystem(system, lambdas, norm_zero_rule), device)
 
 
@@ -248,7 +248,7 @@ def _collect_spots(system_flat, res):
                 o.data = np.concatenate([o.data, xz[sel]])
 
 
-def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rule=0, keep_segments=True):
+def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rule=1, keep_segments=True):
     """solve_system!(system, beam; r_max, retrace) for a Beam, GaussianBeamlet, RayBundle or
     BeamletBundle (System.jl:444-468).  Returns the TraceResult (the reference returns nothing)."""
     if isinstance(beam, (list, tuple)):

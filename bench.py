@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the trace hot path (BASELINE.json configs[1], "C2"):
+AC254-150-AB doublet spot diagram, 2^20 collimated rays (Fibonacci disc, 20 mm), sequential SDF
+lens-surface path, Spotdetector at the vendor back focus.  Metric: ray-surface interactions/s.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one full solve_system! of the ray bundle (all waves).  `value` is measured with the rays
+resident in HBM (device pointers into the C ABI, spot output left on the device); `e2e` goes through
+the same C ABI with pinned HOST buffers, host->device and device->host copies inside the timed
+region.  Rank r of an N-GPU run traces its own 2^20-ray shard (weak scaling, no data-path
+collective: rays are independent, outputs are disjoint slices).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAYS = 1 << 20
+LAMBDA = 707e-9
+WORKLOAD = "C2: AC254-150-AB doublet spot diagram, 2^20 collimated rays, Fibonacci disc d=20mm, Spotdetector at BFL"
+CPU_SAMPLE = 1 << 14
+# algorithmic FP64 work per unit (SURVEY 8(d) cost table): primitive SDF eval 45, triangle test 40, interaction 60
+FLOP_SDF, FLOP_TRI, FLOP_INT = 45.0, 40.0, 60.0
+
+
+def rays_for_rank(rank, n=N_RAYS):
+    """Fibonacci disc of this rank's shard; ranks get discs rotated by the golden angle so shards differ."""
+    from tests import scenes
+    pos, d = scenes.fibonacci_disc(n)
+    if rank:
+        a = rank * 0.1
+        c, s = math.cos(a), math.sin(a)
+        x, z = pos[:, 0].copy(), pos[:, 2].copy()
+        pos[:, 0], pos[:, 2] = c * x - s * z, s * x + c * z
+    return np.ascontiguousarray(pos), np.ascontiguousarray(d)
+
+
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        mhz = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(mhz)}
+
+
+def run_reference(args, rank):
+    """Reference arm: the reference's CPU algorithm for this path (oracle port: Julia is not installed
+    and the reference has no compiled component) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import __graft_entry__ as ge
+    ge.build_oracle()
+    from oracle import oracle as orc
+    from tests import scenes
+    cores = os.cpu_count() or 1
+    osc = scenes.doublet_spot_oracle()
+    pos, d = rays_for_rank(0, N_RAYS)
+    sel = np.linspace(0, N_RAYS - 1, CPU_SAMPLE).astype(np.int64)   # evenly spread over the pupil
+    pos, d = np.ascontiguousarray(pos[sel]), np.ascontiguousarray(d[sel])
+    times, inter = [], 0
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        r = orc.bulk_trace_rays(osc["system"], pos, d, LAMBDA, r_max=100, nthreads=cores, want_segments=False, spot=osc["spot"])
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+            inter = r["interactions"]
+    total = sum(times)
+    value = inter * len(times) / total
+    sample = f"{CPU_SAMPLE} of {N_RAYS} rays per step (evenly spaced over the pupil), threaded driver over rays (BASELINE.md B2/B3)"
+    print(json.dumps({
+        "impl": "reference", "metric": "ray-surface interactions/s", "value": value, "unit": "interactions/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "rays_per_gpu": N_RAYS, "r_max": 100},
+        "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=N_RAYS)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import __graft_entry__ as ge
+    if rank == 0:
+        ge.build_libbmo()
+    if world > 1:
+        dist.barrier()
+    m = ge.load_package()
+    from bmo_b200 import _lib as L
+    from tests import scenes
+    dev = local_rank
+    n = args.rays
+    stream = torch.cuda.current_stream()
+    L.set_stream(stream.cuda_stream, dev)
+
+    sc = scenes.doublet_spot(m)
+    dsys = m.upload_system(sc["system"], [LAMBDA], device=dev)       # system upload: outside the timed region
+    pos_h, dir_h = rays_for_rank(rank, n)
+    lam_h = np.zeros(n, dtype=np.int32)
+    # pinned host buffers (e2e) and resident device copies (value)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    pos_p, dir_p, lam_p = pin(pos_h), pin(dir_h), pin(lam_h)
+    pos_d, dir_d, lam_d = pos_p.cuda(non_blocking=True), dir_p.cuda(non_blocking=True), lam_p.cuda(non_blocking=True)
+    spot_obj_p = torch.empty(n, dtype=torch.int32).pin_memory()
+    spot_xz_p = torch.empty((n, 2), dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    torch.cuda.synchronize()
+
+    def step_device():
+        res = m.trace_rays(dsys, (pos_d.data_ptr(), n), dir_d.data_ptr(), lam_d.data_ptr(), None, None, 100,
+                           keep_segments=False, device_inputs=True)
+        inter = res.interactions
+        res.free()
+        return inter
+
+    def step_e2e():
+        import ctypes as C
+        h = C.c_void_p()
+        L.check(L.lib().bmo_trace_rays(dsys.h, n, C.c_void_p(pos_p.data_ptr()), C.c_void_p(dir_p.data_ptr()), C.c_void_p(lam_p.data_ptr()),
+                                       None, None, 100, 0, C.byref(h)))
+        L.check(L.lib().bmo_result_spots(h, C.c_void_p(spot_obj_p.data_ptr()), C.c_void_p(spot_xz_p.data_ptr())))
+        info = L.bmo_result_info()
+        L.check(L.lib().bmo_result_get_info(h, C.byref(info)))
+        L.lib().bmo_result_free(h)
+        return info.interactions
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        times, inter = [], 0
+        for _ in range(steps):
+            flush.fill_(1)                       # evict inputs from L2 between timed iterations
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            inter = fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        return times, inter
+
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    L.counters_reset(dev)
+    times, inter = timed(step_device, args.steps, args.warmup)
+    c = L.counters(dev)
+    n_total_steps = args.steps + args.warmup
+    times_e, inter_e = timed(step_e2e, args.steps, args.warmup)
+    sampler.stop_flag = True
+
+    def agg(times):
+        t = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)    # max over ranks
+        return float(t.item())
+    tot_ms, tot_ms_e = agg(times), agg(times_e)
+    it = torch.tensor([float(inter), float(inter_e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(it, op=dist.ReduceOp.SUM)
+    inter_all, inter_all_e = float(it[0].item()), float(it[1].item())
+
+    if rank == 0:
+        value = inter_all * args.steps / (tot_ms * 1e-3)
+        e2e = inter_all_e * args.steps / (tot_ms_e * 1e-3)
+        # roofline of the dominant kernel (trace_step, FP64-pipe bound): algorithmic flops per launch / mean launch time
+        flops = (FLOP_SDF * c["sdf_evals"] + FLOP_TRI * c["tri_tests"] + FLOP_INT * c["interactions"])
+        k1_ms, k1_n = c["trace_step_ms"], max(c["trace_step_launches"], 1)
+        achieved = flops / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
+        peak = L.measure_fp64_peak(dev)
+        hbm_peak = None
+        try:
+            hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
+        except Exception:
+            hbm_peak = 6650.0
+        scat = c["scatter_bytes"] / (c["scatter_ms"] * 1e-3) / 1e9 if c["scatter_ms"] > 0 else None
+        out = {
+            "metric": "ray-surface interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "rays_per_gpu": n, "r_max": 100, "l2": "flushed with a 256 MiB write between timed iterations",
+                       "outputs": "spot (x,z) per ray; segment table not kept"},
+            "e2e": {"value": e2e, "unit": "interactions/s", "ms_per_step": tot_ms_e / args.steps,
+                    "h2d_bytes_per_step": int(pos_h.nbytes + dir_h.nbytes + lam_h.nbytes),
+                    "d2h_bytes_per_step": int(spot_obj_p.numel() * 4 + spot_xz_p.numel() * 8)},
+            "gpu_launches": int(c["kernel_launches"] * args.steps / n_total_steps),
+            "roofline": {"bound": "fp64", "kernel": "trace_step<0>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "peak_source": "measured here: DFMA probe (bmo_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
+                         "flops_per_launch": flops / k1_n, "ms_per_launch": k1_ms / k1_n,
+                         "share_of_step": k1_ms / n_total_steps / (tot_ms / args.steps) if tot_ms else None,
+                         "counted": {"sdf_evals_per_step": c["sdf_evals"] / n_total_steps, "interactions_per_step": c["interactions"] / n_total_steps}},
+            "roofline_compaction": {"bound": "hbm", "kernel": "scatter_queue", "achieved": scat, "peak": hbm_peak, "unit": "GB/s",
+                                    "frac": (scat / hbm_peak) if scat else None},
+            "clocks": sampler.summary(),
+        }
+        if not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline():
+    """The oracle port on the host cores over a bounded sample of the same workload (~10-30 s of CPU work)."""
+    import __graft_entry__ as ge
+    ge.build_oracle()
+    from oracle import oracle as orc
+    from tests import scenes
+    cores = os.cpu_count() or 1
+    osc = scenes.doublet_spot_oracle()
+    pos, d = rays_for_rank(0, N_RAYS)
+    sel = np.linspace(0, N_RAYS - 1, CPU_SAMPLE).astype(np.int64)
+    pos, d = np.ascontiguousarray(pos[sel]), np.ascontiguousarray(d[sel])
+    t0 = time.perf_counter()
+    reps, inter = 0, 0
+    while reps < 2 or time.perf_counter() - t0 < 10.0:
+        inter += orc.bulk_trace_rays(osc["system"], pos, d, LAMBDA, r_max=100, nthreads=cores, want_segments=False, spot=osc["spot"])["interactions"]
+        reps += 1
+        if reps >= 8:
+            break
+    dt = time.perf_counter() - t0
+    return {"value": inter / dt, "unit": "interactions/s", "cores": cores, "kind": "port",
+            "sample": f"{reps} x {CPU_SAMPLE} of {N_RAYS} rays (evenly spaced over the pupil), OpenMP threaded driver over rays; "
+                      "restatement of the Julia reference (Julia is not installed), not the reference itself"}
+
+
+if __name__ == "__main__":
+    main()

@@ -115,7 +115,7 @@ typedef struct bmo_tables {
     int32_t n_rows;     const double* n_table;   /* [n_rows][n_lambda] refractive_index(obj, lambda),
                                                     evaluated on the host (Lenses.jl:37-38)        */
     double n_system;                             /* refractive_index(system, lambda) = 1.0 (AbstractSystem.jl:21) */
-    int32_t norm_zero_rule;                      /* 0: zero-vector norm of duals has NaN partials (default), 1: clean zero */
+    int32_t norm_zero_rule;                      /* 1 (use this): zero-vector norm of duals is a clean zero -- pinned by test/runtests.jl:1309-1314; 0: NaN partials */
     int32_t reserved;
 } bmo_tables;
 

@@ -9,7 +9,7 @@
 #include <omp.h>
 #include "orc_optics.hpp"
 
-namespace orc { int g_norm_zero_rule = 0; }
+namespace orc { int g_norm_zero_rule = 1; }  // ZERO rule: pinned by test/runtests.jl:1309-1314 (see orc_math.hpp)
 using namespace orc;
 
 namespace {
@@ -634,7 +634,7 @@ int orc_eval(const char* fn, const int* ih, int ni, const double* a, int na, dou
         out[0] = h.valid; out[1] = h.t; out[2] = h.n.x; out[3] = h.n.y; out[4] = h.n.z; out[5] = part_index(o, h.shape); return 6;
     }
     if (k == "moeller_trumbore") { out[0] = Mesh::moeller_trumbore(V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}, V3{a[6], a[7], a[8]}, V3{a[9], a[10], a[11]}, V3{a[12], a[13], a[14]}); return 1; }
-    if (k == "mesh_vertices") { Mesh* m = M(ih[0]); for (size_t i = 0; i < m->vertices.size(); i++) { out[3 * i] = m->vertices[i].x; out[3 * i + 1] = m->vertices[i].y; out[3 * i + 2] = m->vertices[i].z; } return (int)m->vertices.size(); }
+    if (k == "mesh_vertices") { Mesh* m = M(ih[0]); for (size_t i = 0; i < m->vertices.size(); i++) { out[3 * i] = m->vertices[i].x; out[3 * i + 1] = m->vertices[i].y; out[3 * i + 2] = m->vertices[i].z; } return 3 * (int)m->vertices.size(); }
     if (k == "thickness_shape") { out[0] = S(ih[0])->thickness(); return 1; }
     if (k == "thickness_object") { out[0] = O(ih[0])->thickness(); return 1; }
     if (k == "reflection3d") { V3 r = reflection3d(V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}); out[0] = r.x; out[1] = r.y; out[2] = r.z; return 3; }

@@ -77,7 +77,7 @@ def _chk(rv):
 
 
 def set_norm_zero_rule(rule):
-    """0 = NAN (default), 1 = ZERO -- see orc_math.hpp norm2_/norm3_."""
+    """1 = ZERO (default, pinned by test/runtests.jl:1309-1314), 0 = NAN -- see orc_math.hpp norm2_/norm3_."""
     lib().orc_set_norm_zero_rule(int(rule))
 
 

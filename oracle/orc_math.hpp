@@ -267,9 +267,13 @@ inline Dual min_(Dual a, double b) {
     return {jl_min(a.v, b), {a.p[0] * wx, a.p[1] * wx, a.p[2] * wx}};
 }
 
-// norm of a 2-/3-vector: sqrt(sum of squares).  norm_zero_rule: 0 = NAN (plain sqrt(sum abs2), the
-// default; a zero vector of duals gets NaN partials), 1 = ZERO (scale-first StaticArrays norm: a
-// zero vector returns a clean zero).  Values are identical under both rules.
+// norm of a 2-/3-vector: sqrt(sum of squares).  norm_zero_rule: 1 = ZERO (default; StaticArrays'
+// norm falls back to its scaled variant when sqrt(sum abs2) is 0 and returns a clean zero for a zero
+// vector of duals), 0 = NAN (plain sqrt(sum abs2): zero vector -> NaN partials -> FD normals).
+// The reference's own test pins ZERO: runtests.jl:1309-1314 requires the centre-ray normal at the
+// cemented surface of a ROTATED doublet to be parallel to the ray; under the NAN rule that normal
+// comes from central differences across the kink where the concave cap touches the plano face and
+// is garbage (|n.d| = 0.64), under ZERO the AD gradient is exact.  Values are identical under both.
 extern int g_norm_zero_rule;
 inline double norm2_(double a, double b) { return std::sqrt(a * a + b * b); }
 inline double norm3_(double a, double b, double c) { return std::sqrt(a * a + b * b + c * c); }
