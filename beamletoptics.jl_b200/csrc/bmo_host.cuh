@@ -29,7 +29,7 @@ struct bmo_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evs0 = nullptr, evs1 = nullptr;
     double k1_ms = 0, k3_ms = 0, k3_bytes = 0, k4_ms = 0;  // accumulated device time of trace_step / scatter_queue / pd_field
-    int64_t k1_launches = 0;
+    int64_t k1_launches = 0, interactions_seen = 0;
     bmo::DevCounters* d_counters = nullptr;
     long long* d_totals = nullptr;   // [4] scratch for scans
     long long* h_totals = nullptr;   // pinned

@@ -10,6 +10,8 @@
 //                         numbering of beamsplitter children (deterministic: queue order).
 // With BMO_KEEP_SEGMENTS the segment records are written wave-major by K1 and gathered into
 // beam-major order at the end (K4 gather_segments).
+#include <chrono>
+#include <cstdlib>
 #include "bmo_host.cuh"
 #include "bmo_interact.cuh"
 
@@ -367,29 +369,72 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams 
 
 // ---- K2: exclusive scan of int32 counts with stride (single block, chunked) -----------------------
 // in[i*stride + which] for which in [0, nwhich) -> out (long long), totals[which]
+// Tiles of 1024 coalesced elements: warp shuffle scan, 32 warp totals scanned by warp 0, running carry.
 __global__ void __launch_bounds__(1024) scan_counts(const int32_t* in, int64_t n, int stride, int nwhich, long long* out,
                                                     long long* totals) {
-    __shared__ long long s_sum[1024];
-    const int T = blockDim.x;
-    const int64_t chunk = (n + T - 1) / T;
-    const int64_t b = (int64_t)threadIdx.x * chunk, e = min(b + chunk, n);
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int w = 0; w < nwhich; w++) {
-        long long s = 0;
-        for (int64_t i = b; i < e; i++) s += in[i * stride + w];
-        s_sum[threadIdx.x] = s;
+        if (threadIdx.x == 0) s_carry = 0;
         __syncthreads();
-        // Hillis-Steele inclusive scan over T partial sums
-        for (int o = 1; o < T; o <<= 1) {
-            long long v = threadIdx.x >= o ? s_sum[threadIdx.x - o] : 0;
+        for (int64_t base = 0; base < n; base += 1024) {
+            const int64_t i = base + threadIdx.x;
+            const long long v = i < n ? (long long)in[i * stride + w] : 0;
+            long long x = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o) x += y;
+            }
+            if (lane == 31) s_warp[warp] = x;
             __syncthreads();
-            s_sum[threadIdx.x] += v;
+            if (warp == 0) {
+                long long t = s_warp[lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long y = __shfl_up_sync(0xffffffffu, t, o);
+                    if (lane >= o) t += y;
+                }
+                s_warp[lane] = t;   // inclusive totals of warps 0..lane
+            }
+            __syncthreads();
+            const long long carry = s_carry;
+            const long long excl = carry + (warp ? s_warp[warp - 1] : 0) + (x - v);
+            if (i < n) out[i * nwhich + w] = excl;
+            __syncthreads();
+            if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
             __syncthreads();
         }
-        long long run = threadIdx.x == 0 ? 0 : s_sum[threadIdx.x - 1];
-        for (int64_t i = b; i < e; i++) { out[i * nwhich + w] = run; run += in[i * stride + w]; }
-        if (threadIdx.x == T - 1) totals[w] = s_sum[T - 1];
+        if (threadIdx.x == 0) totals[w] = s_carry;
         __syncthreads();
     }
+}
+
+// Large inputs: per-block local scan (1024 elements) + scan of the block sums + offset add.
+__global__ void __launch_bounds__(1024) scan_local(const int32_t* in, int64_t n, long long* out, int32_t* blk_sum) {
+    __shared__ long long s_warp[32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    const long long v = i < n ? (long long)in[i] : 0;
+    long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        long long t = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+        s_warp[lane] = t;
+    }
+    __syncthreads();
+    if (i < n) out[i] = (warp ? s_warp[warp - 1] : 0) + (x - v);
+    if (threadIdx.x == 0) blk_sum[blockIdx.x] = (int32_t)s_warp[31];
+}
+__global__ void scan_add(long long* out, int64_t n, const long long* blk_off) {
+    const int64_t i = (int64_t)blockIdx.x * 1024 + threadIdx.x;
+    if (i < n) out[i] += blk_off[blockIdx.x];
 }
 
 // ---- K3: scatter compacted successors into the next queue (HBM-bound) ----------------------------
@@ -566,7 +611,7 @@ int32_t bmo_counters_reset(bmo_ctx* c) {
     BMO_CUDA(cudaStreamSynchronize(c->stream));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     c->waves = c->launches = c->px_beamlets = 0;
-    c->k1_ms = c->k3_ms = c->k3_bytes = c->k4_ms = 0; c->k1_launches = 0;
+    c->k1_ms = c->k3_ms = c->k3_bytes = c->k4_ms = 0; c->k1_launches = 0; c->interactions_seen = 0;
     return BMO_OK;
 }
 
@@ -761,6 +806,36 @@ static int32_t ensure_beams(bmo_result* r, int64_t need, cudaStream_t st) {
     return BMO_OK;
 }
 
+// first_seg[b] = exclusive scan of nseg; n_segments = total.  Lazy for traces that keep no segments.
+static int32_t ensure_first_seg(bmo_result* res) {
+    if (res->first_seg) return BMO_OK;
+    bmo_ctx* ctx = res->sys->ctx;
+    cudaStream_t st = ctx->stream;
+    const int64_t nb = res->n_beams;
+    BMO_CUDA(dev_alloc(&res->first_seg, (size_t)nb + 1, st));
+    if (nb <= 16384) {
+        scan_counts<<<1, 1024, 0, st>>>(res->nseg, nb, 1, 1, res->first_seg, ctx->d_totals);
+        BMO_LAUNCH(ctx, "scan_counts(nseg)");
+    } else {
+        const int64_t nblk = (nb + 1023) / 1024;
+        int32_t* bsum = nullptr; long long* boff = nullptr;
+        BMO_CUDA(dev_alloc(&bsum, (size_t)nblk, st));
+        BMO_CUDA(dev_alloc(&boff, (size_t)nblk, st));
+        scan_local<<<(unsigned)nblk, 1024, 0, st>>>(res->nseg, nb, res->first_seg, bsum);
+        BMO_LAUNCH(ctx, "scan_local");
+        scan_counts<<<1, 1024, 0, st>>>(bsum, nblk, 1, 1, boff, ctx->d_totals);
+        BMO_LAUNCH(ctx, "scan_counts(blocks)");
+        scan_add<<<(unsigned)nblk, 1024, 0, st>>>(res->first_seg, nb, boff);
+        BMO_LAUNCH(ctx, "scan_add");
+        dev_free(bsum, st); dev_free(boff, st);
+    }
+    BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaMemcpyAsync(res->first_seg + nb, ctx->d_totals, sizeof(long long), cudaMemcpyDeviceToDevice, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    res->n_segments = ctx->h_totals[0];
+    return BMO_OK;
+}
+
 struct TraceInputs {
     int64_t n;
     const double *pos, *dir, *E0, *grays, *w0, *ge0;
@@ -793,6 +868,10 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
 
     bmo_result* res = new bmo_result();
     res->sys = sys; res->mode = mode; res->R = R; res->nsd = nsd; res->n_roots = n; res->keep = flags & BMO_KEEP_SEGMENTS;
+    static const bool prof = getenv("BMO_HOST_PROFILE") != nullptr;
+    auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double tp0 = tnow();
+    double tp_wave_sync = 0;
     BMO_CUDA(cudaEventRecord(ctx->ev0, st));
     int32_t rc;
     std::vector<void*> tmp;
@@ -820,6 +899,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         init_queue<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ip);
         BMO_LAUNCH(ctx, "init_queue");
     }
+    const double tp1 = tnow();
     const bool use_smem = sys->view.n_poses == 1 && (size_t)sys->view.n_prims * sizeof(bmo_prim) <= 40 * 1024;
     const size_t smem = use_smem ? (size_t)sys->view.n_prims * sizeof(bmo_prim) : 0;
 
@@ -866,7 +946,9 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         BMO_LAUNCH(ctx, "scatter_queue");
         BMO_CUDA(cudaEventRecord(ctx->evs1, st));
         BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        const double tw0 = tnow();
         BMO_CUDA(cudaStreamSynchronize(st));
+        tp_wave_sync += tnow() - tw0;
         {
             float kms = 0, sms = 0;
             BMO_CUDA(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
@@ -882,6 +964,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         ctx->waves++;
         if (wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
     }
+    const double tp2 = tnow();
     res->n_beams = n_beams;
     res->waves = wave;
     free_queue(cur, st); free_queue(next, st); free_queue(scr, st);
@@ -889,14 +972,9 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     for (void* p : tmp) cudaFreeAsync(p, st);
 
     // segment table: first_seg = exclusive scan of nseg, then gather wave-major -> beam-major
-    BMO_CUDA(dev_alloc(&res->first_seg, (size_t)n_beams + 1, st));
-    scan_counts<<<1, 1024, 0, st>>>(res->nseg, n_beams, 1, 1, res->first_seg, ctx->d_totals);
-    BMO_LAUNCH(ctx, "scan_counts(nseg)");
-    BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, sizeof(long long), cudaMemcpyDeviceToHost, st));
-    BMO_CUDA(cudaStreamSynchronize(st));
-    res->n_segments = ctx->h_totals[0];
-    BMO_CUDA(cudaMemcpyAsync(res->first_seg + n_beams, ctx->d_totals, sizeof(long long), cudaMemcpyDeviceToDevice, st));
+    // (spot-only traces compute first_seg lazily, see ensure_first_seg)
     if (res->keep) {
+        if ((rc = ensure_first_seg(res))) return rc;
         res->seg_rows = res->n_segments * R;
         BMO_CUDA(dev_alloc(&res->seg_d, (size_t)nsd * res->seg_rows, st));
         BMO_CUDA(dev_alloc(&res->seg_part, (size_t)res->seg_rows, st));
@@ -915,10 +993,11 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     {
         DevCounters h;
         BMO_CUDA(cudaMemcpy(&h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
-        static thread_local unsigned long long last = 0;
-        (void)last;
-        res->interactions = (int64_t)h.interactions;  // cumulative since reset; bmo_result_get_info reports the delta below
+        res->interactions = (int64_t)h.interactions - ctx->interactions_seen;  // the counter is cumulative since the last reset
+        ctx->interactions_seen = (int64_t)h.interactions;
     }
+    if (prof) fprintf(stderr, "[bmo] trace n=%lld waves=%d: setup %.3f ms, wave loop %.3f ms (of which waiting %.3f), finalize %.3f ms\n",
+                      (long long)n, wave, tp1 - tp0, tp2 - tp1, tp_wave_sync, tnow() - tp2);
     *out = res;
     return BMO_OK;
 }
@@ -929,13 +1008,7 @@ int32_t bmo_trace_rays(bmo_sys* sys, int64_t n, const double* pos, const double*
     TraceInputs in{};
     in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id;
     if (!sys) return fail(BMO_EINVAL, "sys NULL");
-    DevCounters before;
-    BMO_CUDA(cudaSetDevice(sys->ctx->device));
-    BMO_CUDA(cudaStreamSynchronize(sys->ctx->stream));
-    BMO_CUDA(cudaMemcpy(&before, sys->ctx->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
-    int32_t rc = trace_common(sys, E0 ? 1 : 0, in, r_max, flags, out);
-    if (rc == BMO_OK) (*out)->interactions -= (int64_t)before.interactions;
-    return rc;
+    return trace_common(sys, E0 ? 1 : 0, in, r_max, flags, out);
 }
 int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const int32_t* lambda_id, const double* w0, const double* E0,
                            const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out) {
@@ -943,19 +1016,13 @@ int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const in
     TraceInputs in{};
     in.n = n; in.grays = rays; in.w0 = w0; in.ge0 = E0; in.lam = lambda_id; in.pose = pose_id;
     if (!sys) return fail(BMO_EINVAL, "sys NULL");
-    DevCounters before;
-    BMO_CUDA(cudaSetDevice(sys->ctx->device));
-    BMO_CUDA(cudaStreamSynchronize(sys->ctx->stream));
-    BMO_CUDA(cudaMemcpy(&before, sys->ctx->d_counters, sizeof(before), cudaMemcpyDeviceToHost));
-    int32_t rc = trace_common(sys, 2, in, r_max, flags | BMO_KEEP_SEGMENTS, out);
-    if (rc == BMO_OK) (*out)->interactions -= (int64_t)before.interactions;
-    return rc;
+    return trace_common(sys, 2, in, r_max, flags | BMO_KEEP_SEGMENTS, out);
 }
 
 // ---- result access ----------------------------------------------------------------------------------
 int32_t bmo_result_get_info(bmo_result* r, bmo_result_info* info) {
     if (!r || !info) return fail(BMO_EINVAL, "bmo_result_get_info: NULL");
-    info->n_roots = r->n_roots; info->n_beams = r->n_beams; info->n_segments = r->n_segments; info->interactions = r->interactions;
+    info->n_roots = r->n_roots; info->n_beams = r->n_beams; info->n_segments = r->first_seg ? r->n_segments : -1; info->interactions = r->interactions;
     info->rays_per_beam = r->R; info->polarized = r->mode == 1; info->waves = r->waves; info->reserved = 0;
     return BMO_OK;
 }
@@ -971,6 +1038,7 @@ int32_t bmo_result_beams(bmo_result* r, int32_t* parent, int32_t* child_slot, in
     cudaStream_t st = r->sys->ctx->stream;
     const size_t nb = (size_t)r->n_beams;
     int32_t rc;
+    if ((rc = ensure_first_seg(r))) return rc;
     if ((rc = d2h(parent, r->parent, nb, st))) return rc;
     if ((rc = d2h(child_slot, r->slot, nb, st))) return rc;
     if ((rc = d2h(n_seg, r->nseg, nb, st))) return rc;

@@ -47,9 +47,18 @@ class TraceResult:
         self.dsys, self.h = dsys, handle
         info = L.bmo_result_info()
         L.check(L.lib().bmo_result_get_info(handle, C.byref(info)))
-        self.n_roots, self.n_beams, self.n_segments = info.n_roots, info.n_beams, info.n_segments
+        self.n_roots, self.n_beams, self._n_segments = info.n_roots, info.n_beams, info.n_segments
         self.interactions, self.R, self.polarized, self.waves = info.interactions, info.rays_per_beam, bool(info.polarized), info.waves
         self._beams = self._segs = self._spots = None
+
+    @property
+    def n_segments(self):
+        if self._n_segments < 0:     # spot-only trace: the segment count is computed on demand
+            self.beams()
+            info = L.bmo_result_info()
+            L.check(L.lib().bmo_result_get_info(self.h, C.byref(info)))
+            self._n_segments = info.n_segments
+        return self._n_segments
 
     def free(self):
         if self.h:

@@ -179,6 +179,7 @@ def main():
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
+        L.counters_reset(dev)                    # per-kernel counters cover the timed steps only
         times, inter = [], 0
         for _ in range(steps):
             flush.fill_(1)                       # evict inputs from L2 between timed iterations
@@ -196,10 +197,9 @@ def main():
     sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
-    L.counters_reset(dev)
     times, inter = timed(step_device, args.steps, args.warmup)
     c = L.counters(dev)
-    n_total_steps = args.steps + args.warmup
+    n_total_steps = args.steps
     times_e, inter_e = timed(step_e2e, args.steps, args.warmup)
     sampler.stop_flag = True
 

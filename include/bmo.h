@@ -174,7 +174,7 @@ int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const in
 
 /* ---- result access.  Beams are numbered roots first (0..n-1), children in spawn order.         */
 typedef struct bmo_result_info {
-    int64_t n_roots, n_beams, n_segments, interactions;
+    int64_t n_roots, n_beams, n_segments /* -1 until bmo_result_beams / _segments was called on a spot-only trace */, interactions;
     int32_t rays_per_beam;  /* 1 (Beam) or 3 (GaussianBeamlet: chief, waist, divergence)          */
     int32_t polarized;
     int32_t waves;
