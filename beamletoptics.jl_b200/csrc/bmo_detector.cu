@@ -47,7 +47,7 @@ __global__ void pd_flag(ResView R, SysView S, int pd_object, int pose_filter, in
     const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= R.n_beams) return;
     int f = 0;
-    if (R.status[b] == BMO_ST_ABSORBED && R.nseg[b] > 0 && (pose_filter < 0 || R.pose[b] == pose_filter)) {
+    if ((R.status[b] & 0xff) == BMO_ST_ABSORBED && R.nseg[b] > 0 && (pose_filter < 0 || R.pose[b] == pose_filter)) {
         const int64_t row = (R.first_seg[b] + R.nseg[b] - 1) * 3;
         const int part = R.seg_part[row];
         if (part >= 0 && S.parts[part].object == pd_object) f = 1;

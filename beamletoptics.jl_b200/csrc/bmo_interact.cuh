@@ -95,7 +95,8 @@ struct RayOut {
     double n;
     int hint;    // part index or -1
     bool valid;  // false <=> interact3d returned nothing
-    bool err;
+    bool err;    // the reference would throw ArgumentError (non-unit dir / normal)
+    bool warn;   // E0 not orthogonal to dir at atol 1e-14 (PolarizedRays.jl:54-56): flagged, tracing continues
     Cx E0[3];
 };
 
@@ -105,7 +106,7 @@ BMO_NI void interact_refractive(V3 rpos, V3 rdir, double rn, const Cx* rE0, bool
     V3 normal = nrm;
     double n1, n2;
     o.hint = -1;
-    o.err = false;
+    o.err = false; o.warn = false;
     o.valid = true;
     o.pos = rpos + t * rdir;
     if (dot(rdir, nrm) < 0) { n1 = rn; n2 = n_opt; o.hint = self_part; }
@@ -132,25 +133,25 @@ BMO_NI void interact_refractive(V3 rpos, V3 rdir, double rn, const Cx* rE0, bool
         j11 = ts; j22 = tp;
     }
     calculate_global_E0(rdir, o.dir, nrm, j11, j22, rE0, o.E0);
-    if (!e0_orthogonal(o.dir, o.E0)) o.err = true;
+    if (!e0_orthogonal(o.dir, o.E0)) o.warn = true;
     o.n = n2;
 }
 // OpticalComponents/Mirrors.jl:39-69
 BMO_NI void interact_mirror(V3 rpos, V3 rdir, double rn, const Cx* rE0, bool polarized, double t, V3 nrm, RayOut& o) {
-    o.valid = true; o.err = false; o.hint = -1;
+    o.valid = true; o.err = false; o.warn = false; o.hint = -1;
     o.pos = rpos + t * rdir;
     o.dir = reflection3d(rdir, nrm);
     o.n = rn;
     if (polarized) {
         calculate_global_E0(rdir, o.dir, nrm, mkc(-1, 0), mkc(1, 0), rE0, o.E0);
-        if (!e0_orthogonal(o.dir, o.E0)) o.err = true;
+        if (!e0_orthogonal(o.dir, o.E0)) o.warn = true;
     }
 }
 // ThinBeamsplitter.jl:73-106: children restart as Ray(pos, dir, lambda): n = 1, dir re-normalised
 BMO_NI void bs_children(V3 rpos, V3 rdir, const Cx* rE0, bool polarized, double t, V3 nrm, double refl, double trans,
                        RayOut& tr, RayOut& rf) {
     V3 pos = rpos + t * rdir;
-    tr.valid = rf.valid = true; tr.err = rf.err = false; tr.hint = rf.hint = -1;
+    tr.valid = rf.valid = true; tr.err = rf.err = false; tr.warn = rf.warn = false; tr.hint = rf.hint = -1;
     tr.pos = pos; rf.pos = pos;
     tr.n = 1.0; rf.n = 1.0;
     V3 rd = reflection3d(rdir, nrm);
@@ -161,8 +162,8 @@ BMO_NI void bs_children(V3 rpos, V3 rdir, const Cx* rE0, bool polarized, double 
     tr.dir = normalize(rdir);
     rf.dir = normalize(rd);
     if (polarized) {
-        if (!e0_orthogonal(tr.dir, tr.E0)) tr.err = true;
-        if (!e0_orthogonal(rf.dir, rf.E0)) rf.err = true;
+        if (!e0_orthogonal(tr.dir, tr.E0)) tr.warn = true;
+        if (!e0_orthogonal(rf.dir, rf.E0)) rf.warn = true;
     }
 }
 

@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams 
     // ---- interact (dispatch on the object kind / part role) ----
     int nsucc = 0;
     RayOut o1, o2;                 // continuing ray, or (transmitted, reflected) children
-    o1.valid = o2.valid = false; o1.err = o2.err = false;
+    o1.valid = o2.valid = false; o1.err = o2.err = false; o1.warn = o2.warn = false;
     o1.hint = o2.hint = -1;
     bool interacted = false;
     if (active && status == BMO_ST_ACTIVE && hit_part >= 0) {
@@ -300,7 +300,10 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams 
     }
     if (leader) {
         P.B.nseg[beam] = seg + 1;
-        if (nsucc != 1) P.B.status[beam] = status;
+        // bit 8: the reference's E0-orthogonality check (atol 1e-14) failed somewhere along this beam
+        const int old = P.B.status[beam];
+        const int wbit = (old & 0x100) | (((o1.valid && o1.warn) || (o2.valid && o2.warn)) ? 0x100 : 0);
+        P.B.status[beam] = ((nsucc != 1) ? status : (old & 0xff)) | wbit;
     }
 
     // ---- block-local compaction: warp ballots + prefix sums ----

@@ -83,6 +83,8 @@ class TraceResult:
                                             L.ptr(d["first"]), L.ptr(w0), L.ptr(E0), L.ptr(d["lam_id"])))
             if self.R == 3:
                 d["w0"], d["E0"] = w0, E0[0::2] + 1j * E0[1::2]
+            d["e0_warn"] = (d["status"] >> 8) & 1      # E0 orthogonality check (atol 1e-14) failed along the beam
+            d["status"] = d["status"] & 0xff
             self._beams = d
         return self._beams
 

@@ -1,0 +1,67 @@
+"""Batched kinematic pose sweeps (BASELINE config 5): many `translate3d!/rotate3d!` poses of one
+system traced in a single launch, one Photodetector interferogram per pose.
+
+The reference solves one pose at a time (move -> empty!(pd) -> solve_system! -> optical_power(pd),
+test/runtests.jl:2092-2120).  Here every pose is flattened on the host with the unchanged kinematic
+API, the tables are stacked and uploaded once (bmo_system_set_poses), every beamlet is replicated per
+pose with a pose id, and the detector kernel writes fields[pose].
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+from . import beams as bm
+from .flatten import FlatSystem
+from .solver import DeviceSystem, TraceResult, _lambda_ids
+
+
+def flatten_poses(system, lambdas, n_poses, apply_pose, norm_zero_rule=1):
+    """apply_pose(p) moves the host objects into pose p.  Returns (flat of pose 0, stacked tables)."""
+    flats = []
+    for p in range(n_poses):
+        apply_pose(p)
+        flats.append(FlatSystem(system, lambdas, norm_zero_rule))
+    f0 = flats[0]
+    for f in flats[1:]:
+        if (f.n_prims, f.n_parts, f.n_objects, f._verts.shape) != (f0.n_prims, f0.n_parts, f0.n_objects, f0._verts.shape):
+            raise ValueError("poses must not change the topology of the system")
+    arrs = [f.pose_arrays() for f in flats]
+    prims = np.concatenate([a[0] for a in arrs]) if f0.n_prims else np.zeros(8, dtype=np.uint8)
+    verts = np.concatenate([a[1] for a in arrs]) if f0._verts.size else np.zeros((1, 3))
+    bounds = np.concatenate([a[2] for a in arrs])
+    det_pos = np.concatenate([a[3] for a in arrs])
+    det_dir = np.concatenate([a[4] for a in arrs])
+    return f0, tuple(np.ascontiguousarray(x) for x in (prims, verts, bounds, det_pos, det_dir))
+
+
+def solve_pose_sweep(system, beam, n_poses, apply_pose, pd, r_max=100, device=0, want_fields=True):
+    """Trace `beam` (GaussianBeamlet or BeamletBundle) through `n_poses` poses of `system`.
+    Returns dict(fields=(n_poses, n, n) complex, power=(n_poses,), result=TraceResult)."""
+    if isinstance(beam, bm.GaussianBeamlet):
+        beam = bm.BeamletBundle(np.array([beam.rays18()]), [beam.lam], [beam.w0], [beam.E0])
+    lams, lam_id = _lambda_ids(beam.lam)
+    f0, (prims, verts, bounds, det_pos, det_dir) = flatten_poses(system, lams, n_poses, apply_pose)
+    dsys = DeviceSystem(f0, device)
+    L.check(L.lib().bmo_system_set_poses(dsys.h, n_poses, L.ptr(prims), L.ptr(verts), L.ptr(bounds), L.ptr(det_pos), L.ptr(det_dir)))
+    nb = len(beam)
+    rays = np.ascontiguousarray(np.tile(beam.rays.reshape(nb, 18), (n_poses, 1)))
+    lam_ids = np.ascontiguousarray(np.tile(lam_id, n_poses))
+    w0 = np.ascontiguousarray(np.tile(beam.w0, n_poses))
+    E0 = np.tile(beam.E0, n_poses)
+    e = np.ascontiguousarray(np.stack([E0.real, E0.imag], axis=-1))
+    pose_id = np.ascontiguousarray(np.repeat(np.arange(n_poses, dtype=np.int32), nb))
+    h = C.c_void_p()
+    L.check(L.lib().bmo_trace_beamlets(dsys.h, rays.shape[0], L.ptr(rays), L.ptr(lam_ids), L.ptr(w0), L.ptr(e), L.ptr(pose_id), r_max, 0, C.byref(h)))
+    res = TraceResult(dsys, h)
+    pd_index = f0.object_index(pd)
+    n = pd.n
+    fields = np.zeros((n_poses, n * n * 2))
+    L.check(L.lib().bmo_pd_accumulate_poses(dsys.h, res.h, pd_index, n_poses, L.ptr(fields), 0))
+    power = np.zeros(n_poses)
+    L.check(L.lib().bmo_pd_power(dsys.h, pd_index, n_poses, L.ptr(fields), L.ptr(power), 0))
+    out = dict(power=power, result=res, dsys=dsys)
+    if want_fields:
+        z = fields[:, 0::2] + 1j * fields[:, 1::2]
+        out["fields"] = z.reshape(n_poses, n, n).transpose(0, 2, 1)   # stored column-major [i + n*j] -> [pose, i, j]
+    return out

@@ -204,7 +204,9 @@ enum bmo_status {
     BMO_ST_SPLIT = 4,     /* beamsplitter: children spawned, parent stops                          */
     BMO_ST_CLIPPED = 5,   /* Gaussian: waist or divergence ray missed (System.jl:288-296)          */
     BMO_ST_TORN = 6,      /* Gaussian: rays hit different shapes (System.jl:298-304)               */
-    BMO_ST_ERROR = 7      /* reference would throw (non-unit vectors, E0 not orthogonal, ...)      */
+    BMO_ST_ERROR = 7      /* reference would throw ArgumentError (non-unit dir / normal in refraction3d) */
+    /* status & 0x100: a PolarizedRay's E0 failed the reference's orthogonality check (|dir.E0| <= 1e-14,
+       PolarizedRays.jl:54-56) somewhere along the beam; the reference throws, the tracer flags and continues */
 };
 
 /* replaces: interact3d(::AbstractSystem, ::Photodetector, ::GaussianBeamlet, ray_id)

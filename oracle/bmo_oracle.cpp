@@ -539,7 +539,11 @@ long long orc_bulk_trace_rays(int hsys, int n, const double* pos, const double* 
     for (int i = 0; i < n; i++) {
         try {
             Beam b;
-            b.rays.push_back(make_ray(V3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}, V3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]}, lambda[i]));
+            {   // `dir` is the direction of an already constructed Ray (normalised once by Ray(pos, dir, lambda))
+                Ray r0; r0.pos = V3{pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]}; r0.dir = V3{dir[3 * i], dir[3 * i + 1], dir[3 * i + 2]};
+                r0.lambda = lambda[i]; r0.n = 1.0;
+                b.rays.push_back(r0);
+            }
             // Spotdetector hits are recomputed below from the last ray, so give each thread a scratch copy
             // of nothing: interact3d(O_SPOT) pushes into sd->spots, which would race -> trace manually.
             BeamInteraction interaction;
