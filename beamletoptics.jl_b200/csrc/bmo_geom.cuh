@@ -138,32 +138,139 @@ template <class T> BMO_D T member_eval(const bmo_prim* prims, int i, P3<T> q, in
 }
 BMO_D int member_advance(const bmo_prim* prims, int i) { return prims[i].type == BMO_PRIM_MENISCUS ? 4 : 1; }
 
-// UnionSDF.jl:53-56  minimum over members (left fold)
-BMO_NI double shape_sdf(const bmo_prim* prims, int first, int count, V3 p, int zr, Stats& st) {
-    P3<double> q; q.x = p.x; q.y = p.y; q.z = p.z;
-    double m = member_eval(prims, first, q, zr, st);
-    for (int i = first + member_advance(prims, first); i < first + count; i += member_advance(prims, i))
-        m = jl_min(m, member_eval(prims, i, q, zr, st));
+// ---- fast double path ----------------------------------------------------------------------------
+// The marching loop evaluates the SDF ~30x per interaction, so the plain-double evaluation gets a
+// lean restatement.  For finite arguments it returns bit-identical values to prim_eval<double>
+// above (the NaN-propagating branches of Julia's min/max cannot trigger, sqrt(x*x) == |x| is exact in
+// binary64 when x*x neither under- nor overflows); only the sign of an exactly-zero intermediate
+// may differ, which no comparison or non-zero value downstream can observe.  The dual-number
+// (ForwardDiff) and finite-difference evaluations of the normals keep the generic templates.
+BMO_D double fmax_jl(double x, double y) { const double d = x - y; return signbit(d) ? y : x; }  // Base.max, finite args
+BMO_D double fmin_jl(double x, double y) { const double d = x - y; return signbit(d) ? x : y; }  // Base.min, finite args
+BMO_D double pos_part(double x) { return signbit(x) ? 0.0 : x; }                                   // max(x, 0.0)
+BMO_D double neg_part(double x) { return signbit(x) ? x : 0.0; }                                   // min(x, 0.0)
+BMO_D double hyp2(double a, double b) { return sqrt(a * a + b * b); }
+BMO_D bool sq_exact(double a) {   // 2^-463 <= a < 2^465: a*a is a normal number, so sqrt(fl(a*a)) == a
+    const unsigned e = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+    return e - 560u < 928u;
+}
+// norm(max.(d, 0)) of a 2-vector / 3-vector
+BMO_D double pnorm2(double d1, double d2) {
+    const double a = pos_part(d1), b = pos_part(d2);
+    if (b == 0.0) { if (a == 0.0 || sq_exact(a)) return a; }
+    else if (a == 0.0 && sq_exact(b)) return b;
+    return sqrt(a * a + b * b);
+}
+BMO_D double pnorm3(double d1, double d2, double d3) {
+    const double a = pos_part(d1), b = pos_part(d2), c = pos_part(d3);
+    if (a == 0.0 && b == 0.0 && (c == 0.0 || sq_exact(c))) return c;
+    if (a == 0.0 && c == 0.0 && sq_exact(b)) return b;
+    if (b == 0.0 && c == 0.0 && sq_exact(a)) return a;
+    return sqrt(a * a + b * b + c * c);
+}
+BMO_D V3 w2s_f(const bmo_prim& pr, V3 q) {
+    const double dx = q.x - pr.pos[0], dy = q.y - pr.pos[1], dz = q.z - pr.pos[2];
+    if (pr.reserved & 1) return mk3(dx, dy, dz);   // transposed_dir == I (set at upload)
+    return mk3(pr.tdir[0] * dx + pr.tdir[1] * dy + pr.tdir[2] * dz,
+               pr.tdir[3] * dx + pr.tdir[4] * dy + pr.tdir[5] * dz,
+               pr.tdir[6] * dx + pr.tdir[7] * dy + pr.tdir[8] * dz);
+}
+BMO_D double cyl_f(double d1, double d2) { return neg_part(fmax_jl(d1, d2)) + pnorm2(d1, d2); }
+BMO_D double prim_eval_f(const bmo_prim& pr, V3 q) {
+    const V3 p = w2s_f(pr, q);
+    const double a = pr.par[0], b = pr.par[1], c = pr.par[2], d = pr.par[3];
+    switch (pr.type) {
+        case BMO_PRIM_PLANO:
+            return cyl_f(hyp2(p.x, p.z) - b / 2, fabs(p.y - a / 2) - a / 2);
+        case BMO_PRIM_CYLINDER:
+            return cyl_f(hyp2(p.x, p.z) - a, fabs(p.y) - b);
+        case BMO_PRIM_SPHERE:
+            return sqrt(p.x * p.x + p.y * p.y + p.z * p.z) - a;
+        case BMO_PRIM_CONVEX: {
+            const double q1 = hyp2(p.x, p.z), q2 = -p.y + a;
+            const double h = d, R = a, hd = b / 2;
+            const double s = fmax_jl((h - R) * (q1 * q1) + (hd * hd) * (h + R - 2 * q2), h * q1 - hd * q2);
+            if (s < 0.0) return hyp2(q1, q2) - R;
+            if (q1 < hd) return h - q2;
+            return hyp2(q1 - hd, q2 - h);
+        }
+        case BMO_PRIM_CONCAVE: {
+            const double sdf1 = cyl_f(hyp2(p.x, p.z) - b / 2, fabs(p.y + c / 2) - c / 2);
+            const double ya = p.y + a;
+            const double sdf2 = sqrt(p.x * p.x + ya * ya + p.z * p.z) - a;
+            return fmax_jl(sdf1, -sdf2);
+        }
+        case BMO_PRIM_CUTSPHERE: {
+            const double q1 = hyp2(p.x, p.z), q2 = p.y;
+            const double h = b, R = a, w = c;
+            const double s = fmax_jl((h - R) * (q1 * q1) + (w * w) * (h + R - 2 * q2), h * q1 - w * q2);
+            if (s < 0.0) return hyp2(q1, q2) - R;
+            if (q1 < w) return h - q2;
+            return hyp2(q1 - w, q2 - h);
+        }
+        case BMO_PRIM_BOX: {
+            const double qx = fabs(p.x) - a, qy = fabs(p.y) - b, qz = fabs(p.z) - c;
+            return pnorm3(qx, qy, qz) + neg_part(fmax_jl(qx, fmax_jl(qy, qz)));
+        }
+        case BMO_PRIM_RING: {
+            const double px = hyp2(p.x, p.z) - a;
+            const double d1 = fabs(px) - b, d2 = fabs(p.y) - c;
+            return pnorm2(d1, d2) + neg_part(fmax_jl(d1, d2));
+        }
+        case BMO_PRIM_RAPRISM: {
+            const double qx = fabs(p.x) - a, qy = fabs(p.y) - b, qz = fabs(p.z) - c;
+            const double box = pnorm3(qx, qy, qz) + neg_part(fmax_jl(qx, fmax_jl(qy, qz)));
+            const double pln = (p.x + p.y) / 1.4142135623730951;
+            return fmax_jl(box, pln);
+        }
+        default: break;
+    }
+    return 0.0;
+}
+// One SDF shape (a primitive or a UnionSDF) as the marching loop sees it
+struct SdfShape {
+    const bmo_prim* prims;
+    int first, count, zr;
+    double cx, cy, cz, R2;   // conservative bounding sphere (inflated by the flattener)
+};
+// UnionSDF.jl:53-56: minimum over the members (left fold); idx = first member attaining it, which
+// is the member normal3d(::UnionSDF) dispatches to (UnionSDF.jl:86-91) -- the reference evaluates the
+// members a second time for the argmin, the values are the same.  A member is a primitive or a
+// meniscus frame followed by its 3 children (convex, cylinder, concave) evaluated at the frame-local
+// point: max(min(convex, cylinder), -concave) (MeniscusLensSDF.jl:42-46).  Written as one flat loop
+// over the prim records so that prim_eval_f is instantiated once (instruction-cache footprint).
+BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx) {
+    const int end = sh.first + sh.count;
+    double m = 0.0, acc = 0.0;
+    V3 q = p;
+    int men = 0, start = sh.first;
+    bool have = false;
+    for (int i = sh.first; i < end; i++) {
+        const bmo_prim& pr = sh.prims[i];
+        if (pr.type == BMO_PRIM_MENISCUS) { q = w2s_f(pr, p); men = 3; start = i; continue; }
+        double v = prim_eval_f(pr, q);
+        nsdf++;
+        if (men) {
+            if (men == 3) acc = v;                       // convex
+            else if (men == 2) acc = fmin_jl(acc, v);    // cylinder
+            else { v = fmax_jl(acc, -v); q = p; }        // concave closes the member
+            if (--men) continue;
+        } else start = i;
+        if (!have) { m = v; idx = start; have = true; }
+        else { if (v < m) idx = start; m = fmin_jl(m, v); }
+    }
     return m;
 }
-// AbstractSDF.jl:79-95 + UnionSDF.jl:86-91: normal of the arg-min member; ForwardDiff gradient,
-// central differences (eps = 1e-8) if any component of the normalised gradient is NaN.
-BMO_NI V3 shape_normal(const bmo_prim* prims, int first, int count, V3 p, int zr, Stats& st) {
-    P3<double> q; q.x = p.x; q.y = p.y; q.z = p.z;
-    int idx = first;
-    if (count > member_advance(prims, first)) {
-        double m = member_eval(prims, first, q, zr, st);
-        for (int i = first + member_advance(prims, first); i < first + count; i += member_advance(prims, i)) {
-            double v = member_eval(prims, i, q, zr, st);
-            if (v < m) { m = v; idx = i; }
-        }
-    }
+// AbstractSDF.jl:79-95: ForwardDiff gradient of member idx; central differences (eps = 1e-8) if any
+// component of the normalised gradient is NaN.
+BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
     P3<Dual> qd;
     qd.x = mkd(p.x, 1, 0, 0); qd.y = mkd(p.y, 0, 1, 0); qd.z = mkd(p.z, 0, 0, 1);
     Dual g = member_eval(prims, idx, qd, zr, st);
     V3 n = normalize(mk3(g.p0, g.p1, g.p2));
     if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
     const double e = 1e-8;
+    P3<double> q; q.x = p.x; q.y = p.y; q.z = p.z;
     P3<double> a, b;
     V3 gr;
     a = q; b = q; a.x = p.x + e; b.x = p.x - e;
@@ -175,68 +282,67 @@ BMO_NI V3 shape_normal(const bmo_prim* prims, int first, int count, V3 p, int zr
     return normalize(gr);
 }
 
-// AbstractSDF.jl:102-125.  The bounding-sphere test is result-identical: once the march point is
-// outside the (inflated) bounding sphere and moving away, every later point p + s*d (s >= 0) stays
-// outside it, so sdf >= margin > eps_ray for the rest of the reference's 1000 iterations => miss.
-BMO_NI bool march_outside(const bmo_prim* prims, int first, int count, const double* bnd, V3 p, V3 d, int zr, Stats& st,
-                         double& t, V3& n) {
-    double dist = shape_sdf(prims, first, count, p, zr, st);
-    double t0 = dist;
-    const double R2 = bnd[3] * bnd[3];
-    for (int i = 0; i < kMarchIter; i++) {
-        p = p + dist * d;
-        dist = shape_sdf(prims, first, count, p, zr, st);
-        t0 += dist;
-        if (dist < eps_ray) {
-            n = shape_normal(prims, first, count, p, zr, st);
-            t = t0;
-            return true;
-        }
-        V3 v = mk3(p.x - bnd[0], p.y - bnd[1], p.z - bnd[2]);
-        if (dot(v, v) > R2 && dot(v, d) > 0.0) return false;
-        if (!(dist == dist)) return false;  // NaN can never satisfy dist < eps_ray again
-    }
-    return false;
-}
-// AbstractSDF.jl:132-159
-BMO_D bool march_inside(const bmo_prim* prims, int first, int count, const double* bnd, V3 p, V3 d, int zr, Stats& st,
-                        double& t, V3& n) {
-    double t0 = 0;
-    for (int i = 0; i < kMarchIter; i++) {
-        p = p + eps_ins * d;
-        t0 += eps_ins;
-        double dist = shape_sdf(prims, first, count, p, zr, st);
-        if (dist > 0) {
-            double tt;
-            if (!march_outside(prims, first, count, bnd, p, -d, zr, st, tt, n)) return false;
-            t = t0 - tt;
-            return true;
-        }
-    }
-    return false;
-}
-// AbstractSDF.jl:166-181
-BMO_NI bool sdf_intersect(const bmo_prim* prims, int first, int count, const double* bnd, V3 pos, V3 dir, int zr, Stats& st,
-                         double& t, V3& n) {
-    // Guaranteed miss: origin outside the bounding sphere and the line never enters it.
-    {
-        V3 v = mk3(pos.x - bnd[0], pos.y - bnd[1], pos.z - bnd[2]);
-        double cc = dot(v, v) - bnd[3] * bnd[3];
+// intersect3d(::AbstractSDF, ray) (AbstractSDF.jl:166-181) with _raymarch_outside (:102-125) and
+// _raymarch_inside (:132-159) folded into one loop, so that the SDF and the normal are each evaluated
+// from a single call site (the compiler then keeps the whole march in registers):
+//   INIT  d0 = sdf(pos): outside (> eps_srf) -> OUT; else normal(pos), leaving (dir.n > 0) -> miss, else IN
+//   IN    fixed 1 m steps until sdf > 0, then OUT along -dir; t = t_in - t_out
+//   OUT   p += dist*d; dist = sdf(p); t0 += dist; dist < eps_ray -> hit with normal(p)
+// The reference re-evaluates sdf(p) when it enters _raymarch_outside; the value is the same.
+// The bounding-sphere tests are result-identical: once the march point is outside the (inflated)
+// sphere and moving away, every later point p + s*d (s >= 0) stays outside it, so sdf >= margin >
+// eps_ray for the rest of the reference's 1000 iterations => miss.
+// `nsdf` counts primitive evaluations in a register; the out-of-line normal evaluation reports its
+// own count through a stack temporary that only lives around the call.
+BMO_D bool sdf_intersect_f(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, double& t, V3& n) {
+    {   // guaranteed miss: origin outside the bounding sphere and the line never enters it
+        const V3 v = mk3(pos.x - sh.cx, pos.y - sh.cy, pos.z - sh.cz);
+        const double cc = dot(v, v) - sh.R2;
         if (cc > 0.0) {
-            double b = dot(v, dir);
+            const double b = dot(v, dir);
             if (b >= 0.0) return false;
             if (b * b - dot(dir, dir) * cc < 0.0) return false;
         }
     }
-    double s0 = shape_sdf(prims, first, count, pos, zr, st);
-    if (s0 > eps_srf) return march_outside(prims, first, count, bnd, pos, dir, zr, st, t, n);
-    V3 nn = shape_normal(prims, first, count, pos, zr, st);
-    if (dot(dir, nn) <= 0) return march_inside(prims, first, count, bnd, pos, dir, zr, st, t, n);
-    return false;
+    enum { INIT = 0, IN = 1, OUT = 2 };
+    int mode = INIT, it = 0;
+    bool back = false;
+    V3 p = pos, d = dir;
+    double t0 = 0.0, tin = 0.0;
+    for (;;) {
+        int idx;
+        const double dist = shape_sdf_f(sh, p, nsdf, idx);
+        if (mode == OUT) {
+            t0 += dist;
+            if (!(dist < eps_ray)) {
+                const V3 v = mk3(p.x - sh.cx, p.y - sh.cy, p.z - sh.cz);
+                if (dot(v, v) > sh.R2 && dot(v, d) > 0.0) return false;
+                if (++it >= kMarchIter || !(dist == dist)) return false;   // NaN can never satisfy dist < eps_ray again
+                p = p + dist * d;
+                continue;
+            }
+        } else if (mode == INIT) {
+            if (dist > eps_srf) { mode = OUT; t0 = dist; p = p + dist * d; continue; }
+        } else {  // IN
+            if (dist > 0) { mode = OUT; back = true; d = -d; t0 = dist; it = 0; p = p + dist * d; continue; }
+            if (++it >= kMarchIter) return false;
+            p = p + eps_ins * d; tin += eps_ins;
+            continue;
+        }
+        {
+            Stats tmp; tmp.sdf = 0; tmp.tri = 0;
+            n = member_normal(sh.prims, idx, p, sh.zr, tmp);
+            nsdf += tmp.sdf;
+        }
+        if (mode == OUT) { t = back ? tin - t0 : t0; return true; }
+        if (!(dot(d, n) <= 0)) return false;   // on the surface, heading out
+        mode = IN; it = 0;
+        p = p + eps_ins * d; tin = eps_ins;
+    }
 }
 
 // ---- meshes -----------------------------------------------------------------------------------
-BMO_D V3 load_vertex(const double* verts, int64_t i) { return mk3(verts[3 * i], verts[3 * i + 1], verts[3 * i + 2]); }
+BMO_D V3 load_vertex(const double* verts, int64_t i) { return mk3(__ldg(verts + 3 * i), __ldg(verts + 3 * i + 1), __ldg(verts + 3 * i + 2)); }
 BMO_D double r32(double x) { return (double)(float)x; }
 // Mesh.jl:203-237  (k_eps = l_eps = 1e-9); returns +Inf on a miss.  For Float32 meshes (STL,
 // Mesh.jl:48-70) the edge vectors are formed in Float32 like the reference's Point3{Float32} math.
@@ -291,7 +397,13 @@ BMO_D bool box_hit(const BvhNode& nd, V3 o, V3 d, double tbest) {
     return tmin <= tmax;
 }
 // Mesh.jl:244-267: closest triangle, strict-min in face order => lowest face index wins ties.
-BMO_NI bool mesh_intersect(const SysView& S, int mesh_id, int pose, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
+// The mesh tables are passed by value: taking the address of the kernel parameter block would make
+// the compiler copy it to local memory.
+struct MeshTabs {
+    const MeshView* meshes; const double* vertices; const int32_t* faces; const BvhNode* nodes; const int32_t* bvh_faces;
+    int64_t n_vertices; int32_t n_poses, pad;
+};
+BMO_NI bool mesh_intersect(const MeshTabs S, int mesh_id, int pose, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
     const MeshView mv = S.meshes[mesh_id];
     const double* verts = S.vertices + 3 * ((int64_t)pose * S.n_vertices + mv.first_vertex);
     const int32_t* faces = S.faces + 3 * mv.first_face;
@@ -300,8 +412,8 @@ BMO_NI bool mesh_intersect(const SysView& S, int mesh_id, int pose, V3 pos, V3 d
     if (mv.n_nodes == 0 || S.n_poses > 1) {  // small meshes (and posed sweeps): reference order
         for (int64_t i = 0; i < mv.n_faces; i++) {
             st.tri++;
-            double tt = moeller_trumbore(load_vertex(verts, faces[3 * i]), load_vertex(verts, faces[3 * i + 1]),
-                                         load_vertex(verts, faces[3 * i + 2]), pos, dir, mv.f32);
+            double tt = moeller_trumbore(load_vertex(verts, __ldg(faces + 3 * i)), load_vertex(verts, __ldg(faces + 3 * i + 1)),
+                                         load_vertex(verts, __ldg(faces + 3 * i + 2)), pos, dir, mv.f32);
             if (tt < t0) { t0 = tt; fid = i; }
         }
     } else {
@@ -317,8 +429,8 @@ BMO_NI bool mesh_intersect(const SysView& S, int mesh_id, int pose, V3 pos, V3 d
                 for (int k = 0; k < nd.count; k++) {
                     int64_t f = order[nd.first + k];
                     st.tri++;
-                    double tt = moeller_trumbore(load_vertex(verts, faces[3 * f]), load_vertex(verts, faces[3 * f + 1]),
-                                                 load_vertex(verts, faces[3 * f + 2]), pos, dir, mv.f32);
+                    double tt = moeller_trumbore(load_vertex(verts, __ldg(faces + 3 * f)), load_vertex(verts, __ldg(faces + 3 * f + 1)),
+                                                 load_vertex(verts, __ldg(faces + 3 * f + 2)), pos, dir, mv.f32);
                     if (tt < t0 || (tt == t0 && tt < INFINITY && f < fid)) { t0 = tt; fid = f; }
                 }
             } else if (sp < 62) {
@@ -329,63 +441,68 @@ BMO_NI bool mesh_intersect(const SysView& S, int mesh_id, int pose, V3 pos, V3 d
     }
     if (fid < 0) return false;
     t = t0;
-    n = face_normal(load_vertex(verts, faces[3 * fid]), load_vertex(verts, faces[3 * fid + 1]), load_vertex(verts, faces[3 * fid + 2]), mv.f32);
+    n = face_normal(load_vertex(verts, __ldg(faces + 3 * fid)), load_vertex(verts, __ldg(faces + 3 * fid + 1)), load_vertex(verts, __ldg(faces + 3 * fid + 2)), mv.f32);
     return true;
 }
 
 // ---- shapes, objects, system --------------------------------------------------------------------
 struct TraceCtx {
-    const SysView* S;
-    const bmo_prim* prims;  // prim table of this ray's pose (shared memory copy when n_poses == 1)
+    MeshTabs M;
+    const bmo_object* objects;
+    int n_parts, zr;
+    const bmo_prim* prims;   // prim table of this ray's pose (shared-memory copy when staged)
+    const bmo_part* parts;   // part table (shared-memory copy when staged)
+    const double* bounds;    // [n_parts][4] bounding spheres of this ray's pose
     int pose;
 };
 // intersect3d(shape, ray)
-BMO_NI bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
-    const bmo_part& pt = C.S->parts[part];
+BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
+    const bmo_part& pt = C.parts[part];
     if (pt.shape_kind == BMO_SHAPE_SDF) {
-        const double* bnd = C.S->bounds + 4 * ((int64_t)C.pose * C.S->n_parts + part);
-        return sdf_intersect(C.prims, pt.first, pt.count, bnd, pos, dir, C.S->zr, st, t, n);
+        const double* bnd = C.bounds + 4 * part;
+        SdfShape sh;
+        sh.prims = C.prims; sh.first = pt.first; sh.count = pt.count; sh.zr = C.zr;
+        sh.cx = bnd[0]; sh.cy = bnd[1]; sh.cz = bnd[2]; sh.R2 = bnd[3] * bnd[3];
+        return sdf_intersect_f(sh, pos, dir, st.sdf, t, n);
     }
-    return mesh_intersect(*C.S, pt.first, C.pose, pos, dir, st, t, n);
+    Stats tmp; tmp.sdf = 0; tmp.tri = 0;
+    const bool hit = mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, t, n);
+    st.tri += tmp.tri;
+    return hit;
 }
-// intersect3d(object, ray): AbstractRay.jl:118-155; PlateBeamsplitter.jl:160-187
-BMO_D Hit object_intersect(const TraceCtx& C, int obj, V3 pos, V3 dir, Stats& st) {
-    const bmo_object& ob = C.S->objects[obj];
-    Hit best; best.part = -1; best.t = INFINITY; best.n = mk3(0, 0, 0);
-    if (ob.kind == BMO_OBJ_PLATE_BS) {
-        double tc, ts; V3 nc, ns;
-        bool hc = part_intersect(C, ob.first_part + 1, pos, dir, st, tc, nc);
-        bool hs = part_intersect(C, ob.first_part, pos, dir, st, ts, ns);
-        if (!hc && !hs) return best;
-        bool coat = !hs ? true : (!hc ? false : (jl_isapprox(tc, ts) ? true : (tc < ts)));
-        if (coat) { best.t = tc; best.n = nc; best.part = ob.first_part + 1; }
-        else { best.t = ts; best.n = ns; best.part = ob.first_part; }
-        return best;
-    }
-    for (int k = 0; k < ob.n_parts; k++) {
-        double t; V3 n;
-        if (!part_intersect(C, ob.first_part + k, pos, dir, st, t, n)) continue;
-        if (best.part < 0 || t < best.t) { best.t = t; best.n = n; best.part = ob.first_part + k; }
-    }
-    return best;
-}
-// System.jl:57-72
-BMO_D Hit trace_all(const TraceCtx& C, V3 pos, V3 dir, Stats& st) {
+// tracing_step! (System.jl:57-110).  trace_one: the hinted shape is accepted without comparing
+// against other objects.  On a miss, trace_all: every object in Leaves order, strict-min t; inside an
+// object the parts in shape(object) order, strict-min t (AbstractRay.jl:118-155), except that a plate
+// beamsplitter prefers its coating whenever t_coating ~ t_substrate (PlateBeamsplitter.jl:160-187).
+// The hinted part is not intersected again by trace_all (same ray, same shape => the same miss).
+// One loop over [hint, part 0, part 1, ...] so that part_intersect has a single call site.
+BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st) {
     Hit res; res.part = -1; res.t = INFINITY; res.n = mk3(0, 0, 0);
-    for (int o = 0; o < C.S->n_objects; o++) {
-        Hit h = object_intersect(C, o, pos, dir, st);
-        if (h.part < 0) continue;
-        if (res.part < 0 || h.t < res.t) res = h;
+    Hit ob; ob.part = -1; ob.t = INFINITY; ob.n = mk3(0, 0, 0);   // best of the current object
+    int cur_obj = -1;
+    const int n_parts = C.n_parts;
+    for (int it = hint_part >= 0 ? -1 : 0; it <= n_parts; it++) {
+        const int part = it < 0 ? hint_part : it;
+        const int obj = (it >= 0 && it < n_parts) ? C.parts[part].object : -1;
+        if (it >= 0 && obj != cur_obj) {       // object boundary: trace_all's comparison (System.jl:62-67)
+            if (ob.part >= 0 && (res.part < 0 || ob.t < res.t)) res = ob;
+            ob.part = -1; ob.t = INFINITY;
+            cur_obj = obj;
+            if (it == n_parts) break;
+        }
+        double t; V3 n;
+        const bool hit = (it >= 0 && part == hint_part) ? false : part_intersect(C, part, pos, dir, st, t, n);
+        if (it < 0) {
+            if (hit) { res.t = t; res.n = n; res.part = part; return res; }
+            continue;
+        }
+        if (!hit) continue;
+        bool take = ob.part < 0 || t < ob.t;
+        if (C.parts[part].role == BMO_ROLE_COATING && C.objects[obj].kind == BMO_OBJ_PLATE_BS && ob.part >= 0)
+            take = jl_isapprox(t, ob.t) ? true : (t < ob.t);   // parts = (substrate, coating)
+        if (take) { ob.t = t; ob.n = n; ob.part = part; }
     }
     return res;
-}
-// System.jl:74-110: the hinted shape is accepted without comparing against other objects
-BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st) {
-    if (hint_part >= 0) {
-        Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
-        if (part_intersect(C, hint_part, pos, dir, st, h.t, h.n)) { h.part = hint_part; return h; }
-    }
-    return trace_all(C, pos, dir, st);
 }
 
 }  // namespace bmo

@@ -2,10 +2,13 @@
 //
 // One wave = one `tracing_step!` + `interact3d` of every live beam (System.jl:100-154, 274-318).
 // Kernels per wave:
-//   K1 trace_step<MODE>   one thread per ray (Gaussian beamlets: chief/waist/divergence in adjacent
-//                         lanes, 10 triples per warp): intersect -> interact -> block-local queue
-//                         compaction with warp ballots + prefix sums, successors written to scratch.
-//   K2 scan_counts        exclusive scan of the per-block successor / spawn counts.
+//   K1 intersect_wave     one thread per ray: trace_one / trace_all (SDF sphere tracing, Moeller-
+//                         Trumbore behind the BVH) -> hit record (t, normal, part).  Register-lean on
+//                         purpose: the FP64 marching loop is latency bound, occupancy is what feeds it.
+//   K2 interact_wave<MODE> one thread per ray (Gaussian beamlets: chief/waist/divergence in adjacent
+//                         lanes, 10 triples per warp): interact3d -> block-local queue compaction
+//                         with warp ballots + prefix sums, successors written to scratch.
+//      scan_counts        exclusive scan of the per-block successor / spawn counts.
 //   K3 scatter_queue      HBM-bound copy of the compacted successors into the next queue and
 //                         numbering of beamsplitter children (deterministic: queue order).
 // With BMO_KEEP_SEGMENTS the segment records are written wave-major by K1 and gathered into
@@ -42,11 +45,27 @@ struct BeamTab {
     double *w0, *e0, *plen, *popl, *spot_xz;
 };
 
+struct HitBuf {
+    double* d = nullptr;      // [4][cap]: t, nx, ny, nz
+    int32_t* part = nullptr;  // [cap]: -1 = miss
+    int64_t cap = 0;
+};
+
+struct IntersectParams {
+    SysView S;
+    Queue cur;
+    HitBuf hit;
+    int64_t n_rays;
+    int32_t r_max, pad;
+    DevCounters* counters;
+};
+
 struct StepParams {
     SysView S;
     Queue cur, scr;
+    HitBuf hit;
     int64_t count;       // beams in the current queue
-    int32_t r_max, use_smem, keep, pad;
+    int32_t r_max, keep;
     WaveBuf wave;
     BeamTab B;
     int32_t* blk_cnt;    // [nblocks][2] successors, spawns
@@ -65,25 +84,80 @@ BMO_D V3 shfl3(V3 v, int l) {
     return mk3(__shfl_sync(0xffffffffu, v.x, l), __shfl_sync(0xffffffffu, v.y, l), __shfl_sync(0xffffffffu, v.z, l));
 }
 
-// ---- K1 ---------------------------------------------------------------------------------------
+// ---- K1: intersect ------------------------------------------------------------------------------
+constexpr int IBLOCK = 128;
+// STAGED: the small system tables (prims, parts, bounds) live in shared memory -- a compile-time fact,
+// so that the marching loop reads them with LDS instead of generic loads.
+template <int MINB, bool STAGED>
+__global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SysView& S = P.S;
+    // shared-memory copies of the small system tables: prims | parts | bounds
+    bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
+    bmo_part* s_parts = reinterpret_cast<bmo_part*>(smem_raw + (size_t)S.n_prims * sizeof(bmo_prim));
+    double* s_bounds = reinterpret_cast<double*>(smem_raw + (size_t)S.n_prims * sizeof(bmo_prim) + (size_t)S.n_parts * sizeof(bmo_part));
+    if (STAGED) {
+        const int nw = S.n_prims * (int)(sizeof(bmo_prim) / 8), nq = S.n_parts * (int)(sizeof(bmo_part) / 8);
+        const double* src = reinterpret_cast<const double*>(S.prims);
+        double* dst = reinterpret_cast<double*>(s_prims);
+        for (int k = threadIdx.x; k < nw; k += IBLOCK) dst[k] = src[k];
+        src = reinterpret_cast<const double*>(S.parts);
+        dst = reinterpret_cast<double*>(s_parts);
+        for (int k = threadIdx.x; k < nq; k += IBLOCK) dst[k] = src[k];
+        for (int k = threadIdx.x; k < 4 * S.n_parts; k += IBLOCK) s_bounds[k] = S.bounds[k];
+        __syncthreads();
+    }
+
+    const int64_t ri = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
+    const bool active = ri < P.n_rays;
+    Stats st; st.sdf = 0; st.tri = 0;
+    if (active) {
+        const int64_t qs = P.cur.cap;
+        const double* q = P.cur.d;
+        const V3 pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
+        const V3 dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
+        const int hint = P.cur.i[I_HINT * qs + ri];
+        const int pose = P.cur.i[I_POSE * qs + ri];
+        const bool budget = P.cur.i[I_SEG * qs + ri] + 1 < P.r_max;   // `while length(rays) < r_max` (System.jl:133)
+        TraceCtx C;
+        C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
+        C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
+        C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
+        C.pose = pose;
+        if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
+        else {
+            C.prims = S.prims + (int64_t)pose * S.n_prims;
+            C.parts = S.parts;
+            C.bounds = S.bounds + 4 * (int64_t)pose * S.n_parts;
+        }
+        Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+        if (budget) h = tracing_step(C, pos, dir, hint, st);   // System.jl:100-110
+        const int64_t hs = P.hit.cap;
+        P.hit.d[ri] = h.t; P.hit.d[hs + ri] = h.n.x; P.hit.d[2 * hs + ri] = h.n.y; P.hit.d[3 * hs + ri] = h.n.z;
+        P.hit.part[ri] = h.part;
+    }
+    unsigned sd = st.sdf, tr = st.tri;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sd) atomicAdd(&P.counters->sdf, (unsigned long long)sd);
+        if (tr) atomicAdd(&P.counters->tri, (unsigned long long)tr);
+    }
+}
+
+// ---- K2: interact + block-local compaction ----------------------------------------------------------
 template <int MODE>
-__global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams P) {
+__global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepParams P) {
     constexpr int R = Cfg<MODE>::R;
     constexpr int UNITS = Cfg<MODE>::UNITS;
     constexpr int NWARP = Cfg<MODE>::NWARP;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
     __shared__ int s_wcnt[NWARP][2];
     __shared__ int s_woff[NWARP][2];
 
     const SysView& S = P.S;
-    if (P.use_smem) {
-        const int nwords = S.n_prims * (int)(sizeof(bmo_prim) / 8);
-        const double* src = reinterpret_cast<const double*>(S.prims);
-        double* dst = reinterpret_cast<double*>(s_prims);
-        for (int k = threadIdx.x; k < nwords; k += blockDim.x) dst[k] = src[k];
-        __syncthreads();
-    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int uib, r;
     bool lane_ok = true;
@@ -97,10 +171,11 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams 
 
     V3 pos = mk3(0, 0, 0), dir = mk3(0, 1, 0);
     double rn = 1.0;
-    int lam = 0, hint = -1, beam = 0, seg = 0, pose = 0;
+    int lam = 0, beam = 0, seg = 0, pose = 0;
     Cx E0[3];
     E0[0] = E0[1] = E0[2] = mkc(0, 0);
     double acc_lsum = 0, acc_lpar = 0, acc_opl = 0;
+    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
     if (active) {
         const double* q = P.cur.d;
         pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
@@ -112,25 +187,20 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams 
         }
         if (MODE == 2) { acc_lsum = q[F_X0 * qs + ri]; acc_lpar = q[(F_X0 + 1) * qs + ri]; acc_opl = q[(F_X0 + 2) * qs + ri]; }
         const int32_t* qi = P.cur.i;
-        lam = qi[I_LAM * qs + ri]; hint = qi[I_HINT * qs + ri]; beam = qi[I_BEAM * qs + ri];
+        lam = qi[I_LAM * qs + ri]; beam = qi[I_BEAM * qs + ri];
         seg = qi[I_SEG * qs + ri]; pose = qi[I_POSE * qs + ri];
+        const int64_t hs = P.hit.cap;
+        h.t = P.hit.d[ri]; h.n = mk3(P.hit.d[hs + ri], P.hit.d[2 * hs + ri], P.hit.d[3 * hs + ri]);
+        h.part = P.hit.part[ri];
     }
 
-    Stats st; st.sdf = 0; st.tri = 0;
-    TraceCtx C;
-    C.S = &S;
-    C.pose = pose;
-    C.prims = P.use_smem ? s_prims : (S.prims + (int64_t)pose * S.n_prims);
-
-    // ---- intersect (System.jl:100-110) ----
-    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+    // ---- outcome of tracing_step! (System.jl:100-110, intersect_wave) ----
     int status = BMO_ST_ACTIVE;
     if (active) {
-        if (seg + 1 >= P.r_max) status = BMO_ST_RMAX;          // `while length(rays) < r_max`, System.jl:133 / :281
-        else {
-            h = tracing_step(C, pos, dir, hint, st);
-            if (h.part < 0) status = BMO_ST_MISS;
-        }
+        if (seg + 1 >= P.r_max) {          // `while length(rays) < r_max`, System.jl:133 / :281: not traced
+            status = BMO_ST_RMAX;
+            h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+        } else if (h.part < 0) status = BMO_ST_MISS;
     }
     double seg_t = h.t;       // t stored in this lane's segment record (Inf <=> intersection === nothing)
     int hit_part = h.part;    // part the interaction dispatches on (Gaussian: the chief's)
@@ -315,19 +385,8 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) trace_step(const StepParams 
     int wsoff = __popc(b2 & lt);                     // spawn events of lower lanes
     if (lane == 0) { s_wcnt[warp][0] = __popc(b1) + __popc(b2); s_wcnt[warp][1] = __popc(b2); }
     // statistics ride on the same barrier
-    unsigned long long ia = interacted ? 1ull : 0ull;
-    unsigned sd = st.sdf, tr = st.tri;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        ia += __shfl_xor_sync(full, ia, o);
-        sd += __shfl_xor_sync(full, sd, o);
-        tr += __shfl_xor_sync(full, tr, o);
-    }
-    if (lane == 0) {
-        if (ia) atomicAdd(&P.counters->interactions, ia);
-        if (sd) atomicAdd(&P.counters->sdf, (unsigned long long)sd);
-        if (tr) atomicAdd(&P.counters->tri, (unsigned long long)tr);
-    }
+    const unsigned ia = __popc(__ballot_sync(full, interacted));
+    if (lane == 0 && ia) atomicAdd(&P.counters->interactions, (unsigned long long)ia);
     __syncthreads();
     if (threadIdx.x == 0) {
         int a = 0, b = 0;
@@ -650,6 +709,13 @@ static int32_t validate_tables(const bmo_tables* t) {
     return BMO_OK;
 }
 
+// bit 0 of bmo_prim.reserved: transposed_orientation is exactly the identity (w2s_f skips the products)
+static int32_t prim_flags(const bmo_prim& p) {
+    static const double I[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    for (int k = 0; k < 9; k++) if (p.tdir[k] != I[k]) return 0;
+    return 1;
+}
+
 template <class T> static int32_t upload(T** dptr, const T* h, size_t n) {
     BMO_CUDA(cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T)));
     if (n) BMO_CUDA(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
@@ -664,6 +730,7 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
     bmo_sys* s = new bmo_sys();
     s->ctx = ctx;
     s->prims.assign(t->prims, t->prims + t->n_prims);
+    for (auto& pr : s->prims) pr.reserved = prim_flags(pr);
     s->parts.assign(t->parts, t->parts + t->n_parts);
     s->objects.assign(t->objects, t->objects + t->n_objects);
     s->lambdas.assign(t->lambdas, t->lambdas + t->n_lambda);
@@ -748,7 +815,9 @@ int32_t bmo_system_set_poses(bmo_sys* s, int32_t n_poses, const bmo_prim* prims,
         if ((rc = reup(&s->d_detpose, s->h_detpose.data(), s->h_detpose.size()))) return rc;
     } else {
         if (!prims || !bounds || (!vertices && s->n_vertices > 0) || !det_pos || !det_dir) return fail(BMO_EINVAL, "bmo_system_set_poses: NULL table");
-        if ((rc = reup(&s->d_prims, prims, np * s->prims.size()))) return rc;
+        std::vector<bmo_prim> pp(prims, prims + np * s->prims.size());
+        for (auto& pr : pp) pr.reserved = prim_flags(pr);
+        if ((rc = reup(&s->d_prims, pp.data(), pp.size()))) return rc;
         if ((rc = reup(&s->d_vertices, vertices, np * 3 * (size_t)s->n_vertices))) return rc;
         if ((rc = reup(&s->d_bounds, bounds, np * 4 * s->parts.size()))) return rc;
         std::vector<double> dp(np * 12 * s->objects.size());
@@ -893,6 +962,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
 
     if ((rc = ensure_beams(res, n, st))) return rc;
     Queue cur, next, scr;
+    HitBuf hit;
     if ((rc = alloc_queue(cur, n * R, nfq, NI_Q, st))) return rc;
     {
         InitParams ip{};
@@ -903,8 +973,11 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         BMO_LAUNCH(ctx, "init_queue");
     }
     const double tp1 = tnow();
-    const bool use_smem = sys->view.n_poses == 1 && (size_t)sys->view.n_prims * sizeof(bmo_prim) <= 40 * 1024;
-    const size_t smem = use_smem ? (size_t)sys->view.n_prims * sizeof(bmo_prim) : 0;
+    // small single-pose systems: prims / parts / bounds are staged through shared memory
+    const SysView& V = sys->view;
+    const size_t table_bytes = (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + 4 * sizeof(double));
+    const bool staged = V.n_poses == 1 && table_bytes <= 40 * 1024;
+    const size_t smem = staged ? table_bytes : 0;
 
     int64_t count = n, n_beams = n;
     int32_t* blk_cnt = nullptr; long long* blk_off = nullptr; int64_t blk_cap = 0;
@@ -930,15 +1003,34 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
             BMO_CUDA(dev_alloc(&wb.seg, (size_t)wb.count, st));
             res->wavebufs.push_back(wb);
         }
-        StepParams sp{};
-        sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.count = count; sp.r_max = r_max; sp.use_smem = use_smem; sp.keep = res->keep;
-        sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.counters = ctx->d_counters;
+        if (hit.cap < count * R) {
+            dev_free(hit.d, st); dev_free(hit.part, st);
+            hit.cap = count * R;
+            BMO_CUDA(dev_alloc(&hit.d, (size_t)4 * hit.cap, st));
+            BMO_CUDA(dev_alloc(&hit.part, (size_t)hit.cap, st));
+        }
+        IntersectParams xp{};
+        xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = count * R; xp.r_max = r_max;
+        xp.counters = ctx->d_counters;
         BMO_CUDA(cudaEventRecord(ctx->evk0, st));
-        if (mode == 0) trace_step<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, smem, st>>>(sp);
-        else if (mode == 1) trace_step<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, smem, st>>>(sp);
-        else trace_step<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, smem, st>>>(sp);
-        BMO_LAUNCH(ctx, "trace_step");
+        {
+            static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 4;   // tuning knob: resident blocks per SM the kernel is compiled for
+            const unsigned grid = (unsigned)((count * R + IBLOCK - 1) / IBLOCK);
+            if (!staged) intersect_wave<4, false><<<grid, IBLOCK, 0, st>>>(xp);
+            else if (minb <= 3) intersect_wave<3, true><<<grid, IBLOCK, smem, st>>>(xp);
+            else if (minb == 4) intersect_wave<4, true><<<grid, IBLOCK, smem, st>>>(xp);
+            else if (minb == 5) intersect_wave<5, true><<<grid, IBLOCK, smem, st>>>(xp);
+            else intersect_wave<6, true><<<grid, IBLOCK, smem, st>>>(xp);
+        }
+        BMO_LAUNCH(ctx, "intersect_wave");
         BMO_CUDA(cudaEventRecord(ctx->evk1, st));
+        StepParams sp{};
+        sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = count; sp.r_max = r_max; sp.keep = res->keep;
+        sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.counters = ctx->d_counters;
+        if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+        else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
+        else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
+        BMO_LAUNCH(ctx, "interact_wave");
         scan_counts<<<1, 1024, 0, st>>>(blk_cnt, nblocks, 2, 2, blk_off, ctx->d_totals);
         BMO_LAUNCH(ctx, "scan_counts");
         ScatterParams cp{};
@@ -971,6 +1063,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     res->n_beams = n_beams;
     res->waves = wave;
     free_queue(cur, st); free_queue(next, st); free_queue(scr, st);
+    dev_free(hit.d, st); dev_free(hit.part, st);
     dev_free(blk_cnt, st); dev_free(blk_off, st);
     for (void* p : tmp) cudaFreeAsync(p, st);
 

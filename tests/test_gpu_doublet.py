@@ -59,6 +59,33 @@ def test_doublet_segments_match_oracle(bmo, orc, rotate):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("rotate", [False, True])
+def test_doublet_bitwise_equal_to_oracle(bmo, orc, rotate):
+    """Plain-Ray tracing only uses +, -, *, /, sqrt (IEEE-exact on both sides, no FMA contraction on
+    either), so the CUDA path must reproduce the oracle bit for bit -- this pins the "bit-identical"
+    claims of the fast SDF evaluation (bmo_geom.cuh) much harder than the 1e-9 tolerance does."""
+    n = 4096
+    sc, osc = scenes.doublet_spot(bmo, rotate), scenes.doublet_spot_oracle(rotate)
+    pos, d = scenes.fibonacci_disc(n, diameter=25.0e-3)      # includes rays at / beyond the lens edge
+    if rotate:
+        from bmo_b200 import linalg as la
+        Rm = np.array(la.matmul(la.rotate3d((0, 0, 1), np.radians(45)), la.rotate3d((1, 0, 0), np.radians(-60))))
+        pos, d = pos @ Rm.T + np.array([0.05, 0.05, 0.05]), d @ Rm.T
+    src = bmo.RayBundle(pos, d, 707e-9)
+    res = bmo.solve_system_(sc["system"], src, r_max=100)
+    ref = orc.bulk_trace_rays(osc["system"], src.pos, src.dir, 707e-9, max_seg=8, spot=osc["spot"])
+    beams, seg = res.beams(), res.segments()
+    assert np.array_equal(beams["nseg"], ref["nseg"])
+    rows = np.concatenate([beams["first"][i] + np.arange(beams["nseg"][i]) for i in range(n)])
+    rsel = np.concatenate([ref["seg"][i, :beams["nseg"][i]] for i in range(n)])
+    assert np.array_equal(seg["pos"][rows], rsel[:, 0:3])
+    assert np.array_equal(seg["dir"][rows], rsel[:, 3:6])
+    assert np.array_equal(seg["t"][rows], rsel[:, 7])
+    fin = np.isfinite(rsel[:, 7])
+    assert np.array_equal(seg["nrm"][rows][fin], rsel[:, 8:11][fin])
+
+
+@pytest.mark.gpu
 def test_doublet_single_beam_rebuild(bmo, orc):
     """solve_system!(system, ::Beam): 4 segments, n = [1, n1, n2, 1] (test/runtests.jl:1304-1306)."""
     sc = scenes.doublet_spot(bmo)
