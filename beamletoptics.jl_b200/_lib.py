@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(_HERE, "libbmo.so")
 
 KEEP_SEGMENTS = 1
 INPUT_DEVICE = 2
+PD_REFERENCE_ORDER = 4
 
 STATUS_NAMES = ["ACTIVE", "MISS", "ABSORBED", "RMAX", "SPLIT", "CLIPPED", "TORN", "ERROR"]
 

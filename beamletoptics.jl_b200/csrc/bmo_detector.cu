@@ -4,8 +4,19 @@
 // electric_field(gauss, r, z) (Gaussian.jl:381-392) -> point_on_beam (Beam.jl:177-205) +
 // gauss_parameters (Gaussian.jl:298-353) -> electric_field(r, z, E0, w0, w, k, psi, R)
 // (OpticUtils.jl:87-89), one thread per pixel, beamlet records staged through shared memory.
-// Per-beamlet constants (lengths, OPL, reference phase, projection) are hoisted into the records;
-// everything that depends on the pixel keeps the reference's operation order (k*z is O(1e7) rad).
+// Two kernels:
+//   pd_field_fast (default)  the per-pair arithmetic is strength-reduced: along one chief segment the
+//       waist / divergence ray heights are affine in the arclength s (y0_r = A_r + s B_r), so the two
+//       line-plane intersections, the normalisations and tan(pi/2 - acos(c)) collapse to
+//       m_r = c_r / sqrt(1 - c_r^2) with c_r^2 = (alpha_r + s beta_r)^2 / |y0_r|^2; the local waist w0
+//       cancels out of E0 (w0_beam / w0) * w0 / w; the Gouy phase enters as (cos psi, sin psi) =
+//       (sqrt(1 - R zeta), -+ sqrt(R zeta)) instead of atan2 + sincos; k z (O(1e7) rad) is reduced by
+//       2 pi with two FMAs before sincos.  Algebraically identical to the reference, rounding differs
+//       at the 1e-9 rad level (the reference's own k*z carries 1 ulp(1e7) = 2e-9 rad); tolerance of
+//       the path: 1e-8 relative L2 (north_star).  Pixels whose z falls on an earlier chief segment
+//       (tilted detectors, Beam.jl:186-199) take the reference-order path below.
+//   pd_field (BMO_PD_REFERENCE_ORDER)  every pair evaluated in the reference's operation order;
+//       kept as the cross-check of the fast kernel at full detector sizes.
 #include "bmo_host.cuh"
 #include "bmo_interact.cuh"
 
@@ -33,6 +44,19 @@ struct PdRec {
     double pad;
 };
 static_assert(sizeof(PdRec) % 8 == 0, "PdRec must be a whole number of doubles");
+
+// Strength-reduced record of the same beamlet (last chief segment), see pd_field_fast.
+struct PdFast {
+    double p0[3], d0[3];
+    double Ad[3], Bd[3], alpd, betd;   // divergence ray: y0(s) = Ad + s Bd, (y0 . dir_d)/|dir_d| = alpd + s betd
+    double Aw[3], Bw[3], alpw, betw;   // waist ray
+    double l0, temp, k;
+    double cre, cim;                   // E0_beam * w0_beam * sqrt(proj) * exp(i ref_phi)
+    double multi;                      // > 0: the beam has earlier segments (z < temp must be checked)
+    double generic;                    // > 0: degenerate geometry, use the reference-order path for every pixel
+    double pad;
+};
+static_assert(sizeof(PdFast) % 8 == 0, "PdFast must be a whole number of doubles");
 
 struct ResView {
     const double* seg_d; const int32_t* seg_part; int64_t rows;
@@ -95,12 +119,42 @@ __global__ void pd_build(ResView R, SysView S, const int32_t* flags, const long 
     rc.first_row = (double)f; rc.nseg = (double)n; rc.pose = (double)R.pose[b]; rc.pad = 0;
     recs[offs[b]] = rc;
 }
+// PdRec -> PdFast (after the records have been grouped by pose)
+__global__ void pd_make_fast(const PdRec* recs, PdFast* fast, int64_t m) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= m) return;
+    const PdRec rc = recs[b];
+    const int n = (int)rc.nseg;
+    PdFast fr;
+    const V3 p0 = mk3(rc.p0[0], rc.p0[1], rc.p0[2]), d0 = mk3(rc.d0[0], rc.d0[1], rc.d0[2]);
+    fr.generic = 0.0;
+    for (int q = 0; q < 2; q++) {
+        const V3 rp = q == 0 ? mk3(rc.dp[0], rc.dp[1], rc.dp[2]) : mk3(rc.wp[0], rc.wp[1], rc.wp[2]);
+        const V3 rd = q == 0 ? mk3(rc.dd[0], rc.dd[1], rc.dd[2]) : mk3(rc.wd[0], rc.wd[1], rc.wd[2]);
+        const double denom = dot(d0, rd);                     // line_plane_distance3d, LinearAlgebraUtils.jl:127-136
+        if (!(fabs(denom) > 1e-6)) fr.generic = 1.0;
+        const double a = dot(p0 - rp, d0) / denom, bq = dot(d0, d0) / denom;   // il(s) = a + s bq for point = p0 + s d0
+        const V3 A = rp + a * rd - p0, B = bq * rd - d0;
+        const double ind = 1.0 / norm(rd);
+        double* Ao = q == 0 ? fr.Ad : fr.Aw; double* Bo = q == 0 ? fr.Bd : fr.Bw;
+        Ao[0] = A.x; Ao[1] = A.y; Ao[2] = A.z; Bo[0] = B.x; Bo[1] = B.y; Bo[2] = B.z;
+        (q == 0 ? fr.alpd : fr.alpw) = dot(A, rd) * ind;
+        (q == 0 ? fr.betd : fr.betw) = dot(B, rd) * ind;
+    }
+    for (int k = 0; k < 3; k++) { fr.p0[k] = rc.p0[k]; fr.d0[k] = rc.d0[k]; }
+    fr.l0 = rc.l0; fr.temp = rc.temp; fr.k = rc.k;
+    const Cx C = ((mkc(rc.e0r, rc.e0i) * rc.w0b) * mkc(rc.cr, rc.ci)) * rc.sq;
+    fr.cre = C.re; fr.cim = C.im;
+    fr.multi = n > 1 ? 1.0 : 0.0;
+    fr.pad = 0;
+    fast[b] = fr;
+}
 
 constexpr int PD_TILE = 16;   // 16 x 16 pixels per block
 constexpr int PD_BATCH = 32;  // beamlet records staged per smem tile
 
 struct PdParams {
-    const PdRec* recs; int64_t n_recs;
+    const PdRec* recs; const PdFast* fast; int64_t n_recs;
     ResView R;
     double* field;            // [n_fields][n*n*2] column-major [i + n*j], re/im interleaved
     const double* det_pose;   // [n_poses][n_objects][12]
@@ -115,6 +169,64 @@ BMO_D double lin_coord(int i, int n, double lo, double hi) {
     return (1 - t) * lo + t * hi;
 }
 
+// One pixel-beamlet pair in the reference's operation order (Photodetector.jl:98-103, Beam.jl:177-205,
+// Gaussian.jl:298-353, 381-392, OpticUtils.jl:87-89)
+BMO_NI Cx pd_pair_reference(const PdRec& rc, V3 p1, const double* seg_d, int64_t rows) {
+    const V3 p0 = mk3(rc.p0[0], rc.p0[1], rc.p0[2]), d0 = mk3(rc.d0[0], rc.d0[1], rc.d0[2]);
+    // projection of the pixel onto the beamlet axis (Photodetector.jl:98-101)
+    const double l1 = dot(p1 - p0, d0);
+    const V3 p2 = p0 + l1 * d0;
+    const double r = norm(p1 - p2);
+    const double z = rc.l0 + l1;
+    // point_on_beam(gauss, z) (Beam.jl:177-205)
+    V3 point, c_dir = d0, w_pos = mk3(rc.wp[0], rc.wp[1], rc.wp[2]), w_dir = mk3(rc.wd[0], rc.wd[1], rc.wd[2]),
+              d_pos = mk3(rc.dp[0], rc.dp[1], rc.dp[2]), d_dir = mk3(rc.dd[0], rc.dd[1], rc.dd[2]);
+    double c_n = rc.cn;
+    bool found = false;
+    if (rc.nseg > 1.0 && z < rc.temp) {   // an earlier segment: replay the reference's loop
+        const int ns = (int)rc.nseg;
+        const int64_t f = (int64_t)rc.first_row;
+        const double* d = seg_d;
+        double temp = rc.plen;
+        for (int s = 0; s < ns - 1; s++) {
+            const int64_t row = (f + s) * 3;
+            const double len = d[S_T * rows + row];
+            temp += len;
+            if (z < temp) {
+                const double b = temp - z;
+                const V3 sp = mk3(d[S_PX * rows + row], d[S_PY * rows + row], d[S_PZ * rows + row]);
+                c_dir = mk3(d[S_DX * rows + row], d[S_DY * rows + row], d[S_DZ * rows + row]);
+                point = sp + (len - b) * c_dir;
+                c_n = d[S_N * rows + row];
+                w_pos = mk3(d[S_PX * rows + row + 1], d[S_PY * rows + row + 1], d[S_PZ * rows + row + 1]);
+                w_dir = mk3(d[S_DX * rows + row + 1], d[S_DY * rows + row + 1], d[S_DZ * rows + row + 1]);
+                d_pos = mk3(d[S_PX * rows + row + 2], d[S_PY * rows + row + 2], d[S_PZ * rows + row + 2]);
+                d_dir = mk3(d[S_DX * rows + row + 2], d[S_DY * rows + row + 2], d[S_DZ * rows + row + 2]);
+                found = true;
+                break;
+            }
+        }
+    }
+    if (!found) point = p0 + (z - rc.temp) * d0;
+    double w, Rc, psi, w0;
+    gauss_parameters(point, c_dir, c_n, w_pos, w_dir, d_pos, d_dir, rc.lambda, w, Rc, psi, w0);
+    // electric_field(gauss, r, z) (Gaussian.jl:381-392, OpticUtils.jl:87-89)
+    const Cx E0 = mkc(rc.e0r, rc.e0i) * (rc.w0b / w0);
+    Cx e = ((E0 * w0) / w) * exp(-(r * r) / (w * w));
+    e = e * cis(rc.k * z + psi + (rc.k * (r * r) * Rc) / 2);
+    e = e * mkc(rc.cr, rc.ci);
+    return e * rc.sq;
+}
+
+// pixel (i, j) -> world: p1 = dir' * (x, 0, y) + pos   (Photodetector.jl:78,92-96 -- transposed orientation)
+BMO_D V3 pd_pixel(const double* dp, int i, int j, int n, double lo, double hi) {
+    const double x = lin_coord(min(i, n - 1), n, lo, hi), y = lin_coord(min(j, n - 1), n, lo, hi);
+    // T = transpose(dir): T[r][c] = dir[c][r]; dir row-major at dp[3 + 3*r + c]
+    return mk3(dp[3 + 0] * x + dp[3 + 6] * y + dp[0],      // T[1,1]*x + T[1,3]*y + p[1]
+               dp[3 + 1] * x + dp[3 + 7] * y + dp[1],      // T[2,1]*x + T[2,3]*y + p[2]
+               dp[3 + 2] * x + dp[3 + 8] * y + dp[2]);     // T[3,1]*x + T[3,3]*y + p[3]
+}
+
 __global__ void __launch_bounds__(PD_TILE* PD_TILE) pd_field(const PdParams P) {
     __shared__ PdRec s_rec[PD_BATCH];
     const int i = blockIdx.x * PD_TILE + threadIdx.x, j = blockIdx.y * PD_TILE + threadIdx.y;
@@ -122,13 +234,7 @@ __global__ void __launch_bounds__(PD_TILE* PD_TILE) pd_field(const PdParams P) {
     const int fld = blockIdx.z;
     const int pose = P.pose0 + fld;
     const bool inside = i < P.n && j < P.n;
-    // pixel -> world: p1 = dir' * (x, 0, y) + pos   (Photodetector.jl:78,92-96 -- transposed orientation)
-    const double* dp = P.det_pose + 12 * ((int64_t)pose * P.n_objects + P.pd_object);
-    const double x = lin_coord(min(i, P.n - 1), P.n, P.lo, P.hi), y = lin_coord(min(j, P.n - 1), P.n, P.lo, P.hi);
-    // T = transpose(dir): T[r][c] = dir[c][r]; dir row-major at dp[3 + 3*r + c]
-    const V3 p1 = mk3(dp[3 + 0] * x + dp[3 + 6] * y + dp[0],      // T[1,1]*x + T[1,3]*y + p[1]
-                      dp[3 + 1] * x + dp[3 + 7] * y + dp[1],      // T[2,1]*x + T[2,3]*y + p[2]
-                      dp[3 + 2] * x + dp[3 + 8] * y + dp[2]);     // T[3,1]*x + T[3,3]*y + p[3]
+    const V3 p1 = pd_pixel(P.det_pose + 12 * ((int64_t)pose * P.n_objects + P.pd_object), i, j, P.n, P.lo, P.hi);
     int64_t rb = 0, re = P.n_recs;
     if (P.pose_off) { rb = P.pose_off[fld]; re = P.pose_off[fld + 1]; }
     Cx acc = mkc(0, 0);
@@ -143,59 +249,108 @@ __global__ void __launch_bounds__(PD_TILE* PD_TILE) pd_field(const PdParams P) {
         }
         __syncthreads();
         if (!inside) continue;
-        for (int q = 0; q < nb; q++) {
-            const PdRec& rc = s_rec[q];
-            const V3 p0 = mk3(rc.p0[0], rc.p0[1], rc.p0[2]), d0 = mk3(rc.d0[0], rc.d0[1], rc.d0[2]);
-            // projection of the pixel onto the beamlet axis (Photodetector.jl:98-101)
-            const double l1 = dot(p1 - p0, d0);
-            const V3 p2 = p0 + l1 * d0;
-            const double r = norm(p1 - p2);
-            const double z = rc.l0 + l1;
-            // point_on_beam(gauss, z) (Beam.jl:177-205)
-            V3 point, c_dir = d0, w_pos = mk3(rc.wp[0], rc.wp[1], rc.wp[2]), w_dir = mk3(rc.wd[0], rc.wd[1], rc.wd[2]),
-                      d_pos = mk3(rc.dp[0], rc.dp[1], rc.dp[2]), d_dir = mk3(rc.dd[0], rc.dd[1], rc.dd[2]);
-            double c_n = rc.cn;
-            bool found = false;
-            if (rc.nseg > 1.0 && z < rc.temp) {   // an earlier segment: replay the reference's loop
-                const int ns = (int)rc.nseg;
-                const int64_t f = (int64_t)rc.first_row, rows = P.R.rows;
-                const double* d = P.R.seg_d;
-                double temp = rc.plen;
-                for (int s = 0; s < ns - 1; s++) {
-                    const int64_t row = (f + s) * 3;
-                    const double len = d[S_T * rows + row];
-                    temp += len;
-                    if (z < temp) {
-                        const double b = temp - z;
-                        const V3 sp = mk3(d[S_PX * rows + row], d[S_PY * rows + row], d[S_PZ * rows + row]);
-                        c_dir = mk3(d[S_DX * rows + row], d[S_DY * rows + row], d[S_DZ * rows + row]);
-                        point = sp + (len - b) * c_dir;
-                        c_n = d[S_N * rows + row];
-                        w_pos = mk3(d[S_PX * rows + row + 1], d[S_PY * rows + row + 1], d[S_PZ * rows + row + 1]);
-                        w_dir = mk3(d[S_DX * rows + row + 1], d[S_DY * rows + row + 1], d[S_DZ * rows + row + 1]);
-                        d_pos = mk3(d[S_PX * rows + row + 2], d[S_PY * rows + row + 2], d[S_PZ * rows + row + 2]);
-                        d_dir = mk3(d[S_DX * rows + row + 2], d[S_DY * rows + row + 2], d[S_DZ * rows + row + 2]);
-                        found = true;
-                        break;
-                    }
-                }
-            }
-            if (!found) point = p0 + (z - rc.temp) * d0;
-            double w, Rc, psi, w0;
-            gauss_parameters(point, c_dir, c_n, w_pos, w_dir, d_pos, d_dir, rc.lambda, w, Rc, psi, w0);
-            // electric_field(gauss, r, z) (Gaussian.jl:381-392, OpticUtils.jl:87-89)
-            const Cx E0 = mkc(rc.e0r, rc.e0i) * (rc.w0b / w0);
-            Cx e = ((E0 * w0) / w) * exp(-(r * r) / (w * w));
-            e = e * cis(rc.k * z + psi + (rc.k * (r * r) * Rc) / 2);
-            e = e * mkc(rc.cr, rc.ci);
-            e = e * rc.sq;
-            acc = acc + e;
-        }
+        for (int q = 0; q < nb; q++) acc = acc + pd_pair_reference(s_rec[q], p1, P.R.seg_d, P.R.rows);
     }
     if (inside) {
         double* f = P.field + ((int64_t)fld * P.n * P.n + (int64_t)i + (int64_t)P.n * j) * 2;
         f[0] += acc.re;
         f[1] += acc.im;
+    }
+}
+
+// sincos of a large phase: Cody-Waite reduction by 2 pi (two FMAs, exact for |x| < 2^50 / ...) keeps
+// CUDA's sincos on its fast path (its own slow path starts at |x| > 105615)
+BMO_D void sincos_reduced(double x, double* sn, double* cs) {
+    const double n = rint(x * 0.15915494309189535);
+    double r = fma(n, -6.283185307179586, x);
+    r = fma(n, -2.4492935982947064e-16, r);
+    sincos(r, sn, cs);
+}
+
+constexpr int PDF_TX = 32, PDF_TY = 8, PDF_PX = 2;   // 32 x 16 pixels per block, 2 pixels (rows j, j + 8) per thread
+constexpr int PDF_BATCH = 48;                        // beamlet records per shared-memory tile
+
+BMO_D Cx pd_pair_fast(const PdFast& rc, V3 p1, bool& slow) {
+    const double vx = p1.x - rc.p0[0], vy = p1.y - rc.p0[1], vz = p1.z - rc.p0[2];
+    const double l1 = vx * rc.d0[0] + vy * rc.d0[1] + vz * rc.d0[2];
+    const double qx = vx - l1 * rc.d0[0], qy = vy - l1 * rc.d0[1], qz = vz - l1 * rc.d0[2];   // p1 - p2
+    const double r2 = qx * qx + qy * qy + qz * qz;
+    const double z = rc.l0 + l1;
+    slow = rc.generic > 0.0 || (rc.multi > 0.0 && z < rc.temp);
+    const double s = z - rc.temp;
+    // ray heights / slopes in the plane through point_on_beam(z), perpendicular to the chief
+    const double ydx = rc.Ad[0] + s * rc.Bd[0], ydy = rc.Ad[1] + s * rc.Bd[1], ydz = rc.Ad[2] + s * rc.Bd[2];
+    const double ywx = rc.Aw[0] + s * rc.Bw[0], ywy = rc.Aw[1] + s * rc.Bw[1], ywz = rc.Aw[2] + s * rc.Bw[2];
+    const double y2d = ydx * ydx + ydy * ydy + ydz * ydz, y2w = ywx * ywx + ywy * ywy + ywz * ywz;
+    const double nd = rc.alpd + s * rc.betd, nw = rc.alpw + s * rc.betw;
+    double c2d = (nd * nd) / y2d, c2w = (nw * nw) / y2w;       // cos^2 of the angle between height vector and ray (NaN at y = 0)
+    c2d = c2d > 1.0 ? 1.0 : c2d; c2w = c2w > 1.0 ? 1.0 : c2w;  // clamp of angle3d (LinearAlgebraUtils.jl:103-108)
+    const double id = rsqrt(1.0 - c2d), iw = rsqrt(1.0 - c2w);
+    const double E = nd * id + nw * iw;                          // E_kt = y_d m_d + y_w m_w
+    const double F2 = c2d * (id * id) + c2w * (iw * iw);         // F_kt^2 = m_d^2 + m_w^2
+    const double w2 = y2d + y2w;
+    const double iw2 = 1.0 / w2;
+    double R = E * iw2;                                          // curvature E_kt / w^2
+    double t = (E * E) * iw2 / F2;                               // R * zeta in [0, 1]
+    t = t > 1.0 ? 1.0 : t;
+    double cpsi = sqrt(1.0 - t), spsi = sqrt(t);                 // psi = -atan2(1, sqrt(1/t - 1))
+    if (!(R < 0.0)) spsi = -spsi;                                // R < 0 flips the sign of psi
+    if (isnan(R)) R = 0.0;                                       // Gaussian.jl:348-351
+    if (isnan(t)) { cpsi = 1.0; spsi = 0.0; }
+    const double amp = sqrt(iw2) * exp(-r2 * iw2);               // (w0 / w) exp(-r^2/w^2) with w0 cancelled against E0
+    double sn, cs;
+    sincos_reduced(rc.k * z + (rc.k * r2 * R) * 0.5, &sn, &cs);
+    const double re = cs * cpsi - sn * spsi, im = sn * cpsi + cs * spsi;
+    return mkc((rc.cre * re - rc.cim * im) * amp, (rc.cre * im + rc.cim * re) * amp);
+}
+
+__global__ void __launch_bounds__(PDF_TX* PDF_TY, 2) pd_field_fast(const PdParams P) {
+    __shared__ PdFast s_rec[PDF_BATCH];
+    const int tid = threadIdx.y * PDF_TX + threadIdx.x;
+    const int i = blockIdx.x * PDF_TX + threadIdx.x;
+    const int j0 = blockIdx.y * (PDF_TY * PDF_PX) + threadIdx.y;
+    const int fld = blockIdx.z;
+    const int pose = P.pose0 + fld;
+    const double* dp = P.det_pose + 12 * ((int64_t)pose * P.n_objects + P.pd_object);
+    V3 p1[PDF_PX];
+    Cx acc[PDF_PX];
+    bool inside[PDF_PX];
+#pragma unroll
+    for (int u = 0; u < PDF_PX; u++) {
+        const int j = j0 + u * PDF_TY;
+        inside[u] = i < P.n && j < P.n;
+        p1[u] = pd_pixel(dp, i, j, P.n, P.lo, P.hi);
+        acc[u] = mkc(0, 0);
+    }
+    int64_t rb = 0, re = P.n_recs;
+    if (P.pose_off) { rb = P.pose_off[fld]; re = P.pose_off[fld + 1]; }
+    for (int64_t base = rb; base < re; base += PDF_BATCH) {
+        const int nb = (int)min((int64_t)PDF_BATCH, re - base);
+        __syncthreads();
+        {
+            const int nw = nb * (int)(sizeof(PdFast) / 8);
+            const double* src = reinterpret_cast<const double*>(P.fast + base);
+            double* dst = reinterpret_cast<double*>(s_rec);
+            for (int k = tid; k < nw; k += PDF_TX * PDF_TY) dst[k] = src[k];
+        }
+        __syncthreads();
+        for (int q = 0; q < nb; q++) {
+#pragma unroll
+            for (int u = 0; u < PDF_PX; u++) {
+                bool slow;
+                Cx e = pd_pair_fast(s_rec[q], p1[u], slow);
+                if (slow) e = pd_pair_reference(P.recs[base + q], p1[u], P.R.seg_d, P.R.rows);
+                acc[u] = acc[u] + e;
+            }
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < PDF_PX; u++) {
+        if (!inside[u]) continue;
+        const int j = j0 + u * PDF_TY;
+        double* f = P.field + ((int64_t)fld * P.n * P.n + (int64_t)i + (int64_t)P.n * j) * 2;
+        f[0] += acc[u].re;
+        f[1] += acc[u].im;
     }
 }
 
@@ -275,6 +430,8 @@ static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t po
         BMO_CUDA(cudaMemcpyAsync(d_field, fields, fbytes, cudaMemcpyHostToDevice, st));
     }
     int32_t* d_flags = nullptr; long long* d_offs = nullptr; PdRec* d_recs = nullptr; long long* d_pose_off = nullptr;
+    PdFast* d_fast = nullptr;
+    const bool ref_order = flags & BMO_PD_REFERENCE_ORDER;
     const int64_t nb = r->n_beams;
     BMO_CUDA(dev_alloc(&d_flags, (size_t)nb, st));
     BMO_CUDA(dev_alloc(&d_offs, (size_t)nb, st));
@@ -309,12 +466,22 @@ static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t po
             BMO_CUDA(cudaMemcpyAsync(d_pose_off, off.data(), off.size() * sizeof(long long), cudaMemcpyHostToDevice, st));
             BMO_CUDA(cudaStreamSynchronize(st));
         }
+        if (!ref_order) {
+            BMO_CUDA(dev_alloc(&d_fast, (size_t)m, st));
+            pd_make_fast<<<(unsigned)((m + 127) / 128), 128, 0, st>>>(d_recs, d_fast, m);
+            ctx->launches++;
+        }
         PdParams pp{};
-        pp.recs = d_recs; pp.n_recs = m; pp.R = rv; pp.field = d_field; pp.det_pose = sys->view.det_pose; pp.pose_off = d_pose_off;
+        pp.recs = d_recs; pp.fast = d_fast; pp.n_recs = m; pp.R = rv; pp.field = d_field; pp.det_pose = sys->view.det_pose; pp.pose_off = d_pose_off;
         pp.n = n; pp.pd_object = pd_object; pp.n_objects = sys->view.n_objects; pp.pose0 = pose0; pp.lo = ob.pd_lo; pp.hi = ob.pd_hi;
-        dim3 grid((n + PD_TILE - 1) / PD_TILE, (n + PD_TILE - 1) / PD_TILE, n_fields), block(PD_TILE, PD_TILE);
         BMO_CUDA(cudaEventRecord(ctx->evk0, st));
-        pd_field<<<grid, block, 0, st>>>(pp);
+        if (ref_order) {
+            dim3 grid((n + PD_TILE - 1) / PD_TILE, (n + PD_TILE - 1) / PD_TILE, n_fields), block(PD_TILE, PD_TILE);
+            pd_field<<<grid, block, 0, st>>>(pp);
+        } else {
+            dim3 grid((n + PDF_TX - 1) / PDF_TX, (n + PDF_TY * PDF_PX - 1) / (PDF_TY * PDF_PX), n_fields), block(PDF_TX, PDF_TY);
+            pd_field_fast<<<grid, block, 0, st>>>(pp);
+        }
         BMO_CUDA(cudaEventRecord(ctx->evk1, st));
         ctx->launches++;
         cudaError_t e = cudaGetLastError();
@@ -331,7 +498,7 @@ static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t po
     ctx->pd_ms = ms;
     if (m > 0) { float kms = 0; BMO_CUDA(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1)); ctx->k4_ms += kms; }
     if (!on_dev) dev_free(d_field, st);
-    dev_free(d_flags, st); dev_free(d_offs, st); dev_free(d_recs, st); dev_free(d_pose_off, st);
+    dev_free(d_flags, st); dev_free(d_offs, st); dev_free(d_recs, st); dev_free(d_pose_off, st); dev_free(d_fast, st);
     return BMO_OK;
 }
 

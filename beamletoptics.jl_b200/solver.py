@@ -170,10 +170,13 @@ def trace_beamlets(dsys, rays, lam_id, w0, E0, pose_id=None, r_max=100):
     return TraceResult(dsys, h)
 
 
-def pd_accumulate(dsys, result, pd_index, field, pose=0):
-    """field: (n, n) complex128 Fortran-ordered host array; the beamlet fields are ADDED to it."""
+def pd_accumulate(dsys, result, pd_index, field, pose=0, reference_order=False):
+    """field: (n, n) complex128 Fortran-ordered host array; the beamlet fields are ADDED to it.
+    reference_order=True evaluates every pixel-beamlet pair in the reference's operation order
+    (BMO_PD_REFERENCE_ORDER) instead of the strength-reduced default kernel."""
     assert field.flags["F_CONTIGUOUS"] and field.dtype == np.complex128
-    L.check(L.lib().bmo_pd_accumulate(dsys.h, result.h, int(pd_index), int(pose), L.ptr(field), 0))
+    flags = L.PD_REFERENCE_ORDER if reference_order else 0
+    L.check(L.lib().bmo_pd_accumulate(dsys.h, result.h, int(pd_index), int(pose), L.ptr(field), flags))
 
 
 # ---- rebuilding the reference's host objects from the segment table --------------------------------

@@ -115,6 +115,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-detector", action="store_true", help="skip the secondary Photodetector (C3) measurement")
+    ap.add_argument("--c3-side", type=int, default=64, help="beamlets per side of the C3 lattice block (256 = the full 65536-beamlet config)")
+    ap.add_argument("--c3-pixels", type=int, default=2048)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -248,12 +251,75 @@ def main():
                                     "frac": (scat / hbm_peak) if scat else None},
             "clocks": sampler.summary(),
         }
+        if not args.no_detector:
+            out["detector"] = bench_detector(m, L, dev, stream, args.c3_side, args.c3_pixels, max(2, min(args.steps, 3)), 1, flush, peak)
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+FLOP_PAIR_REF = 760.0   # flop-equivalents per pixel-beamlet pair in the reference's operation sequence
+FLOP_PAIR = 245.0       # the same weights (add/mul 1, sqrt/div 8, transcendental 40) over the strength-reduced sequence of
+                        # pd_field_fast, counted op by op in DESIGN.md "K4" -- the work the kernel actually has to do
+
+
+def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_tflops):
+    """Metric 2 (Photodetector px-beamlets/s) on the C3 workload: Keplerian expander + Photodetector(40 mm, pd_n),
+    k_side^2 beamlets of the C3 lattice (pitch 8 mm / 256, w0 = 1.5 pitch, lambda = 1 um).  The default run uses the central
+    64 x 64 block of the 256 x 256 lattice (bounded so that bench.py stays within minutes); the pair rate does not depend on it."""
+    import ctypes as C
+    import torch
+    from tests import scenes2 as s2
+    sc = s2.expander(m, pd_n)
+    lat = s2.beamlet_lattice(k_side, aperture=8e-3 * k_side / 256)
+    nb = k_side * k_side
+    bundle = m.BeamletBundle.from_params(lat["pos"], lat["dir"], lat["lam"], lat["w0"], M2=lat["M2"], P0=1e-3 / 65536, support=lat["support"])
+    dsys = m.upload_system(sc["system"], [lat["lam"]], device=dev)
+    res = m.trace_beamlets(dsys, bundle.rays, np.zeros(nb, np.int32), bundle.w0, bundle.E0)
+    pd_index = dsys.flat.object_index(sc["pd"])
+    field_d = torch.zeros(pd_n * pd_n * 2, dtype=torch.float64, device="cuda")
+    field_h = torch.zeros(pd_n * pd_n * 2, dtype=torch.float64).pin_memory()
+
+    def run(ptr, flags):
+        L.check(L.lib().bmo_pd_accumulate(dsys.h, res.h, pd_index, 0, C.c_void_p(ptr), flags))
+
+    out = {}
+    for name, ptr, flags in (("device", field_d.data_ptr(), L.INPUT_DEVICE), ("e2e", field_h.data_ptr(), 0)):
+        for _ in range(warmup):
+            run(ptr, flags)
+        L.counters_reset(dev)
+        times = []
+        for _ in range(steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            run(ptr, flags)
+            e1.record(stream)
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1))
+        c = L.counters(dev)
+        out[name] = dict(ms=sum(times) / steps, pairs=c["px_beamlets"] / steps, k4_ms=c["pd_field_ms"] / steps, launches=c["kernel_launches"] / steps)
+    pairs = out["device"]["pairs"]
+    ach = FLOP_PAIR * pairs / (out["device"]["k4_ms"] * 1e-3) / 1e12
+    res.free()
+    return {
+        "metric": "Photodetector px-beamlets/s", "unit": "px-beamlets/s",
+        "value": pairs / (out["device"]["ms"] * 1e-3), "ms_per_step": out["device"]["ms"],
+        "e2e": {"value": pairs / (out["e2e"]["ms"] * 1e-3), "ms_per_step": out["e2e"]["ms"],
+                "h2d_bytes_per_step": int(field_h.numel() * 8), "d2h_bytes_per_step": int(field_h.numel() * 8)},
+        "config": {"workload": f"C3: Keplerian beam expander, {nb} of 65536 GaussianBeamlets (central block of the 256x256 lattice) onto a {pd_n}^2 Photodetector, coherent field sum",
+                   "beamlets": nb, "pixels": pd_n * pd_n, "pairs_per_step": pairs},
+        "gpu_launches": out["device"]["launches"],
+        "roofline": {"bound": "fp64", "kernel": "pd_field_fast", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s (FP64 flop-equivalents)",
+                     "frac": ach / peak_tflops if peak_tflops else None, "ms_per_launch": out["device"]["k4_ms"],
+                     "flop_equiv_per_pair": FLOP_PAIR, "reference_sequence_flop_equiv_per_pair": FLOP_PAIR_REF,
+                     "achieved_in_reference_sequence_units": ach * FLOP_PAIR_REF / FLOP_PAIR,
+                     "share_of_step": out["device"]["k4_ms"] / out["device"]["ms"]},
+    }
 
 
 def cpu_baseline():

@@ -126,6 +126,9 @@ typedef struct bmo_result bmo_result;  /* device-resident result of one trace ca
 /* flags of bmo_trace_* */
 #define BMO_KEEP_SEGMENTS 1u  /* keep the full segment table (needed to rebuild Beam trees / run the PD kernel) */
 #define BMO_INPUT_DEVICE 2u   /* input arrays are device pointers (already resident in HBM)        */
+/* flag of bmo_pd_accumulate*: evaluate every pixel-beamlet pair in the reference's operation order
+ * (slower; the default kernel is algebraically identical, strength-reduced, within 1e-8 rel. L2)   */
+#define BMO_PD_REFERENCE_ORDER 4u
 
 typedef struct bmo_counters {
     int64_t interactions;   /* hits that reached interact3d (a Gaussian triple counts 3)           */

@@ -29,7 +29,7 @@ def test_c3_expander_field(bmo, orc):
     assert np.abs(ref).max() > 0
     assert _rel_l2(sc["pd"].field, ref) <= FIELD_TOL
     assert _rel_l2(np.abs(sc["pd"].field) ** 2, np.abs(ref) ** 2) <= FIELD_TOL
-    assert abs(sc["pd"].optical_power() - osc["pd"].pd_power()) <= 1e-10 * osc["pd"].pd_power()
+    assert abs(sc["pd"].optical_power() - osc["pd"].pd_power()) <= FIELD_TOL * osc["pd"].pd_power()   # optical_power = trapz of the intensity: same 1e-8 tolerance
     # the bundle constructor is the vectorised GaussianBeamlet constructor
     g0 = bmo.GaussianBeamlet(lat["pos"][3], lat["dir"], lat["lam"], lat["w0"], M2=lat["M2"], P0=lat["P0"], support=lat["support"])
     assert np.array_equal(np.array(g0.rays18()), bundle.rays[3].ravel()) and g0.E0 == bundle.E0[3]
@@ -119,5 +119,77 @@ def test_c5_mzi_pose_sweep(bmo, orc):
         assert _rel_l2(out["fields"][p], ref) <= FIELD_TOL, p
         powers.append(o["pd"].pd_power())
     powers = np.array(powers)
-    assert np.abs(out["power"] - powers).max() <= 1e-10 * powers.max()
+    assert np.abs(out["power"] - powers).max() <= FIELD_TOL * powers.max()
     assert powers.max() / max(powers.min(), 1e-30) > 5      # the sweep crosses a fringe
+
+
+@pytest.mark.gpu
+def test_pd_fast_kernel_matches_reference_order(bmo):
+    """Size-independent property at a detector size the CPU oracle cannot reach in seconds: the
+    strength-reduced Photodetector kernel agrees with the reference-operation-order kernel
+    (BMO_PD_REFERENCE_ORDER) on a 1024^2 detector with 1024 overlapping beamlets."""
+    k, n = 32, 1024
+    sc = s2.expander(bmo, n)
+    lat = s2.beamlet_lattice(k)
+    bundle = bmo.BeamletBundle.from_params(lat["pos"], lat["dir"], lat["lam"], lat["w0"], M2=lat["M2"], P0=lat["P0"], support=lat["support"])
+    lams, lam_id = [lat["lam"]], np.zeros(k * k, np.int32)
+    dsys = bmo.upload_system(sc["system"], lams)
+    res = bmo.trace_beamlets(dsys, bundle.rays, lam_id, bundle.w0, bundle.E0)
+    pd_index = dsys.flat.object_index(sc["pd"])
+    fast = np.zeros((n, n), np.complex128, order="F")
+    slow = np.zeros((n, n), np.complex128, order="F")
+    bmo.pd_accumulate(dsys, res, pd_index, fast)
+    bmo.pd_accumulate(dsys, res, pd_index, slow, reference_order=True)
+    assert np.abs(slow).max() > 0
+    assert _rel_l2(fast, slow) <= FIELD_TOL / 4
+    assert _rel_l2(np.abs(fast) ** 2, np.abs(slow) ** 2) <= FIELD_TOL / 4
+    assert bmo.counters()["px_beamlets"] >= 2 * k * k * n * n
+
+
+@pytest.mark.gpu
+def test_pd_tilted_detector_behind_fold_mirror(bmo, orc):
+    """SURVEY hard part 6: a tilted detector close to a fold mirror -- for part of the pixels z = l0 + l1
+    falls before the start of the last chief segment, so point_on_beam (Beam.jl:186-199) selects the
+    segment in front of the mirror.  Field vs the oracle, and fast kernel vs reference-order kernel."""
+    n = 64
+    beam = dict(pos=(0.0, -0.05, 0.0), dir=(0.0, 1.0, 0.0), lam=1e-6, w0=2e-3, M2=1.0, P0=1e-3, support=(1.0, 0.0, 0.0))
+
+    def build(F):
+        m = F.SquarePlanoMirror2D(2 * s2.INCH)
+        m.zrotate3d_(np.radians(45))
+        pd = F.Photodetector(30e-3, n)
+        return m, pd
+
+    # where does the folded beam go?  (same construction on both sides; the probe is a plain Beam)
+    m, pd = build(s2.ProductFactory2(bmo))
+    probe = bmo.Beam(beam["pos"], beam["dir"], beam["lam"])
+    bmo.solve_system_(bmo.System([m]), probe)
+    assert len(probe.rays) == 2
+    d = np.array(probe.rays[1].dir)
+    hit = np.array(probe.rays[1].pos)
+    assert abs(abs(d[0]) - 1.0) < 1e-12          # folded into +-x
+    ang = -np.sign(d[0]) * np.radians(90) + np.radians(35)       # detector normal (local y) -> fold direction, then 35 deg of tilt
+    where = hit + 4e-3 * d                       # 4 mm behind the mirror: l1 reaches -8 mm on a 30 mm detector
+
+    fields = []
+    for F in (s2.ProductFactory2(bmo), s2.OracleFactory2()):
+        m, pd = build(F)
+        pd.zrotate3d_(float(ang)); pd.translate3d_([float(x) for x in where])
+        system = F.System([m, pd])
+        if F.__class__ is s2.ProductFactory2:
+            g = bmo.GaussianBeamlet(beam["pos"], beam["dir"], beam["lam"], beam["w0"], M2=beam["M2"], P0=beam["P0"], support=beam["support"])
+            res = bmo.solve_system_(system, g)
+            fields.append(pd.field.copy())
+            dsys = bmo.upload_system(system, [beam["lam"]])
+            r2 = bmo.trace_beamlets(dsys, np.array([g.rays18()]), np.zeros(1, np.int32), np.array([g.w0]), np.array([g.E0]))
+            slow = np.zeros((n, n), np.complex128, order="F")
+            bmo.pd_accumulate(dsys, r2, dsys.flat.object_index(pd), slow, reference_order=True)
+            fields.append(slow)
+        else:
+            og = orc.gaussian_beamlet(beam["pos"], beam["dir"], beam["lam"], beam["w0"], M2=beam["M2"], P0=beam["P0"], support=beam["support"])
+            orc.solve_system_(system, og)
+            fields.append(pd.pd_field(n))
+    fast, slow, ref = fields
+    assert np.abs(ref).max() > 0
+    assert _rel_l2(slow, ref) <= FIELD_TOL
+    assert _rel_l2(fast, ref) <= FIELD_TOL
