@@ -25,8 +25,8 @@ thread_local std::string g_last_error;
 // double fields (SoA, stride = capacity): px py pz dx dy dz n | E0 re/im x3 (polarized) |
 //                                         lsum lpar oplpar (gaussian chief accumulators)
 enum { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_N, F_X0 };
-// int fields: lambda id, hinted part, beam, segment index, pose | scratch: child slot, local spawn index
-enum { I_LAM = 0, I_HINT, I_BEAM, I_SEG, I_POSE, NI_Q, I_SLOT = NI_Q, I_LSPAWN, NI_S };
+// int fields: lambda id, hinted part, beam (-1 = dead slot), segment index, pose
+enum { I_LAM = 0, I_HINT, I_BEAM, I_SEG, I_POSE, NI_Q, I_PUNIT = NI_Q, NI_S };   // I_PUNIT (scratch only): queue unit of the parent
 // segment record rows
 enum { S_PX = 0, S_PY, S_PZ, S_DX, S_DY, S_DZ, S_N, S_T, S_NX, S_NY, S_NZ, S_E0 };
 
@@ -68,7 +68,8 @@ struct StepParams {
     int32_t r_max, keep;
     WaveBuf wave;
     BeamTab B;
-    int32_t* blk_cnt;    // [nblocks][2] successors, spawns
+    int32_t* blk_cnt;    // [nblocks] spawn events per block
+    unsigned long long* wave_totals;   // [2] units alive after this wave, spawn events of this wave
     DevCounters* counters;
 };
 
@@ -109,7 +110,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
     }
 
     const int64_t ri = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
-    const bool active = ri < P.n_rays;
+    const bool active = ri < P.n_rays && P.cur.i[I_BEAM * P.cur.cap + ri] >= 0;
     Stats st; st.sdf = 0; st.tri = 0;
     if (active) {
         const int64_t qs = P.cur.cap;
@@ -164,10 +165,11 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepPara
     if (MODE == 2) { uib = warp * 10 + lane / 3; r = lane % 3; lane_ok = lane < 30; }
     else { uib = threadIdx.x; r = 0; }
     const int64_t unit = (int64_t)blockIdx.x * UNITS + uib;
-    const bool active = lane_ok && unit < P.count;
-    const bool leader = active && r == 0;
+    const bool in_queue = lane_ok && unit < P.count;
     const int64_t ri = unit * R + r;
     const int64_t qs = P.cur.cap;
+    const bool active = in_queue && P.cur.i[I_BEAM * qs + ri] >= 0;   // dead slots wait for the next compaction
+    const bool leader = active && r == 0;
 
     V3 pos = mk3(0, 0, 0), dir = mk3(0, 1, 0);
     double rn = 1.0;
@@ -353,6 +355,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepPara
     }
 
     // ---- bookkeeping: counters, segment record, per-beam state ----
+    if (P.keep && in_queue && !active) P.wave.beam[ri] = -1;
     if (P.keep && active) {
         const int64_t ws = P.wave.count;
         double* w = P.wave.d;
@@ -376,55 +379,73 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepPara
         P.B.status[beam] = ((nsucc != 1) ? status : (old & 0xff)) | wbit;
     }
 
-    // ---- block-local compaction: warp ballots + prefix sums ----
+    // ---- successors ----
+    // nsucc == 1: the continuing ray overwrites its own queue slot (no data movement between waves);
+    // nsucc == 0: the slot is marked dead (beam = -1) and removed by the next compaction (K3);
+    // nsucc == 2: beamsplitter children go to the block's scratch area in queue order (warp ballot +
+    //             prefix sums), spawn_children numbers them deterministically and puts the transmitted
+    //             child into the parent's slot, the reflected child at the tail of the queue.
     const unsigned full = 0xffffffffu;
-    const unsigned b1 = __ballot_sync(full, leader && nsucc >= 1);
     const unsigned b2 = __ballot_sync(full, leader && nsucc == 2);
     const unsigned lt = lanemask_lt();
-    int woff = __popc(b1 & lt) + __popc(b2 & lt);   // successors of lower lanes in this warp
     int wsoff = __popc(b2 & lt);                     // spawn events of lower lanes
-    if (lane == 0) { s_wcnt[warp][0] = __popc(b1) + __popc(b2); s_wcnt[warp][1] = __popc(b2); }
-    // statistics ride on the same barrier
+    const unsigned alive = __popc(__ballot_sync(full, leader && nsucc >= 1)) + __popc(b2);
+    if (lane == 0) { s_wcnt[warp][0] = (int)alive; s_wcnt[warp][1] = __popc(b2); }
     const unsigned ia = __popc(__ballot_sync(full, interacted));
     if (lane == 0 && ia) atomicAdd(&P.counters->interactions, (unsigned long long)ia);
     __syncthreads();
     if (threadIdx.x == 0) {
         int a = 0, b = 0;
-        for (int k = 0; k < NWARP; k++) { s_woff[k][0] = a; s_woff[k][1] = b; a += s_wcnt[k][0]; b += s_wcnt[k][1]; }
-        P.blk_cnt[2 * blockIdx.x] = a;
-        P.blk_cnt[2 * blockIdx.x + 1] = b;
+        for (int k = 0; k < NWARP; k++) { s_woff[k][1] = b; a += s_wcnt[k][0]; b += s_wcnt[k][1]; }
+        P.blk_cnt[blockIdx.x] = b;
+        if (a) atomicAdd(P.wave_totals, (unsigned long long)a);        // units alive in the next wave
+        if (b) atomicAdd(P.wave_totals + 1, (unsigned long long)b);    // spawn events
     }
     __syncthreads();
-    if (MODE == 2) { woff = __shfl_sync(full, woff, base); wsoff = __shfl_sync(full, wsoff, base); }
-    if (active && nsucc > 0) {
-        const int64_t ss = P.scr.cap;
-        const int64_t su0 = (int64_t)blockIdx.x * (2 * UNITS) + s_woff[warp][0] + woff;
-        const int lspawn = s_woff[warp][1] + wsoff;
-        for (int k = 0; k < nsucc; k++) {
-            const RayOut& o = (k == 0) ? o1 : o2;
-            const int64_t si = (su0 + k) * R + r;
-            double* d = P.scr.d;
-            d[F_PX * ss + si] = o.pos.x; d[F_PY * ss + si] = o.pos.y; d[F_PZ * ss + si] = o.pos.z;
-            d[F_DX * ss + si] = o.dir.x; d[F_DY * ss + si] = o.dir.y; d[F_DZ * ss + si] = o.dir.z;
-            d[F_N * ss + si] = o.n;
+    if (MODE == 2) wsoff = __shfl_sync(full, wsoff, base);
+    if (active) {
+        int32_t* qi = P.cur.i;
+        if (nsucc == 1) {
+            double* d = P.cur.d;
+            d[F_PX * qs + ri] = o1.pos.x; d[F_PY * qs + ri] = o1.pos.y; d[F_PZ * qs + ri] = o1.pos.z;
+            d[F_DX * qs + ri] = o1.dir.x; d[F_DY * qs + ri] = o1.dir.y; d[F_DZ * qs + ri] = o1.dir.z;
+            d[F_N * qs + ri] = o1.n;
             if (MODE == 1) {
 #pragma unroll
-                for (int c = 0; c < 3; c++) { d[(F_X0 + 2 * c) * ss + si] = o.E0[c].re; d[(F_X0 + 2 * c + 1) * ss + si] = o.E0[c].im; }
+                for (int c = 0; c < 3; c++) { d[(F_X0 + 2 * c) * qs + ri] = o1.E0[c].re; d[(F_X0 + 2 * c + 1) * qs + ri] = o1.E0[c].im; }
             }
-            if (MODE == 2) {
-                d[F_X0 * ss + si] = n_lsum; d[(F_X0 + 1) * ss + si] = n_lpar; d[(F_X0 + 2) * ss + si] = n_opl;
-                const Cx e = (k == 0) ? g_et : g_er;
-                d[(F_X0 + 3) * ss + si] = g_w0; d[(F_X0 + 4) * ss + si] = e.re; d[(F_X0 + 5) * ss + si] = e.im;
-                d[(F_X0 + 6) * ss + si] = g_plen; d[(F_X0 + 7) * ss + si] = g_popl;
+            if (MODE == 2) { d[F_X0 * qs + ri] = n_lsum; d[(F_X0 + 1) * qs + ri] = n_lpar; d[(F_X0 + 2) * qs + ri] = n_opl; }
+            qi[I_HINT * qs + ri] = o1.hint;
+            qi[I_SEG * qs + ri] = seg + 1;
+        } else {
+            qi[I_BEAM * qs + ri] = -1;
+        }
+        if (nsucc == 2) {
+            const int64_t ss = P.scr.cap;
+            const int lspawn = s_woff[warp][1] + wsoff;
+            for (int k = 0; k < 2; k++) {
+                const RayOut& o = (k == 0) ? o1 : o2;
+                const int64_t si = (((int64_t)blockIdx.x * UNITS + lspawn) * 2 + k) * R + r;
+                double* d = P.scr.d;
+                d[F_PX * ss + si] = o.pos.x; d[F_PY * ss + si] = o.pos.y; d[F_PZ * ss + si] = o.pos.z;
+                d[F_DX * ss + si] = o.dir.x; d[F_DY * ss + si] = o.dir.y; d[F_DZ * ss + si] = o.dir.z;
+                d[F_N * ss + si] = o.n;
+                if (MODE == 1) {
+#pragma unroll
+                    for (int c = 0; c < 3; c++) { d[(F_X0 + 2 * c) * ss + si] = o.E0[c].re; d[(F_X0 + 2 * c + 1) * ss + si] = o.E0[c].im; }
+                }
+                if (MODE == 2) {
+                    d[F_X0 * ss + si] = n_lsum; d[(F_X0 + 1) * ss + si] = n_lpar; d[(F_X0 + 2) * ss + si] = n_opl;
+                    const Cx e = (k == 0) ? g_et : g_er;
+                    d[(F_X0 + 3) * ss + si] = g_w0; d[(F_X0 + 4) * ss + si] = e.re; d[(F_X0 + 5) * ss + si] = e.im;
+                    d[(F_X0 + 6) * ss + si] = g_plen; d[(F_X0 + 7) * ss + si] = g_popl;
+                }
+                int32_t* iq = P.scr.i;
+                iq[I_LAM * ss + si] = lam;
+                iq[I_BEAM * ss + si] = beam;       // parent beam
+                iq[I_POSE * ss + si] = pose;
+                iq[I_PUNIT * ss + si] = (int32_t)unit;
             }
-            int32_t* iq = P.scr.i;
-            iq[I_LAM * ss + si] = lam;
-            iq[I_HINT * ss + si] = (nsucc == 2) ? -1 : o1.hint;
-            iq[I_BEAM * ss + si] = beam;
-            iq[I_SEG * ss + si] = (nsucc == 2) ? 0 : seg + 1;
-            iq[I_POSE * ss + si] = pose;
-            iq[I_SLOT * ss + si] = (nsucc == 2) ? k : -1;
-            iq[I_LSPAWN * ss + si] = lspawn;
         }
     }
 }
@@ -499,53 +520,91 @@ __global__ void scan_add(long long* out, int64_t n, const long long* blk_off) {
     if (i < n) out[i] += blk_off[blockIdx.x];
 }
 
-// ---- K3: scatter compacted successors into the next queue (HBM-bound) ----------------------------
-struct ScatterParams {
-    Queue scr, next;
+// ---- beamsplitter children: deterministic numbering in queue order ---------------------------------
+struct SpawnParams {
+    Queue scr, q;
     const int32_t* blk_cnt;
-    const long long* blk_off;  // [nblocks][2]
+    const long long* blk_off;  // exclusive scan of blk_cnt
     BeamTab B;
     int64_t n_beams;           // beams that exist before this wave's spawns
+    int64_t n_slots;           // queue units before this wave's spawns
     int32_t nf, mode, units, R;
 };
-__global__ void __launch_bounds__(256) scatter_queue(const ScatterParams P) {
+__global__ void __launch_bounds__(256) spawn_children(const SpawnParams P) {
     const int b = blockIdx.x;
-    const int cnt = P.blk_cnt[2 * b];
+    const int cnt = P.blk_cnt[b];
     if (cnt == 0) return;
-    const long long off = P.blk_off[2 * b], spoff = P.blk_off[2 * b + 1];
-    const int64_t ss = P.scr.cap, ns = P.next.cap;
+    const long long off = P.blk_off[b];
+    const int64_t ss = P.scr.cap, qs = P.q.cap;
     const int R = P.R;
-    for (int j = threadIdx.x; j < cnt * R; j += blockDim.x) {
-        const int64_t si = ((int64_t)b * (2 * P.units)) * R + j;
-        const int64_t di = off * R + j;
-        const int r = j % R;
-        for (int f = 0; f < P.nf; f++) P.next.d[f * ns + di] = P.scr.d[f * ss + si];
+    for (int j = threadIdx.x; j < cnt * 2 * R; j += blockDim.x) {
+        const int ls = j / (2 * R), k = (j / R) & 1, r = j % R;
+        const int64_t si = (((int64_t)b * P.units + ls) * 2 + k) * R + r;
+        const long long rank = off + ls;
         const int32_t* iq = P.scr.i;
-        int beam = iq[I_BEAM * ss + si];
-        const int slot = iq[I_SLOT * ss + si];
+        const int64_t du = (k == 0) ? (int64_t)iq[I_PUNIT * ss + si] : P.n_slots + rank;
+        const int64_t di = du * R + r;
+        for (int f = 0; f < P.nf; f++) P.q.d[f * qs + di] = P.scr.d[f * ss + si];
+        const int parent = iq[I_BEAM * ss + si];
         const int lam = iq[I_LAM * ss + si], pose = iq[I_POSE * ss + si];
-        if (slot >= 0) {
-            const int parent = beam;
-            beam = (int)(P.n_beams + 2 * (spoff + iq[I_LSPAWN * ss + si]) + slot);
-            if (r == 0) {
-                P.B.parent[beam] = parent; P.B.slot[beam] = slot; P.B.nseg[beam] = 0; P.B.status[beam] = BMO_ST_ACTIVE;
-                P.B.lam[beam] = lam; P.B.pose[beam] = pose;
-                if (P.mode == 2) {
-                    P.B.w0[beam] = P.scr.d[(F_X0 + 3) * ss + si];
-                    P.B.e0[2 * beam] = P.scr.d[(F_X0 + 4) * ss + si];
-                    P.B.e0[2 * beam + 1] = P.scr.d[(F_X0 + 5) * ss + si];
-                    P.B.plen[beam] = P.scr.d[(F_X0 + 6) * ss + si];
-                    P.B.popl[beam] = P.scr.d[(F_X0 + 7) * ss + si];
-                }
+        const int beam = (int)(P.n_beams + 2 * rank + k);
+        if (r == 0) {
+            P.B.parent[beam] = parent; P.B.slot[beam] = k; P.B.nseg[beam] = 0; P.B.status[beam] = BMO_ST_ACTIVE;
+            P.B.lam[beam] = lam; P.B.pose[beam] = pose;
+            if (P.mode == 2) {
+                P.B.w0[beam] = P.scr.d[(F_X0 + 3) * ss + si];
+                P.B.e0[2 * beam] = P.scr.d[(F_X0 + 4) * ss + si];
+                P.B.e0[2 * beam + 1] = P.scr.d[(F_X0 + 5) * ss + si];
+                P.B.plen[beam] = P.scr.d[(F_X0 + 6) * ss + si];
+                P.B.popl[beam] = P.scr.d[(F_X0 + 7) * ss + si];
             }
-            P.B.spot_obj[(int64_t)beam * R + r] = -1;
         }
-        int32_t* nq = P.next.i;
-        nq[I_LAM * ns + di] = lam;
-        nq[I_HINT * ns + di] = iq[I_HINT * ss + si];
-        nq[I_BEAM * ns + di] = beam;
-        nq[I_SEG * ns + di] = iq[I_SEG * ss + si];
-        nq[I_POSE * ns + di] = pose;
+        P.B.spot_obj[(int64_t)beam * R + r] = -1;
+        int32_t* nq = P.q.i;
+        nq[I_LAM * qs + di] = lam;
+        nq[I_HINT * qs + di] = -1;
+        nq[I_BEAM * qs + di] = beam;
+        nq[I_SEG * qs + di] = 0;
+        nq[I_POSE * qs + di] = pose;
+    }
+}
+
+// ---- K3: queue compaction (HBM-bound) ----------------------------------------------------------------
+// Dead slots are squeezed out when they make up more than half of the queue: per block, warp ballots
+// + prefix sums give every live unit its rank; scan_counts turns the block counts into offsets; the
+// scatter moves the live units to the front of the other queue buffer, order preserved.
+constexpr int CBLOCK = 256;
+__global__ void __launch_bounds__(CBLOCK) compact_count(const int32_t* qi, int64_t cap, int64_t n_slots, int R, int32_t* blk_cnt) {
+    __shared__ int s_w[CBLOCK / 32];
+    const int64_t u = (int64_t)blockIdx.x * CBLOCK + threadIdx.x;
+    const bool live = u < n_slots && qi[I_BEAM * cap + u * R] >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0;
+        for (int k = 0; k < CBLOCK / 32; k++) a += s_w[k];
+        blk_cnt[blockIdx.x] = a;
+    }
+}
+__global__ void __launch_bounds__(CBLOCK) compact_scatter(Queue src, Queue dst, int64_t n_slots, int R, int nf, const long long* blk_off) {
+    __shared__ int s_w[CBLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t u = (int64_t)blockIdx.x * CBLOCK + threadIdx.x;
+    const int64_t ss = src.cap, ds = dst.cap;
+    const bool live = u < n_slots && src.i[I_BEAM * ss + u * R] >= 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) s_w[warp] = __popc(bal);
+    __syncthreads();
+    int woff = 0;
+    for (int k = 0; k < warp; k++) woff += s_w[k];
+    if (!live) return;
+    const int64_t du = blk_off[blockIdx.x] + woff + __popc(bal & lanemask_lt());
+    for (int r = 0; r < R; r++) {
+        const int64_t si = u * R + r, di = du * R + r;
+        for (int f = 0; f < nf; f++) dst.d[f * ds + di] = src.d[f * ss + si];
+#pragma unroll
+        for (int f = 0; f < NI_Q; f++) dst.i[f * ds + di] = src.i[f * ss + si];
     }
 }
 
@@ -589,7 +648,7 @@ __global__ void init_queue(const InitParams P) {
 }
 __global__ void gather_segments(WaveBuf w, int R, int nsd, const long long* first_seg, double* seg_d, int32_t* seg_part, int64_t rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.count) return;
+    if (i >= w.count || w.beam[i] < 0) return;
     const int r = (int)(i % R);
     const int64_t row = (first_seg[w.beam[i]] + w.seg[i]) * R + r;
     for (int f = 0; f < nsd; f++) seg_d[f * rows + row] = w.d[f * w.count + i];
@@ -636,7 +695,7 @@ int32_t bmo_init(int32_t device, bmo_ctx** out) {
     BMO_CUDA(cudaMalloc((void**)&c->d_counters, sizeof(DevCounters)));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     BMO_CUDA(cudaMalloc((void**)&c->d_totals, 4 * sizeof(long long)));
-    BMO_CUDA(cudaMallocHost((void**)&c->h_totals, 4 * sizeof(long long)));
+    BMO_CUDA(cudaMallocHost((void**)&c->h_totals, 16 * sizeof(long long)));
     cudaMemPool_t pool;
     BMO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;  // keep freed blocks cached: the wave loop reuses them every call
@@ -839,6 +898,21 @@ static int32_t alloc_queue(Queue& q, int64_t cap, int nf, int ni, cudaStream_t s
     BMO_CUDA(dev_alloc(&q.i, (size_t)ni * cap, st));
     return BMO_OK;
 }
+// enlarge a queue (SoA planes of stride cap) keeping its contents
+static int32_t grow_queue(Queue& q, int64_t new_cap, int nf, int ni, cudaStream_t st) {
+    Queue nq;
+    int32_t rc = alloc_queue(nq, new_cap, nf, ni, st);
+    if (rc) return rc;
+    if (q.cap) {
+        BMO_CUDA(cudaMemcpy2DAsync(nq.d, (size_t)new_cap * sizeof(double), q.d, (size_t)q.cap * sizeof(double), (size_t)q.cap * sizeof(double), nf,
+                                   cudaMemcpyDeviceToDevice, st));
+        BMO_CUDA(cudaMemcpy2DAsync(nq.i, (size_t)new_cap * sizeof(int32_t), q.i, (size_t)q.cap * sizeof(int32_t), (size_t)q.cap * sizeof(int32_t), ni,
+                                   cudaMemcpyDeviceToDevice, st));
+    }
+    dev_free(q.d, st); dev_free(q.i, st);
+    q = nq;
+    return BMO_OK;
+}
 static void free_queue(Queue& q, cudaStream_t st) { dev_free(q.d, st); dev_free(q.i, st); q.cap = 0; }
 
 static BeamTab beamtab(bmo_result* r) {
@@ -979,86 +1053,147 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     const bool staged = V.n_poses == 1 && table_bytes <= 40 * 1024;
     const size_t smem = staged ? table_bytes : 0;
 
-    int64_t count = n, n_beams = n;
+    // Beamsplitters are the only objects that add beams: without them the queue never grows, the
+    // continuing rays are updated in place and the host only looks at the device every `chunk` waves.
+    bool has_splitter = false;
+    for (const bmo_object& ob : sys->objects)
+        has_splitter |= ob.kind == BMO_OBJ_THIN_BS || ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_CUBE_BS;
+    const int chunk = has_splitter ? 1 : 4;
+    if ((int)ctx->wave_ev.size() < 2 * chunk) {
+        const size_t old = ctx->wave_ev.size();
+        ctx->wave_ev.resize(2 * chunk);
+        for (size_t k = old; k < ctx->wave_ev.size(); k++) BMO_CUDA(cudaEventCreate(&ctx->wave_ev[k]));
+    }
+    unsigned long long* d_wtot = nullptr;      // [r_max + 8][2]: units alive after wave w, spawn events of wave w
+    const size_t n_wtot = (size_t)2 * (r_max + 8);
+    BMO_CUDA(dev_alloc(&d_wtot, n_wtot, st));
+    BMO_CUDA(cudaMemsetAsync(d_wtot, 0, n_wtot * sizeof(unsigned long long), st));
+    unsigned long long* h_wtot = (unsigned long long*)ctx->h_totals;   // pinned, >= 2 * chunk entries
+
+    int64_t n_slots = n, alive = n, n_beams = n;
     int32_t* blk_cnt = nullptr; long long* blk_off = nullptr; int64_t blk_cap = 0;
-    int wave = 0;
-    while (count > 0) {
-        const int64_t nblocks = (count + units - 1) / units;
-        const int64_t scr_cap = nblocks * 2 * units * R;
-        if (scr.cap < scr_cap) { free_queue(scr, st); if ((rc = alloc_queue(scr, scr_cap, nfs, NI_S, st))) return rc; }
-        if (next.cap < 2 * count * R) { free_queue(next, st); if ((rc = alloc_queue(next, 2 * count * R, nfq, NI_Q, st))) return rc; }
-        if (blk_cap < nblocks) {
-            dev_free(blk_cnt, st); dev_free(blk_off, st);
-            BMO_CUDA(dev_alloc(&blk_cnt, (size_t)2 * nblocks, st));
-            BMO_CUDA(dev_alloc(&blk_off, (size_t)2 * nblocks, st));
-            blk_cap = nblocks;
+    int wave = 0, waves_done = 0;
+    while (alive > 0) {
+        if (wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
+        int launched = 0;
+        for (int c = 0; c < chunk; c++, launched++) {
+            const int64_t nblocks = (n_slots + units - 1) / units;
+            if (has_splitter) {
+                // every live unit may add one unit (the reflected child) and two beams in this wave
+                if (cur.cap < (n_slots + alive) * R) {
+                    if ((rc = grow_queue(cur, 2 * (n_slots + alive) * R, nfq, NI_Q, st))) return rc;
+                }
+                const int64_t scr_cap = nblocks * 2 * units * R;
+                if (scr.cap < scr_cap) { free_queue(scr, st); if ((rc = alloc_queue(scr, scr_cap, nfs, NI_S, st))) return rc; }
+                if ((rc = ensure_beams(res, n_beams + 2 * alive, st))) return rc;
+            }
+            if (blk_cap < nblocks) {
+                dev_free(blk_cnt, st); dev_free(blk_off, st);
+                BMO_CUDA(dev_alloc(&blk_cnt, (size_t)nblocks, st));
+                BMO_CUDA(dev_alloc(&blk_off, (size_t)nblocks, st));
+                blk_cap = nblocks;
+            }
+            WaveBuf wb{};
+            if (res->keep) {
+                wb.count = n_slots * R;
+                BMO_CUDA(dev_alloc(&wb.d, (size_t)nsd * wb.count, st));
+                BMO_CUDA(dev_alloc(&wb.part, (size_t)wb.count, st));
+                BMO_CUDA(dev_alloc(&wb.beam, (size_t)wb.count, st));
+                BMO_CUDA(dev_alloc(&wb.seg, (size_t)wb.count, st));
+                res->wavebufs.push_back(wb);
+            }
+            if (hit.cap < n_slots * R) {
+                dev_free(hit.d, st); dev_free(hit.part, st);
+                hit.cap = n_slots * R;
+                BMO_CUDA(dev_alloc(&hit.d, (size_t)4 * hit.cap, st));
+                BMO_CUDA(dev_alloc(&hit.part, (size_t)hit.cap, st));
+            }
+            IntersectParams xp{};
+            xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = n_slots * R; xp.r_max = r_max;
+            xp.counters = ctx->d_counters;
+            BMO_CUDA(cudaEventRecord(ctx->wave_ev[2 * c], st));
+            {
+                static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 6;   // tuning knob: resident blocks per SM the kernel is compiled for
+                const unsigned grid = (unsigned)((n_slots * R + IBLOCK - 1) / IBLOCK);
+                if (!staged) intersect_wave<4, false><<<grid, IBLOCK, 0, st>>>(xp);
+                else if (minb <= 3) intersect_wave<3, true><<<grid, IBLOCK, smem, st>>>(xp);
+                else if (minb == 4) intersect_wave<4, true><<<grid, IBLOCK, smem, st>>>(xp);
+                else if (minb == 5) intersect_wave<5, true><<<grid, IBLOCK, smem, st>>>(xp);
+                else intersect_wave<6, true><<<grid, IBLOCK, smem, st>>>(xp);
+            }
+            BMO_LAUNCH(ctx, "intersect_wave");
+            BMO_CUDA(cudaEventRecord(ctx->wave_ev[2 * c + 1], st));
+            StepParams sp{};
+            sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
+            sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
+            if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+            else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
+            else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
+            BMO_LAUNCH(ctx, "interact_wave");
+            wave++;
+            if (wave > r_max + 1) { launched++; break; }
         }
-        if ((rc = ensure_beams(res, n_beams + 2 * count, st))) return rc;
-        WaveBuf wb{};
-        if (res->keep) {
-            wb.count = count * R;
-            BMO_CUDA(dev_alloc(&wb.d, (size_t)nsd * wb.count, st));
-            BMO_CUDA(dev_alloc(&wb.part, (size_t)wb.count, st));
-            BMO_CUDA(dev_alloc(&wb.beam, (size_t)wb.count, st));
-            BMO_CUDA(dev_alloc(&wb.seg, (size_t)wb.count, st));
-            res->wavebufs.push_back(wb);
-        }
-        if (hit.cap < count * R) {
-            dev_free(hit.d, st); dev_free(hit.part, st);
-            hit.cap = count * R;
-            BMO_CUDA(dev_alloc(&hit.d, (size_t)4 * hit.cap, st));
-            BMO_CUDA(dev_alloc(&hit.part, (size_t)hit.cap, st));
-        }
-        IntersectParams xp{};
-        xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = count * R; xp.r_max = r_max;
-        xp.counters = ctx->d_counters;
-        BMO_CUDA(cudaEventRecord(ctx->evk0, st));
-        {
-            static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 4;   // tuning knob: resident blocks per SM the kernel is compiled for
-            const unsigned grid = (unsigned)((count * R + IBLOCK - 1) / IBLOCK);
-            if (!staged) intersect_wave<4, false><<<grid, IBLOCK, 0, st>>>(xp);
-            else if (minb <= 3) intersect_wave<3, true><<<grid, IBLOCK, smem, st>>>(xp);
-            else if (minb == 4) intersect_wave<4, true><<<grid, IBLOCK, smem, st>>>(xp);
-            else if (minb == 5) intersect_wave<5, true><<<grid, IBLOCK, smem, st>>>(xp);
-            else intersect_wave<6, true><<<grid, IBLOCK, smem, st>>>(xp);
-        }
-        BMO_LAUNCH(ctx, "intersect_wave");
-        BMO_CUDA(cudaEventRecord(ctx->evk1, st));
-        StepParams sp{};
-        sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = count; sp.r_max = r_max; sp.keep = res->keep;
-        sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.counters = ctx->d_counters;
-        if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
-        else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
-        else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
-        BMO_LAUNCH(ctx, "interact_wave");
-        scan_counts<<<1, 1024, 0, st>>>(blk_cnt, nblocks, 2, 2, blk_off, ctx->d_totals);
-        BMO_LAUNCH(ctx, "scan_counts");
-        ScatterParams cp{};
-        cp.scr = scr; cp.next = next; cp.blk_cnt = blk_cnt; cp.blk_off = blk_off; cp.B = beamtab(res); cp.n_beams = n_beams;
-        cp.nf = nfq; cp.mode = mode; cp.units = units; cp.R = R;
-        BMO_CUDA(cudaEventRecord(ctx->evs0, st));
-        scatter_queue<<<(unsigned)nblocks, 256, 0, st>>>(cp);
-        BMO_LAUNCH(ctx, "scatter_queue");
-        BMO_CUDA(cudaEventRecord(ctx->evs1, st));
-        BMO_CUDA(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, 2 * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        // one look at the device per chunk: units alive / spawn events of the waves just launched
+        const int w0 = wave - launched;
+        BMO_CUDA(cudaMemcpyAsync(h_wtot, d_wtot + 2 * w0, (size_t)2 * launched * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
         const double tw0 = tnow();
         BMO_CUDA(cudaStreamSynchronize(st));
         tp_wave_sync += tnow() - tw0;
-        {
-            float kms = 0, sms = 0;
-            BMO_CUDA(cudaEventElapsedTime(&kms, ctx->evk0, ctx->evk1));
-            BMO_CUDA(cudaEventElapsedTime(&sms, ctx->evs0, ctx->evs1));
-            ctx->k1_ms += kms; ctx->k1_launches++;
-            ctx->k3_ms += sms;
-            ctx->k3_bytes += (double)ctx->h_totals[0] * R * (2.0 * (nfq * 8 + NI_Q * 4) + 2 * 4);
+        int64_t prev_alive = alive;
+        for (int c = 0; c < launched; c++) {
+            if (prev_alive > 0) {       // waves launched on an already empty queue are no-ops and not counted
+                float kms = 0;
+                BMO_CUDA(cudaEventElapsedTime(&kms, ctx->wave_ev[2 * c], ctx->wave_ev[2 * c + 1]));
+                ctx->k1_ms += kms; ctx->k1_launches++;
+                waves_done++; ctx->waves++;
+            }
+            prev_alive = (int64_t)h_wtot[2 * c];
         }
-        count = ctx->h_totals[0];
-        n_beams += 2 * ctx->h_totals[1];
-        std::swap(cur, next);
-        wave++;
-        ctx->waves++;
-        if (wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
+        alive = (int64_t)h_wtot[2 * (launched - 1)];
+        const int64_t spawns = (int64_t)h_wtot[2 * (launched - 1) + 1];   // chunk == 1 whenever spawns are possible
+        if (spawns > 0) {
+            const int64_t nblocks = (n_slots + units - 1) / units;
+            scan_counts<<<1, 1024, 0, st>>>(blk_cnt, nblocks, 1, 1, blk_off, ctx->d_totals);
+            BMO_LAUNCH(ctx, "scan_counts");
+            SpawnParams cp{};
+            cp.scr = scr; cp.q = cur; cp.blk_cnt = blk_cnt; cp.blk_off = blk_off; cp.B = beamtab(res); cp.n_beams = n_beams; cp.n_slots = n_slots;
+            cp.nf = nfq; cp.mode = mode; cp.units = units; cp.R = R;
+            spawn_children<<<(unsigned)nblocks, 256, 0, st>>>(cp);
+            BMO_LAUNCH(ctx, "spawn_children");
+            n_slots += spawns;
+            n_beams += 2 * spawns;
+        }
+        // K3: squeeze the dead slots out once they are the majority
+        if (alive > 0 && 2 * alive <= n_slots && n_slots >= 4096) {
+            const int64_t cblocks = (n_slots + CBLOCK - 1) / CBLOCK;
+            if (blk_cap < cblocks) {
+                dev_free(blk_cnt, st); dev_free(blk_off, st);
+                BMO_CUDA(dev_alloc(&blk_cnt, (size_t)cblocks, st));
+                BMO_CUDA(dev_alloc(&blk_off, (size_t)cblocks, st));
+                blk_cap = cblocks;
+            }
+            const int64_t want = has_splitter ? 2 * alive * R : alive * R;
+            if (next.cap < want) { free_queue(next, st); if ((rc = alloc_queue(next, want, nfq, NI_Q, st))) return rc; }
+            BMO_CUDA(cudaEventRecord(ctx->evs0, st));
+            compact_count<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur.i, cur.cap, n_slots, R, blk_cnt);
+            BMO_LAUNCH(ctx, "compact_count");
+            scan_counts<<<1, 1024, 0, st>>>(blk_cnt, cblocks, 1, 1, blk_off, ctx->d_totals);
+            BMO_LAUNCH(ctx, "scan_counts");
+            compact_scatter<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur, next, n_slots, R, nfq, blk_off);
+            BMO_LAUNCH(ctx, "compact_scatter");
+            BMO_CUDA(cudaEventRecord(ctx->evs1, st));
+            BMO_CUDA(cudaStreamSynchronize(st));
+            float sms = 0;
+            BMO_CUDA(cudaEventElapsedTime(&sms, ctx->evs0, ctx->evs1));
+            ctx->k3_ms += sms;
+            // algorithmic bytes: the alive flag of every slot, then read + write of every surviving ray
+            ctx->k3_bytes += (double)n_slots * 4 * 2 + (double)alive * R * 2.0 * (nfq * 8 + NI_Q * 4);
+            std::swap(cur, next);
+            n_slots = alive;
+        }
     }
+    dev_free(d_wtot, st);
+    wave = waves_done;
     const double tp2 = tnow();
     res->n_beams = n_beams;
     res->waves = wave;
