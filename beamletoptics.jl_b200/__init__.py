@@ -20,6 +20,8 @@ from .shapes import (BoxSDF, CircularFlatMesh, ConcaveSphericalSurfaceSDF, Conve
                      RightAnglePrismSDF, RingSDF, SphereSDF, ThinLensSDF, UnionSDF, load_stl)
 from .solver import DeviceSystem, TraceResult, pd_accumulate, solve_system_, trace_beamlets, trace_rays, upload_system
 from .sweep import flatten_poses, solve_pose_sweep
+from . import parallel
+from .parallel import solve_system_sharded
 
 
 # function-style kinematic API of the reference: translate3d!(obj, v) -> translate3d_(obj, v)

@@ -1058,10 +1058,12 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     bool has_splitter = false;
     for (const bmo_object& ob : sys->objects)
         has_splitter |= ob.kind == BMO_OBJ_THIN_BS || ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_CUBE_BS;
-    const int chunk = has_splitter ? 1 : 4;
-    if ((int)ctx->wave_ev.size() < 2 * chunk) {
+    // waves per look at the device: 1 (most rays that miss everything die on the first wave, so the
+    // compaction decision is worth an early look), then 3, then 4, 4, ...
+    const int max_chunk = has_splitter ? 1 : 4;
+    if ((int)ctx->wave_ev.size() < 2 * max_chunk) {
         const size_t old = ctx->wave_ev.size();
-        ctx->wave_ev.resize(2 * chunk);
+        ctx->wave_ev.resize(2 * max_chunk);
         for (size_t k = old; k < ctx->wave_ev.size(); k++) BMO_CUDA(cudaEventCreate(&ctx->wave_ev[k]));
     }
     unsigned long long* d_wtot = nullptr;      // [r_max + 8][2]: units alive after wave w, spawn events of wave w
@@ -1076,6 +1078,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     while (alive > 0) {
         if (wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
         int launched = 0;
+        const int chunk = has_splitter ? 1 : (wave == 0 ? 1 : (wave == 1 ? 3 : max_chunk));
         for (int c = 0; c < chunk; c++, launched++) {
             const int64_t nblocks = (n_slots + units - 1) / units;
             if (has_splitter) {

@@ -217,6 +217,10 @@ def main():
         dist.all_reduce(it, op=dist.ReduceOp.SUM)
     inter_all, inter_all_e = float(it[0].item()), float(it[1].item())
 
+    peak = L.measure_fp64_peak(dev)
+    det = None
+    if not args.no_detector:
+        det = bench_detector(m, L, dev, stream, args.c3_side, args.c3_pixels, max(2, min(args.steps, 3)), 1, flush, peak, rank, world)
     if rank == 0:
         value = inter_all * args.steps / (tot_ms * 1e-3)
         e2e = inter_all_e * args.steps / (tot_ms_e * 1e-3)
@@ -224,13 +228,12 @@ def main():
         flops = (FLOP_SDF * c["sdf_evals"] + FLOP_TRI * c["tri_tests"] + FLOP_INT * c["interactions"])
         k1_ms, k1_n = c["trace_step_ms"], max(c["trace_step_launches"], 1)
         achieved = flops / (k1_ms * 1e-3) / 1e12 if k1_ms > 0 else None
-        peak = L.measure_fp64_peak(dev)
         hbm_peak = None
         try:
             hbm_peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]
         except Exception:
             hbm_peak = 6650.0
-        scat = c["scatter_bytes"] / (c["scatter_ms"] * 1e-3) / 1e9 if c["scatter_ms"] > 0 else None
+        comp = bench_compaction(m, L, dev, dsys, n, hbm_peak)
         out = {
             "metric": "ray-surface interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -241,18 +244,17 @@ def main():
                     "h2d_bytes_per_step": int(pos_h.nbytes + dir_h.nbytes + lam_h.nbytes),
                     "d2h_bytes_per_step": int(spot_obj_p.numel() * 4 + spot_xz_p.numel() * 8)},
             "gpu_launches": int(c["kernel_launches"] * args.steps / n_total_steps),
-            "roofline": {"bound": "fp64", "kernel": "trace_step<0>", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "intersect_wave", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
                          "peak_source": "measured here: DFMA probe (bmo_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": flops / k1_n, "ms_per_launch": k1_ms / k1_n,
                          "share_of_step": k1_ms / n_total_steps / (tot_ms / args.steps) if tot_ms else None,
                          "counted": {"sdf_evals_per_step": c["sdf_evals"] / n_total_steps, "interactions_per_step": c["interactions"] / n_total_steps}},
-            "roofline_compaction": {"bound": "hbm", "kernel": "scatter_queue", "achieved": scat, "peak": hbm_peak, "unit": "GB/s",
-                                    "frac": (scat / hbm_peak) if scat else None},
+            "roofline_compaction": comp,
             "clocks": sampler.summary(),
         }
-        if not args.no_detector:
-            out["detector"] = bench_detector(m, L, dev, stream, args.c3_side, args.c3_pixels, max(2, min(args.steps, 3)), 1, flush, peak)
+        if det is not None:
+            out["detector"] = det
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
@@ -266,7 +268,7 @@ FLOP_PAIR = 245.0       # the same weights (add/mul 1, sqrt/div 8, transcendenta
                         # pd_field_fast, counted op by op in DESIGN.md "K4" -- the work the kernel actually has to do
 
 
-def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_tflops):
+def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_tflops, rank=0, world=1):
     """Metric 2 (Photodetector px-beamlets/s) on the C3 workload: Keplerian expander + Photodetector(40 mm, pd_n),
     k_side^2 beamlets of the C3 lattice (pitch 8 mm / 256, w0 = 1.5 pitch, lambda = 1 um).  The default run uses the central
     64 x 64 block of the 256 x 256 lattice (bounded so that bench.py stays within minutes); the pair rate does not depend on it."""
@@ -274,7 +276,10 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
     import torch
     from tests import scenes2 as s2
     sc = s2.expander(m, pd_n)
+    import torch.distributed as dist
     lat = s2.beamlet_lattice(k_side, aperture=8e-3 * k_side / 256)
+    pitch = 8e-3 / 256
+    lat["pos"][:, 0] += (rank - (world - 1) / 2) * k_side * pitch      # rank r holds the r-th block of the lattice (along x)
     nb = k_side * k_side
     bundle = m.BeamletBundle.from_params(lat["pos"], lat["dir"], lat["lam"], lat["w0"], M2=lat["M2"], P0=1e-3 / 65536, support=lat["support"])
     dsys = m.upload_system(sc["system"], [lat["lam"]], device=dev)
@@ -284,7 +289,11 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
     field_h = torch.zeros(pd_n * pd_n * 2, dtype=torch.float64).pin_memory()
 
     def run(ptr, flags):
+        if flags & L.INPUT_DEVICE:
+            field_d.zero_()                      # partial field of this rank
         L.check(L.lib().bmo_pd_accumulate(dsys.h, res.h, pd_index, 0, C.c_void_p(ptr), flags))
+        if world > 1 and (flags & L.INPUT_DEVICE):
+            dist.all_reduce(field_d, op=dist.ReduceOp.SUM)
 
     out = {}
     for name, ptr, flags in (("device", field_d.data_ptr(), L.INPUT_DEVICE), ("e2e", field_h.data_ptr(), 0)):
@@ -295,6 +304,8 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
         for _ in range(steps):
             flush.fill_(1)
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             run(ptr, flags)
@@ -302,17 +313,29 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
         c = L.counters(dev)
-        out[name] = dict(ms=sum(times) / steps, pairs=c["px_beamlets"] / steps, k4_ms=c["pd_field_ms"] / steps, launches=c["kernel_launches"] / steps)
+        tot = torch.tensor([sum(times) / steps], dtype=torch.float64, device="cuda")
+        pr = torch.tensor([c["px_beamlets"] / steps], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)       # max over ranks
+            dist.all_reduce(pr, op=dist.ReduceOp.SUM)        # whole-job pairs
+        out[name] = dict(ms=float(tot.item()), pairs=float(pr.item()), k4_ms=c["pd_field_ms"] / steps, launches=c["kernel_launches"] / steps,
+                         pairs_rank=c["px_beamlets"] / steps)
+        if name == "device" and world > 1:       # the e2e leg (host field) is a single-GPU notion: rank-local, no collective
+            break
+    if "e2e" not in out:
+        out["e2e"] = dict(out["device"])
     pairs = out["device"]["pairs"]
-    ach = FLOP_PAIR * pairs / (out["device"]["k4_ms"] * 1e-3) / 1e12
+    ach = FLOP_PAIR * out["device"]["pairs_rank"] / (out["device"]["k4_ms"] * 1e-3) / 1e12
     res.free()
     return {
         "metric": "Photodetector px-beamlets/s", "unit": "px-beamlets/s",
         "value": pairs / (out["device"]["ms"] * 1e-3), "ms_per_step": out["device"]["ms"],
         "e2e": {"value": pairs / (out["e2e"]["ms"] * 1e-3), "ms_per_step": out["e2e"]["ms"],
                 "h2d_bytes_per_step": int(field_h.numel() * 8), "d2h_bytes_per_step": int(field_h.numel() * 8)},
-        "config": {"workload": f"C3: Keplerian beam expander, {nb} of 65536 GaussianBeamlets (central block of the 256x256 lattice) onto a {pd_n}^2 Photodetector, coherent field sum",
-                   "beamlets": nb, "pixels": pd_n * pd_n, "pairs_per_step": pairs},
+        "config": {"workload": f"C3: Keplerian beam expander, {nb} of 65536 GaussianBeamlets per GPU (a {k_side}x{k_side} block of the 256x256 lattice) onto a {pd_n}^2 Photodetector, coherent field sum"
+                               + (f", all-reduce of the {pd_n}^2 complex128 field over {world} GPUs inside the timed region" if world > 1 else ""),
+                   "beamlets_per_gpu": nb, "pixels": pd_n * pd_n, "pairs_per_step": pairs},
+        "n_gpus": world, "scaling": "weak",
         "gpu_launches": out["device"]["launches"],
         "roofline": {"bound": "fp64", "kernel": "pd_field_fast", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s (FP64 flop-equivalents)",
                      "frac": ach / peak_tflops if peak_tflops else None, "ms_per_launch": out["device"]["k4_ms"],
@@ -320,6 +343,29 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
                      "achieved_in_reference_sequence_units": ach * FLOP_PAIR_REF / FLOP_PAIR,
                      "share_of_step": out["device"]["k4_ms"] / out["device"]["ms"]},
     }
+
+
+def bench_compaction(m, L, dev, dsys, n, hbm_peak):
+    """K3 (queue compaction, HBM-bound) does not run in C2 proper -- every ray lives for all 4 waves.  Overfilling the pupil
+    (disc of 40 mm on the 25.4 mm doublet: 60 % of the rays miss everything on the first wave) makes the dead slots the
+    majority, which triggers one compaction of the 2^20-slot queue; achieved GB/s = algorithmic bytes / CUDA-event time."""
+    import torch
+    from tests import scenes
+    pos, d = scenes.fibonacci_disc(n, diameter=40e-3)
+    pos_d, dir_d = torch.from_numpy(pos).cuda(), torch.from_numpy(d).cuda()
+    lam_d = torch.zeros(n, dtype=torch.int32, device="cuda")
+    best = None
+    for it in range(4):
+        L.counters_reset(dev)
+        res = m.trace_rays(dsys, (pos_d.data_ptr(), n), dir_d.data_ptr(), lam_d.data_ptr(), None, None, 100, keep_segments=False, device_inputs=True)
+        res.free()
+        c = L.counters(dev)
+        if it and c["scatter_ms"] > 0:
+            gbs = c["scatter_bytes"] / (c["scatter_ms"] * 1e-3) / 1e9
+            best = gbs if best is None else max(best, gbs)
+    return {"bound": "hbm", "kernel": "compact_count + scan_counts + compact_scatter", "achieved": best, "peak": hbm_peak, "unit": "GB/s",
+            "frac": (best / hbm_peak) if best else None, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
+            "workload": "C2 doublet with an overfilled pupil (40 mm disc): one compaction of the 2^20-slot queue to the ~40 % live rays"}
 
 
 def cpu_baseline():

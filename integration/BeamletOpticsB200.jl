@@ -1,0 +1,304 @@
+# BeamletOpticsB200.jl -- reference-side binding of libbmo.so (the B200-native trace hot path).
+#
+# This is the file a BeamletOptics.jl maintainer would add (e.g. as a package extension): a new
+# `CUDASystem <: AbstractSystem` whose `solve_system!` methods flatten `Leaves(system.objects)` into the
+# plain tables of include/bmo.h and `ccall` the library.  Constructors, kinematics (`translate3d!`,
+# `rotate3d!`, ...), `Beam` / `GaussianBeamlet` / `Photodetector` / `Spotdetector` stay the reference's
+# own Julia objects; results land where the reference puts them (`pd.field`, `sd.data`, `beam.rays`).
+#
+# NOT EXERCISED IN THIS REPOSITORY: Julia is not installed in the build image.  The same ABI is driven
+# and tested from Python (beamletoptics.jl_b200/_lib.py, flatten.py, solver.py); this file mirrors that
+# code one to one.  Struct layouts below must match include/bmo.h (checked on the Python side by
+# tests/test_abi.py::test_struct_layouts_match_header).
+module BeamletOpticsB200
+
+using BeamletOptics
+using BeamletOptics: AbstractSystem, AbstractObject, AbstractSDF, AbstractMesh, UnionSDF, MeniscusLensSDF,
+    PlanoSurfaceSDF, CylinderSDF, SphereSDF, ConvexSphericalSurfaceSDF, ConcaveSphericalSurfaceSDF,
+    CutSphereSDF, BoxSDF, RingSDF, RightAnglePrismSDF, Mesh, Lens, Prism, DoubletLens, AbstractReflectiveOptic,
+    ThinBeamsplitter, AbstractPlateBeamsplitter, CubeBeamsplitter, Photodetector, Spotdetector,
+    IntersectableObject, NonInteractableObject, Beam, Ray, PolarizedRay, GaussianBeamlet, Intersection,
+    position, orientation, transposed_orientation, shape, objects, refractive_index, wavelength, vertices, faces
+using StaticArrays, GeometryBasics
+
+const libbmo = get(ENV, "LIBBMO", "libbmo.so")
+
+# ---- include/bmo.h, field for field ----------------------------------------------------------------
+struct BmoPrim                      # bmo_prim
+    type::Int32; reserved::Int32
+    pos::NTuple{3,Float64}; tdir::NTuple{9,Float64}; par::NTuple{4,Float64}
+end
+struct BmoPart                      # bmo_part
+    object::Int32; role::Int32; shape_kind::Int32; first::Int32; count::Int32; n_row::Int32
+    reflectance::Float64; transmittance::Float64; bound::NTuple{4,Float64}
+end
+struct BmoObject                    # bmo_object
+    kind::Int32; first_part::Int32; n_parts::Int32; pd_n::Int32
+    pos::NTuple{3,Float64}; dir::NTuple{9,Float64}; pd_lo::Float64; pd_hi::Float64
+end
+struct BmoMesh                      # bmo_mesh
+    first_vertex::Int64; n_vertices::Int64; first_face::Int64; n_faces::Int64; f32::Int32; reserved::Int32
+end
+struct BmoTables                    # bmo_tables
+    n_prims::Int32;    prims::Ptr{BmoPrim}
+    n_parts::Int32;    parts::Ptr{BmoPart}
+    n_objects::Int32;  objects::Ptr{BmoObject}
+    n_meshes::Int32;   meshes::Ptr{BmoMesh}
+    n_vertices::Int64; vertices::Ptr{Float64}
+    n_faces::Int64;    faces::Ptr{Int32}
+    n_lambda::Int32;   lambdas::Ptr{Float64}
+    n_rows::Int32;     n_table::Ptr{Float64}
+    n_system::Float64
+    norm_zero_rule::Int32; reserved::Int32
+end
+struct BmoResultInfo
+    n_roots::Int64; n_beams::Int64; n_segments::Int64; interactions::Int64
+    rays_per_beam::Int32; polarized::Int32; waves::Int32; reserved::Int32
+end
+
+const PRIM = Dict(PlanoSurfaceSDF => 0, CylinderSDF => 1, SphereSDF => 2, ConvexSphericalSurfaceSDF => 3,
+    ConcaveSphericalSurfaceSDF => 4, CutSphereSDF => 5, BoxSDF => 6, RingSDF => 7, RightAnglePrismSDF => 8)
+const KEEP_SEGMENTS = UInt32(1)
+
+check(rc) = rc == 0 || error(unsafe_string(ccall((:bmo_last_error, libbmo), Cstring, ())))
+
+rowmajor(M) = ntuple(k -> Float64(M[(k - 1) ÷ 3 + 1, (k - 1) % 3 + 1]), 9)
+
+# par[] per primitive type, exactly the fields each sdf(...) method reads (see bmo.h enum bmo_prim_type)
+params(s::PlanoSurfaceSDF) = (s.thickness, s.diameter, 0.0, 0.0)
+params(s::CylinderSDF) = (s.radius, s.height, 0.0, 0.0)
+params(s::SphereSDF) = (s.radius, 0.0, 0.0, 0.0)
+params(s::ConvexSphericalSurfaceSDF) = (s.radius, s.diameter, s.sag, s.height)
+params(s::ConcaveSphericalSurfaceSDF) = (s.radius, s.diameter, s.sag, 0.0)
+params(s::CutSphereSDF) = (s.radius, s.height, s.w, 0.0)
+params(s::BoxSDF) = (s.x / 2, s.y / 2, s.z / 2, 0.0)          # half extents, as PrimitiveSDF.jl:41-46 uses them
+params(s::RingSDF) = (s.inner_radius, s.hwidth, s.hthickness, 0.0)
+params(s::RightAnglePrismSDF) = (s.x / 2, s.y / 2, s.z / 2, 0.0)
+
+prim(s::AbstractSDF) = BmoPrim(PRIM[Base.typename(typeof(s)).wrapper], 0, Tuple(Float64.(position(s))),
+    rowmajor(transposed_orientation(s)), Float64.(params(s)))
+
+function emit_sdf!(prims, s::AbstractSDF)
+    first = length(prims)
+    for m in (s isa UnionSDF ? s.sdfs : (s,))
+        if m isa MeniscusLensSDF        # frame + children posed relative to it (MeniscusLensSDF.jl:42-46)
+            push!(prims, BmoPrim(9, 0, Tuple(Float64.(position(m))), rowmajor(transposed_orientation(m)), (0.0, 0.0, 0.0, 0.0)))
+            push!(prims, prim(m.convex), prim(m.cylinder), prim(m.concave))
+        else
+            push!(prims, prim(m))
+        end
+    end
+    return first, length(prims) - first
+end
+
+"""Wraps a reference `System`; `solve_system!` on it runs on the GPU."""
+struct CUDASystem{S<:AbstractSystem} <: AbstractSystem
+    system::S
+    device::Int
+end
+CUDASystem(s::AbstractSystem) = CUDASystem(s, 0)
+BeamletOptics.objects(cs::CUDASystem) = objects(cs.system)
+BeamletOptics.refractive_index(cs::CUDASystem, λ) = refractive_index(cs.system, λ)
+
+const CTX = Dict{Int,Ptr{Cvoid}}()
+function context(dev)
+    get!(CTX, dev) do
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:bmo_init, libbmo), Int32, (Int32, Ref{Ptr{Cvoid}}), dev, h))
+        h[]
+    end
+end
+
+kind_of(o::DoubletLens) = (5, (o.front, o.back), (1, 2))
+kind_of(o::CubeBeamsplitter) = (4, (o.front, o.back, o.coating), (1, 2, 4))
+kind_of(o::AbstractPlateBeamsplitter) = (3, (o.substrate, o.coating), (3, 4))
+kind_of(o::ThinBeamsplitter) = (2, (o,), (0,))
+kind_of(o::AbstractReflectiveOptic) = (1, (o,), (0,))
+kind_of(o::Photodetector) = (6, (o,), (0,))
+kind_of(o::Spotdetector) = (7, (o,), (0,))
+kind_of(o::IntersectableObject) = (8, (o,), (0,))
+kind_of(o::AbstractObject) = (0, (o,), (0,))                 # Lens, Prism: AbstractRefractiveOptic
+
+"""Leaves(system.objects) -> tables of include/bmo.h (same order: it is trace_all's tie-break order)."""
+function flatten(cs::CUDASystem, λs::Vector{Float64}; norm_zero_rule = 1)
+    prims, parts, objs, meshes = BmoPrim[], BmoPart[], BmoObject[], BmoMesh[]
+    verts, fcs, ntab, owners = Float64[], Int32[], Float64[], Any[]
+    leaves = [o for o in objects(cs) if !(o isa NonInteractableObject)]
+    for (oi, o) in enumerate(leaves)
+        kind, subs, roles = kind_of(o)
+        sh0 = length(subs) == 1 ? shape(o) : nothing
+        push!(objs, BmoObject(kind, length(parts), length(subs), o isa Photodetector ? length(o.x) : 0,
+            sh0 === nothing ? (0.0, 0.0, 0.0) : Tuple(Float64.(position(sh0))),
+            sh0 === nothing ? ntuple(_ -> 0.0, 9) : rowmajor(orientation(sh0)),
+            o isa Photodetector ? first(o.x) : 0.0, o isa Photodetector ? last(o.x) : 0.0))
+        for (sub, role) in zip(subs, roles)
+            sh = shape(sub)
+            n_row = -1
+            if hasmethod(refractive_index, Tuple{typeof(sub),Float64})
+                n_row = length(ntab) ÷ length(λs)
+                append!(ntab, (Float64(refractive_index(sub, λ)) for λ in λs))   # KeyError for an untabulated λ, like the reference
+            end
+            c, r = bounding_sphere(sh)
+            bound = (c[1], c[2], c[3], r * (1 + 1e-9) + 1e-6)
+            R = sub isa ThinBeamsplitter ? (sub.reflectance, sub.transmittance) : (0.0, 0.0)
+            if sh isa AbstractSDF
+                first, count = emit_sdf!(prims, sh)
+                push!(parts, BmoPart(oi - 1, role, 0, first, count, n_row, R[1], R[2], bound))
+            else
+                V, F = vertices(sh), faces(sh)
+                push!(meshes, BmoMesh(length(verts) ÷ 3, size(V, 1), length(fcs) ÷ 3, size(F, 1), eltype(V) == Float32 ? 1 : 0, 0))
+                push!(parts, BmoPart(oi - 1, role, 1, length(meshes) - 1, 1, n_row, R[1], R[2], bound))
+                append!(verts, Float64.(permutedims(V)))          # xyz triples; Float32 values widened, not rescaled
+                append!(fcs, Int32.(permutedims(F) .- 1))
+            end
+            push!(owners, sub)
+        end
+    end
+    return (; prims, parts, objs, meshes, verts, fcs, ntab, owners, leaves, λs, norm_zero_rule)
+end
+
+# conservative world-space bounding sphere of a shape (only used for result-identical early exits)
+function bounding_sphere(sh::AbstractMesh)
+    V = vertices(sh); c = vec(sum(V, dims = 1)) ./ size(V, 1)
+    return c, maximum(norm(V[i, :] .- c) for i in 1:size(V, 1))
+end
+function bounding_sphere(sh::AbstractSDF)
+    # half of a generous axis-aligned extent in the local frame, see shapes.py:local_bound for the per-type radii
+    ms = sh isa UnionSDF ? sh.sdfs : (sh,)
+    c = sum(Float64.(position(m)) for m in ms) ./ length(ms)
+    return c, maximum(norm(Float64.(position(m)) .- c) + local_radius(m) for m in ms)
+end
+local_radius(s::PlanoSurfaceSDF) = hypot(s.diameter / 2, s.thickness)
+local_radius(s::CylinderSDF) = hypot(s.radius, s.height)
+local_radius(s::SphereSDF) = s.radius
+local_radius(s::ConvexSphericalSurfaceSDF) = hypot(s.diameter / 2, s.sag)
+local_radius(s::ConcaveSphericalSurfaceSDF) = hypot(s.diameter / 2, s.sag)
+local_radius(s::CutSphereSDF) = s.radius
+local_radius(s::BoxSDF) = norm((s.x, s.y, s.z)) / 2
+local_radius(s::RingSDF) = hypot(s.inner_radius + s.hwidth, s.hthickness)
+local_radius(s::RightAnglePrismSDF) = norm((s.x, s.y, s.z)) / 2
+local_radius(s::MeniscusLensSDF) = maximum(norm(position(c)) + local_radius(c) for c in (s.convex, s.cylinder, s.concave))
+
+function upload(cs::CUDASystem, f)
+    sys = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve f begin
+        t = BmoTables(length(f.prims), pointer(f.prims), length(f.parts), pointer(f.parts), length(f.objs), pointer(f.objs),
+            length(f.meshes), pointer(f.meshes), length(f.verts) ÷ 3, pointer(f.verts), length(f.fcs) ÷ 3, pointer(f.fcs),
+            length(f.λs), pointer(f.λs), length(f.ntab) ÷ length(f.λs), pointer(f.ntab), 1.0, f.norm_zero_rule, 0)
+        check(ccall((:bmo_system_upload, libbmo), Int32, (Ptr{Cvoid}, Ref{BmoTables}, Ref{Ptr{Cvoid}}), context(cs.device), t, sys))
+    end
+    return sys[]
+end
+
+"""
+    solve_system!(cs::CUDASystem, beams::AbstractVector{<:Beam}; r_max = 100, retrace = true)
+
+Replaces the serial loop of `src/System.jl:463-468`: all beams are traced in one call of
+`bmo_trace_rays`; `Spotdetector.data` receives the hits in ray order, and each `Beam` gets its
+segments back (`rays`, `children`) unless `rebuild = false` (throughput runs).
+"""
+function BeamletOptics.solve_system!(cs::CUDASystem, beams::AbstractVector{<:Beam{T,R}}; r_max = 100, retrace = true, rebuild = true) where {T,R}
+    λs = unique(Float64(wavelength(first(b.rays))) for b in beams)
+    f = flatten(cs, λs); sys = upload(cs, f)
+    n = length(beams)
+    pos = Matrix{Float64}(undef, 3, n); dir = similar(pos); lam = Vector{Int32}(undef, n)
+    E0 = R <: PolarizedRay ? Matrix{Float64}(undef, 6, n) : nothing
+    for (i, b) in enumerate(beams)
+        r = first(b.rays)
+        pos[:, i] .= position(r); dir[:, i] .= BeamletOptics.direction(r); lam[i] = findfirst(==(Float64(wavelength(r))), λs) - 1
+        E0 === nothing || (E0[:, i] .= reinterpret(Float64, collect(ComplexF64.(r.E0))))
+    end
+    res = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve pos dir lam E0 begin
+        check(ccall((:bmo_trace_rays, libbmo), Int32,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Int32, UInt32, Ref{Ptr{Cvoid}}),
+            sys, n, pos, dir, lam, E0 === nothing ? C_NULL : pointer(E0), C_NULL, r_max, rebuild ? KEEP_SEGMENTS : UInt32(0), res))
+    end
+    collect_spots!(f, res[])
+    rebuild && rebuild_beams!(beams, f, res[])
+    ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), res[])
+    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)
+    return nothing
+end
+BeamletOptics.solve_system!(cs::CUDASystem, bg::BeamletOptics.AbstractBeamGroup; kw...) = BeamletOptics.solve_system!(cs, BeamletOptics.beams(bg); kw...)
+BeamletOptics.solve_system!(cs::CUDASystem, b::Beam; kw...) = BeamletOptics.solve_system!(cs, [b]; kw...)
+
+"""GaussianBeamlets: `bmo_trace_beamlets`, then `bmo_pd_accumulate` adds into every `Photodetector.field`."""
+function BeamletOptics.solve_system!(cs::CUDASystem, gs::AbstractVector{<:GaussianBeamlet}; r_max = 100, retrace = true)
+    λs = unique(Float64(g.λ) for g in gs)
+    f = flatten(cs, λs); sys = upload(cs, f)
+    n = length(gs)
+    rays = Array{Float64}(undef, 6, 3, n)          # [pos; dir] x (chief, waist, divergence) x beamlet
+    for (i, g) in enumerate(gs), (k, b) in enumerate((g.chief, g.waist, g.divergence))
+        r = first(b.rays); rays[1:3, k, i] .= position(r); rays[4:6, k, i] .= BeamletOptics.direction(r)
+    end
+    lam = Int32[findfirst(==(Float64(g.λ)), λs) - 1 for g in gs]
+    w0 = Float64[g.w0 for g in gs]; E0 = ComplexF64[g.E0 for g in gs]
+    res = Ref{Ptr{Cvoid}}(C_NULL)
+    GC.@preserve rays lam w0 E0 begin
+        check(ccall((:bmo_trace_beamlets, libbmo), Int32,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{ComplexF64}, Ptr{Int32}, Int32, UInt32, Ref{Ptr{Cvoid}}),
+            sys, n, rays, lam, w0, E0, C_NULL, r_max, UInt32(0), res))
+    end
+    for (oi, o) in enumerate(f.leaves)
+        o isa Photodetector || continue
+        fld = o.field                                # Matrix{ComplexF64}, column-major [i, j]: exactly the ABI's layout
+        GC.@preserve fld check(ccall((:bmo_pd_accumulate, libbmo), Int32,
+            (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Ptr{ComplexF64}, UInt32), sys, res[], oi - 1, 0, fld, UInt32(0)))
+    end
+    collect_spots!(f, res[])
+    rebuild_beamlets!(gs, f, res[])
+    ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), res[])
+    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)
+    return nothing
+end
+BeamletOptics.solve_system!(cs::CUDASystem, g::GaussianBeamlet; kw...) = BeamletOptics.solve_system!(cs, [g]; kw...)
+
+function info(res)
+    i = Ref(BmoResultInfo(0, 0, 0, 0, 0, 0, 0, 0))
+    check(ccall((:bmo_result_get_info, libbmo), Int32, (Ptr{Cvoid}, Ref{BmoResultInfo}), res, i)); i[]
+end
+
+function collect_spots!(f, res)
+    nfo = info(res); n = nfo.n_beams * nfo.rays_per_beam
+    obj = Vector{Int32}(undef, n); xz = Matrix{Float64}(undef, 2, n)
+    check(ccall((:bmo_result_spots, libbmo), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}), res, obj, xz))
+    for i in 1:n                                        # roots first, children in spawn order
+        obj[i] >= 0 && push!(f.leaves[obj[i] + 1], Point2(xz[1, i], xz[2, i]))
+    end
+end
+
+# Beam trees from the segment table: bmo_result_beams (parent, child slot, nseg, first_seg) +
+# bmo_result_segments (pos, dir, n, t, normal, object, part); t = Inf <=> intersection === nothing.
+function rebuild_beams!(beams, f, res)
+    nfo = info(res); nb = nfo.n_beams
+    parent = Vector{Int32}(undef, nb); slot = similar(parent); nseg = similar(parent); status = similar(parent)
+    first_seg = Vector{Int64}(undef, nb)
+    check(ccall((:bmo_result_beams, libbmo), Int32,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
+        res, parent, slot, nseg, status, first_seg, C_NULL, C_NULL, C_NULL))
+    ns = info(res).n_segments
+    pos = Matrix{Float64}(undef, 3, ns); dir = similar(pos); nrm = similar(pos)
+    n = Vector{Float64}(undef, ns); t = similar(n); obj = Vector{Int32}(undef, ns); part = similar(obj)
+    check(ccall((:bmo_result_segments, libbmo), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
+        res, pos, dir, n, t, nrm, obj, part, C_NULL))
+    made = Vector{Any}(undef, nb)
+    for b in 1:nb
+        root = b <= length(beams)
+        λ = wavelength(first((root ? beams[b] : made[parent[b] + 1]).rays))
+        rays = map(first_seg[b] + 1:first_seg[b] + nseg[b]) do s
+            r = Ray(Point3(pos[:, s]...), Point3(dir[:, s]...), λ); r.dir = Point3(dir[:, s]...); r.n = n[s]
+            isfinite(t[s]) && (r.intersection = Intersection(t[s], Point3(nrm[:, s]...), f.leaves[obj[s] + 1], shape(f.owners[part[s] + 1])))
+            r
+        end
+        if root
+            beams[b].rays = rays; empty!(beams[b].children); made[b] = beams[b]
+        else
+            p = made[parent[b] + 1]; made[b] = Beam(rays, p, typeof(p)[]); push!(p.children, made[b])
+        end
+    end
+end
+rebuild_beamlets!(gs, f, res) = nothing   # same pattern with rays_per_beam == 3 and bmo_result_beams' w0 / E0 columns
+
+end # module
