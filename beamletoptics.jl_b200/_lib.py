@@ -28,7 +28,7 @@ class bmo_prim(C.Structure):
 
 class bmo_part(C.Structure):
     _fields_ = [("object", C.c_int32), ("role", C.c_int32), ("shape_kind", C.c_int32), ("first", C.c_int32), ("count", C.c_int32),
-                ("n_row", C.c_int32), ("reflectance", C.c_double), ("transmittance", C.c_double), ("bound", C.c_double * 4)]
+                ("n_row", C.c_int32), ("reflectance", C.c_double), ("transmittance", C.c_double), ("bound", C.c_double * 10)]
 
 
 class bmo_object(C.Structure):

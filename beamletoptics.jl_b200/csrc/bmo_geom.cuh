@@ -11,6 +11,7 @@ constexpr double eps_srf = 1e-9;   // SDFs/AbstractSDF.jl:1
 constexpr double eps_ray = 1e-10;  // :2
 constexpr double eps_ins = 1.0;    // :3
 constexpr int kMarchIter = 1000;   // :105,135
+constexpr int NBOUND = 10;         // doubles per part bound: sphere centre xyz + radius, box lo xyz + hi xyz
 
 struct BvhNode {
     double lo[3], hi[3];
@@ -34,7 +35,7 @@ struct SysView {
     const BvhNode* nodes;
     const int32_t* bvh_faces;
     const double* n_table;
-    const double* bounds;    // [n_poses][n_parts][4]
+    const double* bounds;    // [n_poses][n_parts][NBOUND]: sphere (centre, radius), box (lo, hi)
     const double* det_pose;  // [n_poses][n_objects][12] pos(3) dir(9 row-major)
     const double* lambdas;   // [n_lambda]
     int32_t n_prims, n_parts, n_objects, n_meshes, n_lambda, n_poses, zr, pad;
@@ -452,14 +453,14 @@ struct TraceCtx {
     int n_parts, zr;
     const bmo_prim* prims;   // prim table of this ray's pose (shared-memory copy when staged)
     const bmo_part* parts;   // part table (shared-memory copy when staged)
-    const double* bounds;    // [n_parts][4] bounding spheres of this ray's pose
+    const double* bounds;    // [n_parts][NBOUND] bounds of this ray's pose
     int pose;
 };
 // intersect3d(shape, ray)
 BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
     const bmo_part& pt = C.parts[part];
     if (pt.shape_kind == BMO_SHAPE_SDF) {
-        const double* bnd = C.bounds + 4 * part;
+        const double* bnd = C.bounds + NBOUND * part;
         SdfShape sh;
         sh.prims = C.prims; sh.first = pt.first; sh.count = pt.count; sh.zr = C.zr;
         sh.cx = bnd[0]; sh.cy = bnd[1]; sh.cz = bnd[2]; sh.R2 = bnd[3] * bnd[3];
@@ -470,6 +471,26 @@ BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st
     st.tri += tmp.tri;
     return hit;
 }
+// slab test of the ray (t >= 0) against an axis-aligned box, entry distance compared with t_best
+BMO_D bool box_may_hit(const double* bx, V3 o, V3 d, double t_best) {
+    double tmin = 0.0, tmax = INFINITY;
+    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (dd[k] == 0.0) {
+            if (oo[k] < bx[k] || oo[k] > bx[3 + k]) return false;
+        } else {
+            const double inv = 1.0 / dd[k];
+            double t1 = (bx[k] - oo[k]) * inv, t2 = (bx[3 + k] - oo[k]) * inv;
+            if (t1 > t2) { const double tt = t1; t1 = t2; t2 = tt; }
+            if (t1 > tmin) tmin = t1;
+            if (t2 < tmax) tmax = t2;
+        }
+    }
+    // 1e-9 relative slack for the rounding of the slab arithmetic (the box itself is inflated by 1e-6)
+    return tmin <= tmax * (1 + 1e-9) + 1e-12 && tmin * (1 - 1e-9) - 1e-9 <= t_best;
+}
+
 // tracing_step! (System.jl:57-110).  trace_one: the hinted shape is accepted without comparing
 // against other objects.  On a miss, trace_all: every object in Leaves order, strict-min t; inside an
 // object the parts in shape(object) order, strict-min t (AbstractRay.jl:118-155), except that a plate
@@ -491,7 +512,22 @@ BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& 
             if (it == n_parts) break;
         }
         double t; V3 n;
-        const bool hit = (it >= 0 && part == hint_part) ? false : part_intersect(C, part, pos, dir, st, t, n);
+        bool hit = false;
+        if (!(it >= 0 && part == hint_part)) {
+            // Result-identical cull: a hit point lies within 1e-10 of the part's surface, hence inside its
+            // (1e-6-inflated) box.  If the ray misses the box the part cannot be hit; if it enters the box
+            // only beyond the closest hit found so far, the part cannot win trace_all's strict `<`.
+            // (A plate beamsplitter's substrate / coating are never culled against the best hit: its
+            // coating is preferred on approximate equality, PlateBeamsplitter.jl:176-179.)
+            const double* bx = C.bounds + NBOUND * part + 4;
+            const bool plate = it >= 0 && C.objects[obj].kind == BMO_OBJ_PLATE_BS;
+            double t_best = INFINITY;          // closest hit so far: earlier objects (res) and earlier parts of this object (ob)
+            if (it >= 0 && !plate) {
+                if (res.part >= 0) t_best = res.t;
+                if (ob.part >= 0 && ob.t < t_best) t_best = ob.t;
+            }
+            if (box_may_hit(bx, pos, dir, t_best)) hit = part_intersect(C, part, pos, dir, st, t, n);
+        }
         if (it < 0) {
             if (hit) { res.t = t; res.n = n; res.part = part; return res; }
             continue;

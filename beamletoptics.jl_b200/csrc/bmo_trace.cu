@@ -105,7 +105,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
         src = reinterpret_cast<const double*>(S.parts);
         dst = reinterpret_cast<double*>(s_parts);
         for (int k = threadIdx.x; k < nq; k += IBLOCK) dst[k] = src[k];
-        for (int k = threadIdx.x; k < 4 * S.n_parts; k += IBLOCK) s_bounds[k] = S.bounds[k];
+        for (int k = threadIdx.x; k < NBOUND * S.n_parts; k += IBLOCK) s_bounds[k] = S.bounds[k];
         __syncthreads();
     }
 
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
         else {
             C.prims = S.prims + (int64_t)pose * S.n_prims;
             C.parts = S.parts;
-            C.bounds = S.bounds + 4 * (int64_t)pose * S.n_parts;
+            C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
         }
         Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
         if (budget) h = tracing_step(C, pos, dir, hint, st);   // System.jl:100-110
@@ -819,9 +819,9 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
         for (int k = 0; k < 3; k++) s->h_detpose[12 * o + k] = t->objects[o].pos[k];
         for (int k = 0; k < 9; k++) s->h_detpose[12 * o + 3 + k] = t->objects[o].dir[k];
     }
-    s->h_bounds.assign((size_t)4 * t->n_parts, 0.0);
+    s->h_bounds.assign((size_t)NBOUND * t->n_parts, 0.0);
     for (int p = 0; p < t->n_parts; p++)
-        for (int k = 0; k < 4; k++) s->h_bounds[4 * p + k] = t->parts[p].bound[k];
+        for (int k = 0; k < NBOUND; k++) s->h_bounds[NBOUND * p + k] = t->parts[p].bound[k];
     std::vector<double> ntab(t->n_table, t->n_table + (size_t)std::max(t->n_rows, 0) * t->n_lambda);
     if ((rc = upload(&s->d_prims, s->prims.data(), s->prims.size()))) return rc;
     if ((rc = upload(&s->d_parts, s->parts.data(), s->parts.size()))) return rc;
@@ -878,7 +878,7 @@ int32_t bmo_system_set_poses(bmo_sys* s, int32_t n_poses, const bmo_prim* prims,
         for (auto& pr : pp) pr.reserved = prim_flags(pr);
         if ((rc = reup(&s->d_prims, pp.data(), pp.size()))) return rc;
         if ((rc = reup(&s->d_vertices, vertices, np * 3 * (size_t)s->n_vertices))) return rc;
-        if ((rc = reup(&s->d_bounds, bounds, np * 4 * s->parts.size()))) return rc;
+        if ((rc = reup(&s->d_bounds, bounds, np * NBOUND * s->parts.size()))) return rc;
         std::vector<double> dp(np * 12 * s->objects.size());
         for (size_t i = 0; i < np * s->objects.size(); i++) {
             for (int k = 0; k < 3; k++) dp[12 * i + k] = det_pos[3 * i + k];
@@ -1049,7 +1049,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     const double tp1 = tnow();
     // small single-pose systems: prims / parts / bounds are staged through shared memory
     const SysView& V = sys->view;
-    const size_t table_bytes = (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + 4 * sizeof(double));
+    const size_t table_bytes = (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double));
     const bool staged = V.n_poses == 1 && table_bytes <= 40 * 1024;
     const size_t smem = staged ? table_bytes : 0;
 

@@ -24,7 +24,7 @@ _KIND = {"refractive": OBJ_REFRACTIVE, "mirror": OBJ_MIRROR, "thin_bs": OBJ_THIN
 _ROLES = {"plate_bs": (ROLE_SUBSTRATE, ROLE_COATING), "cube_bs": (ROLE_FRONT, ROLE_BACK, ROLE_COATING),
           "doublet": (ROLE_FRONT, ROLE_BACK)}
 
-BOUND_REL, BOUND_ABS = 1e-9, 1e-6   # inflation of the bounding spheres (see bmo_geom.cuh march_outside)
+BOUND_REL, BOUND_ABS = 1e-9, 1e-6   # inflation of the bounding spheres / boxes (see bmo_geom.cuh sdf_intersect_f, tracing_step)
 
 
 def _prim_record(s):
@@ -102,7 +102,10 @@ class FlatSystem:
                 else:
                     raise TypeError(f"unsupported shape {type(shape).__name__}")
                 c, r = shape.local_bound()
-                pr.bound[:] = (c[0], c[1], c[2], r * (1 + BOUND_REL) + BOUND_ABS)
+                lo, hi = sh._box_of(shape.box_points())        # world AABB of everything with sdf <= 0 / of the mesh
+                pad = [BOUND_ABS + BOUND_REL * max(abs(lo[k]), abs(hi[k])) for k in range(3)]
+                pr.bound[:] = (c[0], c[1], c[2], r * (1 + BOUND_REL) + BOUND_ABS,
+                               lo[0] - pad[0], lo[1] - pad[1], lo[2] - pad[2], hi[0] + pad[0], hi[1] + pad[1], hi[2] + pad[2])
                 if hasattr(s_obj, "refractive_index"):
                     pr.n_row = len(ntab)
                     ntab.append([float(s_obj.refractive_index(lam)) for lam in self.lambdas])

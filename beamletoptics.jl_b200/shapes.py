@@ -108,6 +108,24 @@ class PrimSDF(AbstractSDF):
     def sag(self):
         return self.par[2]
 
+    def local_box(self):
+        """Axis-aligned box, in the primitive's own frame, that contains every point with sdf <= 0."""
+        a, b, c, d = self.par
+        t = self.type
+        if t == PLANO: return (-b / 2, 0.0, -b / 2), (b / 2, a, b / 2)
+        if t == CYLINDER: return (-a, -b, -a), (a, b, a)
+        if t in (SPHERE, CUTSPHERE): return (-a, -a, -a), (a, a, a)
+        if t == CONVEX: return (-b / 2, 0.0, -b / 2), (b / 2, c, b / 2)          # cap between the vertex y = 0 and y = sag
+        if t == CONCAVE: return (-b / 2, -c, -b / 2), (b / 2, 0.0, b / 2)        # cylinder slab y in [-sag, 0] minus the sphere
+        if t in (BOX, RAPRISM): return (-a, -b, -c), (a, b, c)
+        if t == RING: return (-(a + b), -c, -(a + b)), (a + b, c, a + b)
+        raise ValueError(t)
+
+    def box_points(self):
+        """Corners of local_box() in the frame this shape's pose maps to (world for top-level shapes)."""
+        lo, hi = self.local_box()
+        return [la.add(self.pos, la.matvec(self.dir, q)) for q in _corners(lo, hi)]
+
     def local_bound(self):
         a, b, c, d = self.par
         t = self.type
@@ -148,6 +166,14 @@ def CutSphereSDF(radius, height):                  # PrimitiveSDF.jl:97-110
     return PrimSDF(CUTSPHERE, (radius, height, math.sqrt(radius * radius - height * height)))
 
 
+def _corners(lo, hi):
+    return [(x, y, z) for x in (lo[0], hi[0]) for y in (lo[1], hi[1]) for z in (lo[2], hi[2])]
+
+
+def _box_of(points):
+    return (tuple(min(q[k] for q in points) for k in range(3)), tuple(max(q[k] for q in points) for k in range(3)))
+
+
 def _enclose(spheres):
     n = len(spheres)
     c = tuple(sum(s[0][k] for s in spheres) / n for k in range(3))
@@ -170,6 +196,10 @@ class MeniscusLensSDF(AbstractSDF):
     def local_bound(self):
         c, r = _enclose([self.convex.local_bound(), self.cylinder.local_bound()])
         return la.add(self.pos, la.matvec(self.dir, c)), r
+
+    def box_points(self):   # max(min(convex, cylinder), -concave) <= min(convex, cylinder): inside convex or cylinder
+        pts = self.convex.box_points() + self.cylinder.box_points()
+        return [la.add(self.pos, la.matvec(self.dir, q)) for q in pts]
 
 
 class UnionSDF(AbstractSDF):
@@ -205,6 +235,9 @@ class UnionSDF(AbstractSDF):
 
     def local_bound(self):
         return _enclose([s.local_bound() for s in self.sdfs])
+
+    def box_points(self):
+        return [q for s in self.sdfs for q in s.box_points()]
 
 
 def ThinLensSDF(r1, r2, d=25.4e-3):   # SphericalLensSDF.jl:245-253
@@ -279,6 +312,10 @@ class Mesh(AbstractShape):
         c = self.vertices.mean(axis=0)
         r = float(np.sqrt(((self.vertices - c) ** 2).sum(axis=1)).max())
         return tuple(float(x) for x in c), r
+
+    def box_points(self):
+        lo, hi = self.vertices.min(axis=0), self.vertices.max(axis=0)
+        return [tuple(float(x) for x in lo), tuple(float(x) for x in hi)]
 
 
 def RectangularFlatMesh(width, height):   # Mesh.jl:282-303

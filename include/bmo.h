@@ -69,8 +69,10 @@ typedef struct bmo_part {
     int32_t n_row;       /* row of n_table for refractive parts, else -1                          */
     double reflectance;  /* coating amplitudes sqrt(R), sqrt(1-R^2)  (ThinBeamsplitter.jl:43-51)   */
     double transmittance;
-    double bound[4];     /* conservative world-space bounding sphere (centre, radius); only used for
-                            result-identical early exits of guaranteed misses                     */
+    double bound[10];    /* conservative world-space bounds of the part: sphere (centre xyz, radius) and
+                            axis-aligned box (lo xyz, hi xyz), both inflated; only used for
+                            result-identical early exits (guaranteed misses, parts that cannot beat
+                            the closest hit found so far)                                         */
 } bmo_part;
 
 /* ---- objects in `Leaves(system.objects)` order (tie-break order of trace_all, System.jl:57-72).
@@ -157,7 +159,7 @@ int32_t bmo_counters_reset(bmo_ctx* ctx);
 int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* tables, bmo_sys** sys);
 int32_t bmo_system_free(bmo_sys* sys);
 /* Batched kinematic poses (replaces translate3d!/rotate3d! between solves, AbstractShape.jl:56-94,
- * Mesh.jl:78-96): pose p uses prims[p*n_prims ...], vertices[p*n_vertices ...], bounds[p*n_parts*4 ...].
+ * Mesh.jl:78-96): pose p uses prims[p*n_prims ...], vertices[p*n_vertices ...], bounds[p*n_parts*10 ...].
  * Rays select their pose with pose_id.  n_poses = 1 restores the uploaded tables.                */
 int32_t bmo_system_set_poses(bmo_sys* sys, int32_t n_poses, const bmo_prim* prims, const double* vertices,
                              const double* bounds, const double* det_pos /* [n_poses][n_objects][3] */,
