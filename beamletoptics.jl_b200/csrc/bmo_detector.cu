@@ -17,6 +17,7 @@
 //       (tilted detectors, Beam.jl:186-199) take the reference-order path below.
 //   pd_field (BMO_PD_REFERENCE_ORDER)  every pair evaluated in the reference's operation order;
 //       kept as the cross-check of the fast kernel at full detector sizes.
+#include <cstdlib>
 #include "bmo_host.cuh"
 #include "bmo_interact.cuh"
 
@@ -258,16 +259,33 @@ __global__ void __launch_bounds__(PD_TILE* PD_TILE) pd_field(const PdParams P) {
     }
 }
 
-// sincos of a large phase: Cody-Waite reduction by 2 pi (two FMAs, exact for |x| < 2^50 / ...) keeps
-// CUDA's sincos on its fast path (its own slow path starts at |x| > 105615)
+// sincos of a large phase (k z is O(1e7) rad; CUDA's sincos leaves its fast path at |x| > 105615):
+// Cody-Waite reduction by pi/2 with two FMAs (n < 2^31, residual error n * 1.5e-33), then the
+// fdlibm minimax kernels on [-pi/4, pi/4] (error < 1 ulp) and the quadrant swap.
 BMO_D void sincos_reduced(double x, double* sn, double* cs) {
-    const double n = rint(x * 0.15915494309189535);
-    double r = fma(n, -6.283185307179586, x);
-    r = fma(n, -2.4492935982947064e-16, r);
-    sincos(r, sn, cs);
+    const double n = rint(x * 0.6366197723675814);          // 2 / pi
+    double r = fma(n, -1.5707963267948966, x);              // pi/2 hi
+    r = fma(n, -6.123233995736766e-17, r);                  // pi/2 lo
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s0 = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int q = (int)(long long)n;
+    const double sv = (q & 1) ? c0 : s0, cv = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -sv : sv;
+    *cs = ((q + 1) & 2) ? -cv : cv;
 }
 
-constexpr int PDF_TX = 32, PDF_TY = 8, PDF_PX = 2;   // 32 x 16 pixels per block, 2 pixels (rows j, j + 8) per thread
+constexpr int PDF_TX = 32, PDF_TY = 8;   // 256 threads; each thread owns PX pixels (rows j, j + 8, ...) of a 32 x (8 PX) tile
 constexpr int PDF_BATCH = 48;                        // beamlet records per shared-memory tile
 
 BMO_D Cx pd_pair_fast(const PdFast& rc, V3 p1, bool& slow) {
@@ -283,28 +301,33 @@ BMO_D Cx pd_pair_fast(const PdFast& rc, V3 p1, bool& slow) {
     const double ywx = rc.Aw[0] + s * rc.Bw[0], ywy = rc.Aw[1] + s * rc.Bw[1], ywz = rc.Aw[2] + s * rc.Bw[2];
     const double y2d = ydx * ydx + ydy * ydy + ydz * ydz, y2w = ywx * ywx + ywy * ywy + ywz * ywz;
     const double nd = rc.alpd + s * rc.betd, nw = rc.alpw + s * rc.betw;
-    double c2d = (nd * nd) / y2d, c2w = (nw * nw) / y2w;       // cos^2 of the angle between height vector and ray (NaN at y = 0)
+    // cos^2 of the angle between height vector and ray, c_r^2 = n_r^2 / y_r^2: one reciprocal serves both
+    // (NaN at y = 0, like the reference's y0 / 0)
+    const double ip = 1.0 / (y2d * y2w);
+    double c2d = (nd * nd) * (y2w * ip), c2w = (nw * nw) * (y2d * ip);
     c2d = c2d > 1.0 ? 1.0 : c2d; c2w = c2w > 1.0 ? 1.0 : c2w;  // clamp of angle3d (LinearAlgebraUtils.jl:103-108)
     const double id = rsqrt(1.0 - c2d), iw = rsqrt(1.0 - c2w);
     const double E = nd * id + nw * iw;                          // E_kt = y_d m_d + y_w m_w
     const double F2 = c2d * (id * id) + c2w * (iw * iw);         // F_kt^2 = m_d^2 + m_w^2
-    const double w2 = y2d + y2w;
-    const double iw2 = 1.0 / w2;
+    const double rw = rsqrt(y2d + y2w);                          // 1 / w
+    const double iw2 = rw * rw;
     double R = E * iw2;                                          // curvature E_kt / w^2
-    double t = (E * E) * iw2 / F2;                               // R * zeta in [0, 1]
-    t = t > 1.0 ? 1.0 : t;
-    double cpsi = sqrt(1.0 - t), spsi = sqrt(t);                 // psi = -atan2(1, sqrt(1/t - 1))
+    // psi = -atan2(1, sqrt(1/(R zeta) - 1)), R zeta = E^2 / (w^2 F^2):  sin|psi| = |E| / (w F), cos psi = sqrt(1 - sin^2)
+    double spsi = fabs(E) * rw * rsqrt(F2);
+    spsi = spsi > 1.0 ? 1.0 : spsi;
+    double cpsi = sqrt(1.0 - spsi * spsi);
     if (!(R < 0.0)) spsi = -spsi;                                // R < 0 flips the sign of psi
     if (isnan(R)) R = 0.0;                                       // Gaussian.jl:348-351
-    if (isnan(t)) { cpsi = 1.0; spsi = 0.0; }
-    const double amp = sqrt(iw2) * exp(-r2 * iw2);               // (w0 / w) exp(-r^2/w^2) with w0 cancelled against E0
+    if (isnan(spsi) || isnan(cpsi)) { cpsi = 1.0; spsi = 0.0; }
+    const double amp = rw * exp(-r2 * iw2);                      // (w0 / w) exp(-r^2/w^2) with w0 cancelled against E0
     double sn, cs;
     sincos_reduced(rc.k * z + (rc.k * r2 * R) * 0.5, &sn, &cs);
     const double re = cs * cpsi - sn * spsi, im = sn * cpsi + cs * spsi;
     return mkc((rc.cre * re - rc.cim * im) * amp, (rc.cre * im + rc.cim * re) * amp);
 }
 
-__global__ void __launch_bounds__(PDF_TX* PDF_TY, 2) pd_field_fast(const PdParams P) {
+template <int PDF_PX, int MINB>
+__global__ void __launch_bounds__(PDF_TX* PDF_TY, MINB) pd_field_fast(const PdParams P) {
     __shared__ PdFast s_rec[PDF_BATCH];
     const int tid = threadIdx.y * PDF_TX + threadIdx.x;
     const int i = blockIdx.x * PDF_TX + threadIdx.x;
@@ -479,8 +502,17 @@ static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t po
             dim3 grid((n + PD_TILE - 1) / PD_TILE, (n + PD_TILE - 1) / PD_TILE, n_fields), block(PD_TILE, PD_TILE);
             pd_field<<<grid, block, 0, st>>>(pp);
         } else {
-            dim3 grid((n + PDF_TX - 1) / PDF_TX, (n + PDF_TY * PDF_PX - 1) / (PDF_TY * PDF_PX), n_fields), block(PDF_TX, PDF_TY);
-            pd_field_fast<<<grid, block, 0, st>>>(pp);
+            static const int variant = getenv("BMO_PD_VARIANT") ? atoi(getenv("BMO_PD_VARIANT")) : 14;   // tuning knob: 10*PX + MINB
+            const int px = (variant == 22 || variant == 24) ? 2 : 1;
+            dim3 grid((n + PDF_TX - 1) / PDF_TX, (n + PDF_TY * px - 1) / (PDF_TY * px), n_fields), block(PDF_TX, PDF_TY);
+            switch (variant) {
+                case 13: pd_field_fast<1, 3><<<grid, block, 0, st>>>(pp); break;
+                case 15: pd_field_fast<1, 5><<<grid, block, 0, st>>>(pp); break;
+                case 16: pd_field_fast<1, 6><<<grid, block, 0, st>>>(pp); break;
+                case 22: pd_field_fast<2, 2><<<grid, block, 0, st>>>(pp); break;
+                case 24: pd_field_fast<2, 4><<<grid, block, 0, st>>>(pp); break;
+                default: pd_field_fast<1, 4><<<grid, block, 0, st>>>(pp); break;
+            }
         }
         BMO_CUDA(cudaEventRecord(ctx->evk1, st));
         ctx->launches++;

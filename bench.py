@@ -264,7 +264,7 @@ def main():
 
 
 FLOP_PAIR_REF = 760.0   # flop-equivalents per pixel-beamlet pair in the reference's operation sequence
-FLOP_PAIR = 245.0       # the same weights (add/mul 1, sqrt/div 8, transcendental 40) over the strength-reduced sequence of
+FLOP_PAIR = 226.0       # the same weights (add/mul 1, sqrt/div 8, transcendental 40) over the strength-reduced sequence of
                         # pd_field_fast, counted op by op in DESIGN.md "K4" -- the work the kernel actually has to do
 
 
