@@ -28,12 +28,13 @@ struct bmo_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr, evk0 = nullptr, evk1 = nullptr, evs0 = nullptr, evs1 = nullptr;
-    std::vector<cudaEvent_t> wave_ev;   // (start, stop) of intersect_wave for each wave of a chunk
+    std::vector<cudaEvent_t> ev_pool;        // 10 events per sub-batch slot
+    std::vector<cudaStream_t> aux_streams;   // streams of the sub-batches of a pipelined trace call (created on demand)
     double k1_ms = 0, k3_ms = 0, k3_bytes = 0, k4_ms = 0;  // accumulated device time of trace_step / scatter_queue / pd_field
     int64_t k1_launches = 0, interactions_seen = 0;
     bmo::DevCounters* d_counters = nullptr;
     long long* d_totals = nullptr;   // [4] scratch for scans
-    long long* h_totals = nullptr;   // pinned, 16 entries
+    long long* h_totals = nullptr;   // pinned, 8 entries for the scans + 8 per sub-batch slot
     int64_t waves = 0, launches = 0, px_beamlets = 0;
     double trace_ms = 0, pd_ms = 0;
     int sm_count = 148;

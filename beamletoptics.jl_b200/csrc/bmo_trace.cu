@@ -611,7 +611,7 @@ __global__ void __launch_bounds__(CBLOCK) compact_scatter(Queue src, Queue dst, 
 // ---- init / gather ---------------------------------------------------------------------------------
 struct InitParams {
     Queue q;
-    int64_t n;
+    int64_t n, beam0;   // beam0: global id of this sub-batch's first root beam
     int mode;
     const double *pos, *dir, *E0, *grays, *w0, *ge0;
     const int32_t *lam, *pose;
@@ -639,11 +639,12 @@ __global__ void init_queue(const InitParams P) {
     d[F_N * s + i] = 1.0;  // Ray(pos, dir, lambda): n = 1 (Rays.jl:32-42)
     int32_t* q = P.q.i;
     const int lam = P.lam ? P.lam[u] : 0, pose = P.pose ? P.pose[u] : 0;
-    q[I_LAM * s + i] = lam; q[I_HINT * s + i] = -1; q[I_BEAM * s + i] = (int)u; q[I_SEG * s + i] = 0; q[I_POSE * s + i] = pose;
-    P.B.spot_obj[i] = -1;
+    const int64_t g = P.beam0 + u;   // global beam id; inputs are this sub-batch's slices, tables are global
+    q[I_LAM * s + i] = lam; q[I_HINT * s + i] = -1; q[I_BEAM * s + i] = (int)g; q[I_SEG * s + i] = 0; q[I_POSE * s + i] = pose;
+    P.B.spot_obj[g * R + r] = -1;
     if (r == 0) {
-        P.B.parent[u] = -1; P.B.slot[u] = -1; P.B.nseg[u] = 0; P.B.status[u] = BMO_ST_ACTIVE; P.B.lam[u] = lam; P.B.pose[u] = pose;
-        if (P.mode == 2) { P.B.w0[u] = P.w0[u]; P.B.e0[2 * u] = P.ge0[2 * u]; P.B.e0[2 * u + 1] = P.ge0[2 * u + 1]; P.B.plen[u] = 0; P.B.popl[u] = 0; }
+        P.B.parent[g] = -1; P.B.slot[g] = -1; P.B.nseg[g] = 0; P.B.status[g] = BMO_ST_ACTIVE; P.B.lam[g] = lam; P.B.pose[g] = pose;
+        if (P.mode == 2) { P.B.w0[g] = P.w0[u]; P.B.e0[2 * g] = P.ge0[2 * u]; P.B.e0[2 * g + 1] = P.ge0[2 * u + 1]; P.B.plen[g] = 0; P.B.popl[g] = 0; }
     }
 }
 __global__ void gather_segments(WaveBuf w, int R, int nsd, const long long* first_seg, double* seg_d, int32_t* seg_part, int64_t rows) {
@@ -695,7 +696,7 @@ int32_t bmo_init(int32_t device, bmo_ctx** out) {
     BMO_CUDA(cudaMalloc((void**)&c->d_counters, sizeof(DevCounters)));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     BMO_CUDA(cudaMalloc((void**)&c->d_totals, 4 * sizeof(long long)));
-    BMO_CUDA(cudaMallocHost((void**)&c->h_totals, 16 * sizeof(long long)));
+    BMO_CUDA(cudaMallocHost((void**)&c->h_totals, 8 * 9 * sizeof(long long)));   // scans + 8 sub-batch slots
     cudaMemPool_t pool;
     BMO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;  // keep freed blocks cached: the wave loop reuses them every call
@@ -999,8 +1000,235 @@ template <class T> static int32_t stage_in(const T* h, size_t n, bool on_device,
     return BMO_OK;
 }
 
-static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int32_t r_max, uint32_t flags, bmo_result** out) {
-    if (!sys || !out) return fail(BMO_EINVAL, "trace: NULL argument");
+// One sub-batch of a trace call: a contiguous range of root beams with its own queue, hit buffer and
+// stream.  Device-resident inputs and systems with beamsplitters use a single sub-batch; host inputs of
+// splitter-free systems are cut into several, so that the host->device copy of batch k+1 and the
+// device->host copy of the Spotdetector hits of batch k-1 overlap the waves of batch k (rays are
+// independent; without splitters beam ids are the ray indices, so the sub-batches write disjoint
+// slices of the result tables).
+struct SubTrace {
+    bmo_sys* sys = nullptr; bmo_ctx* ctx = nullptr; bmo_result* res = nullptr;
+    cudaStream_t st = nullptr;
+    int mode = 0, R = 1, nfq = 0, nfs = 0, nsd = 0, units = 0;
+    int32_t r_max = 0;
+    bool has_splitter = false, staged = false, on_dev = false, pipelined = false;
+    int64_t beam0 = 0, n = 0;              // global id of the first root beam, number of root beams
+    TraceInputs in{};                      // device pointers of this sub-batch's inputs
+    std::vector<void*> tmp;                // staged input copies
+    Queue cur, next, scr;
+    HitBuf hit;
+    int32_t* blk_cnt = nullptr; long long* blk_off = nullptr; int64_t blk_cap = 0;
+    unsigned long long* d_wtot = nullptr;  // [r_max + 8][2]: units alive after wave w, spawn events of wave w
+    unsigned long long* h_wtot = nullptr;  // pinned, 2 * 4 entries
+    long long* d_scan_tot = nullptr;       // scratch total of scan_counts
+    std::vector<cudaEvent_t> ev;           // (start, stop) of intersect_wave for each wave of a chunk
+    cudaEvent_t evs0 = nullptr, evs1 = nullptr;
+    int64_t n_slots = 0, alive = 0, n_beams = 0;
+    int wave = 0, waves_done = 0, launched = 0, slot = 0;
+    int32_t* spot_obj_out = nullptr; double* spot_xz_out = nullptr;   // host destinations of the Spotdetector hits (optional)
+    double host_wait_ms = 0;
+
+    int32_t begin(const TraceInputs& in_h);
+    int32_t enqueue_chunk();
+    int32_t finish_chunk();
+    void release();
+};
+
+static double tnow_ms() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+int32_t SubTrace::begin(const TraceInputs& in_h) {
+    int32_t rc;
+    in = in_h;
+    const int64_t o = beam0;
+    if (mode == 2) {
+        if ((rc = stage_in(in_h.grays ? in_h.grays + o * 18 : nullptr, (size_t)n * 18, on_dev, st, &in.grays, tmp))) return rc;
+        if ((rc = stage_in(in_h.w0 ? in_h.w0 + o : nullptr, (size_t)n, on_dev, st, &in.w0, tmp))) return rc;
+        if ((rc = stage_in(in_h.ge0 ? in_h.ge0 + o * 2 : nullptr, (size_t)n * 2, on_dev, st, &in.ge0, tmp))) return rc;
+    } else {
+        if ((rc = stage_in(in_h.pos + o * 3, (size_t)n * 3, on_dev, st, &in.pos, tmp))) return rc;
+        if ((rc = stage_in(in_h.dir + o * 3, (size_t)n * 3, on_dev, st, &in.dir, tmp))) return rc;
+        if (mode == 1 && (rc = stage_in(in_h.E0 + o * 6, (size_t)n * 6, on_dev, st, &in.E0, tmp))) return rc;
+    }
+    if ((rc = stage_in(in_h.lam ? in_h.lam + o : nullptr, (size_t)n, on_dev, st, &in.lam, tmp))) return rc;
+    if ((rc = stage_in(in_h.pose ? in_h.pose + o : nullptr, (size_t)n, on_dev, st, &in.pose, tmp))) return rc;
+    if ((rc = alloc_queue(cur, n * R, nfq, NI_Q, st))) return rc;
+    InitParams ip{};
+    ip.q = cur; ip.n = n; ip.beam0 = beam0; ip.mode = mode; ip.pos = in.pos; ip.dir = in.dir; ip.E0 = in.E0; ip.grays = in.grays;
+    ip.w0 = in.w0; ip.ge0 = in.ge0; ip.lam = in.lam; ip.pose = in.pose; ip.B = beamtab(res);
+    const int64_t tot = n * R;
+    init_queue<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ip);
+    BMO_LAUNCH(ctx, "init_queue");
+    const int max_chunk = has_splitter ? 1 : 4;
+    // events and the pinned read-back slots come from per-context pools (slot = index of the sub-batch)
+    const size_t e0 = (size_t)slot * 10;
+    while (ctx->ev_pool.size() < e0 + 10) {
+        cudaEvent_t e;
+        BMO_CUDA(cudaEventCreate(&e));
+        ctx->ev_pool.push_back(e);
+    }
+    ev.assign(ctx->ev_pool.begin() + e0, ctx->ev_pool.begin() + e0 + 2 * max_chunk);
+    evs0 = ctx->ev_pool[e0 + 8]; evs1 = ctx->ev_pool[e0 + 9];
+    const size_t n_wtot = (size_t)2 * (r_max + 8);
+    BMO_CUDA(dev_alloc(&d_wtot, n_wtot, st));
+    BMO_CUDA(cudaMemsetAsync(d_wtot, 0, n_wtot * sizeof(unsigned long long), st));
+    BMO_CUDA(dev_alloc(&d_scan_tot, 4, st));
+    h_wtot = (unsigned long long*)ctx->h_totals + 8 * (1 + slot);   // slot 0 of h_totals stays with the scans
+    n_slots = n; alive = n; n_beams = 0;   // n_beams is only meaningful for the single sub-batch of splitter systems (set by the caller)
+    return BMO_OK;
+}
+
+// enqueue the next waves on this sub-batch's stream and the read-back of their totals
+int32_t SubTrace::enqueue_chunk() {
+    int32_t rc;
+    launched = 0;
+    // waves per look at the device: 1 (most rays that miss everything die on the first wave, so the
+    // compaction decision is worth an early look), then 3, then 4, 4, ...
+    // (pipelined sub-batches enqueue 4 at once: an idle stream costs more than a late compaction)
+    const int chunk = has_splitter ? 1 : (pipelined ? 4 : (wave == 0 ? 1 : (wave == 1 ? 3 : 4)));
+    for (int c = 0; c < chunk; c++) {
+        const int64_t nblocks = (n_slots + units - 1) / units;
+        if (has_splitter) {
+            // every live unit may add one unit (the reflected child) and two beams in this wave
+            if (cur.cap < (n_slots + alive) * R) {
+                if ((rc = grow_queue(cur, 2 * (n_slots + alive) * R, nfq, NI_Q, st))) return rc;
+            }
+            const int64_t scr_cap = nblocks * 2 * units * R;
+            if (scr.cap < scr_cap) { free_queue(scr, st); if ((rc = alloc_queue(scr, scr_cap, nfs, NI_S, st))) return rc; }
+            if ((rc = ensure_beams(res, n_beams + 2 * alive, st))) return rc;
+        }
+        if (blk_cap < nblocks) {
+            dev_free(blk_cnt, st); dev_free(blk_off, st);
+            BMO_CUDA(dev_alloc(&blk_cnt, (size_t)nblocks, st));
+            BMO_CUDA(dev_alloc(&blk_off, (size_t)nblocks, st));
+            blk_cap = nblocks;
+        }
+        WaveBuf wb{};
+        if (res->keep) {
+            wb.count = n_slots * R;
+            BMO_CUDA(dev_alloc(&wb.d, (size_t)nsd * wb.count, st));
+            BMO_CUDA(dev_alloc(&wb.part, (size_t)wb.count, st));
+            BMO_CUDA(dev_alloc(&wb.beam, (size_t)wb.count, st));
+            BMO_CUDA(dev_alloc(&wb.seg, (size_t)wb.count, st));
+            res->wavebufs.push_back(wb);
+        }
+        if (hit.cap < n_slots * R) {
+            dev_free(hit.d, st); dev_free(hit.part, st);
+            hit.cap = n_slots * R;
+            BMO_CUDA(dev_alloc(&hit.d, (size_t)4 * hit.cap, st));
+            BMO_CUDA(dev_alloc(&hit.part, (size_t)hit.cap, st));
+        }
+        IntersectParams xp{};
+        xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = n_slots * R; xp.r_max = r_max;
+        xp.counters = ctx->d_counters;
+        BMO_CUDA(cudaEventRecord(ev[2 * c], st));
+        {
+            static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 6;   // tuning knob: resident blocks per SM the kernel is compiled for
+            const SysView& V = sys->view;
+            const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
+            const unsigned grid = (unsigned)((n_slots * R + IBLOCK - 1) / IBLOCK);
+            if (!staged) intersect_wave<4, false><<<grid, IBLOCK, 0, st>>>(xp);
+            else if (minb <= 3) intersect_wave<3, true><<<grid, IBLOCK, smem, st>>>(xp);
+            else if (minb == 4) intersect_wave<4, true><<<grid, IBLOCK, smem, st>>>(xp);
+            else if (minb == 5) intersect_wave<5, true><<<grid, IBLOCK, smem, st>>>(xp);
+            else if (minb <= 7) intersect_wave<6, true><<<grid, IBLOCK, smem, st>>>(xp);
+            else intersect_wave<8, true><<<grid, IBLOCK, smem, st>>>(xp);
+        }
+        BMO_LAUNCH(ctx, "intersect_wave");
+        BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
+        StepParams sp{};
+        sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
+        sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
+        if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+        else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
+        else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
+        BMO_LAUNCH(ctx, "interact_wave");
+        wave++;
+        launched++;
+        if (wave > r_max + 1) break;
+    }
+    BMO_CUDA(cudaMemcpyAsync(h_wtot, d_wtot + 2 * (wave - launched), (size_t)2 * launched * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    return BMO_OK;
+}
+
+// one look at the device: units alive / spawn events of the waves just launched; children, compaction
+int32_t SubTrace::finish_chunk() {
+    int32_t rc;
+    const double tw0 = tnow_ms();
+    BMO_CUDA(cudaStreamSynchronize(st));
+    host_wait_ms += tnow_ms() - tw0;
+    int64_t prev_alive = alive;
+    for (int c = 0; c < launched; c++) {
+        if (prev_alive > 0) {       // waves launched on an already empty queue are no-ops and not counted
+            float kms = 0;
+            BMO_CUDA(cudaEventElapsedTime(&kms, ev[2 * c], ev[2 * c + 1]));
+            ctx->k1_ms += kms; ctx->k1_launches++;
+            waves_done++;
+        }
+        prev_alive = (int64_t)h_wtot[2 * c];
+    }
+    alive = (int64_t)h_wtot[2 * (launched - 1)];
+    const int64_t spawns = (int64_t)h_wtot[2 * (launched - 1) + 1];   // chunk == 1 whenever spawns are possible
+    if (spawns > 0) {
+        const int64_t nblocks = (n_slots + units - 1) / units;
+        scan_counts<<<1, 1024, 0, st>>>(blk_cnt, nblocks, 1, 1, blk_off, d_scan_tot);
+        BMO_LAUNCH(ctx, "scan_counts");
+        SpawnParams cp{};
+        cp.scr = scr; cp.q = cur; cp.blk_cnt = blk_cnt; cp.blk_off = blk_off; cp.B = beamtab(res); cp.n_beams = n_beams; cp.n_slots = n_slots;
+        cp.nf = nfq; cp.mode = mode; cp.units = units; cp.R = R;
+        spawn_children<<<(unsigned)nblocks, 256, 0, st>>>(cp);
+        BMO_LAUNCH(ctx, "spawn_children");
+        n_slots += spawns;
+        n_beams += 2 * spawns;
+    }
+    // K3: squeeze the dead slots out once they are the majority
+    if (alive > 0 && 2 * alive <= n_slots && n_slots >= 4096) {
+        const int64_t cblocks = (n_slots + CBLOCK - 1) / CBLOCK;
+        if (blk_cap < cblocks) {
+            dev_free(blk_cnt, st); dev_free(blk_off, st);
+            BMO_CUDA(dev_alloc(&blk_cnt, (size_t)cblocks, st));
+            BMO_CUDA(dev_alloc(&blk_off, (size_t)cblocks, st));
+            blk_cap = cblocks;
+        }
+        const int64_t want = has_splitter ? 2 * alive * R : alive * R;
+        if (next.cap < want) { free_queue(next, st); if ((rc = alloc_queue(next, want, nfq, NI_Q, st))) return rc; }
+        BMO_CUDA(cudaEventRecord(evs0, st));
+        compact_count<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur.i, cur.cap, n_slots, R, blk_cnt);
+        BMO_LAUNCH(ctx, "compact_count");
+        scan_counts<<<1, 1024, 0, st>>>(blk_cnt, cblocks, 1, 1, blk_off, d_scan_tot);
+        BMO_LAUNCH(ctx, "scan_counts");
+        compact_scatter<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur, next, n_slots, R, nfq, blk_off);
+        BMO_LAUNCH(ctx, "compact_scatter");
+        BMO_CUDA(cudaEventRecord(evs1, st));
+        BMO_CUDA(cudaStreamSynchronize(st));
+        float sms = 0;
+        BMO_CUDA(cudaEventElapsedTime(&sms, evs0, evs1));
+        ctx->k3_ms += sms;
+        // algorithmic bytes: the alive flag of every slot, then read + write of every surviving ray
+        ctx->k3_bytes += (double)n_slots * 4 * 2 + (double)alive * R * 2.0 * (nfq * 8 + NI_Q * 4);
+        std::swap(cur, next);
+        n_slots = alive;
+    }
+    if (alive == 0 && spot_xz_out) {   // this sub-batch is done: its Spotdetector hits go home while the others still trace
+        const int64_t o = beam0 * R, m = n * R;
+        if (spot_obj_out) BMO_CUDA(cudaMemcpyAsync(spot_obj_out + o, res->spot_obj + o, (size_t)m * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        BMO_CUDA(cudaMemcpyAsync(spot_xz_out + 2 * o, res->spot_xz + 2 * o, (size_t)2 * m * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    return BMO_OK;
+}
+
+void SubTrace::release() {
+    free_queue(cur, st); free_queue(next, st); free_queue(scr, st);
+    dev_free(hit.d, st); dev_free(hit.part, st);
+    dev_free(blk_cnt, st); dev_free(blk_off, st);
+    dev_free(d_wtot, st); dev_free(d_scan_tot, st);
+    for (void* p : tmp) cudaFreeAsync(p, st);
+    tmp.clear();
+    ev.clear();
+}
+
+static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int32_t r_max, uint32_t flags, bmo_result** out,
+                            int32_t* spot_obj_out = nullptr, double* spot_xz_out = nullptr) {
+    if (!sys) return fail(BMO_EINVAL, "trace: NULL argument");
     if (in_h.n <= 0) return fail(BMO_EINVAL, "trace: n must be > 0");
     if (r_max < 1) return fail(BMO_EINVAL, "trace: r_max must be >= 1");
     bmo_ctx* ctx = sys->ctx;
@@ -1008,203 +1236,87 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     cudaStream_t st = ctx->stream;
     const bool on_dev = flags & BMO_INPUT_DEVICE;
     const int R = mode == 2 ? 3 : 1;
-    const int nfq = nf_queue(mode), nfs = nf_scratch(mode), nsd = nf_seg(mode);
-    const int units = mode == 2 ? Cfg<2>::UNITS : Cfg<0>::UNITS;
     const int64_t n = in_h.n;
 
     bmo_result* res = new bmo_result();
-    res->sys = sys; res->mode = mode; res->R = R; res->nsd = nsd; res->n_roots = n; res->keep = flags & BMO_KEEP_SEGMENTS;
+    res->sys = sys; res->mode = mode; res->R = R; res->nsd = nf_seg(mode); res->n_roots = n; res->keep = flags & BMO_KEEP_SEGMENTS;
     static const bool prof = getenv("BMO_HOST_PROFILE") != nullptr;
-    auto tnow = [] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
-    const double tp0 = tnow();
-    double tp_wave_sync = 0;
+    const double tp0 = tnow_ms();
     BMO_CUDA(cudaEventRecord(ctx->ev0, st));
     int32_t rc;
-    std::vector<void*> tmp;
-    TraceInputs in = in_h;
-    if (mode == 2) {
-        if ((rc = stage_in(in_h.grays, (size_t)n * 18, on_dev, st, &in.grays, tmp))) return rc;
-        if ((rc = stage_in(in_h.w0, (size_t)n, on_dev, st, &in.w0, tmp))) return rc;
-        if ((rc = stage_in(in_h.ge0, (size_t)n * 2, on_dev, st, &in.ge0, tmp))) return rc;
-    } else {
-        if ((rc = stage_in(in_h.pos, (size_t)n * 3, on_dev, st, &in.pos, tmp))) return rc;
-        if ((rc = stage_in(in_h.dir, (size_t)n * 3, on_dev, st, &in.dir, tmp))) return rc;
-        if (mode == 1 && (rc = stage_in(in_h.E0, (size_t)n * 6, on_dev, st, &in.E0, tmp))) return rc;
-    }
-    if ((rc = stage_in(in_h.lam, (size_t)n, on_dev, st, &in.lam, tmp))) return rc;
-    if ((rc = stage_in(in_h.pose, (size_t)n, on_dev, st, &in.pose, tmp))) return rc;
-
     if ((rc = ensure_beams(res, n, st))) return rc;
-    Queue cur, next, scr;
-    HitBuf hit;
-    if ((rc = alloc_queue(cur, n * R, nfq, NI_Q, st))) return rc;
-    {
-        InitParams ip{};
-        ip.q = cur; ip.n = n; ip.mode = mode; ip.pos = in.pos; ip.dir = in.dir; ip.E0 = in.E0; ip.grays = in.grays;
-        ip.w0 = in.w0; ip.ge0 = in.ge0; ip.lam = in.lam; ip.pose = in.pose; ip.B = beamtab(res);
-        const int64_t tot = n * R;
-        init_queue<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ip);
-        BMO_LAUNCH(ctx, "init_queue");
-    }
-    const double tp1 = tnow();
-    // small single-pose systems: prims / parts / bounds are staged through shared memory
-    const SysView& V = sys->view;
-    const size_t table_bytes = (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double));
-    const bool staged = V.n_poses == 1 && table_bytes <= 40 * 1024;
-    const size_t smem = staged ? table_bytes : 0;
 
     // Beamsplitters are the only objects that add beams: without them the queue never grows, the
-    // continuing rays are updated in place and the host only looks at the device every `chunk` waves.
+    // continuing rays are updated in place and the host only looks at the device every few waves.
     bool has_splitter = false;
     for (const bmo_object& ob : sys->objects)
         has_splitter |= ob.kind == BMO_OBJ_THIN_BS || ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_CUBE_BS;
-    // waves per look at the device: 1 (most rays that miss everything die on the first wave, so the
-    // compaction decision is worth an early look), then 3, then 4, 4, ...
-    const int max_chunk = has_splitter ? 1 : 4;
-    if ((int)ctx->wave_ev.size() < 2 * max_chunk) {
-        const size_t old = ctx->wave_ev.size();
-        ctx->wave_ev.resize(2 * max_chunk);
-        for (size_t k = old; k < ctx->wave_ev.size(); k++) BMO_CUDA(cudaEventCreate(&ctx->wave_ev[k]));
-    }
-    unsigned long long* d_wtot = nullptr;      // [r_max + 8][2]: units alive after wave w, spawn events of wave w
-    const size_t n_wtot = (size_t)2 * (r_max + 8);
-    BMO_CUDA(dev_alloc(&d_wtot, n_wtot, st));
-    BMO_CUDA(cudaMemsetAsync(d_wtot, 0, n_wtot * sizeof(unsigned long long), st));
-    unsigned long long* h_wtot = (unsigned long long*)ctx->h_totals;   // pinned, >= 2 * chunk entries
+    const SysView& V = sys->view;
+    const size_t table_bytes = (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double));
+    const bool staged = V.n_poses == 1 && table_bytes <= 40 * 1024;
 
-    int64_t n_slots = n, alive = n, n_beams = n;
-    int32_t* blk_cnt = nullptr; long long* blk_off = nullptr; int64_t blk_cap = 0;
-    int wave = 0, waves_done = 0;
-    while (alive > 0) {
-        if (wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
-        int launched = 0;
-        const int chunk = has_splitter ? 1 : (wave == 0 ? 1 : (wave == 1 ? 3 : max_chunk));
-        for (int c = 0; c < chunk; c++, launched++) {
-            const int64_t nblocks = (n_slots + units - 1) / units;
-            if (has_splitter) {
-                // every live unit may add one unit (the reflected child) and two beams in this wave
-                if (cur.cap < (n_slots + alive) * R) {
-                    if ((rc = grow_queue(cur, 2 * (n_slots + alive) * R, nfq, NI_Q, st))) return rc;
-                }
-                const int64_t scr_cap = nblocks * 2 * units * R;
-                if (scr.cap < scr_cap) { free_queue(scr, st); if ((rc = alloc_queue(scr, scr_cap, nfs, NI_S, st))) return rc; }
-                if ((rc = ensure_beams(res, n_beams + 2 * alive, st))) return rc;
+    // sub-batches (see SubTrace): only host inputs of splitter-free systems are pipelined
+    static const int max_sub = getenv("BMO_SUBBATCHES") ? std::min(8, std::max(1, atoi(getenv("BMO_SUBBATCHES")))) : 4;
+    int n_sub = 1;
+    if (!on_dev && !has_splitter && !res->keep) n_sub = (int)std::min<int64_t>(max_sub, std::max<int64_t>(1, n / (128 * 1024)));
+    while ((int)ctx->aux_streams.size() < n_sub - 1) {
+        cudaStream_t s2;
+        BMO_CUDA(cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking));
+        ctx->aux_streams.push_back(s2);
+    }
+    cudaEvent_t ev_fork = nullptr;
+    if (n_sub > 1) {   // the auxiliary streams start after everything already queued on the caller's stream (result tables included)
+        BMO_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        BMO_CUDA(cudaEventRecord(ev_fork, st));
+    }
+    std::vector<SubTrace> subs((size_t)n_sub);
+    for (int k = 0; k < n_sub; k++) {
+        SubTrace& s = subs[k];
+        s.sys = sys; s.ctx = ctx; s.res = res; s.st = k == 0 ? st : ctx->aux_streams[k - 1]; s.slot = k;
+        s.mode = mode; s.R = R; s.nfq = nf_queue(mode); s.nfs = nf_scratch(mode); s.nsd = res->nsd;
+        s.units = mode == 2 ? Cfg<2>::UNITS : Cfg<0>::UNITS;
+        s.r_max = r_max; s.has_splitter = has_splitter; s.staged = staged; s.on_dev = on_dev; s.pipelined = n_sub > 1;
+        s.beam0 = n * k / n_sub; s.n = n * (k + 1) / n_sub - s.beam0;
+        s.spot_obj_out = spot_obj_out; s.spot_xz_out = spot_xz_out;
+        if (k > 0) BMO_CUDA(cudaStreamWaitEvent(s.st, ev_fork, 0));
+        if ((rc = s.begin(in_h))) return rc;
+        s.n_beams = n;
+        if ((rc = s.enqueue_chunk())) return rc;     // the first sub-batch is already copying / tracing while the others are set up
+    }
+    const double tp1 = tnow_ms();
+    // Every sub-batch always has its next chunk of waves in flight: as soon as the host has looked at
+    // the totals of one chunk it enqueues the next one on that stream, before it waits for the
+    // following sub-batch (they finish roughly in order: their input copies are serialised on the link).
+    for (bool any = true; any;) {
+        any = false;
+        for (auto& s : subs) {
+            if (s.launched == 0) continue;
+            if ((rc = s.finish_chunk())) return rc;
+            s.launched = 0;
+            if (prof) fprintf(stderr, "[bmo]   sub-batch %d: chunk done at %.3f ms (waited %.3f), alive %lld\n", s.slot, tnow_ms() - tp0, s.host_wait_ms, (long long)s.alive);
+            if (s.alive > 0) {
+                if (s.wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
+                if ((rc = s.enqueue_chunk())) return rc;
+                any = true;
             }
-            if (blk_cap < nblocks) {
-                dev_free(blk_cnt, st); dev_free(blk_off, st);
-                BMO_CUDA(dev_alloc(&blk_cnt, (size_t)nblocks, st));
-                BMO_CUDA(dev_alloc(&blk_off, (size_t)nblocks, st));
-                blk_cap = nblocks;
-            }
-            WaveBuf wb{};
-            if (res->keep) {
-                wb.count = n_slots * R;
-                BMO_CUDA(dev_alloc(&wb.d, (size_t)nsd * wb.count, st));
-                BMO_CUDA(dev_alloc(&wb.part, (size_t)wb.count, st));
-                BMO_CUDA(dev_alloc(&wb.beam, (size_t)wb.count, st));
-                BMO_CUDA(dev_alloc(&wb.seg, (size_t)wb.count, st));
-                res->wavebufs.push_back(wb);
-            }
-            if (hit.cap < n_slots * R) {
-                dev_free(hit.d, st); dev_free(hit.part, st);
-                hit.cap = n_slots * R;
-                BMO_CUDA(dev_alloc(&hit.d, (size_t)4 * hit.cap, st));
-                BMO_CUDA(dev_alloc(&hit.part, (size_t)hit.cap, st));
-            }
-            IntersectParams xp{};
-            xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = n_slots * R; xp.r_max = r_max;
-            xp.counters = ctx->d_counters;
-            BMO_CUDA(cudaEventRecord(ctx->wave_ev[2 * c], st));
-            {
-                static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 6;   // tuning knob: resident blocks per SM the kernel is compiled for
-                const unsigned grid = (unsigned)((n_slots * R + IBLOCK - 1) / IBLOCK);
-                if (!staged) intersect_wave<4, false><<<grid, IBLOCK, 0, st>>>(xp);
-                else if (minb <= 3) intersect_wave<3, true><<<grid, IBLOCK, smem, st>>>(xp);
-                else if (minb == 4) intersect_wave<4, true><<<grid, IBLOCK, smem, st>>>(xp);
-                else if (minb == 5) intersect_wave<5, true><<<grid, IBLOCK, smem, st>>>(xp);
-                else intersect_wave<6, true><<<grid, IBLOCK, smem, st>>>(xp);
-            }
-            BMO_LAUNCH(ctx, "intersect_wave");
-            BMO_CUDA(cudaEventRecord(ctx->wave_ev[2 * c + 1], st));
-            StepParams sp{};
-            sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
-            sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
-            if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
-            else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
-            else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
-            BMO_LAUNCH(ctx, "interact_wave");
-            wave++;
-            if (wave > r_max + 1) { launched++; break; }
-        }
-        // one look at the device per chunk: units alive / spawn events of the waves just launched
-        const int w0 = wave - launched;
-        BMO_CUDA(cudaMemcpyAsync(h_wtot, d_wtot + 2 * w0, (size_t)2 * launched * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-        const double tw0 = tnow();
-        BMO_CUDA(cudaStreamSynchronize(st));
-        tp_wave_sync += tnow() - tw0;
-        int64_t prev_alive = alive;
-        for (int c = 0; c < launched; c++) {
-            if (prev_alive > 0) {       // waves launched on an already empty queue are no-ops and not counted
-                float kms = 0;
-                BMO_CUDA(cudaEventElapsedTime(&kms, ctx->wave_ev[2 * c], ctx->wave_ev[2 * c + 1]));
-                ctx->k1_ms += kms; ctx->k1_launches++;
-                waves_done++; ctx->waves++;
-            }
-            prev_alive = (int64_t)h_wtot[2 * c];
-        }
-        alive = (int64_t)h_wtot[2 * (launched - 1)];
-        const int64_t spawns = (int64_t)h_wtot[2 * (launched - 1) + 1];   // chunk == 1 whenever spawns are possible
-        if (spawns > 0) {
-            const int64_t nblocks = (n_slots + units - 1) / units;
-            scan_counts<<<1, 1024, 0, st>>>(blk_cnt, nblocks, 1, 1, blk_off, ctx->d_totals);
-            BMO_LAUNCH(ctx, "scan_counts");
-            SpawnParams cp{};
-            cp.scr = scr; cp.q = cur; cp.blk_cnt = blk_cnt; cp.blk_off = blk_off; cp.B = beamtab(res); cp.n_beams = n_beams; cp.n_slots = n_slots;
-            cp.nf = nfq; cp.mode = mode; cp.units = units; cp.R = R;
-            spawn_children<<<(unsigned)nblocks, 256, 0, st>>>(cp);
-            BMO_LAUNCH(ctx, "spawn_children");
-            n_slots += spawns;
-            n_beams += 2 * spawns;
-        }
-        // K3: squeeze the dead slots out once they are the majority
-        if (alive > 0 && 2 * alive <= n_slots && n_slots >= 4096) {
-            const int64_t cblocks = (n_slots + CBLOCK - 1) / CBLOCK;
-            if (blk_cap < cblocks) {
-                dev_free(blk_cnt, st); dev_free(blk_off, st);
-                BMO_CUDA(dev_alloc(&blk_cnt, (size_t)cblocks, st));
-                BMO_CUDA(dev_alloc(&blk_off, (size_t)cblocks, st));
-                blk_cap = cblocks;
-            }
-            const int64_t want = has_splitter ? 2 * alive * R : alive * R;
-            if (next.cap < want) { free_queue(next, st); if ((rc = alloc_queue(next, want, nfq, NI_Q, st))) return rc; }
-            BMO_CUDA(cudaEventRecord(ctx->evs0, st));
-            compact_count<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur.i, cur.cap, n_slots, R, blk_cnt);
-            BMO_LAUNCH(ctx, "compact_count");
-            scan_counts<<<1, 1024, 0, st>>>(blk_cnt, cblocks, 1, 1, blk_off, ctx->d_totals);
-            BMO_LAUNCH(ctx, "scan_counts");
-            compact_scatter<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur, next, n_slots, R, nfq, blk_off);
-            BMO_LAUNCH(ctx, "compact_scatter");
-            BMO_CUDA(cudaEventRecord(ctx->evs1, st));
-            BMO_CUDA(cudaStreamSynchronize(st));
-            float sms = 0;
-            BMO_CUDA(cudaEventElapsedTime(&sms, ctx->evs0, ctx->evs1));
-            ctx->k3_ms += sms;
-            // algorithmic bytes: the alive flag of every slot, then read + write of every surviving ray
-            ctx->k3_bytes += (double)n_slots * 4 * 2 + (double)alive * R * 2.0 * (nfq * 8 + NI_Q * 4);
-            std::swap(cur, next);
-            n_slots = alive;
         }
     }
-    dev_free(d_wtot, st);
-    wave = waves_done;
-    const double tp2 = tnow();
-    res->n_beams = n_beams;
+    const double tp2 = tnow_ms();
+    int wave = 0;
+    double tp_wave_sync = 0;
+    for (auto& s : subs) { wave = std::max(wave, s.waves_done); tp_wave_sync += s.host_wait_ms; }
+    ctx->waves += wave;
+    res->n_beams = has_splitter ? subs[0].n_beams : n;
     res->waves = wave;
-    free_queue(cur, st); free_queue(next, st); free_queue(scr, st);
-    dev_free(hit.d, st); dev_free(hit.part, st);
-    dev_free(blk_cnt, st); dev_free(blk_off, st);
-    for (void* p : tmp) cudaFreeAsync(p, st);
-
+    // join: the caller's stream continues after every sub-batch (copies of the Spotdetector hits included)
+    for (int k = 1; k < n_sub; k++) {
+        BMO_CUDA(cudaEventRecord(ev_fork, subs[k].st));
+        BMO_CUDA(cudaStreamWaitEvent(st, ev_fork, 0));
+        BMO_CUDA(cudaStreamSynchronize(subs[k].st));
+    }
+    for (auto& s : subs) s.release();
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    const int nsd = res->nsd;
     // segment table: first_seg = exclusive scan of nseg, then gather wave-major -> beam-major
     // (spot-only traces compute first_seg lazily, see ensure_first_seg)
     if (res->keep) {
@@ -1230,9 +1342,10 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         res->interactions = (int64_t)h.interactions - ctx->interactions_seen;  // the counter is cumulative since the last reset
         ctx->interactions_seen = (int64_t)h.interactions;
     }
-    if (prof) fprintf(stderr, "[bmo] trace n=%lld waves=%d: setup %.3f ms, wave loop %.3f ms (of which waiting %.3f), finalize %.3f ms\n",
-                      (long long)n, wave, tp1 - tp0, tp2 - tp1, tp_wave_sync, tnow() - tp2);
-    *out = res;
+    if (prof) fprintf(stderr, "[bmo] trace n=%lld waves=%d sub-batches=%d: setup %.3f ms, wave loop %.3f ms (of which waiting %.3f), finalize %.3f ms\n",
+                      (long long)n, wave, n_sub, tp1 - tp0, tp2 - tp1, tp_wave_sync, tnow_ms() - tp2);
+    if (out) *out = res;
+    else bmo_result_free(res);
     return BMO_OK;
 }
 
@@ -1243,6 +1356,18 @@ int32_t bmo_trace_rays(bmo_sys* sys, int64_t n, const double* pos, const double*
     in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id;
     if (!sys) return fail(BMO_EINVAL, "sys NULL");
     return trace_common(sys, E0 ? 1 : 0, in, r_max, flags, out);
+}
+int32_t bmo_trace_rays_spots(bmo_sys* sys, int64_t n, const double* pos, const double* dir, const int32_t* lambda_id, const double* E0,
+                             const int32_t* pose_id, int32_t r_max, uint32_t flags, int32_t* det_object, double* xz, bmo_result** out) {
+    if (!pos || !dir) return fail(BMO_EINVAL, "bmo_trace_rays_spots: pos/dir NULL");
+    if (!xz) return fail(BMO_EINVAL, "bmo_trace_rays_spots: xz NULL");
+    if (!sys) return fail(BMO_EINVAL, "sys NULL");
+    for (const bmo_object& ob : sys->objects)
+        if (ob.kind == BMO_OBJ_THIN_BS || ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_CUBE_BS)
+            return fail(BMO_EINVAL, "bmo_trace_rays_spots: the system has beamsplitters (beams != rays); use bmo_trace_rays + bmo_result_spots");
+    TraceInputs in{};
+    in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id;
+    return trace_common(sys, E0 ? 1 : 0, in, r_max, flags & ~BMO_KEEP_SEGMENTS, out, det_object, xz);
 }
 int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const int32_t* lambda_id, const double* w0, const double* E0,
                            const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out) {

@@ -158,6 +158,25 @@ def trace_rays(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100, keep_se
     return TraceResult(dsys, h)
 
 
+def trace_rays_spots(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100):
+    """bmo_trace_rays_spots: trace a bundle through a splitter-free system and return the Spotdetector
+    hits (det_object (n,), xz (n, 2)) and the TraceResult -- host copies pipelined with the waves."""
+    pos = np.ascontiguousarray(pos, dtype=np.float64)
+    dir = np.ascontiguousarray(dir, dtype=np.float64)
+    lam_id = np.ascontiguousarray(lam_id, dtype=np.int32)
+    n = pos.shape[0]
+    e = None
+    if E0 is not None:
+        ec = np.ascontiguousarray(E0, dtype=np.complex128)
+        e = np.ascontiguousarray(np.stack([ec.real, ec.imag], axis=-1).reshape(n, 6))
+    pid = None if pose_id is None else np.ascontiguousarray(pose_id, dtype=np.int32)
+    obj, xz = np.zeros(n, np.int32), np.zeros((n, 2))
+    h = C.c_void_p()
+    L.check(L.lib().bmo_trace_rays_spots(dsys.h, n, L.ptr(pos), L.ptr(dir), L.ptr(lam_id), L.ptr(e), L.ptr(pid), r_max, 0,
+                                         L.ptr(obj), L.ptr(xz), C.byref(h)))
+    return obj, xz, TraceResult(dsys, h)
+
+
 def trace_beamlets(dsys, rays, lam_id, w0, E0, pose_id=None, r_max=100):
     rays = np.ascontiguousarray(rays, dtype=np.float64).reshape(-1, 18)
     lam_id = np.ascontiguousarray(lam_id, dtype=np.int32)
@@ -287,7 +306,12 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
     if isinstance(beam, bm.RayBundle):
         lams, lam_id = _lambda_ids(beam.lam)
         dsys = upload_system(system, lams, device, norm_zero_rule)
-        res = trace_rays(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max, keep_segments)
+        splitters = any(o.kind in ("thin_bs", "plate_bs", "cube_bs") for o in dsys.flat.objects)
+        if not keep_segments and not splitters:      # one beam per ray: fused trace + Spotdetector read-back (pipelined copies)
+            obj, xz, res = trace_rays_spots(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max)
+            res._spots = (obj, xz)
+        else:
+            res = trace_rays(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max, keep_segments)
         beam.result = res
         _collect_spots(dsys.flat, res)
         return res

@@ -171,9 +171,9 @@ def main():
     def step_e2e():
         import ctypes as C
         h = C.c_void_p()
-        L.check(L.lib().bmo_trace_rays(dsys.h, n, C.c_void_p(pos_p.data_ptr()), C.c_void_p(dir_p.data_ptr()), C.c_void_p(lam_p.data_ptr()),
-                                       None, None, 100, 0, C.byref(h)))
-        L.check(L.lib().bmo_result_spots(h, C.c_void_p(spot_obj_p.data_ptr()), C.c_void_p(spot_xz_p.data_ptr())))
+        # solve_system! + Spotdetector.data in one C-ABI call: host buffers in, host buffers out
+        L.check(L.lib().bmo_trace_rays_spots(dsys.h, n, C.c_void_p(pos_p.data_ptr()), C.c_void_p(dir_p.data_ptr()), C.c_void_p(lam_p.data_ptr()),
+                                             None, None, 100, 0, C.c_void_p(spot_obj_p.data_ptr()), C.c_void_p(spot_xz_p.data_ptr()), C.byref(h)))
         info = L.bmo_result_info()
         L.check(L.lib().bmo_result_get_info(h, C.byref(info)))
         L.lib().bmo_result_free(h)

@@ -171,6 +171,16 @@ int32_t bmo_system_set_poses(bmo_sys* sys, int32_t n_poses, const bmo_prim* prim
 int32_t bmo_trace_rays(bmo_sys* sys, int64_t n, const double* pos, const double* dir, const int32_t* lambda_id,
                        const double* E0, const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out);
 
+/* bmo_trace_rays + bmo_result_spots in one call, for systems without beamsplitters (one beam per ray):
+ * replaces `solve_system!(system, beams(bg))` followed by reading `Spotdetector.data`
+ * (System.jl:463-468, Spotdetector.jl:50-61).  det_object (NULL ok) / xz: [n] / [n][2] host arrays.
+ * With host inputs the rays are traced in sub-batches on separate streams, so that the host->device
+ * copy of one sub-batch and the device->host copy of the hits of another overlap the waves of a
+ * third (pinned host memory makes the copies truly asynchronous).  out may be NULL.              */
+int32_t bmo_trace_rays_spots(bmo_sys* sys, int64_t n, const double* pos, const double* dir, const int32_t* lambda_id,
+                             const double* E0, const int32_t* pose_id, int32_t r_max, uint32_t flags,
+                             int32_t* det_object, double* xz, bmo_result** out);
+
 /* replaces: solve_system!(system, ::GaussianBeamlet) (System.jl:274-318) for n root beamlets.
  * rays: [n][3 (chief, waist, divergence)][6 (pos, dir)]; w0, E0 (re,im): beamlet fields
  * (Gaussian.jl:33-42).                                                                           */
