@@ -150,8 +150,10 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
 }
 
 // ---- K2: interact + block-local compaction ----------------------------------------------------------
-template <int MODE>
-__global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepParams P) {
+// The body is shared by the stand-alone kernel (hit records read from the buffer K1 wrote) and by the
+// fused kernel of splitter-free plain-ray systems (hit still in registers, FUSED = true).
+template <int MODE, bool FUSED>
+BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
     constexpr int R = Cfg<MODE>::R;
     constexpr int UNITS = Cfg<MODE>::UNITS;
     constexpr int NWARP = Cfg<MODE>::NWARP;
@@ -191,9 +193,12 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepPara
         const int32_t* qi = P.cur.i;
         lam = qi[I_LAM * qs + ri]; beam = qi[I_BEAM * qs + ri];
         seg = qi[I_SEG * qs + ri]; pose = qi[I_POSE * qs + ri];
-        const int64_t hs = P.hit.cap;
-        h.t = P.hit.d[ri]; h.n = mk3(P.hit.d[hs + ri], P.hit.d[2 * hs + ri], P.hit.d[3 * hs + ri]);
-        h.part = P.hit.part[ri];
+        if (FUSED) h = h_reg;
+        else {
+            const int64_t hs = P.hit.cap;
+            h.t = P.hit.d[ri]; h.n = mk3(P.hit.d[hs + ri], P.hit.d[2 * hs + ri], P.hit.d[3 * hs + ri]);
+            h.part = P.hit.part[ri];
+        }
     }
 
     // ---- outcome of tracing_step! (System.jl:100-110, intersect_wave) ----
@@ -448,6 +453,72 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepPara
             }
         }
     }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepParams P) {
+    Hit none; none.part = -1; none.t = INFINITY; none.n = mk3(0, 0, 0);
+    interact_body<MODE, false>(P, none);
+}
+
+// ---- K1+K2 fused: plain rays through a system without beamsplitters (the sequential lens-stack path) --
+// One thread per ray does tracing_step! and interact3d back to back: the hit record never leaves the
+// registers and the ray state is read once.  Needs IBLOCK == Cfg<0>::BLOCK == Cfg<0>::UNITS.
+template <int MINB, bool STAGED>
+__global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) {
+    static_assert(IBLOCK == Cfg<0>::BLOCK && Cfg<0>::UNITS == IBLOCK, "fused_wave0 maps one thread to one ray like interact_wave<0>");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SysView& S = P.S;
+    bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
+    bmo_part* s_parts = reinterpret_cast<bmo_part*>(smem_raw + (size_t)S.n_prims * sizeof(bmo_prim));
+    double* s_bounds = reinterpret_cast<double*>(smem_raw + (size_t)S.n_prims * sizeof(bmo_prim) + (size_t)S.n_parts * sizeof(bmo_part));
+    if (STAGED) {
+        const int nw = S.n_prims * (int)(sizeof(bmo_prim) / 8), nq = S.n_parts * (int)(sizeof(bmo_part) / 8);
+        const double* src = reinterpret_cast<const double*>(S.prims);
+        double* dst = reinterpret_cast<double*>(s_prims);
+        for (int k = threadIdx.x; k < nw; k += IBLOCK) dst[k] = src[k];
+        src = reinterpret_cast<const double*>(S.parts);
+        dst = reinterpret_cast<double*>(s_parts);
+        for (int k = threadIdx.x; k < nq; k += IBLOCK) dst[k] = src[k];
+        for (int k = threadIdx.x; k < NBOUND * S.n_parts; k += IBLOCK) s_bounds[k] = S.bounds[k];
+        __syncthreads();
+    }
+    const int64_t ri = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
+    const int64_t qs = P.cur.cap;
+    const bool active = ri < P.count && P.cur.i[I_BEAM * qs + ri] >= 0;
+    Stats st; st.sdf = 0; st.tri = 0;
+    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+    if (active) {
+        const double* q = P.cur.d;
+        const V3 pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
+        const V3 dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
+        const int hint = P.cur.i[I_HINT * qs + ri];
+        const int pose = P.cur.i[I_POSE * qs + ri];
+        const bool budget = P.cur.i[I_SEG * qs + ri] + 1 < P.r_max;
+        TraceCtx C;
+        C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
+        C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
+        C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
+        C.pose = pose;
+        if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
+        else {
+            C.prims = S.prims + (int64_t)pose * S.n_prims;
+            C.parts = S.parts;
+            C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
+        }
+        if (budget) h = tracing_step(C, pos, dir, hint, st);
+    }
+    unsigned sd = st.sdf, tr = st.tri;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (sd) atomicAdd(&P.counters->sdf, (unsigned long long)sd);
+        if (tr) atomicAdd(&P.counters->tri, (unsigned long long)tr);
+    }
+    interact_body<0, true>(P, h);
 }
 
 // ---- K2: exclusive scan of int32 counts with stride (single block, chunked) -----------------------
@@ -1117,14 +1188,29 @@ int32_t SubTrace::enqueue_chunk() {
             BMO_CUDA(dev_alloc(&hit.d, (size_t)4 * hit.cap, st));
             BMO_CUDA(dev_alloc(&hit.part, (size_t)hit.cap, st));
         }
-        IntersectParams xp{};
-        xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = n_slots * R; xp.r_max = r_max;
-        xp.counters = ctx->d_counters;
+        StepParams sp{};
+        sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
+        sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
+        static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 6;   // tuning knob: resident blocks per SM the kernel is compiled for
+        // tuning knob: 0 never fuse, 1 fuse in pipelined (launch-bound) calls [default], 2 always fuse.  Measured on C2:
+        // the fused kernel carries the interaction's registers through the march (0.282 vs 0.209 + 0.058 ms per
+        // wave), so it only pays where the number of launches is what limits the call.
+        static const int fuse_policy = getenv("BMO_FUSE") ? atoi(getenv("BMO_FUSE")) : 1;
+        const bool allow_fused = fuse_policy == 2 || (fuse_policy == 1 && pipelined);
+        const SysView& V = sys->view;
+        const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
         BMO_CUDA(cudaEventRecord(ev[2 * c], st));
-        {
-            static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 6;   // tuning knob: resident blocks per SM the kernel is compiled for
-            const SysView& V = sys->view;
-            const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
+        if (mode == 0 && !has_splitter && allow_fused) {
+            // sequential lens-stack path: intersect + interact in one kernel, hit records stay in registers
+            if (!staged) fused_wave0<4, false><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
+            else if (minb <= 4) fused_wave0<4, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+            else fused_wave0<6, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+            BMO_LAUNCH(ctx, "fused_wave0");
+            BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
+        } else {
+            IntersectParams xp{};
+            xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = n_slots * R; xp.r_max = r_max;
+            xp.counters = ctx->d_counters;
             const unsigned grid = (unsigned)((n_slots * R + IBLOCK - 1) / IBLOCK);
             if (!staged) intersect_wave<4, false><<<grid, IBLOCK, 0, st>>>(xp);
             else if (minb <= 3) intersect_wave<3, true><<<grid, IBLOCK, smem, st>>>(xp);
@@ -1132,16 +1218,13 @@ int32_t SubTrace::enqueue_chunk() {
             else if (minb == 5) intersect_wave<5, true><<<grid, IBLOCK, smem, st>>>(xp);
             else if (minb <= 7) intersect_wave<6, true><<<grid, IBLOCK, smem, st>>>(xp);
             else intersect_wave<8, true><<<grid, IBLOCK, smem, st>>>(xp);
+            BMO_LAUNCH(ctx, "intersect_wave");
+            BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
+            if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+            else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
+            else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
+            BMO_LAUNCH(ctx, "interact_wave");
         }
-        BMO_LAUNCH(ctx, "intersect_wave");
-        BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
-        StepParams sp{};
-        sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
-        sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
-        if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
-        else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
-        else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
-        BMO_LAUNCH(ctx, "interact_wave");
         wave++;
         launched++;
         if (wave > r_max + 1) break;
