@@ -18,7 +18,7 @@ from .components import (ConcaveSphericalMirror, CubeBeamsplitter, DiscreteRefra
 from .shapes import (BoxSDF, CircularFlatMesh, ConcaveSphericalSurfaceSDF, ConvexSphericalSurfaceSDF, CubeMesh, CuboidMesh, CutSphereSDF,
                      CylinderSDF, Mesh, MeniscusLensSDF, PlanoSurfaceSDF, QuadraticFlatMesh, RectangularFlatMesh, RetroMesh,
                      RightAnglePrismSDF, RingSDF, SphereSDF, ThinLensSDF, UnionSDF, load_stl)
-from .solver import DeviceSystem, TraceResult, pd_accumulate, solve_system_, trace_beamlets, trace_rays, trace_rays_spots, upload_system
+from .solver import DeviceSystem, TraceResult, pd_accumulate, retrace, solve_system_, trace_beamlets, trace_rays, trace_rays_spots, upload_system
 from .sweep import flatten_poses, solve_pose_sweep
 from . import parallel
 from .parallel import solve_system_sharded

@@ -69,6 +69,7 @@ class bmo_result_info(C.Structure):
 EXPORTS = [
     "bmo_init", "bmo_shutdown", "bmo_last_error", "bmo_set_stream", "bmo_counters_get", "bmo_counters_reset",
     "bmo_system_upload", "bmo_system_free", "bmo_system_set_poses", "bmo_trace_rays", "bmo_trace_rays_spots", "bmo_trace_beamlets",
+    "bmo_retrace",
     "bmo_result_get_info", "bmo_result_beams", "bmo_result_segments", "bmo_result_spots", "bmo_result_spots_device",
     "bmo_result_free", "bmo_pd_accumulate", "bmo_pd_accumulate_poses", "bmo_pd_power", "bmo_measure_fp64_peak",
 ]
@@ -95,6 +96,7 @@ def lib():
         L.bmo_trace_rays.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_uint32, C.POINTER(_vp)]
         L.bmo_trace_rays_spots.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_uint32, _vp, _vp, C.POINTER(_vp)]
         L.bmo_trace_beamlets.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_uint32, C.POINTER(_vp)]
+        L.bmo_retrace.argtypes = [_vp, _vp, C.c_int32, C.c_uint32, C.POINTER(_vp)]
         L.bmo_result_get_info.argtypes = [_vp, C.POINTER(bmo_result_info)]
         L.bmo_result_beams.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
         L.bmo_result_segments.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]

@@ -496,16 +496,20 @@ BMO_D bool box_may_hit(const double* bx, V3 o, V3 d, double t_best) {
 // object the parts in shape(object) order, strict-min t (AbstractRay.jl:118-155), except that a plate
 // beamsplitter prefers its coating whenever t_coating ~ t_substrate (PlateBeamsplitter.jl:160-187).
 // The hinted part is not intersected again by trace_all (same ray, same shape => the same miss).
-// One loop over [hint, part 0, part 1, ...] so that part_intersect has a single call site.
-BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st) {
+// One loop over [hint, part lo, part lo+1, ...] so that part_intersect has a single call site.
+// [lo, hi) is the range of parts that trace_all looks at: the whole system for tracing_step!, the parts
+// of one object (or one hinted shape) for retrace_system!'s `intersect3d(object(_intersection), ray)` /
+// `intersect3d(shape(_hint), ray)` (System.jl:209-218); hi < 0 means C.n_parts.
+BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st, const int lo = 0, const int hi = -1) {
     Hit res; res.part = -1; res.t = INFINITY; res.n = mk3(0, 0, 0);
     Hit ob; ob.part = -1; ob.t = INFINITY; ob.n = mk3(0, 0, 0);   // best of the current object
     int cur_obj = -1;
-    const int n_parts = C.n_parts;
-    for (int it = hint_part >= 0 ? -1 : 0; it <= n_parts; it++) {
-        const int part = it < 0 ? hint_part : it;
-        const int obj = (it >= 0 && it < n_parts) ? C.parts[part].object : -1;
-        if (it >= 0 && obj != cur_obj) {       // object boundary: trace_all's comparison (System.jl:62-67)
+    const int n_parts = hi < 0 ? C.n_parts : hi;
+    for (int it = hint_part >= 0 ? lo - 1 : lo; it <= n_parts; it++) {
+        const bool all = it >= lo;                    // false: the trace_one iteration on the hinted part
+        const int part = all ? it : hint_part;
+        const int obj = (all && it < n_parts) ? C.parts[part].object : -1;
+        if (all && obj != cur_obj) {       // object boundary: trace_all's comparison (System.jl:62-67)
             if (ob.part >= 0 && (res.part < 0 || ob.t < res.t)) res = ob;
             ob.part = -1; ob.t = INFINITY;
             cur_obj = obj;
@@ -513,22 +517,22 @@ BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& 
         }
         double t; V3 n;
         bool hit = false;
-        if (!(it >= 0 && part == hint_part)) {
+        if (!(all && part == hint_part)) {
             // Result-identical cull: a hit point lies within 1e-10 of the part's surface, hence inside its
             // (1e-6-inflated) box.  If the ray misses the box the part cannot be hit; if it enters the box
             // only beyond the closest hit found so far, the part cannot win trace_all's strict `<`.
             // (A plate beamsplitter's substrate / coating are never culled against the best hit: its
             // coating is preferred on approximate equality, PlateBeamsplitter.jl:176-179.)
             const double* bx = C.bounds + NBOUND * part + 4;
-            const bool plate = it >= 0 && C.objects[obj].kind == BMO_OBJ_PLATE_BS;
+            const bool plate = all && C.objects[obj].kind == BMO_OBJ_PLATE_BS;
             double t_best = INFINITY;          // closest hit so far: earlier objects (res) and earlier parts of this object (ob)
-            if (it >= 0 && !plate) {
+            if (all && !plate) {
                 if (res.part >= 0) t_best = res.t;
                 if (ob.part >= 0 && ob.t < t_best) t_best = ob.t;
             }
             if (box_may_hit(bx, pos, dir, t_best)) hit = part_intersect(C, part, pos, dir, st, t, n);
         }
-        if (it < 0) {
+        if (!all) {
             if (hit) { res.t = t; res.n = n; res.part = part; return res; }
             continue;
         }

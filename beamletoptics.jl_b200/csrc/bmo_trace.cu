@@ -25,8 +25,9 @@ thread_local std::string g_last_error;
 // double fields (SoA, stride = capacity): px py pz dx dy dz n | E0 re/im x3 (polarized) |
 //                                         lsum lpar oplpar (gaussian chief accumulators)
 enum { F_PX = 0, F_PY, F_PZ, F_DX, F_DY, F_DZ, F_N, F_X0 };
-// int fields: lambda id, hinted part, beam (-1 = dead slot), segment index, pose
-enum { I_LAM = 0, I_HINT, I_BEAM, I_SEG, I_POSE, NI_Q, I_PUNIT = NI_Q, NI_S };   // I_PUNIT (scratch only): queue unit of the parent
+// int fields: lambda id, hinted part, beam (-1 = dead slot), segment index, pose, retrace cursor (beam of
+// the previous solution whose stored path this beam re-validates, -1 = not retracing)
+enum { I_LAM = 0, I_HINT, I_BEAM, I_SEG, I_POSE, I_RETR, NI_Q, I_PUNIT = NI_Q, NI_S };   // I_PUNIT (scratch only): queue unit of the parent
 // segment record rows
 enum { S_PX = 0, S_PY, S_PZ, S_DX, S_DY, S_DZ, S_N, S_T, S_NX, S_NY, S_NZ, S_E0 };
 
@@ -48,7 +49,18 @@ struct BeamTab {
 struct HitBuf {
     double* d = nullptr;      // [4][cap]: t, nx, ny, nz
     int32_t* part = nullptr;  // [cap]: -1 = miss
+    int32_t* flag = nullptr;  // [cap], retrace calls only: 0 ordinary tracing_step!, 1 stored path re-validated, 2 path left
     int64_t cap = 0;
+};
+
+// Previous solution of the same beams (retrace_system!, System.jl:188-428): what the stored rays hit.
+struct RetraceView {
+    const int32_t* nseg = nullptr;         // [beams] stored rays per beam
+    const long long* first_seg = nullptr;  // [beams] first row of the beam in the beam-major segment table
+    const int32_t* seg_part = nullptr;     // [rows * R] part hit by each stored ray (-1: intersection === nothing)
+    const int32_t* child = nullptr;        // [beams][2] stored children (transmitted, reflected), -1: none
+    const double* w0 = nullptr;            // [beams] stored beamlet waists
+    int32_t on = 0, pad = 0;
 };
 
 struct IntersectParams {
@@ -71,6 +83,7 @@ struct StepParams {
     int32_t* blk_cnt;    // [nblocks] spawn events per block
     unsigned long long* wave_totals;   // [2] units alive after this wave, spawn events of this wave
     DevCounters* counters;
+    RetraceView rt;
 };
 
 template <int MODE> struct Cfg {
@@ -149,6 +162,126 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
     }
 }
 
+// ---- K1r: intersect of a retrace call (retrace_system!, System.jl:188-255 / :326-428) ----------------
+// Units are laid out like K2 (Gaussian: chief / waist / divergence in adjacent lanes, 10 triples per
+// warp) because the decision "is the stored path still valid" is taken per beam.  A beam that carries a
+// retrace cursor (I_RETR >= 0) intersects only what the reference intersects:
+//   stored ray `seg` has no intersection                -> the stored solution ends here (cleanup, :200-206)
+//   a hint came with the previous interaction           -> intersect3d(shape(_hint), ray)        (:213-218)
+//   otherwise                                           -> intersect3d(object(_intersection), ray) (:209-211)
+// pass 0 does that restricted intersection; if it misses (Gaussian: the three rays disagree,
+// `_beams_hits_same_shape`, :367-381) the tail is dropped and solve_leaf! continues with trace_system!, whose
+// first tracing_step! has no hint (:132-137): pass 1, the ordinary full trace, for exactly those beams and
+// for the beams that are not retracing.  flag: 0 ordinary step, 1 re-validated (K2 must not apply the
+// r_max test: retrace_system! has none), 2 stored path left in this wave.
+template <int MODE, bool STAGED>
+__global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 4) retrace_intersect_wave(const StepParams P) {
+    constexpr int R = Cfg<MODE>::R;
+    constexpr int UNITS = Cfg<MODE>::UNITS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const SysView& S = P.S;
+    bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
+    bmo_part* s_parts = reinterpret_cast<bmo_part*>(smem_raw + (size_t)S.n_prims * sizeof(bmo_prim));
+    double* s_bounds = reinterpret_cast<double*>(smem_raw + (size_t)S.n_prims * sizeof(bmo_prim) + (size_t)S.n_parts * sizeof(bmo_part));
+    if (STAGED) {
+        const int nw = S.n_prims * (int)(sizeof(bmo_prim) / 8), nq = S.n_parts * (int)(sizeof(bmo_part) / 8);
+        const double* src = reinterpret_cast<const double*>(S.prims);
+        double* dst = reinterpret_cast<double*>(s_prims);
+        for (int k = threadIdx.x; k < nw; k += Cfg<MODE>::BLOCK) dst[k] = src[k];
+        src = reinterpret_cast<const double*>(S.parts);
+        dst = reinterpret_cast<double*>(s_parts);
+        for (int k = threadIdx.x; k < nq; k += Cfg<MODE>::BLOCK) dst[k] = src[k];
+        for (int k = threadIdx.x; k < NBOUND * S.n_parts; k += Cfg<MODE>::BLOCK) s_bounds[k] = S.bounds[k];
+        __syncthreads();
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int uib, r;
+    bool lane_ok = true;
+    if (MODE == 2) { uib = warp * 10 + lane / 3; r = lane % 3; lane_ok = lane < 30; }
+    else { uib = threadIdx.x; r = 0; }
+    const int64_t unit = (int64_t)blockIdx.x * UNITS + uib;
+    const int64_t ri = unit * R + r;
+    const int64_t qs = P.cur.cap;
+    const bool active = lane_ok && unit < P.count && P.cur.i[I_BEAM * qs + ri] >= 0;
+
+    Stats st; st.sdf = 0; st.tri = 0;
+    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+    V3 pos = mk3(0, 0, 0), dir = mk3(0, 1, 0);
+    int hint = -1, pose = 0, seg = 0, pb = -1;
+    if (active) {
+        const double* q = P.cur.d;
+        pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
+        dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
+        hint = P.cur.i[I_HINT * qs + ri];
+        pose = P.cur.i[I_POSE * qs + ri];
+        seg = P.cur.i[I_SEG * qs + ri];
+        pb = P.cur.i[I_RETR * qs + ri];
+    }
+    const bool budget = seg + 1 < P.r_max;   // `while length(rays) < r_max` (System.jl:133), trace_system! only
+    TraceCtx C;
+    C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
+    C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
+    C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
+    C.pose = pose;
+    if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
+    else {
+        C.prims = S.prims + (int64_t)pose * S.n_prims;
+        C.parts = S.parts;
+        C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
+    }
+    const bool in_phase = active && pb >= 0;
+    int lo = 0, hi = 0;
+    bool restricted = false;
+    if (in_phase && seg < P.rt.nseg[pb]) {
+        const int ppart = P.rt.seg_part[(P.rt.first_seg[pb] + seg) * R];   // what the stored (chief) ray hit
+        if (ppart >= 0) {
+            restricted = true;
+            if (hint >= 0) { lo = hint; hi = hint + 1; }
+            else { const bmo_object& ob = S.objects[S.parts[ppart].object]; lo = ob.first_part; hi = lo + ob.n_parts; }
+        }
+    }
+    bool ok = false;
+    int flag = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 2; pass++) {
+        bool run;
+        int hp = -1, plo = lo, phi = hi;
+        if (pass == 0) run = restricted;
+        else { run = active && budget && !(in_phase && ok); hp = in_phase ? -1 : hint; plo = 0; phi = S.n_parts; }
+        if (run) h = tracing_step(C, pos, dir, hp, st, plo, phi);
+        if (pass == 0) {
+            ok = restricted && h.part >= 0;
+            if (MODE == 2) {   // Gaussian.jl:171-180: all three rays must hit the same shape
+                __syncwarp();
+                const int base = lane - r, lw = min(base + 1, 31), ld = min(base + 2, 31);
+                const int pc = __shfl_sync(0xffffffffu, h.part, base), pw = __shfl_sync(0xffffffffu, h.part, lw),
+                          pd = __shfl_sync(0xffffffffu, h.part, ld);
+                ok = restricted && pc >= 0 && pc == pw && pw == pd;
+            }
+            if (in_phase) {
+                flag = ok ? 1 : 2;
+                if (!ok) { h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0); }
+            }
+        }
+    }
+    if (active) {
+        const int64_t hs = P.hit.cap;
+        P.hit.d[ri] = h.t; P.hit.d[hs + ri] = h.n.x; P.hit.d[2 * hs + ri] = h.n.y; P.hit.d[3 * hs + ri] = h.n.z;
+        P.hit.part[ri] = h.part;
+        P.hit.flag[ri] = flag;
+    }
+    unsigned sd = st.sdf, tr = st.tri;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        tr += __shfl_xor_sync(0xffffffffu, tr, o);
+    }
+    if (lane == 0) {
+        if (sd) atomicAdd(&P.counters->sdf, (unsigned long long)sd);
+        if (tr) atomicAdd(&P.counters->tri, (unsigned long long)tr);
+    }
+}
+
 // ---- K2: interact + block-local compaction ----------------------------------------------------------
 // The body is shared by the stand-alone kernel (hit records read from the buffer K1 wrote) and by the
 // fused kernel of splitter-free plain-ray systems (hit still in registers, FUSED = true).
@@ -200,11 +333,14 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
             h.part = P.hit.part[ri];
         }
     }
+    // retrace calls (K1r): how this wave's intersection was obtained, and the beam's retrace cursor
+    int rflag = 0, pb = -1;
+    if (!FUSED && P.rt.on && active) { rflag = P.hit.flag[ri]; pb = P.cur.i[I_RETR * qs + ri]; }
 
     // ---- outcome of tracing_step! (System.jl:100-110, intersect_wave) ----
     int status = BMO_ST_ACTIVE;
     if (active) {
-        if (seg + 1 >= P.r_max) {          // `while length(rays) < r_max`, System.jl:133 / :281: not traced
+        if (seg + 1 >= P.r_max && rflag != 1) {   // `while length(rays) < r_max`, System.jl:133 / :281: not traced (retrace_system! has no such test)
             status = BMO_ST_RMAX;
             h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
         } else if (h.part < 0) status = BMO_ST_MISS;
@@ -359,6 +495,24 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
         }
     }
 
+    // ---- retrace cursor (System.jl:238-247 / :402-411) ----
+    // A re-validated ray whose successor exists in the stored solution replaces that successor and the
+    // beam keeps retracing; if it was the last stored ray the new ray is pushed, the children are dropped
+    // and solve_leaf! continues with trace_system!, whose first tracing_step! has no hint.  Children of a
+    // re-validated splitter hit keep their stored paths (children!, AbstractBeam.jl:59-76): they start
+    // with the cursor of the stored child; Gaussian children also keep their stored w0
+    // (_modify_beam_head!, Gaussian.jl:154-162, copies wavelength and E0 only).
+    int retr_next = -1, retr_child0 = -1, retr_child1 = -1;
+    if (rflag == 1 && pb >= 0) {
+        const int np = P.rt.nseg[pb];
+        if (nsucc == 1) {
+            if (seg + 1 < np) retr_next = pb;
+            else o1.hint = -1;
+        } else if (nsucc == 2 && seg + 1 == np) {
+            retr_child0 = P.rt.child[2 * pb]; retr_child1 = P.rt.child[2 * pb + 1];
+        }
+    }
+
     // ---- bookkeeping: counters, segment record, per-beam state ----
     if (P.keep && in_queue && !active) P.wave.beam[ri] = -1;
     if (P.keep && active) {
@@ -422,6 +576,7 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
             if (MODE == 2) { d[F_X0 * qs + ri] = n_lsum; d[(F_X0 + 1) * qs + ri] = n_lpar; d[(F_X0 + 2) * qs + ri] = n_opl; }
             qi[I_HINT * qs + ri] = o1.hint;
             qi[I_SEG * qs + ri] = seg + 1;
+            if (P.rt.on) qi[I_RETR * qs + ri] = retr_next;
         } else {
             qi[I_BEAM * qs + ri] = -1;
         }
@@ -442,13 +597,15 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
                 if (MODE == 2) {
                     d[F_X0 * ss + si] = n_lsum; d[(F_X0 + 1) * ss + si] = n_lpar; d[(F_X0 + 2) * ss + si] = n_opl;
                     const Cx e = (k == 0) ? g_et : g_er;
-                    d[(F_X0 + 3) * ss + si] = g_w0; d[(F_X0 + 4) * ss + si] = e.re; d[(F_X0 + 5) * ss + si] = e.im;
+                    const int rc = (k == 0) ? retr_child0 : retr_child1;
+                    d[(F_X0 + 3) * ss + si] = rc >= 0 ? P.rt.w0[rc] : g_w0; d[(F_X0 + 4) * ss + si] = e.re; d[(F_X0 + 5) * ss + si] = e.im;
                     d[(F_X0 + 6) * ss + si] = g_plen; d[(F_X0 + 7) * ss + si] = g_popl;
                 }
                 int32_t* iq = P.scr.i;
                 iq[I_LAM * ss + si] = lam;
                 iq[I_BEAM * ss + si] = beam;       // parent beam
                 iq[I_POSE * ss + si] = pose;
+                iq[I_RETR * ss + si] = (k == 0) ? retr_child0 : retr_child1;
                 iq[I_PUNIT * ss + si] = (int32_t)unit;
             }
         }
@@ -637,6 +794,7 @@ __global__ void __launch_bounds__(256) spawn_children(const SpawnParams P) {
         nq[I_BEAM * qs + di] = beam;
         nq[I_SEG * qs + di] = 0;
         nq[I_POSE * qs + di] = pose;
+        nq[I_RETR * qs + di] = iq[I_RETR * ss + si];
     }
 }
 
@@ -687,6 +845,7 @@ struct InitParams {
     const double *pos, *dir, *E0, *grays, *w0, *ge0;
     const int32_t *lam, *pose;
     BeamTab B;
+    int32_t retrace, pad;   // retrace: root beam g re-validates beam g of the previous solution
 };
 __global__ void init_queue(const InitParams P) {
     const int R = P.mode == 2 ? 3 : 1;
@@ -712,12 +871,49 @@ __global__ void init_queue(const InitParams P) {
     const int lam = P.lam ? P.lam[u] : 0, pose = P.pose ? P.pose[u] : 0;
     const int64_t g = P.beam0 + u;   // global beam id; inputs are this sub-batch's slices, tables are global
     q[I_LAM * s + i] = lam; q[I_HINT * s + i] = -1; q[I_BEAM * s + i] = (int)g; q[I_SEG * s + i] = 0; q[I_POSE * s + i] = pose;
+    q[I_RETR * s + i] = P.retrace ? (int)g : -1;
     P.B.spot_obj[g * R + r] = -1;
     if (r == 0) {
         P.B.parent[g] = -1; P.B.slot[g] = -1; P.B.nseg[g] = 0; P.B.status[g] = BMO_ST_ACTIVE; P.B.lam[g] = lam; P.B.pose[g] = pose;
         if (P.mode == 2) { P.B.w0[g] = P.w0[u]; P.B.e0[2 * g] = P.ge0[2 * u]; P.B.e0[2 * g + 1] = P.ge0[2 * u + 1]; P.B.plen[g] = 0; P.B.popl[g] = 0; }
     }
 }
+// ---- retrace: roots and children of the previous solution --------------------------------------------
+// The root beams of a retrace call start from the first stored ray of the previous solution's roots
+// (retrace_system! keeps ray 1 as it is, System.jl:198).
+struct PrevRoots {
+    const double* seg_d; const long long* first_seg; int64_t rows;   // previous segment table [nsd][rows]
+    const int32_t *lam, *pose; const double *w0, *e0;
+    int64_t n; int mode;
+    double *pos, *dir, *E0, *grays, *ow0, *oe0; int32_t *olam, *opose;
+};
+__global__ void gather_prev_roots(const PrevRoots P) {
+    const int R = P.mode == 2 ? 3 : 1;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= P.n * R) return;
+    const int64_t b = i / R;
+    const int r = (int)(i % R);
+    const int64_t row = P.first_seg[b] * R + r;
+    double v[6];
+    for (int k = 0; k < 6; k++) v[k] = P.seg_d[(S_PX + k) * P.rows + row];
+    if (P.mode == 2) { for (int k = 0; k < 6; k++) P.grays[i * 6 + k] = v[k]; }
+    else {
+        for (int k = 0; k < 3; k++) { P.pos[3 * b + k] = v[k]; P.dir[3 * b + k] = v[3 + k]; }
+        if (P.mode == 1) for (int k = 0; k < 6; k++) P.E0[6 * b + k] = P.seg_d[(S_E0 + k) * P.rows + row];
+    }
+    if (r == 0) {
+        P.olam[b] = P.lam[b]; P.opose[b] = P.pose[b];
+        if (P.mode == 2) { P.ow0[b] = P.w0[b]; P.oe0[2 * b] = P.e0[2 * b]; P.oe0[2 * b + 1] = P.e0[2 * b + 1]; }
+    }
+}
+// child[2 * parent + slot] = beam (children are numbered after the roots; slot 0 transmitted, 1 reflected)
+__global__ void build_child_table(const int32_t* parent, const int32_t* slot, int64_t n_roots, int64_t n_beams, int32_t* child) {
+    const int64_t i = n_roots + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_beams) return;
+    const int p = parent[i], k = slot[i];
+    if (p >= 0 && (k == 0 || k == 1)) child[2 * (int64_t)p + k] = (int32_t)i;
+}
+
 __global__ void gather_segments(WaveBuf w, int R, int nsd, const long long* first_seg, double* seg_d, int32_t* seg_part, int64_t rows) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= w.count || w.beam[i] < 0) return;
@@ -1027,7 +1223,7 @@ static int32_t ensure_beams(bmo_result* r, int64_t need, cudaStream_t st) {
 // first_seg[b] = exclusive scan of nseg; n_segments = total.  Lazy for traces that keep no segments.
 static int32_t ensure_first_seg(bmo_result* res) {
     if (res->first_seg) return BMO_OK;
-    bmo_ctx* ctx = res->sys->ctx;
+    bmo_ctx* ctx = res->ctx;
     cudaStream_t st = ctx->stream;
     const int64_t nb = res->n_beams;
     BMO_CUDA(dev_alloc(&res->first_seg, (size_t)nb + 1, st));
@@ -1098,6 +1294,7 @@ struct SubTrace {
     int wave = 0, waves_done = 0, launched = 0, slot = 0;
     int32_t* spot_obj_out = nullptr; double* spot_xz_out = nullptr;   // host destinations of the Spotdetector hits (optional)
     double host_wait_ms = 0;
+    RetraceView rt;                        // retrace calls: the previous solution
 
     int32_t begin(const TraceInputs& in_h);
     int32_t enqueue_chunk();
@@ -1125,7 +1322,7 @@ int32_t SubTrace::begin(const TraceInputs& in_h) {
     if ((rc = alloc_queue(cur, n * R, nfq, NI_Q, st))) return rc;
     InitParams ip{};
     ip.q = cur; ip.n = n; ip.beam0 = beam0; ip.mode = mode; ip.pos = in.pos; ip.dir = in.dir; ip.E0 = in.E0; ip.grays = in.grays;
-    ip.w0 = in.w0; ip.ge0 = in.ge0; ip.lam = in.lam; ip.pose = in.pose; ip.B = beamtab(res);
+    ip.w0 = in.w0; ip.ge0 = in.ge0; ip.lam = in.lam; ip.pose = in.pose; ip.B = beamtab(res); ip.retrace = rt.on;
     const int64_t tot = n * R;
     init_queue<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ip);
     BMO_LAUNCH(ctx, "init_queue");
@@ -1183,20 +1380,22 @@ int32_t SubTrace::enqueue_chunk() {
             res->wavebufs.push_back(wb);
         }
         if (hit.cap < n_slots * R) {
-            dev_free(hit.d, st); dev_free(hit.part, st);
+            dev_free(hit.d, st); dev_free(hit.part, st); dev_free(hit.flag, st);
             hit.cap = n_slots * R;
             BMO_CUDA(dev_alloc(&hit.d, (size_t)4 * hit.cap, st));
             BMO_CUDA(dev_alloc(&hit.part, (size_t)hit.cap, st));
+            if (rt.on) BMO_CUDA(dev_alloc(&hit.flag, (size_t)hit.cap, st));
         }
         StepParams sp{};
         sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
         sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
+        sp.rt = rt;
         static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 6;   // tuning knob: resident blocks per SM the kernel is compiled for
         // tuning knob: 0 never fuse, 1 fuse in pipelined (launch-bound) calls [default], 2 always fuse.  Measured on C2:
         // the fused kernel carries the interaction's registers through the march (0.282 vs 0.209 + 0.058 ms per
         // wave), so it only pays where the number of launches is what limits the call.
         static const int fuse_policy = getenv("BMO_FUSE") ? atoi(getenv("BMO_FUSE")) : 1;
-        const bool allow_fused = fuse_policy == 2 || (fuse_policy == 1 && pipelined);
+        const bool allow_fused = !rt.on && (fuse_policy == 2 || (fuse_policy == 1 && pipelined));
         const SysView& V = sys->view;
         const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
         BMO_CUDA(cudaEventRecord(ev[2 * c], st));
@@ -1207,6 +1406,17 @@ int32_t SubTrace::enqueue_chunk() {
             else fused_wave0<6, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
             BMO_LAUNCH(ctx, "fused_wave0");
             BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
+        } else if (rt.on) {
+            // retrace call: K1r re-validates the stored path where there is one, ordinary tracing_step! elsewhere
+            if (mode == 0) { if (staged) retrace_intersect_wave<0, true><<<(unsigned)nblocks, Cfg<0>::BLOCK, smem, st>>>(sp); else retrace_intersect_wave<0, false><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp); }
+            else if (mode == 1) { if (staged) retrace_intersect_wave<1, true><<<(unsigned)nblocks, Cfg<1>::BLOCK, smem, st>>>(sp); else retrace_intersect_wave<1, false><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp); }
+            else { if (staged) retrace_intersect_wave<2, true><<<(unsigned)nblocks, Cfg<2>::BLOCK, smem, st>>>(sp); else retrace_intersect_wave<2, false><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp); }
+            BMO_LAUNCH(ctx, "retrace_intersect_wave");
+            BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
+            if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+            else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
+            else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
+            BMO_LAUNCH(ctx, "interact_wave");
         } else {
             IntersectParams xp{};
             xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = n_slots * R; xp.r_max = r_max;
@@ -1301,7 +1511,7 @@ int32_t SubTrace::finish_chunk() {
 
 void SubTrace::release() {
     free_queue(cur, st); free_queue(next, st); free_queue(scr, st);
-    dev_free(hit.d, st); dev_free(hit.part, st);
+    dev_free(hit.d, st); dev_free(hit.part, st); dev_free(hit.flag, st);
     dev_free(blk_cnt, st); dev_free(blk_off, st);
     dev_free(d_wtot, st); dev_free(d_scan_tot, st);
     for (void* p : tmp) cudaFreeAsync(p, st);
@@ -1310,7 +1520,7 @@ void SubTrace::release() {
 }
 
 static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int32_t r_max, uint32_t flags, bmo_result** out,
-                            int32_t* spot_obj_out = nullptr, double* spot_xz_out = nullptr) {
+                            int32_t* spot_obj_out = nullptr, double* spot_xz_out = nullptr, const RetraceView* prev_rt = nullptr) {
     if (!sys) return fail(BMO_EINVAL, "trace: NULL argument");
     if (in_h.n <= 0) return fail(BMO_EINVAL, "trace: n must be > 0");
     if (r_max < 1) return fail(BMO_EINVAL, "trace: r_max must be >= 1");
@@ -1322,7 +1532,8 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     const int64_t n = in_h.n;
 
     bmo_result* res = new bmo_result();
-    res->sys = sys; res->mode = mode; res->R = R; res->nsd = nf_seg(mode); res->n_roots = n; res->keep = flags & BMO_KEEP_SEGMENTS;
+    res->sys = sys; res->ctx = sys->ctx; res->part_object.resize(sys->parts.size()); for (size_t i = 0; i < sys->parts.size(); i++) res->part_object[i] = sys->parts[i].object;
+    res->n_objects = (int32_t)sys->objects.size(); res->mode = mode; res->R = R; res->nsd = nf_seg(mode); res->n_roots = n; res->keep = flags & BMO_KEEP_SEGMENTS;
     static const bool prof = getenv("BMO_HOST_PROFILE") != nullptr;
     const double tp0 = tnow_ms();
     BMO_CUDA(cudaEventRecord(ctx->ev0, st));
@@ -1361,6 +1572,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         s.r_max = r_max; s.has_splitter = has_splitter; s.staged = staged; s.on_dev = on_dev; s.pipelined = n_sub > 1;
         s.beam0 = n * k / n_sub; s.n = n * (k + 1) / n_sub - s.beam0;
         s.spot_obj_out = spot_obj_out; s.spot_xz_out = spot_xz_out;
+        if (prev_rt) s.rt = *prev_rt;
         if (k > 0) BMO_CUDA(cudaStreamWaitEvent(s.st, ev_fork, 0));
         if ((rc = s.begin(in_h))) return rc;
         s.n_beams = n;
@@ -1452,6 +1664,56 @@ int32_t bmo_trace_rays_spots(bmo_sys* sys, int64_t n, const double* pos, const d
     in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id;
     return trace_common(sys, E0 ? 1 : 0, in, r_max, flags & ~BMO_KEEP_SEGMENTS, out, det_object, xz);
 }
+// solve_system!(system, beam; retrace = true) on beams that already hold a solution (System.jl:444-461 with
+// retrace_system!, :188-255 / :326-428): the roots restart from their stored first rays and every beam of
+// the previous tree re-validates its stored path against the previously hit objects / hinted shapes.
+int32_t bmo_retrace(bmo_sys* sys, bmo_result* prev, int32_t r_max, uint32_t flags, bmo_result** out) {
+    if (!sys || !prev) return fail(BMO_EINVAL, "bmo_retrace: NULL argument");
+    if (!prev->keep || !prev->seg_part || !prev->seg_d) return fail(BMO_ESTATE, "bmo_retrace: the previous result has no segment table (trace it with BMO_KEEP_SEGMENTS)");
+    if (sys->ctx != prev->ctx) return fail(BMO_EINVAL, "bmo_retrace: system and previous result live on different contexts");
+    // the stored intersections name parts and objects by index: the system must have the same structure
+    // (kinematics between the solves change poses, not the object list)
+    if (sys->parts.size() != prev->part_object.size() || (int32_t)sys->objects.size() != prev->n_objects)
+        return fail(BMO_EINVAL, "bmo_retrace: the system's objects / parts differ from those of the previous solution");
+    for (size_t i = 0; i < sys->parts.size(); i++)
+        if (sys->parts[i].object != prev->part_object[i]) return fail(BMO_EINVAL, "bmo_retrace: part/object layout differs from the previous solution");
+    bmo_ctx* ctx = sys->ctx;
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    int32_t rc;
+    if ((rc = ensure_first_seg(prev))) return rc;
+    const int mode = prev->mode, R = prev->R;
+    const int64_t n = prev->n_roots;
+    PrevRoots pr{};
+    pr.seg_d = prev->seg_d; pr.first_seg = prev->first_seg; pr.rows = prev->seg_rows; pr.lam = prev->lam; pr.pose = prev->pose;
+    pr.w0 = prev->w0; pr.e0 = prev->e0; pr.n = n; pr.mode = mode;
+    if (mode == 2) {
+        BMO_CUDA(dev_alloc(&pr.grays, (size_t)n * 18, st)); BMO_CUDA(dev_alloc(&pr.ow0, (size_t)n, st)); BMO_CUDA(dev_alloc(&pr.oe0, (size_t)n * 2, st));
+    } else {
+        BMO_CUDA(dev_alloc(&pr.pos, (size_t)n * 3, st)); BMO_CUDA(dev_alloc(&pr.dir, (size_t)n * 3, st));
+        if (mode == 1) BMO_CUDA(dev_alloc(&pr.E0, (size_t)n * 6, st));
+    }
+    BMO_CUDA(dev_alloc(&pr.olam, (size_t)n, st)); BMO_CUDA(dev_alloc(&pr.opose, (size_t)n, st));
+    gather_prev_roots<<<(unsigned)((n * R + 255) / 256), 256, 0, st>>>(pr);
+    BMO_LAUNCH(ctx, "gather_prev_roots");
+    int32_t* child = nullptr;
+    BMO_CUDA(dev_alloc(&child, (size_t)2 * prev->n_beams, st));
+    BMO_CUDA(cudaMemsetAsync(child, 0xff, (size_t)2 * prev->n_beams * sizeof(int32_t), st));
+    if (prev->n_beams > n) {
+        build_child_table<<<(unsigned)((prev->n_beams - n + 255) / 256), 256, 0, st>>>(prev->parent, prev->slot, n, prev->n_beams, child);
+        BMO_LAUNCH(ctx, "build_child_table");
+    }
+    RetraceView rt;
+    rt.nseg = prev->nseg; rt.first_seg = prev->first_seg; rt.seg_part = prev->seg_part; rt.child = child; rt.w0 = prev->w0; rt.on = 1;
+    TraceInputs in{};
+    in.n = n; in.pos = pr.pos; in.dir = pr.dir; in.E0 = pr.E0; in.grays = pr.grays; in.w0 = pr.ow0; in.ge0 = pr.oe0; in.lam = pr.olam; in.pose = pr.opose;
+    uint32_t f = (flags | BMO_INPUT_DEVICE);
+    if (mode == 2) f |= BMO_KEEP_SEGMENTS;
+    rc = trace_common(sys, mode, in, r_max, f, out, nullptr, nullptr, &rt);
+    dev_free(pr.grays, st); dev_free(pr.ow0, st); dev_free(pr.oe0, st); dev_free(pr.pos, st); dev_free(pr.dir, st); dev_free(pr.E0, st);
+    dev_free(pr.olam, st); dev_free(pr.opose, st); dev_free(child, st);
+    return rc;
+}
 int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const int32_t* lambda_id, const double* w0, const double* E0,
                            const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out) {
     if (!rays || !w0 || !E0) return fail(BMO_EINVAL, "bmo_trace_beamlets: rays/w0/E0 NULL");
@@ -1476,8 +1738,8 @@ template <class T> static int32_t d2h(T* dst, const T* src, size_t n, cudaStream
 int32_t bmo_result_beams(bmo_result* r, int32_t* parent, int32_t* child_slot, int32_t* n_seg, int32_t* status, int64_t* first_seg,
                          double* w0, double* E0, int32_t* lambda_id) {
     if (!r) return fail(BMO_EINVAL, "result NULL");
-    BMO_CUDA(cudaSetDevice(r->sys->ctx->device));
-    cudaStream_t st = r->sys->ctx->stream;
+    BMO_CUDA(cudaSetDevice(r->ctx->device));
+    cudaStream_t st = r->ctx->stream;
     const size_t nb = (size_t)r->n_beams;
     int32_t rc;
     if ((rc = ensure_first_seg(r))) return rc;
@@ -1498,8 +1760,8 @@ int32_t bmo_result_segments(bmo_result* r, double* pos, double* dir, double* n, 
                             double* E0) {
     if (!r) return fail(BMO_EINVAL, "result NULL");
     if (!r->keep) return fail(BMO_ESTATE, "bmo_result_segments: trace was run without BMO_KEEP_SEGMENTS");
-    BMO_CUDA(cudaSetDevice(r->sys->ctx->device));
-    cudaStream_t st = r->sys->ctx->stream;
+    BMO_CUDA(cudaSetDevice(r->ctx->device));
+    cudaStream_t st = r->ctx->stream;
     const size_t rows = (size_t)r->seg_rows;
     if (rows == 0) return BMO_OK;
     // device table is SoA [field][row]; the ABI hands out [row][3] arrays -> stage through a host buffer
@@ -1508,7 +1770,7 @@ int32_t bmo_result_segments(bmo_result* r, double* pos, double* dir, double* n, 
     BMO_CUDA(cudaMemcpyAsync(h.data(), r->seg_d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     BMO_CUDA(cudaMemcpyAsync(hp.data(), r->seg_part, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     BMO_CUDA(cudaStreamSynchronize(st));
-    const std::vector<bmo_part>& parts = r->sys->parts;
+    const std::vector<int32_t>& part_object = r->part_object;
     for (size_t i = 0; i < rows; i++) {
         if (pos) { pos[3 * i] = h[S_PX * rows + i]; pos[3 * i + 1] = h[S_PY * rows + i]; pos[3 * i + 2] = h[S_PZ * rows + i]; }
         if (dir) { dir[3 * i] = h[S_DX * rows + i]; dir[3 * i + 1] = h[S_DY * rows + i]; dir[3 * i + 2] = h[S_DZ * rows + i]; }
@@ -1516,15 +1778,15 @@ int32_t bmo_result_segments(bmo_result* r, double* pos, double* dir, double* n, 
         if (t) t[i] = h[S_T * rows + i];
         if (nrm) { nrm[3 * i] = h[S_NX * rows + i]; nrm[3 * i + 1] = h[S_NY * rows + i]; nrm[3 * i + 2] = h[S_NZ * rows + i]; }
         if (part) part[i] = hp[i];
-        if (object) object[i] = hp[i] >= 0 ? parts[hp[i]].object : -1;
+        if (object) object[i] = hp[i] >= 0 ? part_object[hp[i]] : -1;
         if (E0 && r->mode == 1) for (int k = 0; k < 6; k++) E0[6 * i + k] = h[(S_E0 + k) * rows + i];
     }
     return BMO_OK;
 }
 int32_t bmo_result_spots(bmo_result* r, int32_t* det_object, double* xz) {
     if (!r) return fail(BMO_EINVAL, "result NULL");
-    BMO_CUDA(cudaSetDevice(r->sys->ctx->device));
-    cudaStream_t st = r->sys->ctx->stream;
+    BMO_CUDA(cudaSetDevice(r->ctx->device));
+    cudaStream_t st = r->ctx->stream;
     const size_t nr = (size_t)r->n_beams * r->R;
     int32_t rc;
     if ((rc = d2h(det_object, r->spot_obj, nr, st))) return rc;
@@ -1540,8 +1802,8 @@ int32_t bmo_result_spots_device(bmo_result* r, const int32_t** det_object, const
 }
 int32_t bmo_result_free(bmo_result* r) {
     if (!r) return BMO_OK;
-    cudaSetDevice(r->sys->ctx->device);
-    cudaStream_t st = r->sys->ctx->stream;
+    cudaSetDevice(r->ctx->device);
+    cudaStream_t st = r->ctx->stream;
     dev_free(r->parent, st); dev_free(r->slot, st); dev_free(r->nseg, st); dev_free(r->status, st); dev_free(r->lam, st); dev_free(r->pose, st);
     dev_free(r->w0, st); dev_free(r->e0, st); dev_free(r->plen, st); dev_free(r->popl, st);
     dev_free(r->spot_obj, st); dev_free(r->spot_xz, st); dev_free(r->first_seg, st);

@@ -3,11 +3,12 @@
 `solve_system_(system, beam)` flattens the system at call time (poses are static during a trace,
 docs/src/basics/elements.md), uploads the tables, runs the wavefront tracer of libbmo.so and puts
 the results where the reference puts them: `Beam.rays` / `.children`, `Spotdetector.data`,
-`Photodetector.field`.  The reference's `retrace=true` re-validates a stored path against the
-previously hit objects (System.jl:188-428); here every call is a fresh non-sequential trace, which
-gives the same result whenever the path is unchanged (see DESIGN.md "retrace").
+`Photodetector.field`.  With `retrace=True` (the reference's default) a beam that already holds a
+solution is re-validated against the previously hit objects first (retrace_system!,
+System.jl:188-428 -> bmo_retrace); a fresh beam is traced non-sequentially.
 """
 import ctypes as C
+import weakref
 
 import numpy as np
 
@@ -27,8 +28,13 @@ class DeviceSystem:
         h = C.c_void_p()
         L.check(L.lib().bmo_system_upload(self.ctx, C.byref(flat.tables), C.byref(h)))
         self.h = h
+        self._results = weakref.WeakSet()    # results traced through this system
 
     def free(self):
+        """Results are released first: whatever order the garbage collector finalises a reference cycle
+        in, a bmo_result never outlives the bmo_sys it was traced through."""
+        for r in list(self._results):
+            r.free()
         if self.h:
             L.lib().bmo_system_free(self.h)
             self.h = None
@@ -50,6 +56,8 @@ class TraceResult:
         self.n_roots, self.n_beams, self._n_segments = info.n_roots, info.n_beams, info.n_segments
         self.interactions, self.R, self.polarized, self.waves = info.interactions, info.rays_per_beam, bool(info.polarized), info.waves
         self._beams = self._segs = self._spots = None
+        dsys._results.add(self)
+        self.keep = self.R == 3      # segment table kept (set by the trace wrappers; beamlet traces always keep it)
 
     @property
     def n_segments(self):
@@ -155,7 +163,9 @@ def trace_rays(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100, keep_se
             e = np.ascontiguousarray(np.stack([ec.real, ec.imag], axis=-1).reshape(pos.shape[0], 6))
         pid = None if pose_id is None else np.ascontiguousarray(pose_id, dtype=np.int32)
         L.check(L.lib().bmo_trace_rays(dsys.h, pos.shape[0], L.ptr(pos), L.ptr(dir), L.ptr(lam_id), L.ptr(e), L.ptr(pid), r_max, flags, C.byref(h)))
-    return TraceResult(dsys, h)
+    res = TraceResult(dsys, h)
+    res.keep = bool(keep_segments)
+    return res
 
 
 def trace_rays_spots(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100):
@@ -187,6 +197,31 @@ def trace_beamlets(dsys, rays, lam_id, w0, E0, pose_id=None, r_max=100):
     h = C.c_void_p()
     L.check(L.lib().bmo_trace_beamlets(dsys.h, rays.shape[0], L.ptr(rays), L.ptr(lam_id), L.ptr(w0), L.ptr(e), L.ptr(pid), r_max, 0, C.byref(h)))
     return TraceResult(dsys, h)
+
+
+def retrace(dsys, prev, r_max=100, keep_segments=True):
+    """bmo_retrace: solve_system!(system, beam; retrace=true) for beams that already hold the solution
+    `prev` (a TraceResult with its segment table); `dsys` is the system after the kinematic changes."""
+    flags = L.KEEP_SEGMENTS if keep_segments else 0
+    h = C.c_void_p()
+    L.check(L.lib().bmo_retrace(dsys.h, prev.h, int(r_max), flags, C.byref(h)))
+    res = TraceResult(dsys, h)
+    res.keep = bool(keep_segments) or res.R == 3
+    return res
+
+
+def _previous_solution(beam, dsys, lams):
+    """The stored solution of `beam` if it can be retraced through `dsys` (same object / part structure and
+    wavelength table), else None."""
+    prev = getattr(beam, "_solution", None)
+    if prev is None or prev.h is None or not prev.keep:
+        return None
+    pf, nf = prev.dsys.flat, dsys.flat
+    if prev.dsys.device != dsys.device or len(pf.objects) != len(nf.objects) or pf.tables.n_parts != nf.tables.n_parts:
+        return None
+    if list(getattr(prev, "lams", [])) != list(lams):
+        return None
+    return prev
 
 
 def pd_accumulate(dsys, result, pd_index, field, pose=0, reference_order=False):
@@ -290,15 +325,27 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         r0 = beam.rays[0]
         lams, lam_id = _lambda_ids([r0.lam])
         dsys = upload_system(system, lams, device, norm_zero_rule)
-        E0 = np.array([r0.E0]) if r0.polarized else None
-        res = trace_rays(dsys, np.array([r0.pos]), np.array([r0.dir]), lam_id, E0, None, r_max, True)
+        prev = _previous_solution(beam, dsys, lams) if retrace else None
+        if prev is not None:
+            res = globals()["retrace"](dsys, prev, r_max)
+        else:
+            E0 = np.array([r0.E0]) if r0.polarized else None
+            res = trace_rays(dsys, np.array([r0.pos]), np.array([r0.dir]), lam_id, E0, None, r_max, True)
+        res.lams = lams
+        beam._solution = res
         _rebuild_beam(beam, res, dsys.flat)
         _collect_spots(dsys.flat, res)
         return res
     if isinstance(beam, bm.GaussianBeamlet):
         lams, lam_id = _lambda_ids([beam.lam])
         dsys = upload_system(system, lams, device, norm_zero_rule)
-        res = trace_beamlets(dsys, np.array([beam.rays18()]), lam_id, np.array([beam.w0]), np.array([beam.E0]), None, r_max)
+        prev = _previous_solution(beam, dsys, lams) if retrace else None
+        if prev is not None:
+            res = globals()["retrace"](dsys, prev, r_max)
+        else:
+            res = trace_beamlets(dsys, np.array([beam.rays18()]), lam_id, np.array([beam.w0]), np.array([beam.E0]), None, r_max)
+        res.lams = lams
+        beam._solution = res
         _rebuild_gauss(beam, res, dsys.flat)
         _collect_spots(dsys.flat, res)
         _accumulate_pds(dsys, res)
@@ -307,19 +354,28 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         lams, lam_id = _lambda_ids(beam.lam)
         dsys = upload_system(system, lams, device, norm_zero_rule)
         splitters = any(o.kind in ("thin_bs", "plate_bs", "cube_bs") for o in dsys.flat.objects)
-        if not keep_segments and not splitters:      # one beam per ray: fused trace + Spotdetector read-back (pipelined copies)
+        prev = _previous_solution(beam, dsys, lams) if retrace else None
+        if prev is not None:
+            res = globals()["retrace"](dsys, prev, r_max, keep_segments)
+        elif not keep_segments and not splitters:      # one beam per ray: fused trace + Spotdetector read-back (pipelined copies)
             obj, xz, res = trace_rays_spots(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max)
             res._spots = (obj, xz)
         else:
             res = trace_rays(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max, keep_segments)
-        beam.result = res
+        res.lams = lams
+        beam.result = beam._solution = res
         _collect_spots(dsys.flat, res)
         return res
     if isinstance(beam, bm.BeamletBundle):
         lams, lam_id = _lambda_ids(beam.lam)
         dsys = upload_system(system, lams, device, norm_zero_rule)
-        res = trace_beamlets(dsys, beam.rays, lam_id, beam.w0, beam.E0, None, r_max)
-        beam.result = res
+        prev = _previous_solution(beam, dsys, lams) if retrace else None
+        if prev is not None:
+            res = globals()["retrace"](dsys, prev, r_max)
+        else:
+            res = trace_beamlets(dsys, beam.rays, lam_id, beam.w0, beam.E0, None, r_max)
+        res.lams = lams
+        beam.result = beam._solution = res
         _collect_spots(dsys.flat, res)
         _accumulate_pds(dsys, res)
         return res

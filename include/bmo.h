@@ -187,6 +187,18 @@ int32_t bmo_trace_rays_spots(bmo_sys* sys, int64_t n, const double* pos, const d
 int32_t bmo_trace_beamlets(bmo_sys* sys, int64_t n, const double* rays, const int32_t* lambda_id, const double* w0,
                            const double* E0, const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out);
 
+/* replaces: solve_system!(system, beam; retrace = true) for beams that already hold a solution
+ * (solve_system!, System.jl:444-461; retrace_system! for Beam, :188-255, and GaussianBeamlet, :326-428).
+ * `prev` is the result of an earlier bmo_trace_* / bmo_retrace call (with its segment table) on a system
+ * of the same structure; `sys` carries the poses after the kinematic changes.  Every beam of the previous
+ * tree re-validates its stored path: each stored ray is intersected only with the object it hit before
+ * (or with the shape hinted by the preceding interaction) and interacts again; where the path breaks the
+ * stored tail and children are dropped and the ordinary non-sequential trace continues from there with no
+ * hint.  Children of a re-validated beamsplitter hit keep retracing their own stored paths, and Gaussian
+ * children keep their stored w0 (_modify_beam_head!, Gaussian.jl:154-162).  Like the reference, a retraced
+ * ray does not see objects that moved into its path.  The roots restart from their stored first rays.    */
+int32_t bmo_retrace(bmo_sys* sys, bmo_result* prev, int32_t r_max, uint32_t flags, bmo_result** out);
+
 /* ---- result access.  Beams are numbered roots first (0..n-1), children in spawn order.         */
 typedef struct bmo_result_info {
     int64_t n_roots, n_beams, n_segments /* -1 until bmo_result_beams / _segments was called on a spot-only trace */, interactions;

@@ -406,6 +406,19 @@ int orc_solve(int hsys, int hbeam, int r_max) {
     ORC_CATCH(-1)
 }
 
+// solve_system!(system, beam; r_max, retrace=true) on a beam that may already hold a solution (System.jl:444-461)
+int orc_solve_retrace(int hsys, int hbeam, int r_max) {
+    ORC_TRY
+    System* sys = g_reg.at(hsys).system;
+    sys->flatten();
+    Entry& e = g_reg.at(hbeam);
+    if (e.beam) solve_system(*sys, *e.beam, r_max, true);
+    else if (e.gauss) solve_system(*sys, *e.gauss, r_max, true);
+    else throw std::runtime_error("not a beam");
+    return 0;
+    ORC_CATCH(-1)
+}
+
 // Beam tree export in BFS (level) order.  Layout per ray (24 doubles):
 // pos3 dir3 n lambda t nrm3 obj part E0(6) polarized pad(3)
 static void export_beam(System* sys, Beam* root, std::vector<double>& rays, std::vector<int>& beams) {

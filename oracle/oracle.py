@@ -196,8 +196,13 @@ def gaussian_beamlet(pos, dir, lam=1e-6, w0=1e-3, M2=1.0, P0=1e-3, z0=0.0, suppo
     return new("GaussianBeamlet", list(pos) + list(dir) + [lam, w0, M2, P0, z0] + list(support))
 
 
-def solve_system_(sys, beam_handle, r_max=100):
-    _chk(lib().orc_solve(sys.h, beam_handle.h, int(r_max)))
+def solve_system_(sys, beam_handle, r_max=100, retrace=False):
+    """solve_system!(system, beam; r_max, retrace).  retrace=True re-validates a stored solution first
+    (System.jl:188-428); on a fresh beam both give the same result."""
+    if retrace:
+        _chk(lib().orc_solve_retrace(sys.h, beam_handle.h, int(r_max)))
+    else:
+        _chk(lib().orc_solve(sys.h, beam_handle.h, int(r_max)))
 
 
 RAY_FIELDS = 24

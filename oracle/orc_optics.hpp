@@ -469,12 +469,28 @@ inline Beam* bs_reflected_beam(Object* bs, Ray& ray) {
     b->rays.push_back(make_pol_ray(pos, dir, ray.lambda, E0));
     return b;
 }
-// AbstractBeam.jl:59-76 children!(beam, [t, r]) for a fresh (childless) beam; the retrace
-// "_modify_beam_head!" branch is not needed because the oracle always traces fresh beams.
+// Beam.jl:97-112 _modify_beam_head!(old, new): the first ray of a stored child takes position, direction,
+// wavelength, refractive index (and polarisation) of the freshly computed child; its stored path stays.
+inline void modify_beam_head(Beam& old_, const Beam& new_) {
+    Ray& o = old_.rays.front(); const Ray& n = new_.rays.front();
+    o.pos = n.pos; o.dir = n.dir; o.lambda = n.lambda; o.n = n.n;
+    if (o.polarized) for (int k = 0; k < 3; k++) o.E0[k] = n.E0[k];
+}
+// AbstractBeam.jl:59-76 children!(beam, [t, r]): a childless beam adopts the children; a beam that
+// already has as many children (retracing) only gets their heads modified; anything else is an error.
 inline void set_children(Beam& beam, Beam* t, Beam* r) {
-    beam.drop_children();
-    t->parent = &beam; r->parent = &beam;
-    beam.children = {t, r};
+    if (beam.children.empty()) {
+        t->parent = &beam; r->parent = &beam;
+        beam.children = {t, r};
+        return;
+    }
+    if (beam.children.size() == 2) {
+        modify_beam_head(*beam.children[0], *t);
+        modify_beam_head(*beam.children[1], *r);
+        delete t; delete r;
+        return;
+    }
+    throw std::runtime_error("Adding children to beam failed");
 }
 // ThinBeamsplitter.jl:108-115
 inline BeamInteraction interact_thin_bs(System&, Object* bs, Beam& beam, Ray& ray) {
@@ -606,9 +622,21 @@ inline GaussInteraction interact_gauss_thin_bs(System&, Object* bs, Gauss& g, in
     Gauss* t = bs_child_gauss(bs, g, id, false);
     Gauss* r = bs_child_gauss(bs, g, id, true);
     r->E0 = r->E0 * cis(phi);
-    g.drop_children();
-    for (Gauss* c : {t, r}) { c->parent = &g; c->chief.parent = &g.chief; }  // Gaussian.jl:107-111
-    g.children = {t, r};
+    if (g.children.empty()) {   // AbstractBeam.jl:59-76 children!
+        for (Gauss* c : {t, r}) { c->parent = &g; c->chief.parent = &g.chief; }  // Gaussian.jl:107-111
+        g.children = {t, r};
+    } else if (g.children.size() == 2) {   // retracing: Gaussian.jl:154-162 _modify_beam_head! (w0 is NOT updated)
+        Gauss* nw[2] = {t, r};
+        for (int k = 0; k < 2; k++) {
+            Gauss* o = g.children[k];
+            modify_beam_head(o->chief, nw[k]->chief);
+            modify_beam_head(o->waist, nw[k]->waist);
+            modify_beam_head(o->divergence, nw[k]->divergence);
+            o->lambda = nw[k]->lambda;
+            o->E0 = nw[k]->E0;
+            delete nw[k];
+        }
+    } else throw std::runtime_error("Adding children to beam failed");
     return GaussInteraction{};
 }
 inline void gauss_set_n(Gauss& g, int id, double n) { g.chief.rays[id].n = n; g.waist.rays[id].n = n; g.divergence.rays[id].n = n; }
@@ -725,21 +753,105 @@ inline void trace_system(System& sys, Gauss& g, int r_max) {
     }
 }
 
-// System.jl:444-475  BFS over the beam tree (fresh beams: retrace is a no-op for a 1-ray beam with
-// no intersection -- System.jl:200-206 resets nothing -- so retrace is not restated; re-solving after
-// a pose change is done from a fresh beam, see DESIGN.md "retrace").
-inline void solve_system(System& sys, Beam& root, int r_max = 100) {
+// System.jl:188-255 retrace_system!(system, beam): re-validate the stored path against the previously
+// hit objects (or the hinted shapes) only; the tail is dropped where the path changes.
+inline void retrace_system(System& sys, Beam& beam) {
+    bool cleanup_children = false, cleanup_tail = false, reset_intersection = false;
+    size_t cutoff = 0;   // 1-based like the reference
+    Hint hint;
+    const size_t n0 = beam.rays.size();
+    for (size_t i = 1; i <= n0; i++) {
+        Ray& ray = beam.rays[i - 1];
+        if (!ray.hit.valid) { cleanup_children = cleanup_tail = reset_intersection = true; cutoff = i; break; }
+        if (!hint.valid()) ray.hit = ray.hit.object->intersect(ray);
+        else {
+            Object* ho = hint.object;
+            ray.hit = hint.shape->intersect(ray.pos, ray.dir);
+            if (ray.hit.valid) ray.hit.object = ho;
+        }
+        if (!ray.hit.valid) { cleanup_children = cleanup_tail = reset_intersection = true; cutoff = i; break; }
+        BeamInteraction in = interact3d(sys, ray.hit.object, beam, beam.rays[i - 1]);
+        hint = in.valid ? in.hint : Hint{};
+        if (!in.valid) {
+            if (beam.rays.size() > i) { cleanup_tail = true; cutoff = i; }
+            break;
+        }
+        if (i < beam.rays.size()) {   // Beam.jl:82-95 replace!
+            Ray& nx = beam.rays[i];
+            nx.pos = in.ray.pos; nx.dir = in.ray.dir; nx.lambda = in.ray.lambda; nx.n = in.ray.n;
+            if (nx.polarized) for (int k = 0; k < 3; k++) nx.E0[k] = in.ray.E0[k];
+        } else {
+            cleanup_children = true;
+            beam.rays.push_back(in.ray);
+            break;
+        }
+    }
+    if (cleanup_children) beam.drop_children();
+    if (cleanup_tail) beam.rays.resize(cutoff);
+    if (reset_intersection) beam.rays.back().hit = Hit{};
+}
+// System.jl:326-428
+inline void retrace_system(System& sys, Gauss& g) {
+    bool cleanup_children = false, cleanup_tail = false, reset_intersection = false;
+    size_t cutoff = 0;
+    Hint hint;
+    const size_t n_c = g.chief.rays.size();
+    if (!(n_c == g.waist.rays.size() && n_c == g.divergence.rays.size())) throw std::runtime_error("Gaussian beamlet is broken");
+    for (size_t i = 1; i <= n_c; i++) {
+        Ray &c = g.chief.rays[i - 1], &w = g.waist.rays[i - 1], &d = g.divergence.rays[i - 1];
+        if (!c.hit.valid) { cleanup_children = cleanup_tail = reset_intersection = true; cutoff = i; break; }
+        Object* object;
+        if (!hint.valid()) {
+            object = c.hit.object;
+            c.hit = object->intersect(c); w.hit = object->intersect(w); d.hit = object->intersect(d);
+        } else {
+            object = hint.object;
+            c.hit = hint.shape->intersect(c.pos, c.dir); w.hit = hint.shape->intersect(w.pos, w.dir); d.hit = hint.shape->intersect(d.pos, d.dir);
+        }
+        if (!beams_hit_same_shape(g, (int)i - 1)) { cleanup_children = cleanup_tail = reset_intersection = true; cutoff = i; break; }
+        if (!c.hit.valid) { cleanup_children = cleanup_tail = reset_intersection = true; cutoff = i; break; }
+        c.hit.object = object; w.hit.object = object; d.hit.object = object;
+        GaussInteraction in = interact3d(sys, object, g, (int)i - 1);
+        hint = in.valid ? in.c.hint : Hint{};
+        if (!in.valid) {
+            if (n_c > i) { cleanup_tail = true; cutoff = i; }
+            break;
+        }
+        if (i < n_c) {
+            Beam* bs[3] = {&g.chief, &g.waist, &g.divergence};
+            const BeamInteraction* is[3] = {&in.c, &in.w, &in.d};
+            for (int k = 0; k < 3; k++) {
+                Ray& nx = bs[k]->rays[i];
+                nx.pos = is[k]->ray.pos; nx.dir = is[k]->ray.dir; nx.lambda = is[k]->ray.lambda; nx.n = is[k]->ray.n;
+            }
+        } else {
+            cleanup_children = true;
+            g.chief.rays.push_back(in.c.ray); g.waist.rays.push_back(in.w.ray); g.divergence.rays.push_back(in.d.ray);
+            break;
+        }
+    }
+    if (cleanup_children) g.drop_children();
+    if (cleanup_tail) { g.chief.rays.resize(cutoff); g.waist.rays.resize(cutoff); g.divergence.rays.resize(cutoff); }
+    if (reset_intersection) { g.chief.rays.back().hit = Hit{}; g.waist.rays.back().hit = Hit{}; g.divergence.rays.back().hit = Hit{}; }
+}
+
+// System.jl:444-475  BFS over the beam tree: optional retrace of every beam, then trace of the leaves.
+// (Retracing a fresh 1-ray beam is a no-op: System.jl:200-206 only resets an intersection that is
+// already nothing.)
+inline void solve_system(System& sys, Beam& root, int r_max = 100, bool retrace = false) {
     std::deque<Beam*> q{&root};
     while (!q.empty()) {
         Beam* cur = q.front(); q.pop_front();
+        if (retrace) retrace_system(sys, *cur);
         if (!cur->rays.back().hit.valid) trace_system(sys, *cur, r_max);
         for (auto* c : cur->children) q.push_back(c);
     }
 }
-inline void solve_system(System& sys, Gauss& root, int r_max = 100) {
+inline void solve_system(System& sys, Gauss& root, int r_max = 100, bool retrace = false) {
     std::deque<Gauss*> q{&root};
     while (!q.empty()) {
         Gauss* cur = q.front(); q.pop_front();
+        if (retrace) retrace_system(sys, *cur);
         if (!cur->chief.rays.back().hit.valid) trace_system(sys, *cur, r_max);
         for (auto* c : cur->children) q.push_back(c);
     }
