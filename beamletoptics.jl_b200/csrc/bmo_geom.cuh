@@ -234,21 +234,48 @@ struct SdfShape {
     int first, count, zr;
     double cx, cy, cz, R2;   // conservative bounding sphere (inflated by the flattener)
 };
+// Lower bounds of the first four member values of a union, carried along one march (result-identical
+// work skipping): every member is 1-Lipschitz (exact SDFs, min / max of them), so after the march
+// point has moved by s a member that was worth v is worth at least v - s.  A member whose bound
+// exceeds a value already found at the new point cannot be (or tie with) the minimum, so its
+// evaluation changes neither the union's value nor its arg-min.  Bounds are kept in binary32 with
+// directed rounding (down for bounds, up for steps and for the running minimum) plus a 1e-7 m margin,
+// orders of magnitude above the rounding of the SDF arithmetic itself.
+struct MemberBounds {
+    float b0, b1, b2, b3;
+    int pred;   // prim index of the previous arg-min if it is a plain member (evaluated first), else -1
+    BMO_D void reset() { b0 = b1 = b2 = b3 = -INFINITY; pred = -1; }
+    BMO_D float get(int k) const { return k == 0 ? b0 : (k == 1 ? b1 : (k == 2 ? b2 : b3)); }
+    BMO_D void set(int k, float v) { if (k == 0) b0 = v; else if (k == 1) b1 = v; else if (k == 2) b2 = v; else b3 = v; }
+    BMO_D void moved(double step) {   // the march point moved by at most `step` (>= 0)
+        const float s = __double2float_ru(step);
+        b0 = __fsub_rd(b0, s); b1 = __fsub_rd(b1, s); b2 = __fsub_rd(b2, s); b3 = __fsub_rd(b3, s);
+    }
+};
 // UnionSDF.jl:53-56: minimum over the members (left fold); idx = first member attaining it, which
 // is the member normal3d(::UnionSDF) dispatches to (UnionSDF.jl:86-91) -- the reference evaluates the
 // members a second time for the argmin, the values are the same.  A member is a primitive or a
 // meniscus frame followed by its 3 children (convex, cylinder, concave) evaluated at the frame-local
 // point: max(min(convex, cylinder), -concave) (MeniscusLensSDF.jl:42-46).  Written as one flat loop
 // over the prim records so that prim_eval_f is instantiated once (instruction-cache footprint).
-BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx) {
-    const int end = sh.first + sh.count;
+// The previous arg-min member is evaluated first (its value bounds the minimum from above), then the
+// others in order unless their lower bound rules them out; ties still go to the lowest member index.
+BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx, MemberBounds& lb) {
+    const int first = sh.first, end = sh.first + sh.count;
     double m = 0.0, acc = 0.0;
     V3 q = p;
-    int men = 0, start = sh.first;
+    int men = 0, start = first;
     bool have = false;
-    for (int i = sh.first; i < end; i++) {
+    float m_ub = INFINITY;
+    const int ip = lb.pred;
+    for (int j = ip >= 0 ? first - 1 : first; j < end; j++) {
+        const int i = j < first ? ip : j;
+        if (j >= first && i == ip) continue;                 // evaluated first
         const bmo_prim& pr = sh.prims[i];
         if (pr.type == BMO_PRIM_MENISCUS) { q = w2s_f(pr, p); men = 3; start = i; continue; }
+        const int k = i - first;
+        const bool tracked = men == 0 && k < 4;
+        if (tracked && have && lb.get(k) > m_ub) continue;   // cannot be the minimum at this point
         double v = prim_eval_f(pr, q);
         nsdf++;
         if (men) {
@@ -257,9 +284,12 @@ BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx) {
             else { v = fmax_jl(acc, -v); q = p; }        // concave closes the member
             if (--men) continue;
         } else start = i;
+        if (tracked) lb.set(k, __double2float_rd(v));
         if (!have) { m = v; idx = start; have = true; }
-        else { if (v < m) idx = start; m = fmin_jl(m, v); }
+        else { if (v < m || (v == m && start < idx)) idx = start; m = fmin_jl(m, v); }
+        m_ub = __fadd_ru(__double2float_ru(m), 1e-7f);
     }
+    lb.pred = (idx - first < 4 && sh.prims[idx].type != BMO_PRIM_MENISCUS) ? idx : -1;
     return m;
 }
 // AbstractSDF.jl:79-95: ForwardDiff gradient of member idx; central differences (eps = 1e-8) if any
@@ -310,24 +340,27 @@ BMO_D bool sdf_intersect_f(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, d
     bool back = false;
     V3 p = pos, d = dir;
     double t0 = 0.0, tin = 0.0;
+    MemberBounds lb; lb.reset();
+    // |d| <= max(1, |d|^2): how far the march point moves per unit of step (directions are unit up to rounding)
+    const double dlen = fmax(1.0, dot(dir, dir)) * (1.0 + 1e-9);
     for (;;) {
         int idx;
-        const double dist = shape_sdf_f(sh, p, nsdf, idx);
+        const double dist = shape_sdf_f(sh, p, nsdf, idx, lb);
         if (mode == OUT) {
             t0 += dist;
             if (!(dist < eps_ray)) {
                 const V3 v = mk3(p.x - sh.cx, p.y - sh.cy, p.z - sh.cz);
                 if (dot(v, v) > sh.R2 && dot(v, d) > 0.0) return false;
                 if (++it >= kMarchIter || !(dist == dist)) return false;   // NaN can never satisfy dist < eps_ray again
-                p = p + dist * d;
+                p = p + dist * d; lb.moved(dist * dlen);
                 continue;
             }
         } else if (mode == INIT) {
-            if (dist > eps_srf) { mode = OUT; t0 = dist; p = p + dist * d; continue; }
+            if (dist > eps_srf) { mode = OUT; t0 = dist; p = p + dist * d; lb.moved(dist * dlen); continue; }
         } else {  // IN
-            if (dist > 0) { mode = OUT; back = true; d = -d; t0 = dist; it = 0; p = p + dist * d; continue; }
+            if (dist > 0) { mode = OUT; back = true; d = -d; t0 = dist; it = 0; p = p + dist * d; lb.moved(dist * dlen); continue; }
             if (++it >= kMarchIter) return false;
-            p = p + eps_ins * d; tin += eps_ins;
+            p = p + eps_ins * d; tin += eps_ins; lb.moved(eps_ins * dlen);
             continue;
         }
         {
@@ -338,7 +371,7 @@ BMO_D bool sdf_intersect_f(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, d
         if (mode == OUT) { t = back ? tin - t0 : t0; return true; }
         if (!(dot(d, n) <= 0)) return false;   // on the surface, heading out
         mode = IN; it = 0;
-        p = p + eps_ins * d; tin = eps_ins;
+        p = p + eps_ins * d; tin = eps_ins; lb.moved(eps_ins * dlen);
     }
 }
 
