@@ -10,7 +10,7 @@ from ._lib import BmoError, counters, counters_reset, measure_fp64_peak
 from .beams import (Beam, BeamletBundle, CollimatedSource, GaussianBeamlet, Intersection, PointSource, PolarizedRay, Ray,
                     RayBundle, UniformDiscSource)
 from .components import (ConcaveSphericalMirror, CubeBeamsplitter, DiscreteRefractiveIndex, DoubletLens, IntersectableObject, Lens,
-                         MeshDummy, Mirror, NonInteractableObject, ObjectGroup, Photodetector, Prism, RectangularCompensatorPlate,
+                         MeshDummy, Mirror, NonInteractableObject, ObjectGroup, PSFDetector, Photodetector, Prism, RectangularCompensatorPlate,
                          RectangularPlanoMirror, RectangularPlateBeamsplitter, Retroreflector, RightAnglePrism, RightAnglePrismMirror,
                          RoundPlanoMirror, RoundPlateBeamsplitter, RoundThinBeamsplitter, SellmeierEquation, SphericalDoubletLens,
                          SphericalLens, Spotdetector, SquarePlanoMirror, SquarePlanoMirror2D, StaticSystem, System, ThinBeamsplitter,

@@ -57,7 +57,8 @@ class bmo_counters(C.Structure):
     _fields_ = [("interactions", C.c_int64), ("sdf_evals", C.c_int64), ("tri_tests", C.c_int64), ("waves", C.c_int64),
                 ("kernel_launches", C.c_int64), ("px_beamlets", C.c_int64), ("trace_ms", C.c_double), ("pd_ms", C.c_double),
                 ("trace_step_ms", C.c_double), ("trace_step_launches", C.c_int64), ("scatter_ms", C.c_double),
-                ("scatter_bytes", C.c_double), ("pd_field_ms", C.c_double)]
+                ("scatter_bytes", C.c_double), ("pd_field_ms", C.c_double),
+                ("psf_pairs", C.c_int64), ("psf_ms", C.c_double)]
 
 
 class bmo_result_info(C.Structure):
@@ -69,7 +70,7 @@ class bmo_result_info(C.Structure):
 EXPORTS = [
     "bmo_init", "bmo_shutdown", "bmo_last_error", "bmo_set_stream", "bmo_counters_get", "bmo_counters_reset",
     "bmo_system_upload", "bmo_system_free", "bmo_system_set_poses", "bmo_trace_rays", "bmo_trace_rays_spots", "bmo_trace_beamlets",
-    "bmo_retrace",
+    "bmo_retrace", "bmo_psf_collect", "bmo_psf_count", "bmo_psf_data", "bmo_psf_lims", "bmo_psf_intensity", "bmo_psf_free",
     "bmo_result_get_info", "bmo_result_beams", "bmo_result_segments", "bmo_result_spots", "bmo_result_spots_device",
     "bmo_result_free", "bmo_pd_accumulate", "bmo_pd_accumulate_poses", "bmo_pd_power", "bmo_measure_fp64_peak",
 ]
@@ -106,6 +107,12 @@ def lib():
         L.bmo_pd_accumulate.argtypes = [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_uint32]
         L.bmo_pd_accumulate_poses.argtypes = [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_uint32]
         L.bmo_pd_power.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_uint32]
+        L.bmo_psf_collect.argtypes = [_vp, _vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_int64)]
+        L.bmo_psf_count.argtypes = [_vp, C.POINTER(C.c_int64)]
+        L.bmo_psf_data.argtypes = [_vp, _vp]
+        L.bmo_psf_lims.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_double, C.c_int32, _vp]
+        L.bmo_psf_intensity.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_double, C.c_double, _vp, C.c_uint32]
+        L.bmo_psf_free.argtypes = [_vp]
         L.bmo_measure_fp64_peak.argtypes = [_vp, _dp]
         _lib = L
     return _lib

@@ -279,6 +279,49 @@ class Spotdetector(AbstractObject):
     def empty_(self): self.data = np.zeros((0, 2))
 
 
+class PSFDetector(AbstractObject):
+    """Detectors/PSFDetector.jl:44-68.  The hit records (`PSFData`: hit, dir, opl, proj, k) stay on the device
+    (bmo_psf); `data` downloads them, `intensity` runs the coherent sum kernel (PSFDetector.jl:190-237)."""
+    kind = "psf"
+
+    def __init__(self, width):
+        self.shape = sh.QuadraticFlatMesh(width)
+        self.shape.zrotate3d_(math.pi)
+        self._psf = None        # bmo_psf handle (ctypes void*), filled by solve_system_
+        self._dsys = None       # the DeviceSystem of the last solve (detector pose for intensity / lims)
+        self._index = -1
+
+    def __len__(self):
+        from . import solver
+        return solver.psf_count(self)
+
+    @property
+    def data(self):
+        """(n, 9) array: hit xyz, dir xyz, optical path length, projection factor, wavenumber."""
+        from . import solver
+        return solver.psf_data(self)
+
+    def empty_(self):
+        from . import solver
+        solver.psf_free(self)
+
+    def calc_local_lims(self, crop_factor=1.0, center="centroid"):
+        from . import solver
+        return solver.psf_lims(self, crop_factor, center)
+
+    def intensity(self, n=100, crop_factor=1.0, center="centroid", x_min=math.inf, x_max=math.inf, z_min=math.inf, z_max=math.inf,
+                  x0_shift=0.0, z0_shift=0.0):
+        """-> (xs, zs, I) like intensity(psf; ...) (PSFDetector.jl:190-237); I is (n, n), raw / unscaled."""
+        from . import solver
+        return solver.psf_intensity(self, n, crop_factor, center, x_min, x_max, z_min, z_max, x0_shift, z0_shift)
+
+    def __del__(self):
+        try:
+            self.empty_()
+        except Exception:
+            pass
+
+
 # ---- constructors ------------------------------------------------------------------------------
 def _surf_forward(r, d):    # SphericalLensSDF.jl:423-437
     if math.isinf(r):

@@ -35,7 +35,8 @@ struct bmo_ctx {
     bmo::DevCounters* d_counters = nullptr;
     long long* d_totals = nullptr;   // [4] scratch for scans
     long long* h_totals = nullptr;   // pinned, 8 entries for the scans + 8 per sub-batch slot
-    int64_t waves = 0, launches = 0, px_beamlets = 0;
+    int64_t waves = 0, launches = 0, px_beamlets = 0, psf_pairs = 0;
+    double psf_ms = 0;
     double trace_ms = 0, pd_ms = 0;
     int sm_count = 148;
 };

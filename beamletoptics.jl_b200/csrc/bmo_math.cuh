@@ -163,6 +163,32 @@ BMO_HD Dual norm3_(Dual a, Dual b, Dual c, int zr) {
     return sqrt_(s);
 }
 
+// sincos of a large phase (k z is O(1e7) rad; CUDA's sincos leaves its fast path at |x| > 105615):
+// Cody-Waite reduction by pi/2 with two FMAs (n < 2^31, residual error n * 1.5e-33), then the
+// fdlibm minimax kernels on [-pi/4, pi/4] (error < 1 ulp) and the quadrant swap.
+BMO_D void sincos_reduced(double x, double* sn, double* cs) {
+    const double n = rint(x * 0.6366197723675814);          // 2 / pi
+    double r = fma(n, -1.5707963267948966, x);              // pi/2 hi
+    r = fma(n, -6.123233995736766e-17, r);                  // pi/2 lo
+    const double z = r * r;
+    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
+    ps = fma(z, ps, 2.75573137070700676789e-06);
+    ps = fma(z, ps, -1.98412698298579493134e-04);
+    ps = fma(z, ps, 8.33333333332248946124e-03);
+    ps = fma(z, ps, -1.66666666666666324348e-01);
+    const double s0 = fma(z * r, ps, r);
+    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
+    pc = fma(z, pc, -2.75573143513906633035e-07);
+    pc = fma(z, pc, 2.48015872894767294178e-05);
+    pc = fma(z, pc, -1.38888888888741095749e-03);
+    pc = fma(z, pc, 4.16666666666666019037e-02);
+    const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
+    const int q = (int)(long long)n;
+    const double sv = (q & 1) ? c0 : s0, cv = (q & 1) ? s0 : c0;
+    *sn = (q & 2) ? -sv : sv;
+    *cs = ((q + 1) & 2) ? -cv : cv;
+}
+
 template <class T> struct P3 { T x, y, z; };
 
 }  // namespace bmo

@@ -992,6 +992,7 @@ int32_t bmo_counters_get(bmo_ctx* c, bmo_counters* o) {
     o->trace_ms = c->trace_ms; o->pd_ms = c->pd_ms;
     o->trace_step_ms = c->k1_ms; o->trace_step_launches = c->k1_launches; o->scatter_ms = c->k3_ms; o->scatter_bytes = c->k3_bytes;
     o->pd_field_ms = c->k4_ms;
+    o->psf_pairs = c->psf_pairs; o->psf_ms = c->psf_ms;
     return BMO_OK;
 }
 int32_t bmo_counters_reset(bmo_ctx* c) {
@@ -999,7 +1000,7 @@ int32_t bmo_counters_reset(bmo_ctx* c) {
     BMO_CUDA(cudaSetDevice(c->device));
     BMO_CUDA(cudaStreamSynchronize(c->stream));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
-    c->waves = c->launches = c->px_beamlets = 0;
+    c->waves = c->launches = c->px_beamlets = 0; c->psf_pairs = 0; c->psf_ms = 0;
     c->k1_ms = c->k3_ms = c->k3_bytes = c->k4_ms = 0; c->k1_launches = 0; c->interactions_seen = 0;
     return BMO_OK;
 }

@@ -17,10 +17,10 @@ from . import shapes as sh
 
 SHAPE_SDF, SHAPE_MESH = 0, 1
 ROLE_SINGLE, ROLE_FRONT, ROLE_BACK, ROLE_SUBSTRATE, ROLE_COATING = range(5)
-OBJ_REFRACTIVE, OBJ_MIRROR, OBJ_THIN_BS, OBJ_PLATE_BS, OBJ_CUBE_BS, OBJ_DOUBLET, OBJ_PD, OBJ_SPOT, OBJ_STOP = range(9)
+OBJ_REFRACTIVE, OBJ_MIRROR, OBJ_THIN_BS, OBJ_PLATE_BS, OBJ_CUBE_BS, OBJ_DOUBLET, OBJ_PD, OBJ_SPOT, OBJ_STOP, OBJ_PSF = range(10)
 
 _KIND = {"refractive": OBJ_REFRACTIVE, "mirror": OBJ_MIRROR, "thin_bs": OBJ_THIN_BS, "plate_bs": OBJ_PLATE_BS,
-         "cube_bs": OBJ_CUBE_BS, "doublet": OBJ_DOUBLET, "pd": OBJ_PD, "spot": OBJ_SPOT, "stop": OBJ_STOP}
+         "cube_bs": OBJ_CUBE_BS, "doublet": OBJ_DOUBLET, "pd": OBJ_PD, "spot": OBJ_SPOT, "stop": OBJ_STOP, "psf": OBJ_PSF}
 _ROLES = {"plate_bs": (ROLE_SUBSTRATE, ROLE_COATING), "cube_bs": (ROLE_FRONT, ROLE_BACK, ROLE_COATING),
           "doublet": (ROLE_FRONT, ROLE_BACK)}
 

@@ -335,6 +335,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         beam._solution = res
         _rebuild_beam(beam, res, dsys.flat)
         _collect_spots(dsys.flat, res)
+        _collect_psfs(dsys, res)
         return res
     if isinstance(beam, bm.GaussianBeamlet):
         lams, lam_id = _lambda_ids([beam.lam])
@@ -354,6 +355,8 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         lams, lam_id = _lambda_ids(beam.lam)
         dsys = upload_system(system, lams, device, norm_zero_rule)
         splitters = any(o.kind in ("thin_bs", "plate_bs", "cube_bs") for o in dsys.flat.objects)
+        has_psf = any(isinstance(o, co.PSFDetector) for o in dsys.flat.objects)
+        keep_segments = keep_segments or has_psf       # the PSF records are rebuilt from the segment table
         prev = _previous_solution(beam, dsys, lams) if retrace else None
         if prev is not None:
             res = globals()["retrace"](dsys, prev, r_max, keep_segments)
@@ -365,6 +368,8 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         res.lams = lams
         beam.result = beam._solution = res
         _collect_spots(dsys.flat, res)
+        if has_psf:
+            _collect_psfs(dsys, res)
         return res
     if isinstance(beam, bm.BeamletBundle):
         lams, lam_id = _lambda_ids(beam.lam)
@@ -380,6 +385,72 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         _accumulate_pds(dsys, res)
         return res
     raise TypeError(f"cannot trace {type(beam).__name__}")
+
+
+# ---- PSFDetector (PSFDetector.jl) -----------------------------------------------------------------------
+def _collect_psfs(dsys, res):
+    """interact3d(::PSFDetector, ::Beam, ::Ray) of every beam that ended on a PSF detector (push! order is
+    irrelevant for the sums that use the data)."""
+    for oi, o in enumerate(dsys.flat.objects):
+        if isinstance(o, co.PSFDetector):
+            h = C.c_void_p(o._psf) if o._psf else C.c_void_p()
+            n = C.c_int64(0)
+            L.check(L.lib().bmo_psf_collect(dsys.h, res.h, oi, C.byref(h), C.byref(n)))
+            o._psf, o._dsys, o._index = h.value, dsys, oi
+
+
+def psf_count(psf):
+    if not psf._psf:
+        return 0
+    n = C.c_int64(0)
+    L.check(L.lib().bmo_psf_count(C.c_void_p(psf._psf), C.byref(n)))
+    return int(n.value)
+
+
+def psf_data(psf):
+    n = psf_count(psf)
+    out = np.zeros((n, 9))
+    if n:
+        L.check(L.lib().bmo_psf_data(C.c_void_p(psf._psf), L.ptr(out)))
+    return out
+
+
+def psf_free(psf):
+    if psf._psf:
+        L.lib().bmo_psf_free(C.c_void_p(psf._psf))
+    psf._psf = None
+
+
+def _psf_dsys(psf):
+    """(system, object index) of the solve that filled the detector: lims / intensity use the detector's
+    pose at that solve."""
+    if not psf._psf:
+        raise L.BmoError("the PSFDetector holds no data (solve_system_ first)")
+    return psf._dsys, psf._index
+
+
+def psf_lims(psf, crop_factor=1.0, center="centroid"):
+    dsys, oi = _psf_dsys(psf)
+    lims = np.zeros(4)
+    L.check(L.lib().bmo_psf_lims(dsys.h, C.c_void_p(psf._psf), oi, 0, float(crop_factor), 0 if center == "centroid" else 1, L.ptr(lims)))
+    return tuple(float(x) for x in lims)
+
+
+def psf_intensity(psf, n=100, crop_factor=1.0, center="centroid", x_min=np.inf, x_max=np.inf, z_min=np.inf, z_max=np.inf,
+                  x0_shift=0.0, z0_shift=0.0):
+    dsys, oi = _psf_dsys(psf)
+    lims = list(psf_lims(psf, crop_factor, center))
+    if x_min != np.inf and x_max != np.inf:          # PSFDetector.jl:202-205
+        lims[0], lims[1] = float(x_min), float(x_max)
+    if z_min != np.inf and z_max != np.inf:
+        lims[2], lims[3] = float(z_min), float(z_max)
+    lims = np.array(lims, dtype=np.float64)
+    I = np.zeros((n, n), order="F")
+    L.check(L.lib().bmo_psf_intensity(dsys.h, C.c_void_p(psf._psf), oi, 0, int(n), L.ptr(lims), float(x0_shift), float(z0_shift), L.ptr(I), 0))
+    t = np.arange(n) / (n - 1) if n > 1 else np.zeros(1)
+    xs = ((1 - t) * lims[0] + t * lims[1]) + x0_shift
+    zs = ((1 - t) * lims[2] + t * lims[3]) + z0_shift
+    return xs, zs, I
 
 
 def _accumulate_pds(dsys, res):

@@ -86,7 +86,9 @@ enum bmo_obj_kind {
     BMO_OBJ_DOUBLET = 5,      /* parts: front, back     (DoubletLenses.jl:66-76)                  */
     BMO_OBJ_PHOTODETECTOR = 6,/* (Photodetector.jl:69-107)                                        */
     BMO_OBJ_SPOTDETECTOR = 7, /* (Spotdetector.jl:50-61)                                          */
-    BMO_OBJ_STOP = 8          /* IntersectableObject    (Intersectable.jl:15)                     */
+    BMO_OBJ_STOP = 8,         /* IntersectableObject    (Intersectable.jl:15)                     */
+    BMO_OBJ_PSFDETECTOR = 9   /* PSFDetector            (Detectors/PSFDetector.jl:77-89): absorbs; the hit records are
+                                 rebuilt from the segment table by bmo_psf_collect                */
 };
 typedef struct bmo_object {
     int32_t kind;
@@ -146,6 +148,8 @@ typedef struct bmo_counters {
     double scatter_ms;      /* accumulated device time of the queue scatter kernel (K3)             */
     double scatter_bytes;   /* algorithmic bytes moved by K3 (read + write of the surviving rays)   */
     double pd_field_ms;     /* accumulated device time of the pd_field kernel (K4)                  */
+    int64_t psf_pairs;      /* pixel-hit pairs summed by bmo_psf_intensity                          */
+    double psf_ms;          /* device time of the last psf_intensity kernel (K6)                    */
 } bmo_counters;
 
 int32_t bmo_init(int32_t device, bmo_ctx** ctx);
@@ -246,6 +250,27 @@ int32_t bmo_pd_accumulate(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_
 int32_t bmo_pd_accumulate_poses(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_poses, double* fields, uint32_t flags);
 /* optical_power(pd) = trapz((x, y), |E|^2 / (2 Z0)) (Photodetector.jl:109-116) on the device.    */
 int32_t bmo_pd_power(bmo_sys* sys, int32_t pd_object, int32_t n_fields, const double* fields, double* power, uint32_t flags);
+
+/* ---- PSFDetector (OpticalComponents/Detectors/PSFDetector.jl) ---------------------------------------
+ * bmo_psf is the detector's `data::Vector{PSFData}` on the device.
+ * bmo_psf_collect replaces interact3d(::AbstractSystem, ::PSFDetector, ::Beam{T, Ray{T}}, ::Ray) (:77-89) for every
+ * beam of `r` that ended on `psf_object`: hit position, direction, optical_path_length(beam) (through the
+ * parents), |dir . normal| and 2 pi / lambda are appended to *psf (created when *psf == NULL; the reference's
+ * detector also accumulates until empty!).  `r` must hold its segment table; PolarizedRay results add nothing
+ * (no interact3d method, AbstractSystem.jl:30-33); GaussianBeamlet results are rejected.                      */
+typedef struct bmo_psf bmo_psf;
+int32_t bmo_psf_collect(bmo_sys* sys, bmo_result* r, int32_t psf_object, bmo_psf** psf, int64_t* n_total);
+int32_t bmo_psf_count(bmo_psf* psf, int64_t* n);
+/* host copy of the records: [n][9] = hit xyz, dir xyz, opl, proj, k (PSFData, :1-7)                         */
+int32_t bmo_psf_data(bmo_psf* psf, double* records);
+/* calc_local_lims(psf; crop_factor, center) (:112-141): center 0 = :centroid, 1 = :bbox; lims = x_min, x_max, z_min, z_max */
+int32_t bmo_psf_lims(bmo_sys* sys, bmo_psf* psf, int32_t psf_object, int32_t pose, double crop_factor, int32_t center, double* lims);
+/* intensity(psf; n, ...) (:190-237) on xs = LinRange(lims[0], lims[1], n) .+ x0_shift, zs likewise:
+ * intensity[i + n*j] = |sum_h proj_h cis(k_h (opl_h + (p_ij - hit_h) . dir_h))|^2 (raw, unscaled).  Host pointer, or
+ * device pointer with BMO_INPUT_DEVICE.                                                                     */
+int32_t bmo_psf_intensity(bmo_sys* sys, bmo_psf* psf, int32_t psf_object, int32_t pose, int32_t n, const double* lims,
+                          double x0_shift, double z0_shift, double* intensity, uint32_t flags);
+int32_t bmo_psf_free(bmo_psf* psf);   /* empty!(psf) */
 
 /* FP64 DFMA micro-benchmark used as the roofline denominator of the FP64-bound kernels.          */
 int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops);

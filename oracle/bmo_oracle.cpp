@@ -315,6 +315,11 @@ int orc_new(const char* kind, const double* d, int nd, const int* ih, int ni) {
         o->sd_hw = d[0] / 2;
         return reg_object(o);
     }
+    if (k == "PSFDetector") {  // PSFDetector.jl:62-68
+        Mesh* m = mk_rect_flat_mesh(d[0], d[0]);
+        m->rotate(V3{0, 0, 1}, kPi);
+        return reg_object(mk_obj(O_PSF, m));
+    }
     if (k == "ObjectGroup") { auto* o = new Object(O_GROUP); for (int i = 0; i < ni; i++) o->parts.push_back(O(ih[i])); return reg_object(o); }
     if (k == "System") {
         auto* s = new System();
@@ -519,6 +524,87 @@ double orc_pd_power(int hpd) {
     return p;
     ORC_CATCH(std::nan(""))
 }
+// ---- PSFDetector (PSFDetector.jl) ------------------------------------------------------------------
+// records: 9 doubles per hit (hit xyz, dir xyz, opl, proj, k); returns the number of hits
+int orc_psf_data(int hpsf, double* out, int cap) {
+    ORC_TRY
+    Object* o = O(hpsf);
+    int n = (int)o->psf.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        const PSFData& h = o->psf[i];
+        double* r = out + 9 * i;
+        r[0] = h.hit.x; r[1] = h.hit.y; r[2] = h.hit.z; r[3] = h.dir.x; r[4] = h.dir.y; r[5] = h.dir.z; r[6] = h.opl; r[7] = h.proj; r[8] = h.k;
+    }
+    return n;
+    ORC_CATCH(-1)
+}
+int orc_psf_empty(int hpsf) { ORC_TRY O(hpsf)->psf.clear(); return 0; ORC_CATCH(-1) }
+// calc_local_pos + calc_local_lims (PSFDetector.jl:91-141); center: 0 = :centroid, 1 = :bbox
+static void psf_lims(Object* o, double crop, int center, double lims[4]) {
+    const size_t n = o->psf.size();
+    std::vector<double> xs(n), zs(n);
+    V3 e1 = o->shape->dir.col(0), e3 = o->shape->dir.col(2);
+    for (size_t i = 0; i < n; i++) {
+        V3 loc = o->psf[i].hit - o->shape->pos;
+        xs[i] = dot(loc, e1); zs[i] = dot(loc, e3);
+    }
+    double x0, z0;
+    if (center == 0) {
+        double w = 0, sx = 0, sz = 0;
+        for (size_t i = 0; i < n; i++) { w += o->psf[i].proj; sx += o->psf[i].proj * xs[i]; sz += o->psf[i].proj * zs[i]; }
+        x0 = sx / w; z0 = sz / w;
+    } else {
+        x0 = (*std::min_element(xs.begin(), xs.end()) + *std::max_element(xs.begin(), xs.end())) / 2;
+        z0 = (*std::min_element(zs.begin(), zs.end()) + *std::max_element(zs.begin(), zs.end())) / 2;
+    }
+    double dx = 0, dz = 0;
+    for (size_t i = 0; i < n; i++) { dx = std::max(dx, std::fabs(xs[i] - x0)); dz = std::max(dz, std::fabs(zs[i] - z0)); }
+    lims[0] = x0 - dx * crop; lims[1] = x0 + dx * crop; lims[2] = z0 - dz * crop; lims[3] = z0 + dz * crop;
+}
+int orc_psf_lims(int hpsf, double crop, int center, double* lims) {
+    ORC_TRY
+    Object* o = O(hpsf);
+    if (o->psf.empty()) throw std::runtime_error("PSFDetector holds no data");
+    psf_lims(o, crop, center, lims);
+    return 0;
+    ORC_CATCH(-1)
+}
+// intensity(psf; n, crop_factor, center, x_min, x_max, z_min, z_max, x0_shift, z0_shift) (PSFDetector.jl:190-237).
+// lims_in: NULL or 4 doubles (Inf entries = automatic, pairwise like the reference); out: xs[n], zs[n], I[n*n]
+// column-major [i(x), j(z)].
+int orc_psf_intensity(int hpsf, int n, double crop, int center, const double* lims_in, double x0_shift, double z0_shift,
+                      double* xs, double* zs, double* I) {
+    ORC_TRY
+    Object* o = O(hpsf);
+    if (o->psf.empty()) throw std::runtime_error("PSFDetector holds no data");
+    double lims[4];
+    psf_lims(o, crop, center, lims);
+    if (lims_in) {
+        if (lims_in[0] != kInf && lims_in[1] != kInf) { lims[0] = lims_in[0]; lims[1] = lims_in[1]; }
+        if (lims_in[2] != kInf && lims_in[3] != kInf) { lims[2] = lims_in[2]; lims[3] = lims_in[3]; }
+    }
+    auto lin = [&](int i, double lo, double hi) {   // LinRange getindex (Base.lerpi)
+        double t = (n == 1) ? 0.0 : (double)i / (double)(n - 1);
+        return (1 - t) * lo + t * hi;
+    };
+    for (int i = 0; i < n; i++) { xs[i] = lin(i, lims[0], lims[1]) + x0_shift; zs[i] = lin(i, lims[2], lims[3]) + z0_shift; }
+    V3 e1 = o->shape->dir.col(0), e2 = o->shape->dir.col(2), org = o->shape->pos;
+#pragma omp parallel for schedule(static)   // Threads.@threads over j, PSFDetector.jl:220
+    for (int j = 0; j < n; j++) {
+        for (int i = 0; i < n; i++) {
+            V3 p = org + xs[i] * e1 + zs[j] * e2;
+            Cx acc{0, 0};
+            for (const PSFData& h : o->psf) {
+                double l = dot(p - h.hit, h.dir);
+                acc = acc + h.proj * cis(h.k * (h.opl + l));
+            }
+            I[(size_t)i + (size_t)n * j] = abs2(acc);
+        }
+    }
+    return 0;
+    ORC_CATCH(-1)
+}
+
 int orc_spots(int hsd, double* out, int cap) {
     ORC_TRY
     Object* sd = O(hsd);

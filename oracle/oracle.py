@@ -48,6 +48,9 @@ def lib():
         L.orc_pd_power.argtypes = [C.c_int]
         L.orc_pd_power.restype = C.c_double
         L.orc_spots.argtypes = [C.c_int, _dp, C.c_int]
+        L.orc_psf_data.argtypes = [C.c_int, _dp, C.c_int]
+        L.orc_psf_lims.argtypes = [C.c_int, C.c_double, C.c_int, _dp]
+        L.orc_psf_intensity.argtypes = [C.c_int, C.c_int, C.c_double, C.c_int, _dp, C.c_double, C.c_double, _dp, _dp, _dp]
         L.orc_bulk_trace_rays.argtypes = [C.c_int, C.c_int, _dp, _dp, _dp, C.c_int, C.c_int, C.c_int, _dp, _ip, C.c_int, _dp]
         L.orc_bulk_trace_rays.restype = C.c_longlong
         L.orc_bulk_trace_beamlets.argtypes = [C.c_int, C.c_int, _dp, C.c_int, C.c_int]
@@ -134,6 +137,28 @@ class Handle:
 
     def pd_empty(self): _chk(lib().orc_pd_empty(self.h))
     def pd_power(self): return lib().orc_pd_power(self.h)
+
+    # PSFDetector (PSFDetector.jl)
+    def psf_data(self):
+        n = _chk(lib().orc_psf_data(self.h, None, 0))
+        out = np.zeros((max(n, 1), 9))
+        _chk(lib().orc_psf_data(self.h, out.ctypes.data_as(_dp), n))
+        return out[:n]
+
+    def psf_empty(self): _chk(lib().orc_psf_empty(self.h))
+
+    def psf_lims(self, crop_factor=1.0, center="centroid"):
+        out = np.zeros(4)
+        _chk(lib().orc_psf_lims(self.h, float(crop_factor), 0 if center == "centroid" else 1, out.ctypes.data_as(_dp)))
+        return out
+
+    def psf_intensity(self, n=100, crop_factor=1.0, center="centroid", x_min=np.inf, x_max=np.inf, z_min=np.inf, z_max=np.inf,
+                      x0_shift=0.0, z0_shift=0.0):
+        lims = np.array([x_min, x_max, z_min, z_max], dtype=np.float64)
+        xs, zs, I = np.zeros(n), np.zeros(n), np.zeros(n * n)
+        _chk(lib().orc_psf_intensity(self.h, int(n), float(crop_factor), 0 if center == "centroid" else 1, lims.ctypes.data_as(_dp),
+                                     float(x0_shift), float(z0_shift), xs.ctypes.data_as(_dp), zs.ctypes.data_as(_dp), I.ctypes.data_as(_dp)))
+        return xs, zs, I.reshape(n, n, order="F")
 
     def spots(self):
         n = _chk(lib().orc_spots(self.h, None, 0))

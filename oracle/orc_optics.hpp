@@ -267,7 +267,10 @@ inline void calculate_global_E0(V3 in_dir, V3 out_dir, V3 normal, Cx j11, Cx j22
 // ---------------------------------------------------------------------------------------------
 struct System;
 
-enum ObjKind { O_REFRACTIVE, O_MIRROR, O_THIN_BS, O_PLATE_BS, O_CUBE_BS, O_DOUBLET, O_PD, O_SPOT, O_STOP, O_NONINT, O_GROUP };
+enum ObjKind { O_REFRACTIVE, O_MIRROR, O_THIN_BS, O_PLATE_BS, O_CUBE_BS, O_DOUBLET, O_PD, O_SPOT, O_STOP, O_NONINT, O_GROUP, O_PSF };
+
+// PSFDetector.jl:1-7
+struct PSFData { V3 hit, dir; double opl, proj, k; };
 
 struct Object {
     ObjKind kind;
@@ -281,6 +284,7 @@ struct Object {
     // detectors
     int pd_n = 0; double pd_lo = 0, pd_hi = 0; std::vector<Cx> field;  // Photodetector (column-major [i + n*j])
     std::vector<std::array<double, 2>> spots;                          // Spotdetector
+    std::vector<PSFData> psf;                                          // PSFDetector.data
     double sd_hw = 0;
     explicit Object(ObjKind k) : kind(k) {}
     virtual ~Object() {}
@@ -548,6 +552,17 @@ inline BeamInteraction interact3d(System& sys, Object* obj, Beam& beam, Ray& ray
             double x = dot(loc, obj->shape->dir.col(0));
             double z = dot(loc, obj->shape->dir.col(2));
             obj->spots.push_back({x, z});
+            return BeamInteraction{};
+        }
+        case O_PSF: {  // PSFDetector.jl:77-89 (defined for Beam{T, Ray{T}} only; PolarizedRay -> generic fallback, AbstractSystem.jl:30-33)
+            if (ray.polarized) return BeamInteraction{};
+            PSFData h;
+            h.hit = ray.pos + ray.length() * ray.dir;
+            h.dir = ray.dir;
+            h.opl = beam.opl();
+            h.proj = std::fabs(dot(ray.dir, ray.hit.n));
+            h.k = kTwoPi / ray.lambda;
+            obj->psf.push_back(h);
             return BeamInteraction{};
         }
         default: return BeamInteraction{};  // PD (Photodetector.jl:57-60), STOP, NONINT
