@@ -10,11 +10,11 @@ from ._lib import BmoError, counters, counters_reset, measure_fp64_peak
 from .beams import (Beam, BeamletBundle, CollimatedSource, GaussianBeamlet, Intersection, PointSource, PolarizedRay, Ray,
                     RayBundle, UniformDiscSource)
 from .components import (ConcaveSphericalMirror, CubeBeamsplitter, DiscreteRefractiveIndex, DoubletLens, IntersectableObject, Lens,
-                         MeshDummy, Mirror, NonInteractableObject, ObjectGroup, PSFDetector, Photodetector, Prism, RectangularCompensatorPlate,
+                         MeshDummy, Mirror, NonInteractableObject, ObjectGroup, PSFDetector, Photodetector, PolarizationFilter, Prism, RectangularCompensatorPlate,
                          RectangularPlanoMirror, RectangularPlateBeamsplitter, Retroreflector, RightAnglePrism, RightAnglePrismMirror,
                          RoundPlanoMirror, RoundPlateBeamsplitter, RoundThinBeamsplitter, SellmeierEquation, SphericalDoubletLens,
                          SphericalLens, Spotdetector, SquarePlanoMirror, SquarePlanoMirror2D, StaticSystem, System, ThinBeamsplitter,
-                         ThinLens, inch, lens_shape)
+                         ThinLens, XYBasis, XZBasis, YZBasis, inch, lens_shape)
 from .shapes import (BoxSDF, CircularFlatMesh, ConcaveSphericalSurfaceSDF, ConvexSphericalSurfaceSDF, CubeMesh, CuboidMesh, CutSphereSDF,
                      CylinderSDF, Mesh, MeniscusLensSDF, PlanoSurfaceSDF, QuadraticFlatMesh, RectangularFlatMesh, RetroMesh,
                      RightAnglePrismSDF, RingSDF, SphereSDF, ThinLensSDF, UnionSDF, load_stl)

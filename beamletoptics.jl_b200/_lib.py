@@ -50,7 +50,9 @@ class bmo_tables(C.Structure):
                 ("n_faces", C.c_int64), ("faces", C.POINTER(C.c_int32)),
                 ("n_lambda", C.c_int32), ("lambdas", C.POINTER(C.c_double)),
                 ("n_rows", C.c_int32), ("n_table", C.POINTER(C.c_double)),
-                ("n_system", C.c_double), ("norm_zero_rule", C.c_int32), ("reserved", C.c_int32)]
+                ("n_system", C.c_double),
+                ("n_jones", C.c_int32), ("jones", C.POINTER(C.c_double)),
+                ("norm_zero_rule", C.c_int32), ("reserved", C.c_int32)]
 
 
 class bmo_counters(C.Structure):

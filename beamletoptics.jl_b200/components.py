@@ -279,6 +279,24 @@ class Spotdetector(AbstractObject):
     def empty_(self): self.data = np.zeros((0, 2))
 
 
+def XYBasis(j11, j12, j21, j22): return ((j11, j12, 0.0), (j21, j22, 0.0), (0.0, 0.0, 1.0))     # PolarizedRays.jl:148
+def XZBasis(j11, j12, j21, j22): return ((j11, 0.0, j12), (0.0, 1.0, 0.0), (j21, 0.0, j22))     # :149
+def YZBasis(j11, j12, j21, j22): return ((1.0, 0.0, 0.0), (0.0, j22, j21), (0.0, j12, j11))     # :150
+
+
+class PolarizationFilter(AbstractObject):
+    """Polarizers/PolarizationFilter.jl:5-29: zero-thickness ideal polariser, aligned with the y-axis, transmitting
+    along its local x-axis and blocking z.  `JMat` is the GlobalJonesBasis (3x3, real) of the unrotated element."""
+    kind = "polfilter"
+
+    def __init__(self, edge_length, cutoff_strength=2.220446049250313e-16, JMat=None):
+        self.shape = sh.QuadraticFlatMesh(edge_length)
+        self.shape.zrotate3d_(math.pi)
+        self.shape.set_new_origin3d_()
+        self.JMat = tuple(tuple(float(x) for x in row) for row in (JMat if JMat is not None else XZBasis(1, 0, 0, 0)))
+        self.cutoff = float(cutoff_strength)
+
+
 class PSFDetector(AbstractObject):
     """Detectors/PSFDetector.jl:44-68.  The hit records (`PSFData`: hit, dir, opl, proj, k) stay on the device
     (bmo_psf); `data` downloads them, `intensity` runs the coherent sum kernel (PSFDetector.jl:190-237)."""

@@ -38,6 +38,7 @@ struct SysView {
     const double* bounds;    // [n_poses][n_parts][NBOUND]: sphere (centre, radius), box (lo, hi)
     const double* det_pose;  // [n_poses][n_objects][12] pos(3) dir(9 row-major)
     const double* lambdas;   // [n_lambda]
+    const double* jones;     // [n_jones][10] PolarizationFilter: J (3x3 row-major), cutoff
     int32_t n_prims, n_parts, n_objects, n_meshes, n_lambda, n_poses, zr, pad;
     int64_t n_vertices;
     double n_system;

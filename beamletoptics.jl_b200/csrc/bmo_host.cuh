@@ -55,7 +55,7 @@ struct bmo_sys {
     bmo_prim* d_prims = nullptr; bmo_part* d_parts = nullptr; bmo_object* d_objects = nullptr;
     bmo::MeshView* d_meshes = nullptr; double* d_vertices = nullptr; int32_t* d_faces = nullptr;
     bmo::BvhNode* d_nodes = nullptr; int32_t* d_bvh_faces = nullptr; double* d_ntable = nullptr;
-    double* d_bounds = nullptr; double* d_detpose = nullptr; double* d_lambdas = nullptr;
+    double* d_bounds = nullptr; double* d_detpose = nullptr; double* d_lambdas = nullptr; double* d_jones = nullptr;
     // pose-0 copies to restore after a sweep
     std::vector<double> h_vertices, h_bounds, h_detpose;
 };

@@ -147,6 +147,44 @@ BMO_NI void interact_mirror(V3 rpos, V3 rdir, double rn, const Cx* rE0, bool pol
         if (!e0_orthogonal(o.dir, o.E0)) o.warn = true;
     }
 }
+// Polarizers/PolarizationFilter.jl:31-47 with JonesCalculus.jl:29-46: the Jones matrix is given in the global
+// frame of the unrotated element; P = R J R' follows the element's orientation R and is projected into the
+// plane transverse to the ray, P := Q P Q with Q = I - d d'; E0' = P E0.  The direction does not change.
+// A ray whose |E0'| is approximately the cutoff is terminated (interact3d returns nothing).
+BMO_NI void interact_polfilter(V3 rpos, V3 rdir, double rn, const Cx* rE0, double t, const double* Rm /* row-major 3x3 */,
+                              const double* J /* row-major 3x3, then cutoff */, RayOut& o) {
+    o.err = false; o.warn = false; o.hint = -1;
+    o.pos = rpos + t * rdir;
+    o.dir = rdir;
+    o.n = rn;
+    double RJ[3][3], P[3][3], Q[3][3], QP[3][3];
+    const double dv[3] = {rdir.x, rdir.y, rdir.z};
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) RJ[i][j] = (Rm[3 * i] * J[j] + Rm[3 * i + 1] * J[3 + j]) + Rm[3 * i + 2] * J[6 + j];
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) {
+            P[i][j] = (RJ[i][0] * Rm[3 * j] + RJ[i][1] * Rm[3 * j + 1]) + RJ[i][2] * Rm[3 * j + 2];
+            Q[i][j] = (i == j ? 1.0 : 0.0) - dv[i] * dv[j];
+        }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) QP[i][j] = (Q[i][0] * P[0][j] + Q[i][1] * P[1][j]) + Q[i][2] * P[2][j];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        double p0 = (QP[i][0] * Q[0][0] + QP[i][1] * Q[1][0]) + QP[i][2] * Q[2][0];
+        double p1 = (QP[i][0] * Q[0][1] + QP[i][1] * Q[1][1]) + QP[i][2] * Q[2][1];
+        double p2 = (QP[i][0] * Q[0][2] + QP[i][1] * Q[1][2]) + QP[i][2] * Q[2][2];
+        o.E0[i] = (p0 * rE0[0] + p1 * rE0[1]) + p2 * rE0[2];
+    }
+    const double nrm = sqrt((abs2(o.E0[0]) + abs2(o.E0[1])) + abs2(o.E0[2]));
+    o.valid = !jl_isapprox(nrm, J[9]);
+    if (o.valid && !e0_orthogonal(o.dir, o.E0)) o.warn = true;
+}
 // ThinBeamsplitter.jl:73-106: children restart as Ray(pos, dir, lambda): n = 1, dir re-normalised
 BMO_NI void bs_children(V3 rpos, V3 rdir, const Cx* rE0, bool polarized, double t, V3 nrm, double refl, double trans,
                        RayOut& tr, RayOut& rf) {

@@ -416,6 +416,12 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
             case BMO_OBJ_THIN_BS:
                 split = true;
                 break;
+            case BMO_OBJ_POLFILTER: {   // PolarizationFilter.jl:31-47 (PolarizedRay only; other beams: no method -> nothing)
+                if (!pol) break;
+                const double* dp = S.det_pose + 12 * ((int64_t)pose * S.n_objects + pt.object);
+                interact_polfilter(pos, dir, rn, E0, t, dp + 3, S.jones + 10 * (int64_t)ob.pd_n, o1);
+                break;
+            }
             case BMO_OBJ_SPOTDETECTOR: {  // Spotdetector.jl:50-61
                 const double* dp = S.det_pose + 12 * ((int64_t)pose * S.n_objects + pt.object);
                 V3 hp = pos + t * dir;
@@ -1026,6 +1032,7 @@ static int32_t validate_tables(const bmo_tables* t) {
         const int need = ob.kind == BMO_OBJ_CUBE_BS ? 3 : ((ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_DOUBLET) ? 2 : 1);
         if (ob.n_parts != need) return fail(BMO_EINVAL, "object has the wrong number of parts for its kind");
         if ((ob.kind == BMO_OBJ_REFRACTIVE) && t->parts[ob.first_part].n_row < 0) return fail(BMO_EINVAL, "refractive object without n_row");
+        if (ob.kind == BMO_OBJ_POLFILTER && (!t->jones || ob.pd_n < 0 || ob.pd_n >= t->n_jones)) return fail(BMO_EINVAL, "PolarizationFilter without a row of tables.jones");
     }
     for (int m = 0; m < t->n_meshes; m++) {
         const bmo_mesh& me = t->meshes[m];
@@ -1104,10 +1111,11 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
     if ((rc = upload(&s->d_bounds, s->h_bounds.data(), s->h_bounds.size()))) return rc;
     if ((rc = upload(&s->d_detpose, s->h_detpose.data(), s->h_detpose.size()))) return rc;
     if ((rc = upload(&s->d_lambdas, s->lambdas.data(), s->lambdas.size()))) return rc;
+    if (t->n_jones > 0 && (rc = upload(&s->d_jones, t->jones, (size_t)10 * t->n_jones))) return rc;
     SysView& v = s->view;
     v.prims = s->d_prims; v.parts = s->d_parts; v.objects = s->d_objects; v.meshes = s->d_meshes;
     v.vertices = s->d_vertices; v.faces = s->d_faces; v.nodes = s->d_nodes; v.bvh_faces = s->d_bvh_faces;
-    v.n_table = s->d_ntable; v.bounds = s->d_bounds; v.det_pose = s->d_detpose; v.lambdas = s->d_lambdas;
+    v.n_table = s->d_ntable; v.bounds = s->d_bounds; v.det_pose = s->d_detpose; v.lambdas = s->d_lambdas; v.jones = s->d_jones;
     v.n_prims = t->n_prims; v.n_parts = t->n_parts; v.n_objects = t->n_objects; v.n_meshes = t->n_meshes;
     v.n_lambda = t->n_lambda; v.n_poses = 1; v.zr = t->norm_zero_rule; v.n_vertices = t->n_vertices;
     v.n_system = t->n_system;
@@ -1120,7 +1128,7 @@ int32_t bmo_system_free(bmo_sys* s) {
     cudaStreamSynchronize(s->ctx->stream);
     cudaFree(s->d_prims); cudaFree(s->d_parts); cudaFree(s->d_objects); cudaFree(s->d_meshes); cudaFree(s->d_vertices);
     cudaFree(s->d_faces); cudaFree(s->d_nodes); cudaFree(s->d_bvh_faces); cudaFree(s->d_ntable); cudaFree(s->d_bounds);
-    cudaFree(s->d_detpose); cudaFree(s->d_lambdas);
+    cudaFree(s->d_detpose); cudaFree(s->d_lambdas); cudaFree(s->d_jones);
     delete s;
     return BMO_OK;
 }

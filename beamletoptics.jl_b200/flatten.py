@@ -17,10 +17,10 @@ from . import shapes as sh
 
 SHAPE_SDF, SHAPE_MESH = 0, 1
 ROLE_SINGLE, ROLE_FRONT, ROLE_BACK, ROLE_SUBSTRATE, ROLE_COATING = range(5)
-OBJ_REFRACTIVE, OBJ_MIRROR, OBJ_THIN_BS, OBJ_PLATE_BS, OBJ_CUBE_BS, OBJ_DOUBLET, OBJ_PD, OBJ_SPOT, OBJ_STOP, OBJ_PSF = range(10)
+OBJ_REFRACTIVE, OBJ_MIRROR, OBJ_THIN_BS, OBJ_PLATE_BS, OBJ_CUBE_BS, OBJ_DOUBLET, OBJ_PD, OBJ_SPOT, OBJ_STOP, OBJ_PSF, OBJ_POLFILTER = range(11)
 
 _KIND = {"refractive": OBJ_REFRACTIVE, "mirror": OBJ_MIRROR, "thin_bs": OBJ_THIN_BS, "plate_bs": OBJ_PLATE_BS,
-         "cube_bs": OBJ_CUBE_BS, "doublet": OBJ_DOUBLET, "pd": OBJ_PD, "spot": OBJ_SPOT, "stop": OBJ_STOP, "psf": OBJ_PSF}
+         "cube_bs": OBJ_CUBE_BS, "doublet": OBJ_DOUBLET, "pd": OBJ_PD, "spot": OBJ_SPOT, "stop": OBJ_STOP, "psf": OBJ_PSF, "polfilter": OBJ_POLFILTER}
 _ROLES = {"plate_bs": (ROLE_SUBSTRATE, ROLE_COATING), "cube_bs": (ROLE_FRONT, ROLE_BACK, ROLE_COATING),
           "doublet": (ROLE_FRONT, ROLE_BACK)}
 
@@ -63,7 +63,7 @@ class FlatSystem:
         self.objects = leaves           # device object index -> host object
         self.part_owner = []            # device part index -> host sub-object (Lens of a doublet, coating, ...)
         prims, parts, objs, meshes = [], [], [], []
-        verts, faces, ntab = [], [], []
+        verts, faces, ntab, jones = [], [], [], []
         nv = nf = 0
         for oi, o in enumerate(leaves):
             kind = _KIND[o.kind]
@@ -77,6 +77,9 @@ class FlatSystem:
                 rec.dir[:] = [det_shape.dir[i][j] for i in range(3) for j in range(3)]
             if kind == OBJ_PD:
                 rec.pd_n, rec.pd_lo, rec.pd_hi = o.n, o.lo, o.hi
+            if kind == OBJ_POLFILTER:     # GlobalJonesBasis (3x3, row-major) + cutoff -> tables.jones[pd_n]
+                rec.pd_n = len(jones)
+                jones.append([float(x) for row in o.JMat for x in row] + [float(o.cutoff)])
             objs.append(rec)
             for s_obj, role in zip(sub, roles):
                 shape = s_obj.shape
@@ -129,6 +132,8 @@ class FlatSystem:
         t.n_faces, t.faces = nf, self._faces.ctypes.data_as(C.POINTER(C.c_int32))
         t.n_lambda, t.lambdas = len(self.lambdas), self._lams.ctypes.data_as(C.POINTER(C.c_double))
         t.n_rows, t.n_table = len(ntab), self._ntab.ctypes.data_as(C.POINTER(C.c_double))
+        self._jones = np.array(jones, dtype=np.float64).reshape(len(jones), 10) if jones else np.zeros((0, 10))
+        t.n_jones, t.jones = len(jones), self._jones.ctypes.data_as(C.POINTER(C.c_double))
         t.n_system = float(system.n)
         t.norm_zero_rule = int(norm_zero_rule)
         self.tables = t

@@ -87,6 +87,8 @@ enum bmo_obj_kind {
     BMO_OBJ_PHOTODETECTOR = 6,/* (Photodetector.jl:69-107)                                        */
     BMO_OBJ_SPOTDETECTOR = 7, /* (Spotdetector.jl:50-61)                                          */
     BMO_OBJ_STOP = 8,         /* IntersectableObject    (Intersectable.jl:15)                     */
+    BMO_OBJ_POLFILTER = 10,   /* PolarizationFilter     (Polarizers/PolarizationFilter.jl:31-47, JonesCalculus.jl:29-46):
+                                 pd_n = row of tables.jones; orientation(object) = dir                 */
     BMO_OBJ_PSFDETECTOR = 9   /* PSFDetector            (Detectors/PSFDetector.jl:77-89): absorbs; the hit records are
                                  rebuilt from the segment table by bmo_psf_collect                */
 };
@@ -119,6 +121,8 @@ typedef struct bmo_tables {
     int32_t n_rows;     const double* n_table;   /* [n_rows][n_lambda] refractive_index(obj, lambda),
                                                     evaluated on the host (Lenses.jl:37-38)        */
     double n_system;                             /* refractive_index(system, lambda) = 1.0 (AbstractSystem.jl:21) */
+    int32_t n_jones;    const double* jones;     /* [n_jones][10]: GlobalJonesBasis of a PolarizationFilter, 3x3 real row-major
+                                                    (XZBasis(1,0,0,0) by default), then its cutoff (PolarizationFilter.jl:5-9) */
     int32_t norm_zero_rule;                      /* 1 (use this): zero-vector norm of duals is a clean zero -- pinned by test/runtests.jl:1309-1314; 0: NaN partials */
     int32_t reserved;
 } bmo_tables;

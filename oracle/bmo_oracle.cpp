@@ -315,6 +315,16 @@ int orc_new(const char* kind, const double* d, int nd, const int* ih, int ni) {
         o->sd_hw = d[0] / 2;
         return reg_object(o);
     }
+    if (k == "PolarizationFilter") {  // PolarizationFilter.jl:17-29: d = edge_length [, cutoff, J row-major (9)]
+        Mesh* m = mk_rect_flat_mesh(d[0], d[0]);
+        m->rotate(V3{0, 0, 1}, kPi);
+        m->set_new_origin();
+        auto* o = mk_obj(O_POLFILTER, m);
+        const double xz[9] = {1, 0, 0, 0, 1, 0, 0, 0, 0};   // XZBasis(1, 0, 0, 0) = [j11 0 j12; 0 1 0; j21 0 j22]
+        if (nd >= 2) o->cutoff = d[1];
+        for (int i = 0; i < 9; i++) o->jones[i / 3][i % 3] = nd >= 11 ? d[2 + i] : xz[i];
+        return reg_object(o);
+    }
     if (k == "PSFDetector") {  // PSFDetector.jl:62-68
         Mesh* m = mk_rect_flat_mesh(d[0], d[0]);
         m->rotate(V3{0, 0, 1}, kPi);

@@ -267,7 +267,7 @@ inline void calculate_global_E0(V3 in_dir, V3 out_dir, V3 normal, Cx j11, Cx j22
 // ---------------------------------------------------------------------------------------------
 struct System;
 
-enum ObjKind { O_REFRACTIVE, O_MIRROR, O_THIN_BS, O_PLATE_BS, O_CUBE_BS, O_DOUBLET, O_PD, O_SPOT, O_STOP, O_NONINT, O_GROUP, O_PSF };
+enum ObjKind { O_REFRACTIVE, O_MIRROR, O_THIN_BS, O_PLATE_BS, O_CUBE_BS, O_DOUBLET, O_PD, O_SPOT, O_STOP, O_NONINT, O_GROUP, O_PSF, O_POLFILTER };
 
 // PSFDetector.jl:1-7
 struct PSFData { V3 hit, dir; double opl, proj, k; };
@@ -285,6 +285,8 @@ struct Object {
     int pd_n = 0; double pd_lo = 0, pd_hi = 0; std::vector<Cx> field;  // Photodetector (column-major [i + n*j])
     std::vector<std::array<double, 2>> spots;                          // Spotdetector
     std::vector<PSFData> psf;                                          // PSFDetector.data
+    double jones[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 0}};            // PolarizationFilter.JMat (GlobalJonesBasis, real)
+    double cutoff = 2.220446049250313e-16;                             // PolarizationFilter.cutoff (eps())
     double sd_hw = 0;
     explicit Object(ObjKind k) : kind(k) {}
     virtual ~Object() {}
@@ -553,6 +555,31 @@ inline BeamInteraction interact3d(System& sys, Object* obj, Beam& beam, Ray& ray
             double z = dot(loc, obj->shape->dir.col(2));
             obj->spots.push_back({x, z});
             return BeamInteraction{};
+        }
+        case O_POLFILTER: {  // Polarizers/PolarizationFilter.jl:31-47 + JonesCalculus.jl:29-46 (PolarizedRay only)
+            if (!ray.polarized) return BeamInteraction{};
+            V3 npos = ray.pos + ray.length() * ray.dir;
+            V3 d = ray.dir;
+            const M3& R = obj->shape->dir;
+            double RJ[3][3], P[3][3], Q[3][3], QP[3][3];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)          // R * J
+                RJ[i][j] = (R.m[i][0] * obj->jones[0][j] + R.m[i][1] * obj->jones[1][j]) + R.m[i][2] * obj->jones[2][j];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)          // (R * J) * transpose(R)
+                P[i][j] = (RJ[i][0] * R.m[j][0] + RJ[i][1] * R.m[j][1]) + RJ[i][2] * R.m[j][2];
+            const double dv[3] = {d.x, d.y, d.z};
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)          // Q = I - in_dir * transpose(in_dir)
+                Q[i][j] = (i == j ? 1.0 : 0.0) - dv[i] * dv[j];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)          // Q * P
+                QP[i][j] = (Q[i][0] * P[0][j] + Q[i][1] * P[1][j]) + Q[i][2] * P[2][j];
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++)          // (Q * P) * Q
+                P[i][j] = (QP[i][0] * Q[0][j] + QP[i][1] * Q[1][j]) + QP[i][2] * Q[2][j];
+            Cx E0[3];
+            for (int i = 0; i < 3; i++) E0[i] = (P[i][0] * ray.E0[0] + P[i][1] * ray.E0[1]) + P[i][2] * ray.E0[2];
+            double nrm = std::sqrt((abs2(E0[0]) + abs2(E0[1])) + abs2(E0[2]));
+            if (jl_isapprox(nrm, obj->cutoff)) return BeamInteraction{};     // :41-44 "terminate blocked rays"
+            BeamInteraction out; out.valid = true;
+            out.ray = make_pol_ray_raw(npos, d, ray.lambda, ray.n, E0);
+            return out;
         }
         case O_PSF: {  // PSFDetector.jl:77-89 (defined for Beam{T, Ray{T}} only; PolarizedRay -> generic fallback, AbstractSystem.jl:30-33)
             if (ray.polarized) return BeamInteraction{};
