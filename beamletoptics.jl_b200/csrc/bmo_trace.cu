@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
 // for the beams that are not retracing.  flag: 0 ordinary step, 1 re-validated (K2 must not apply the
 // r_max test: retrace_system! has none), 2 stored path left in this wave.
 template <int MODE, bool STAGED>
-__global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 4) retrace_intersect_wave(const StepParams P) {
+__global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(const StepParams P) {
     constexpr int R = Cfg<MODE>::R;
     constexpr int UNITS = Cfg<MODE>::UNITS;
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -31,6 +31,9 @@ WORKLOAD = "C2: AC254-150-AB doublet spot diagram, 2^20 collimated rays, Fibonac
 CPU_SAMPLE = 1 << 14
 # algorithmic FP64 work per unit (SURVEY 8(d) cost table): primitive SDF eval 45, triangle test 40, interaction 60
 FLOP_SDF, FLOP_TRI, FLOP_INT = 45.0, 40.0, 60.0
+# intersect_wave, 2^20 rays per launch: dram__bytes_read.sum + dram__bytes_write.sum, mean over the 4 waves of one C2 solve
+# (ncu --set full, profiles/r01r_ncu_intersect_wave_after_member_skipping.txt): 70.6 MB read + 71.2 MB written
+K1_DRAM_BYTES_PER_LAUNCH = 141.8e6
 
 
 def rays_for_rank(rank, n=N_RAYS):
@@ -118,6 +121,7 @@ def main():
     ap.add_argument("--no-detector", action="store_true", help="skip the secondary Photodetector (C3) measurement")
     ap.add_argument("--c3-side", type=int, default=64, help="beamlets per side of the C3 lattice block (256 = the full 65536-beamlet config)")
     ap.add_argument("--c3-pixels", type=int, default=2048)
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary retrace (a4) and PSFDetector (N2) measurements")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -221,6 +225,10 @@ def main():
     det = None
     if not args.no_detector:
         det = bench_detector(m, L, dev, stream, args.c3_side, args.c3_pixels, max(2, min(args.steps, 3)), 1, flush, peak, rank, world)
+    extras = None
+    if rank == 0 and not args.no_extras:
+        extras = {"retrace": bench_retrace(m, L, dev, stream, dsys, sc, pos_d, dir_d, lam_d, n, flush),
+                  "psf": bench_psf(m, L, dev, stream, flush, peak)}
     if rank == 0:
         value = inter_all * args.steps / (tot_ms * 1e-3)
         e2e = inter_all_e * args.steps / (tot_ms_e * 1e-3)
@@ -245,7 +253,11 @@ def main():
                     "d2h_bytes_per_step": int(spot_obj_p.numel() * 4 + spot_xz_p.numel() * 8)},
             "gpu_launches": int(c["kernel_launches"] * args.steps / n_total_steps),
             "roofline": {"bound": "fp64", "kernel": "intersect_wave", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 waves of one solve, from the
+                         # ncu --set full capture summarised in profiles/r01r_ncu_intersect_wave_after_member_skipping.txt
+                         "traffic": K1_DRAM_BYTES_PER_LAUNCH * n / N_RAYS, "traffic_algorithmic": 100.0 * n,
+                         "traffic_source": "profiles/r01r_ncu_intersect_wave_after_member_skipping.txt (2^20 rays per launch; algorithmic = 64 B ray state read + 36 B hit record written per ray)",
                          "peak_source": "measured here: DFMA probe (bmo_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": flops / k1_n, "ms_per_launch": k1_ms / k1_n,
                          "share_of_step": k1_ms / n_total_steps / (tot_ms / args.steps) if tot_ms else None,
@@ -255,6 +267,8 @@ def main():
         }
         if det is not None:
             out["detector"] = det
+        if extras is not None:
+            out.update(extras)
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out))
@@ -343,6 +357,88 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
                      "achieved_in_reference_sequence_units": ach * FLOP_PAIR_REF / FLOP_PAIR,
                      "share_of_step": out["device"]["k4_ms"] / out["device"]["ms"]},
     }
+
+
+def _time_ms(fn, stream, flush, steps=5, warmup=2):
+    import torch
+    for _ in range(warmup):
+        fn()
+    ts = []
+    for _ in range(steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    return sum(ts) / len(ts)
+
+
+def bench_retrace(m, L, dev, stream, dsys, sc, pos_d, dir_d, lam_d, n, flush):
+    """solve_system!(...; retrace=true) of the solved C2 bundle (bmo_retrace: every stored ray
+    re-validated against the object it hit before) next to a fresh non-sequential solve that keeps the same outputs
+    (segment table kept in both: the retrace needs the stored path)."""
+    prev = m.trace_rays(dsys, (pos_d.data_ptr(), n), dir_d.data_ptr(), lam_d.data_ptr(), None, None, 100, keep_segments=True, device_inputs=True)
+    prev.keep = True
+    inter = {}
+
+    def fresh():
+        r = m.trace_rays(dsys, (pos_d.data_ptr(), n), dir_d.data_ptr(), lam_d.data_ptr(), None, None, 100, keep_segments=True, device_inputs=True)
+        inter["fresh"] = r.interactions
+        r.free()
+
+    def again():
+        r = m.retrace(dsys, prev, 100, keep_segments=True)
+        inter["retrace"] = r.interactions
+        r.free()
+    ms_f = _time_ms(fresh, stream, flush)
+    L.counters_reset(dev)
+    ms_r = _time_ms(again, stream, flush, steps=5, warmup=2)
+    c = L.counters(dev)
+    prev.free()
+    return {"workload": "C2 bundle, 2^20 rays already solved, same poses: bmo_retrace vs a fresh bmo_trace_rays, segment table kept by both, rays resident in HBM",
+            "fresh_ms": ms_f, "retrace_ms": ms_r, "interactions": inter.get("retrace"), "interactions_fresh": inter.get("fresh"),
+            "retrace_interactions_per_s": inter.get("retrace", 0) / (ms_r * 1e-3),
+            "sdf_evals_per_retrace": c["sdf_evals"] / 7.0}
+
+
+FLOP_PSF_PAIR = 48.0    # per pixel-hit pair: 3 FMA phase, sincos as 40 (the transcendental weight of SURVEY 8(d)), 2 FMA accumulate
+
+
+def bench_psf(m, L, dev, stream, flush, peak_tflops, n_rays=1 << 16, n_px=512):
+    """N2: PSFDetector intensity map (PSFDetector.jl:190-237) of the reference's Airy-disc scene (test/runtests.jl:2765-2802)
+    with 2^16 rays on a 512^2 grid: pixel-hit pairs/s of psf_intensity_kernel."""
+    import ctypes as C
+    import torch
+    from tests import scenes
+    lens = m.SphericalLens(100e-3, math.inf, 1e-3, 25.4e-3, 1.5)
+    psfd = m.PSFDetector(10e-3)
+    psfd.translate3d_([0.0, 200e-3 + 0.13e-3, 0.0])
+    system = m.System([lens, psfd])
+    pos, d = scenes.fibonacci_disc(n_rays, diameter=15e-3, y0=-10e-3)
+    res = m.solve_system_(system, m.RayBundle(pos, d, 1e-6))
+    hits = len(psfd)
+    dsys, oi = psfd._dsys, psfd._index
+    lims = np.array(psfd.calc_local_lims(5.0, "bbox"))
+    out_d = torch.zeros(n_px * n_px, dtype=torch.float64, device="cuda")
+    out_h = torch.zeros(n_px * n_px, dtype=torch.float64).pin_memory()
+
+    def run(ptr, flags):
+        L.check(L.lib().bmo_psf_intensity(dsys.h, C.c_void_p(psfd._psf), oi, 0, n_px, L.ptr(lims), 0.0, 0.0, C.c_void_p(ptr), flags))
+    ms_d = _time_ms(lambda: run(out_d.data_ptr(), L.INPUT_DEVICE), stream, flush, steps=3, warmup=1)
+    k_ms = L.counters(dev)["psf_ms"]
+    ms_h = _time_ms(lambda: run(out_h.data_ptr(), 0), stream, flush, steps=3, warmup=1)
+    pairs = float(hits) * n_px * n_px
+    ach = FLOP_PSF_PAIR * pairs / (k_ms * 1e-3) / 1e12
+    psfd.empty_()
+    res.free()
+    return {"metric": "PSFDetector px-hits/s", "value": pairs / (ms_d * 1e-3), "ms_per_step": ms_d,
+            "e2e": {"value": pairs / (ms_h * 1e-3), "ms_per_step": ms_h, "h2d_bytes_per_step": 32, "d2h_bytes_per_step": n_px * n_px * 8},
+            "config": {"workload": f"Airy-disc scene of test/runtests.jl:2765-2802, {hits} ray hits, {n_px}^2 pixels, crop_factor 5, :bbox window"},
+            "roofline": {"bound": "fp64", "kernel": "psf_intensity_kernel", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s (FP64 flop-equivalents)",
+                         "frac": ach / peak_tflops if peak_tflops else None, "ms_per_launch": k_ms, "flop_equiv_per_pair": FLOP_PSF_PAIR}}
 
 
 def bench_compaction(m, L, dev, dsys, n, hbm_peak):

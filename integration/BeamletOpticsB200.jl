@@ -30,7 +30,7 @@ struct BmoPrim                      # bmo_prim
 end
 struct BmoPart                      # bmo_part
     object::Int32; role::Int32; shape_kind::Int32; first::Int32; count::Int32; n_row::Int32
-    reflectance::Float64; transmittance::Float64; bound::NTuple{4,Float64}
+    reflectance::Float64; transmittance::Float64; bound::NTuple{10,Float64}   # sphere (centre, radius), box (lo, hi)
 end
 struct BmoObject                    # bmo_object
     kind::Int32; first_part::Int32; n_parts::Int32; pd_n::Int32
@@ -49,6 +49,7 @@ struct BmoTables                    # bmo_tables
     n_lambda::Int32;   lambdas::Ptr{Float64}
     n_rows::Int32;     n_table::Ptr{Float64}
     n_system::Float64
+    n_jones::Int32;    jones::Ptr{Float64}      # [n_jones][10]: GlobalJonesBasis (row-major) + cutoff of each PolarizationFilter
     norm_zero_rule::Int32; reserved::Int32
 end
 struct BmoResultInfo
@@ -116,18 +117,25 @@ kind_of(o::ThinBeamsplitter) = (2, (o,), (0,))
 kind_of(o::AbstractReflectiveOptic) = (1, (o,), (0,))
 kind_of(o::Photodetector) = (6, (o,), (0,))
 kind_of(o::Spotdetector) = (7, (o,), (0,))
+kind_of(o::BeamletOptics.PSFDetector) = (9, (o,), (0,))
+kind_of(o::BeamletOptics.PolarizationFilter) = (10, (o,), (0,))
 kind_of(o::IntersectableObject) = (8, (o,), (0,))
 kind_of(o::AbstractObject) = (0, (o,), (0,))                 # Lens, Prism: AbstractRefractiveOptic
 
 """Leaves(system.objects) -> tables of include/bmo.h (same order: it is trace_all's tie-break order)."""
 function flatten(cs::CUDASystem, λs::Vector{Float64}; norm_zero_rule = 1)
     prims, parts, objs, meshes = BmoPrim[], BmoPart[], BmoObject[], BmoMesh[]
-    verts, fcs, ntab, owners = Float64[], Int32[], Float64[], Any[]
+    verts, fcs, ntab, owners, jones = Float64[], Int32[], Float64[], Any[], Float64[]
     leaves = [o for o in objects(cs) if !(o isa NonInteractableObject)]
     for (oi, o) in enumerate(leaves)
         kind, subs, roles = kind_of(o)
         sh0 = length(subs) == 1 ? shape(o) : nothing
-        push!(objs, BmoObject(kind, length(parts), length(subs), o isa Photodetector ? length(o.x) : 0,
+        if o isa BeamletOptics.PolarizationFilter      # tables.jones row: J (3x3, row-major), cutoff
+            J = BeamletOptics.static_data(o.JMat)
+            append!(jones, (Float64(J[i, j]) for i in 1:3 for j in 1:3)); push!(jones, Float64(o.cutoff))
+        end
+        push!(objs, BmoObject(kind, length(parts), length(subs),
+            o isa Photodetector ? length(o.x) : (o isa BeamletOptics.PolarizationFilter ? length(jones) ÷ 10 - 1 : 0),
             sh0 === nothing ? (0.0, 0.0, 0.0) : Tuple(Float64.(position(sh0))),
             sh0 === nothing ? ntuple(_ -> 0.0, 9) : rowmajor(orientation(sh0)),
             o isa Photodetector ? first(o.x) : 0.0, o isa Photodetector ? last(o.x) : 0.0))
@@ -139,7 +147,8 @@ function flatten(cs::CUDASystem, λs::Vector{Float64}; norm_zero_rule = 1)
                 append!(ntab, (Float64(refractive_index(sub, λ)) for λ in λs))   # KeyError for an untabulated λ, like the reference
             end
             c, r = bounding_sphere(sh)
-            bound = (c[1], c[2], c[3], r * (1 + 1e-9) + 1e-6)
+            rr = r * (1 + 1e-9) + 1e-6                  # the sphere's box is a valid (loose) box bound; flatten.py derives a tighter one
+            bound = (c[1], c[2], c[3], rr, c[1] - rr, c[2] - rr, c[3] - rr, c[1] + rr, c[2] + rr, c[3] + rr)
             R = sub isa ThinBeamsplitter ? (sub.reflectance, sub.transmittance) : (0.0, 0.0)
             if sh isa AbstractSDF
                 first, count = emit_sdf!(prims, sh)
@@ -154,7 +163,7 @@ function flatten(cs::CUDASystem, λs::Vector{Float64}; norm_zero_rule = 1)
             push!(owners, sub)
         end
     end
-    return (; prims, parts, objs, meshes, verts, fcs, ntab, owners, leaves, λs, norm_zero_rule)
+    return (; prims, parts, objs, meshes, verts, fcs, ntab, owners, leaves, λs, norm_zero_rule, jones)
 end
 
 # conservative world-space bounding sphere of a shape (only used for result-identical early exits)
@@ -184,7 +193,8 @@ function upload(cs::CUDASystem, f)
     GC.@preserve f begin
         t = BmoTables(length(f.prims), pointer(f.prims), length(f.parts), pointer(f.parts), length(f.objs), pointer(f.objs),
             length(f.meshes), pointer(f.meshes), length(f.verts) ÷ 3, pointer(f.verts), length(f.fcs) ÷ 3, pointer(f.fcs),
-            length(f.λs), pointer(f.λs), length(f.ntab) ÷ length(f.λs), pointer(f.ntab), 1.0, f.norm_zero_rule, 0)
+            length(f.λs), pointer(f.λs), length(f.ntab) ÷ length(f.λs), pointer(f.ntab), 1.0,
+            length(f.jones) ÷ 10, pointer(f.jones), f.norm_zero_rule, 0)
         check(ccall((:bmo_system_upload, libbmo), Int32, (Ptr{Cvoid}, Ref{BmoTables}, Ref{Ptr{Cvoid}}), context(cs.device), t, sys))
     end
     return sys[]
@@ -209,15 +219,27 @@ function BeamletOptics.solve_system!(cs::CUDASystem, beams::AbstractVector{<:Bea
         E0 === nothing || (E0[:, i] .= reinterpret(Float64, collect(ComplexF64.(r.E0))))
     end
     res = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve pos dir lam E0 begin
-        check(ccall((:bmo_trace_rays, libbmo), Int32,
-            (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Int32, UInt32, Ref{Ptr{Cvoid}}),
-            sys, n, pos, dir, lam, E0 === nothing ? C_NULL : pointer(E0), C_NULL, r_max, rebuild ? KEEP_SEGMENTS : UInt32(0), res))
+    prev = retrace ? get(SOLUTIONS, first(beams), C_NULL) : C_NULL     # the stored solution of these beams, if any
+    if prev != C_NULL
+        # retrace_system! (System.jl:188-255) for every beam of the stored trees, then solve_leaf!
+        check(ccall((:bmo_retrace, libbmo), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, UInt32, Ref{Ptr{Cvoid}}), sys, prev, r_max, KEEP_SEGMENTS, res))
+        ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), prev)
+    else
+        GC.@preserve pos dir lam E0 begin
+            check(ccall((:bmo_trace_rays, libbmo), Int32,
+                (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Int32, UInt32, Ref{Ptr{Cvoid}}),
+                sys, n, pos, dir, lam, E0 === nothing ? C_NULL : pointer(E0), C_NULL, r_max, rebuild ? KEEP_SEGMENTS : UInt32(0), res))
+        end
     end
     collect_spots!(f, res[])
+    collect_psfs!(f, sys, res[])
     rebuild && rebuild_beams!(beams, f, res[])
-    ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), res[])
-    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)
+    if rebuild
+        SOLUTIONS[first(beams)] = res[]                # kept on the device for the next solve_system!(...; retrace = true)
+    else
+        ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), res[])
+    end
+    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)      # a bmo_result does not reference its bmo_sys after the trace
     return nothing
 end
 BeamletOptics.solve_system!(cs::CUDASystem, bg::BeamletOptics.AbstractBeamGroup; kw...) = BeamletOptics.solve_system!(cs, BeamletOptics.beams(bg); kw...)
@@ -253,6 +275,42 @@ function BeamletOptics.solve_system!(cs::CUDASystem, gs::AbstractVector{<:Gaussi
     return nothing
 end
 BeamletOptics.solve_system!(cs::CUDASystem, g::GaussianBeamlet; kw...) = BeamletOptics.solve_system!(cs, [g]; kw...)
+
+# Stored solutions (bmo_result with its segment table), keyed by the first beam of the solved vector; the
+# reference keeps the same information inside the Beam objects (rays, intersections, children).
+const SOLUTIONS = IdDict{Any,Ptr{Cvoid}}()
+
+# PSFDetector: the detector's `data` lives on the device (bmo_psf), keyed by the detector object
+const PSFS = IdDict{Any,Tuple{Ptr{Cvoid},Any,Int}}()
+function collect_psfs!(f, sys, res)
+    for (oi, o) in enumerate(f.leaves)
+        o isa BeamletOptics.PSFDetector || continue
+        h = Ref{Ptr{Cvoid}}(haskey(PSFS, o) ? PSFS[o][1] : C_NULL); n = Ref{Int64}(0)
+        check(ccall((:bmo_psf_collect, libbmo), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Ref{Ptr{Cvoid}}, Ref{Int64}), sys, res, oi - 1, h, n))
+        PSFS[o] = (h[], f, oi - 1)
+    end
+end
+"""intensity(psf; n, crop_factor, center, ...) (PSFDetector.jl:190-237) on the GPU: `bmo_psf_lims` + `bmo_psf_intensity`."""
+function gpu_intensity(cs::CUDASystem, psf::BeamletOptics.PSFDetector; n = 100, crop_factor = 1, center = :centroid,
+        x_min = Inf, x_max = Inf, z_min = Inf, z_max = Inf, x0_shift = 0.0, z0_shift = 0.0)
+    h, f, oi = PSFS[psf]
+    sys = upload(cs, flatten(cs, f.λs))
+    lims = zeros(4)
+    check(ccall((:bmo_psf_lims, libbmo), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Float64, Int32, Ptr{Float64}),
+        sys, h, oi, 0, crop_factor, center == :centroid ? 0 : 1, lims))
+    x_min != Inf && x_max != Inf && (lims[1] = x_min; lims[2] = x_max)
+    z_min != Inf && z_max != Inf && (lims[3] = z_min; lims[4] = z_max)
+    I = Matrix{Float64}(undef, n, n)
+    check(ccall((:bmo_psf_intensity, libbmo), Int32,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Float64, Float64, Ptr{Float64}, UInt32),
+        sys, h, oi, 0, n, lims, x0_shift, z0_shift, I, UInt32(0)))
+    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)
+    return LinRange(lims[1], lims[2], n) .+ x0_shift, LinRange(lims[3], lims[4], n) .+ z0_shift, I
+end
+function Base.empty!(psf::BeamletOptics.PSFDetector, ::Type{CUDASystem})
+    haskey(PSFS, psf) && (ccall((:bmo_psf_free, libbmo), Int32, (Ptr{Cvoid},), PSFS[psf][1]); delete!(PSFS, psf))
+    return psf
+end
 
 function info(res)
     i = Ref(BmoResultInfo(0, 0, 0, 0, 0, 0, 0, 0))
