@@ -373,7 +373,8 @@ def _time_ms(fn, stream, flush, steps=5, warmup=2):
         e1.record(stream)
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
-    return sum(ts) / len(ts)
+    print(f"[bench] {getattr(fn, '__name__', 'step')}: ms per step {['%.3f' % t for t in ts]}", file=sys.stderr)
+    return sorted(ts)[len(ts) // 2]      # median of the timed steps
 
 
 def bench_retrace(m, L, dev, stream, dsys, sc, pos_d, dir_d, lam_d, n, flush):
