@@ -4,7 +4,9 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 #include "bmo_geom.cuh"
 
@@ -58,6 +60,11 @@ struct bmo_sys {
     double* d_bounds = nullptr; double* d_detpose = nullptr; double* d_lambdas = nullptr; double* d_jones = nullptr;
     // pose-0 copies to restore after a sweep
     std::vector<double> h_vertices, h_bounds, h_detpose;
+    // high-water marks of earlier branching traces, keyed by (mode, root beams): queue units, beams and scratch
+    // units the call ended with.  The next call of the same shape allocates them up front (no growth copies,
+    // identical request sizes for the pool).
+    struct TraceHint { int64_t slots = 0, beams = 0, scr = 0; };
+    std::map<std::pair<int, int64_t>, TraceHint> hints;
 };
 
 // One wave of segment records (wave-major), gathered into beam-major order at the end of a trace.
@@ -160,8 +167,18 @@ inline void bvh_build(const double* verts, const int32_t* faces, int64_t nf, Bvh
     }
 }
 
+// Stream-ordered allocation from the device's pool (release threshold = infinity, bmo_init).  Large requests
+// are rounded up to size classes (8 per octave, <= 12.5 % slack): the wave loop of a branching trace asks for
+// slightly different sizes on every call, and a pool that only holds blocks of other sizes has to map new
+// physical memory, which blocks the host for milliseconds per gigabyte.
+inline size_t size_class(size_t bytes) {
+    if (bytes < (size_t)1 << 16) return bytes;
+    int lg = 63 - __builtin_clzll((unsigned long long)bytes);
+    const size_t step = (size_t)1 << (lg - 3);
+    return (bytes + step - 1) & ~(step - 1);
+}
 template <class T> inline cudaError_t dev_alloc(T** p, size_t n, cudaStream_t s) {
-    return cudaMallocAsync((void**)p, std::max<size_t>(n, 1) * sizeof(T), s);
+    return cudaMallocAsync((void**)p, size_class(std::max<size_t>(n, 1) * sizeof(T)), s);
 }
 template <class T> inline void dev_free(T*& p, cudaStream_t s) {
     if (p) cudaFreeAsync((void*)p, s);

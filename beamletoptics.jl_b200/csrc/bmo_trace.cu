@@ -618,8 +618,11 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
     }
 }
 
+#ifndef KMINB0
+#define KMINB0 6
+#endif
 template <int MODE>
-__global__ void __launch_bounds__(Cfg<MODE>::BLOCK) interact_wave(const StepParams P) {
+__global__ void __launch_bounds__(Cfg<MODE>::BLOCK, MODE == 0 ? KMINB0 : 1) interact_wave(const StepParams P) {
     Hit none; none.part = -1; none.t = INFINITY; none.n = mk3(0, 0, 0);
     interact_body<MODE, false>(P, none);
 }
@@ -1585,6 +1588,15 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         if (k > 0) BMO_CUDA(cudaStreamWaitEvent(s.st, ev_fork, 0));
         if ((rc = s.begin(in_h))) return rc;
         s.n_beams = n;
+        if (has_splitter) {     // sizes the previous call of this shape ended with (see bmo_sys::hints)
+            auto it = sys->hints.find({mode, n});
+            if (it != sys->hints.end()) {
+                const bmo_sys::TraceHint& hh = it->second;
+                if (hh.slots * R > s.cur.cap && (rc = grow_queue(s.cur, hh.slots * R, s.nfq, NI_Q, s.st))) return rc;
+                if (hh.scr > s.scr.cap) { free_queue(s.scr, s.st); if ((rc = alloc_queue(s.scr, hh.scr, s.nfs, NI_S, s.st))) return rc; }
+                if ((rc = ensure_beams(res, hh.beams, s.st))) return rc;
+            }
+        }
         if ((rc = s.enqueue_chunk())) return rc;     // the first sub-batch is already copying / tracing while the others are set up
     }
     const double tp1 = tnow_ms();
@@ -1612,6 +1624,10 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     ctx->waves += wave;
     res->n_beams = has_splitter ? subs[0].n_beams : n;
     res->waves = wave;
+    if (has_splitter) {
+        bmo_sys::TraceHint& hh = sys->hints[{mode, n}];
+        hh.slots = std::max(hh.slots, subs[0].cur.cap / R); hh.scr = std::max(hh.scr, subs[0].scr.cap); hh.beams = std::max(hh.beams, res->cap_beams);
+    }
     // join: the caller's stream continues after every sub-batch (copies of the Spotdetector hits included)
     for (int k = 1; k < n_sub; k++) {
         BMO_CUDA(cudaEventRecord(ev_fork, subs[k].st));
