@@ -74,7 +74,7 @@ EXPORTS = [
     "bmo_system_upload", "bmo_system_free", "bmo_system_set_poses", "bmo_trace_rays", "bmo_trace_rays_spots", "bmo_trace_beamlets",
     "bmo_retrace", "bmo_psf_collect", "bmo_psf_count", "bmo_psf_data", "bmo_psf_lims", "bmo_psf_intensity", "bmo_psf_free",
     "bmo_result_get_info", "bmo_result_beams", "bmo_result_segments", "bmo_result_spots", "bmo_result_spots_device",
-    "bmo_result_free", "bmo_pd_accumulate", "bmo_pd_accumulate_poses", "bmo_pd_power", "bmo_measure_fp64_peak",
+    "bmo_result_free", "bmo_pd_accumulate", "bmo_pd_accumulate_poses", "bmo_pd_power", "bmo_pd_sweep", "bmo_measure_fp64_peak",
 ]
 
 _lib = None
@@ -109,6 +109,7 @@ def lib():
         L.bmo_pd_accumulate.argtypes = [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_uint32]
         L.bmo_pd_accumulate_poses.argtypes = [_vp, _vp, C.c_int32, C.c_int32, _vp, C.c_uint32]
         L.bmo_pd_power.argtypes = [_vp, C.c_int32, C.c_int32, _vp, _vp, C.c_uint32]
+        L.bmo_pd_sweep.argtypes = [_vp, _vp, C.c_int32, C.c_int32, _vp, _vp, C.c_uint32]
         L.bmo_psf_collect.argtypes = [_vp, _vp, C.c_int32, C.POINTER(_vp), C.POINTER(C.c_int64)]
         L.bmo_psf_count.argtypes = [_vp, C.POINTER(C.c_int64)]
         L.bmo_psf_data.argtypes = [_vp, _vp]

@@ -514,6 +514,37 @@ int32_t bmo_pd_accumulate(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_
 int32_t bmo_pd_accumulate_poses(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_poses, double* fields, uint32_t flags) {
     return pd_run(sys, r, pd_object, 0, n_poses, fields, flags, true);
 }
+// Pose sweep in one call (the loop "move -> empty!(pd) -> solve_system! -> optical_power(pd)" of test/runtests.jl:2092-2120,
+// batched): the per-pose fields start from zero on the device, the power integrals are taken there, and only what the
+// caller asks for comes back -- n_poses doubles instead of n_poses * n^2 complex numbers when `fields` is NULL.
+int32_t bmo_pd_sweep(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_poses, double* fields, double* power, uint32_t flags) {
+    if (!sys || !r) return fail(BMO_EINVAL, "bmo_pd_sweep: NULL argument");
+    if (!fields && !power) return fail(BMO_EINVAL, "bmo_pd_sweep: neither fields nor power requested");
+    if (pd_object < 0 || pd_object >= (int)sys->objects.size() || sys->objects[pd_object].kind != BMO_OBJ_PHOTODETECTOR)
+        return fail(BMO_EINVAL, "bmo_pd_sweep: object is not a Photodetector");
+    if (n_poses < 1 || n_poses > sys->view.n_poses) return fail(BMO_EINVAL, "bmo_pd_sweep: n_poses out of range");
+    bmo_ctx* ctx = sys->ctx;
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bmo_object& ob = sys->objects[pd_object];
+    const int n = ob.pd_n;
+    const size_t cnt = (size_t)n_poses * n * n * 2;
+    double* d_field = nullptr; double* d_p = nullptr;
+    BMO_CUDA(dev_alloc(&d_field, cnt, st));
+    BMO_CUDA(cudaMemsetAsync(d_field, 0, cnt * sizeof(double), st));
+    int32_t rc = pd_run(sys, r, pd_object, 0, n_poses, d_field, (flags | BMO_INPUT_DEVICE), true);
+    if (rc) { dev_free(d_field, st); return rc; }
+    if (power) {
+        BMO_CUDA(dev_alloc(&d_p, (size_t)n_poses, st));
+        pd_power_kernel<<<n_poses, 256, n * sizeof(double), st>>>(d_field, n, ob.pd_lo, ob.pd_hi, d_p);
+        ctx->launches++;
+        BMO_CUDA(cudaMemcpyAsync(power, d_p, (size_t)n_poses * sizeof(double), cudaMemcpyDeviceToHost, st));
+    }
+    if (fields) BMO_CUDA(cudaMemcpyAsync(fields, d_field, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_field, st); dev_free(d_p, st);
+    return BMO_OK;
+}
 int32_t bmo_pd_power(bmo_sys* sys, int32_t pd_object, int32_t n_fields, const double* fields, double* power, uint32_t flags) {
     if (!sys || !fields || !power) return fail(BMO_EINVAL, "bmo_pd_power: NULL argument");
     if (pd_object < 0 || pd_object >= (int)sys->objects.size() || sys->objects[pd_object].kind != BMO_OBJ_PHOTODETECTOR)

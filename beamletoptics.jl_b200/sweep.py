@@ -56,10 +56,10 @@ def solve_pose_sweep(system, beam, n_poses, apply_pose, pd, r_max=100, device=0,
     res = TraceResult(dsys, h)
     pd_index = f0.object_index(pd)
     n = pd.n
-    fields = np.zeros((n_poses, n * n * 2))
-    L.check(L.lib().bmo_pd_accumulate_poses(dsys.h, res.h, pd_index, n_poses, L.ptr(fields), 0))
+    # one call: per-pose fields accumulated and integrated on the device; the fields only come back when asked for
+    fields = np.zeros((n_poses, n * n * 2)) if want_fields else None
     power = np.zeros(n_poses)
-    L.check(L.lib().bmo_pd_power(dsys.h, pd_index, n_poses, L.ptr(fields), L.ptr(power), 0))
+    L.check(L.lib().bmo_pd_sweep(dsys.h, res.h, pd_index, n_poses, L.ptr(fields), L.ptr(power), 0))
     out = dict(power=power, result=res, dsys=dsys)
     if want_fields:
         z = fields[:, 0::2] + 1j * fields[:, 1::2]

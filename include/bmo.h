@@ -276,6 +276,12 @@ int32_t bmo_psf_intensity(bmo_sys* sys, bmo_psf* psf, int32_t psf_object, int32_
                           double x0_shift, double z0_shift, double* intensity, uint32_t flags);
 int32_t bmo_psf_free(bmo_psf* psf);   /* empty!(psf) */
 
+/* pose sweep in one call: replaces the loop `translate3d!(mirror, ...); empty!(pd); solve_system!(system, beam);
+ * optical_power(pd)` (test/runtests.jl:2092-2120, docs/src/tutorials/michelson.md:251-256) after the batched trace:
+ * fields[pose] start from zero on the device, power[pose] = optical_power of each; fields (host, [n_poses][n*n*2]) and
+ * power (host, [n_poses]) may each be NULL -- with fields == NULL only n_poses doubles leave the device.        */
+int32_t bmo_pd_sweep(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_poses, double* fields, double* power, uint32_t flags);
+
 /* FP64 DFMA micro-benchmark used as the roofline denominator of the FP64-bound kernels.          */
 int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops);
 
