@@ -440,6 +440,65 @@ def lens_shape(r1, d1, md1, r2, d2, md2, ct):
     return shape
 
 
+class CylindricalSurface:
+    """CylindricalSDF.jl:149-171: radius of curvature, clear aperture, height of the uncurved direction, mechanical diameter."""
+    def __init__(self, radius, diameter, height, mechanical_diameter=None):
+        self.radius, self.diameter, self.height = float(radius), float(diameter), float(height)
+        self.mechanical_diameter = float(diameter if mechanical_diameter is None else mechanical_diameter)
+
+
+class RectangularFlatSurface:   # CylindricalSDF.jl:218-223
+    def __init__(self, size):
+        self.size = self.diameter = float(size)
+
+
+def cylindric_lens_shape(front, back, ct):
+    """Lenses.jl:331-379 with the surface -> SDF rules of CylindricalSDF.jl:176-205."""
+    f = None if math.isinf(front.radius) else (sh.ConvexCylinderSDF(front.radius, front.diameter, front.height) if front.radius > 0
+                                                 else sh.ConcaveCylinderSDF(front.radius, front.diameter, front.height))
+    flat_back = isinstance(back, RectangularFlatSurface) or math.isinf(back.radius)
+    b = None if flat_back else (sh.ConcaveCylinderSDF(back.radius, back.diameter, back.height) if back.radius > 0
+                                else sh.ConvexCylinderSDF(-back.radius, back.diameter, back.height))
+    l0 = ct - (f.thickness() if f is not None else 0.0)
+    l0 -= b.thickness() if b is not None else 0.0
+    if isinstance(back, RectangularFlatSurface):
+        d_mid, md_mid, h = front.diameter, front.mechanical_diameter, front.height      # :408-414
+    else:
+        if front.height != back.height:
+            raise ValueError("height of front and back surface have to match for cylindric lenses")
+        d_mid, md_mid, h = min(front.diameter, back.diameter), max(front.mechanical_diameter, back.mechanical_diameter), front.height
+    if l0 <= 0:
+        raise ValueError("Lens parameters lead to a box section length of <= 0")
+    mid = sh.BoxSDF(h, l0, d_mid)
+    mid.translate3d_((0.0, l0 / 2, 0.0))
+    if f is not None:
+        mid.translate3d_((0.0, f.thickness(), 0.0))
+        mid = mid + f
+    if b is not None:
+        b.translate3d_((0.0, mid.thickness() + b.thickness(), 0.0))
+        mid = mid + b
+    shape = mid
+    if md_mid > d_mid:
+        rt, rc = mid.thickness(), mid.pos[1] + mid.thickness() / 2
+        if f is not None:
+            rt -= f.thickness(); rc += f.thickness() / 2        # edge_sag(::CylindricalSurface, sdf) = thickness(sdf), CylindricalSDF.jl:173-174
+        if b is not None:
+            rt += b.thickness(); rc += b.thickness() / 2
+        ring = sh.RingSDF(d_mid / 2, (md_mid - d_mid) / 2, rt)
+        ring.translate3d_((0.0, rc, 0.0))
+        shape = shape + ring
+    return shape
+
+
+def CylindricalLens(front, back_or_ct, ct_or_n, n=None):
+    """Lens(front::AbstractCylindricalSurface, [back,] center_thickness, n) (Lenses.jl:331-393)."""
+    if n is None:
+        front_s, back_s, ct, n = front, RectangularFlatSurface(front.diameter), back_or_ct, ct_or_n
+    else:
+        front_s, back_s, ct = front, back_or_ct, ct_or_n
+    return Lens(cylindric_lens_shape(front_s, back_s, ct), n)
+
+
 def ThinLens(R1, R2, d, n):                       # SphericalLenses.jl:42-46
     return Lens(sh.ThinLensSDF(R1, R2, d), n)
 

@@ -124,6 +124,27 @@ template <class T> BMO_NI T prim_eval(const bmo_prim& pr, P3<T> q, int zr, Stats
             T pln = (p.x + p.y) / 1.4142135623730951;  // sqrt(2)
             return max_(box, pln);
         }
+        case BMO_PRIM_CONVEX_CYL: {  // CylindricalSDF.jl:59-78: sdf_cut_disk in (y, z), op_extrude_x (AbstractSDF.jl:229-234)
+            const double r = a, h = b, w = c, hx = d;
+            T p1 = abs_(p.y), p2 = p.z;
+            T s = max_((h - r) * (p1 * p1) + (w * w) * (h + r - 2 * p2), h * p1 - w * p2);
+            T dd;
+            if (s < 0.0) dd = norm2_(p1, p2, zr) - r;
+            else if (p1 < w) dd = h - p2;
+            else dd = norm2_(p1 - w, p2 - h, zr);
+            return cyl_(dd, abs_(p.x) - hx, zr);
+        }
+        case BMO_PRIM_CONCAVE_CYL: {  // CylindricalSDF.jl:120-133
+            const double r = a, sg = d;
+            T psy = p.y + (-r);
+            T d1 = abs_(norm2_(p.z, psy, zr)) - fabs(r);
+            T d2 = abs_(p.x) - c / 2;
+            T cc = cyl_(d1, d2, zr);
+            T ppy = p.y + (-sg / 2 * (r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0)));
+            T qx = abs_(p.x) - c / 2, qy = abs_(ppy) - sg / 2, qz = abs_(p.z) - b / 2;
+            T l = norm3_(max_(qx, 0.0), max_(qy, 0.0), max_(qz, 0.0), zr) + min_(max_(qx, max_(qy, qz)), 0.0);
+            return max_(l, -cc);
+        }
         default: break;
     }
     return T{};
@@ -224,6 +245,25 @@ BMO_D double prim_eval_f(const bmo_prim& pr, V3 q) {
             const double box = pnorm3(qx, qy, qz) + neg_part(fmax_jl(qx, fmax_jl(qy, qz)));
             const double pln = (p.x + p.y) / 1.4142135623730951;
             return fmax_jl(box, pln);
+        }
+        case BMO_PRIM_CONVEX_CYL: {
+            const double r = a, h = b, w = c, hx = d;
+            const double p1 = fabs(p.y), p2 = p.z;
+            const double s = fmax_jl((h - r) * (p1 * p1) + (w * w) * (h + r - 2 * p2), h * p1 - w * p2);
+            double dd;
+            if (s < 0.0) dd = hyp2(p1, p2) - r;
+            else if (p1 < w) dd = h - p2;
+            else dd = hyp2(p1 - w, p2 - h);
+            return cyl_f(dd, fabs(p.x) - hx);
+        }
+        case BMO_PRIM_CONCAVE_CYL: {
+            const double r = a, sg = d;
+            const double psy = p.y + (-r);
+            const double cc = cyl_f(hyp2(p.z, psy) - fabs(r), fabs(p.x) - c / 2);
+            const double ppy = p.y + (-sg / 2 * (r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0)));
+            const double qx = fabs(p.x) - c / 2, qy = fabs(ppy) - sg / 2, qz = fabs(p.z) - b / 2;
+            const double l = pnorm3(qx, qy, qz) + neg_part(fmax_jl(qx, fmax_jl(qy, qz)));
+            return fmax_jl(l, -cc);
         }
         default: break;
     }

@@ -12,7 +12,7 @@ import numpy as np
 from . import linalg as la
 
 # bmo_prim_type (include/bmo.h)
-PLANO, CYLINDER, SPHERE, CONVEX, CONCAVE, CUTSPHERE, BOX, RING, RAPRISM, MENISCUS = range(10)
+PLANO, CYLINDER, SPHERE, CONVEX, CONCAVE, CUTSPHERE, BOX, RING, RAPRISM, MENISCUS, CONVEX_CYL, CONCAVE_CYL = range(12)
 
 
 def sag(r, l):
@@ -96,13 +96,17 @@ class PrimSDF(AbstractSDF):
         super()._set_dir(d)
 
     def has_thickness(self):
-        return self.type in (PLANO, SPHERE, CONVEX, CONCAVE, BOX)
+        return self.type in (PLANO, SPHERE, CONVEX, CONCAVE, BOX, CONVEX_CYL, CONCAVE_CYL)
 
     def thickness(self):
         a, b, c, _ = self.par
+        if self.type == CONVEX_CYL:
+            return self._thickness            # CylindricalSDF.jl:57  abs(sag(radius, diameter))
         return {PLANO: a, SPHERE: 2 * a, CONVEX: c, CONCAVE: 0.0, BOX: 2 * b}.get(self.type, 0.0)
 
     def diameter(self):
+        if self.type == CONVEX_CYL:
+            return self._diameter
         return 2 * self.par[0] if self.type == SPHERE else self.par[1]
 
     def sag(self):
@@ -119,6 +123,10 @@ class PrimSDF(AbstractSDF):
         if t == CONCAVE: return (-b / 2, -c, -b / 2), (b / 2, 0.0, b / 2)        # cylinder slab y in [-sag, 0] minus the sphere
         if t in (BOX, RAPRISM): return (-a, -b, -c), (a, b, c)
         if t == RING: return (-(a + b), -c, -(a + b)), (a + b, c, a + b)
+        if t == CONVEX_CYL: return (-d, -c, b), (d, c, a)      # |x| <= height/2, |y| <= w, cut height <= z <= radius
+        if t == CONCAVE_CYL:                                    # the box of CylindricalSDF.jl:129-131 (the cylinder is cut out of it)
+            y0 = d / 2 if a > 0 else -d / 2
+            return (-c / 2, y0 - d / 2, -b / 2), (c / 2, y0 + d / 2, b / 2)
         raise ValueError(t)
 
     def box_points(self):
@@ -137,6 +145,10 @@ class PrimSDF(AbstractSDF):
         elif t == CUTSPHERE: cl, r = (0.0, 0.0, 0.0), a
         elif t in (BOX, RAPRISM): cl, r = (0.0, 0.0, 0.0), math.sqrt(a * a + b * b + c * c)
         elif t == RING: cl, r = (0.0, 0.0, 0.0), math.hypot(a + b, c)
+        elif t in (CONVEX_CYL, CONCAVE_CYL):
+            lo, hi = self.local_box()
+            cl = tuple((lo[k] + hi[k]) / 2 for k in range(3))
+            r = math.sqrt(sum(((hi[k] - lo[k]) / 2) ** 2 for k in range(3)))
         else: raise ValueError(t)
         return la.add(self.pos, la.matvec(self.dir, cl)), r
 
@@ -158,6 +170,19 @@ def ConvexSphericalSurfaceSDF(radius, diameter):   # SphericalLensSDF.jl:203-217
 def ConcaveSphericalSurfaceSDF(radius, diameter):  # :147-157
     check_sag(radius, diameter)
     return PrimSDF(CONCAVE, (radius, diameter, sag(radius, diameter)))
+
+
+def ConvexCylinderSDF(radius, diameter, height):   # CylindricalSDF.jl:30-55: cut cylinder built along x, turned upright, vertex at the origin
+    h = math.sqrt(radius * radius - (diameter / 2) * (diameter / 2))
+    s = PrimSDF(CONVEX_CYL, (radius, h, math.sqrt(radius * radius - h * h), height / 2))
+    s._thickness, s._diameter = abs(sag(radius, diameter)), diameter
+    s.xrotate3d_(math.pi / 2)
+    s.translate3d_((0.0, radius, 0.0))
+    return s
+
+
+def ConcaveCylinderSDF(radius, diameter, height):  # :92-116 (the sign of the radius selects the side the cylinder is cut from)
+    return PrimSDF(CONCAVE_CYL, (radius, diameter, height, sag(abs(radius), diameter)))
 
 
 def CutSphereSDF(radius, height):                  # PrimitiveSDF.jl:97-110

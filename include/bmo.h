@@ -39,6 +39,10 @@ enum bmo_prim_type {
     BMO_PRIM_BOX = 6,       /* par: half extents x, y, z                         */
     BMO_PRIM_RING = 7,      /* par: inner_radius(+hwidth), hwidth, hthickness    */
     BMO_PRIM_RAPRISM = 8,   /* par: half extents x, y, z                         */
+    BMO_PRIM_CONVEX_CYL = 10, /* ConvexCylinderSDF (CylindricalSDF.jl:30-78); par: radius, cut height sqrt(r^2-(d/2)^2),
+                                 w = sqrt(r^2 - cut height^2), half extrusion height                  */
+    BMO_PRIM_CONCAVE_CYL = 11,/* ConcaveCylinderSDF (CylindricalSDF.jl:92-133); par: radius (signed), diameter, height,
+                                 sag(|radius|, diameter)                                            */
     BMO_PRIM_MENISCUS = 9   /* frame only; followed by 3 child records: convex, cylinder, concave,
                                posed relative to this frame (MeniscusLensSDF.jl:42-46)            */
 };

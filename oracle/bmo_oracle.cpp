@@ -139,6 +139,40 @@ SDF* lens_shape(double r1, double d1, double md1, double r2, double d2, double m
     }
     return shape;
 }
+// OpticalComponents/Lenses.jl:331-379 Lens(front::AbstractCylindricalSurface, back, center_thickness, n) with
+// CylindricalSDF.jl:176-205 (surface -> SDF; r = Inf stands for RectangularFlatSurface / a flat side)
+SDF* cyl_lens_shape(double r1, double d1, double h1, double md1, double r2, double d2, double h2, double md2, double ct) {
+    const bool flat1 = std::isinf(r1), flat2 = std::isinf(r2);
+    PrimSDF* front = flat1 ? nullptr : (r1 > 0 ? mk_convex_cyl(r1, d1, h1) : mk_concave_cyl(r1, d1, h1));
+    PrimSDF* back = flat2 ? nullptr : (r2 > 0 ? mk_concave_cyl(r2, d2, h2) : mk_convex_cyl(-r2, d2, h2));
+    double l0 = ct;
+    l0 -= front ? front->thickness() : 0.0;
+    l0 -= back ? back->thickness() : 0.0;
+    double d_mid, md_mid, h;
+    if (flat1) throw std::runtime_error("cylindric lens: the front surface must be a CylindricalSurface");
+    if (flat2) { d_mid = d1; md_mid = md1; h = h1; }
+    else {
+        if (h1 != h2) throw std::runtime_error("height of front and back surface have to match for cylindric lenses");
+        d_mid = std::min(d1, d2); md_mid = std::max(md1, md2); h = h1;
+    }
+    if (l0 <= 0) throw std::runtime_error("Lens parameters lead to a box section length of <= 0");
+    SDF* mid = mk_box(h, l0, d_mid);
+    mid->translate(V3{0, l0 / 2, 0});
+    if (front) { mid->translate(V3{0, front->thickness(), 0}); mid = sdf_union(mid, front); }
+    if (back) { back->translate(V3{0, mid->thickness() + back->thickness(), 0}); mid = sdf_union(mid, back); }
+    SDF* shape = mid;
+    if (md_mid > d_mid) {
+        double ring_thickness = mid->thickness();
+        double ring_center = mid->pos.y + ring_thickness / 2;   // position(mid): of the box if there is no union, else 0
+        if (front) { double sg = front->thickness(); ring_thickness -= sg; ring_center += sg / 2; }   // edge_sag = thickness (CylindricalSDF.jl:173-174)
+        if (back) { double sg = back->thickness(); ring_thickness += sg; ring_center += sg / 2; }
+        SDF* ring = mk_ring(d_mid / 2, (md_mid - d_mid) / 2, ring_thickness);
+        ring->translate(V3{0, ring_center, 0});
+        shape = sdf_union(shape, ring);
+    }
+    return shape;
+}
+
 // SphericalLensSDF.jl:245-253
 SDF* thin_lens_sdf(double r1, double r2, double d) {
     SDF* front = mk_convex(r1, d);
@@ -237,6 +271,8 @@ int orc_new(const char* kind, const double* d, int nd, const int* ih, int ni) {
     if (k == "NonInteractableObject") return reg_object(mk_obj(O_NONINT, S(ih[0])));
     if (k == "SphericalLens") return reg_object(spherical_lens(d[0], d[1], d[2], d[3], RI(ih[0])));
     if (k == "LensFromSurfaces") return reg_object(mk_refr(lens_shape(d[0], d[1], d[2], d[3], d[4], d[5], d[6]), RI(ih[0])));
+    if (k == "CylindricalLens")   // r1 d1 h1 md1 r2 d2 h2 md2 ct (r2 = Inf: RectangularFlatSurface)
+        return reg_object(mk_refr(cyl_lens_shape(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8]), RI(ih[0])));
     if (k == "ThinLens") return reg_object(mk_refr(thin_lens_sdf(d[0], d[1], d[2]), RI(ih[0])));
     if (k == "SphericalDoubletLens") {  // DoubletLenses.jl:57-64: r1 r2 r3 l1 l2 d, n1 n2
         Object* front = spherical_lens(d[0], d[1], d[3], d[5], RI(ih[0]));

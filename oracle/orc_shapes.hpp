@@ -124,7 +124,7 @@ template <class T> inline T cyl_(T d1, T d2) {
     return min_(max_(d1, d2), 0.0) + norm2_(max_(d1, 0.0), max_(d2, 0.0));
 }
 
-enum PrimType { P_PLANO, P_CYLINDER, P_SPHERE, P_CONVEX, P_CONCAVE, P_CUTSPHERE, P_BOX, P_RING, P_RAPRISM };
+enum PrimType { P_PLANO, P_CYLINDER, P_SPHERE, P_CONVEX, P_CONCAVE, P_CUTSPHERE, P_BOX, P_RING, P_RAPRISM, P_CONVEX_CYL, P_CONCAVE_CYL };
 
 struct PrimSDF : SDF {
     PrimType type;
@@ -133,6 +133,8 @@ struct PrimSDF : SDF {
     // CONVEX: a=radius b=diameter c=sag d=height | CONCAVE: a=radius b=diameter c=sag
     // CUTSPHERE: a=radius b=height c=w | BOX/RAPRISM: a,b,c = half extents
     // RING: a=inner_radius(+hw) b=hwidth c=hthickness
+    // CONVEX_CYL: a=radius b=cut height sqrt(r^2-(d/2)^2) c=w=sqrt(r^2-b^2) d=half extrusion height | CONCAVE_CYL: a=radius b=diameter c=height d=sag(|r|, d)
+    double thick_cyl = 0.0, diam_cyl = 0.0;   // cylindrical surfaces: thickness(s) and the clear aperture
     explicit PrimSDF(PrimType t) : type(t) {}
 
     void set_dir(const M3& dd) override {
@@ -146,11 +148,13 @@ struct PrimSDF : SDF {
             case P_CONVEX: return c;             // :196
             case P_CONCAVE: return 0.0;          // :140
             case P_BOX: return 2 * b;            // PrimitiveSDF.jl:39
+            case P_CONVEX_CYL: return thick_cyl; // CylindricalSDF.jl:57  abs(sag(radius, diameter))
+            case P_CONCAVE_CYL: return 0.0;      // :118
             default: return 0.0;
         }
     }
     bool has_thickness() const override {
-        return type == P_PLANO || type == P_SPHERE || type == P_CONVEX || type == P_CONCAVE || type == P_BOX;
+        return type == P_PLANO || type == P_SPHERE || type == P_CONVEX || type == P_CONCAVE || type == P_BOX || type == P_CONVEX_CYL || type == P_CONCAVE_CYL;
     }
     double diameter() const { return type == P_SPHERE ? 2 * a : b; }
 
@@ -204,6 +208,24 @@ struct PrimSDF : SDF {
                 T d1 = abs_(px) - b, d2 = abs_(p.y) - c;
                 return norm2_(max_(d1, 0.0), max_(d2, 0.0)) + min_(max_(d1, d2), 0.0);
             }
+            case P_CONVEX_CYL: {  // CylindricalSDF.jl:59-78: sdf_cut_disk in (y, z), extruded along x (AbstractSDF.jl:229-234)
+                const double r = a, h = b, w = c, hx = d;
+                T p1 = abs_(p.y), p2 = p.z;
+                T s = max_((h - r) * (p1 * p1) + (w * w) * (h + r - 2 * p2), h * p1 - w * p2);
+                T dd = (s < 0.0) ? norm2_(p1, p2) - r : ((p1 < w) ? h - p2 : norm2_(p1 - w, p2 - h));
+                return cyl_(dd, abs_(p.x) - hx);
+            }
+            case P_CONCAVE_CYL: {  // CylindricalSDF.jl:120-133
+                const double r = a, sg = d;
+                T psy = p.y + (-r);
+                T d1 = abs_(norm2_(p.z, psy)) - std::fabs(r);
+                T d2 = abs_(p.x) - c / 2;
+                T cc = cyl_(d1, d2);
+                T ppy = p.y + (-sg / 2 * (r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0)));
+                T qx = abs_(p.x) - c / 2, qy = abs_(ppy) - sg / 2, qz = abs_(p.z) - b / 2;
+                T l = norm3_(max_(qx, 0.0), max_(qy, 0.0), max_(qz, 0.0)) + min_(max_(qx, max_(qy, qz)), 0.0);
+                return max_(l, -cc);
+            }
             case P_RAPRISM: {  // PrimitiveSDF.jl:204-210
                 T qx = abs_(p.x) - a, qy = abs_(p.y) - b, qz = abs_(p.z) - c;
                 T box = norm3_(max_(qx, 0.0), max_(qy, 0.0), max_(qz, 0.0)) + min_(max_(qx, max_(qy, qz)), 0.0);
@@ -239,6 +261,20 @@ inline PrimSDF* mk_box(double x, double y, double z) {  // :29-37
 }
 inline PrimSDF* mk_ring(double inner_radius, double width, double thick) {  // :146-155
     auto* s = new PrimSDF(P_RING); s->a = inner_radius + width / 2; s->b = width / 2; s->c = thick / 2; return s;
+}
+// CylindricalSDF.jl:41-55: the cut cylinder is built along x, then xrotate3d!(s, pi/2) and translate3d!(s, [0, radius, 0])
+inline PrimSDF* mk_convex_cyl(double r, double d, double h) {
+    auto* s = new PrimSDF(P_CONVEX_CYL);
+    s->a = r; s->b = std::sqrt(r * r - (d / 2) * (d / 2)); s->c = std::sqrt(r * r - s->b * s->b); s->d = h / 2;
+    s->thick_cyl = std::fabs(sag(r, d)); s->diam_cyl = d;
+    s->rotate(V3{1, 0, 0}, kPi / 2);
+    s->translate(V3{0, r, 0});
+    return s;
+}
+inline PrimSDF* mk_concave_cyl(double r, double d, double h) {  // :103-116
+    auto* s = new PrimSDF(P_CONCAVE_CYL);
+    s->a = r; s->b = d; s->c = h; s->d = sag(std::fabs(r), d); s->diam_cyl = d;
+    return s;
 }
 inline PrimSDF* mk_raprism(double leg, double height) {  // :195-202
     auto* s = new PrimSDF(P_RAPRISM); s->a = leg / 2; s->b = leg / 2; s->c = height / 2; return s;
