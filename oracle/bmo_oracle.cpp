@@ -8,6 +8,7 @@
 #include <functional>
 #include <omp.h>
 #include "orc_optics.hpp"
+#include "orc_asphere.hpp"
 
 namespace orc { int g_norm_zero_rule = 1; }  // ZERO rule: pinned by test/runtests.jl:1309-1314 (see orc_math.hpp)
 using namespace orc;
@@ -48,7 +49,21 @@ SDF* surf_backward(double r, double d) {
     b->rotate(V3{0, 0, 1}, kPi);
     return b;
 }
-double edge_sag_of(SDF* s) { return static_cast<PrimSDF*>(s)->c; }  // SphericalLensSDF.jl:421
+// edge_sag(surface, sdf): SphericalLensSDF.jl:421 (the stored sag) / AsphericalLensSDF.jl:434-443 (signed sag at the rim)
+double edge_sag_of(SDF* s) {
+    if (auto* a = dynamic_cast<AsphSDF*>(s)) return a->edge_sag();
+    return static_cast<PrimSDF*>(s)->c;
+}
+// EvenAsphericalSurface -> SDF (AsphericalLensSDF.jl:452-474): no rotation for the backward orientation
+struct AsphDesc { double k; std::vector<double> coeffs; };
+SDF* asph_forward(const AsphDesc& a, double r, double d) {
+    if (std::isinf(r)) return nullptr;
+    return new AsphSDF(r > 0, a.coeffs, r, a.k, d);
+}
+SDF* asph_backward(const AsphDesc& a, double r, double d) {
+    if (std::isinf(r)) return nullptr;
+    return new AsphSDF(!(r > 0), a.coeffs, r, a.k, d);
+}
 double sgn(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : 0.0); }
 
 // SDFs/MeniscusLensSDF.jl:122-189
@@ -82,13 +97,15 @@ SDF* meniscus_lens_sdf(double r1, double d1, SDF* front, double r2, double d2, S
 }
 
 // OpticalComponents/Lenses.jl:176-291  Lens(front_surface, back_surface, center_thickness, n)
-SDF* lens_shape(double r1, double d1, double md1, double r2, double d2, double md2, double ct) {
+SDF* lens_shape(double r1, double d1, double md1, double r2, double d2, double md2, double ct,
+                const AsphDesc* a1 = nullptr, const AsphDesc* a2 = nullptr) {
     double d_mid = std::min(d1, d2), md_mid = std::max(md1, md2);
     double l0 = ct;
-    SDF* front = surf_forward(r1, d1);
+    SDF* front = a1 ? asph_forward(*a1, r1, d1) : surf_forward(r1, d1);
     l0 -= front ? front->thickness() : 0.0;
-    SDF* back = surf_backward(r2, d2);
+    SDF* back = a2 ? asph_backward(*a2, r2, d2) : surf_backward(r2, d2);
     l0 -= back ? back->thickness() : 0.0;
+    if (l0 <= 0 && (a1 || a2)) throw std::invalid_argument("only spherical meniscus lenses are supported (Lenses.jl:188-190)");
     if (!front && !back) return mk_plano(ct, d_mid);  // Lenses.jl:303-311
     SDF* shape;
     if (l0 <= 0) {
@@ -271,6 +288,15 @@ int orc_new(const char* kind, const double* d, int nd, const int* ih, int ni) {
     if (k == "NonInteractableObject") return reg_object(mk_obj(O_NONINT, S(ih[0])));
     if (k == "SphericalLens") return reg_object(spherical_lens(d[0], d[1], d[2], d[3], RI(ih[0])));
     if (k == "LensFromSurfaces") return reg_object(mk_refr(lens_shape(d[0], d[1], d[2], d[3], d[4], d[5], d[6]), RI(ih[0])));
+    if (k == "AsphericLens") {
+        // r1 d1 md1 k1 nc1 | r2 d2 md2 k2 nc2 | ct | coeffs1... coeffs2...   (nc < 0: SphericalSurface / CircularFlatSurface)
+        int nc1 = (int)d[4], nc2 = (int)d[9];
+        AsphDesc a1, a2;
+        int o = 11;
+        if (nc1 >= 0) { a1.k = d[3]; a1.coeffs.assign(d + o, d + o + nc1); o += nc1; }
+        if (nc2 >= 0) { a2.k = d[8]; a2.coeffs.assign(d + o, d + o + nc2); o += nc2; }
+        return reg_object(mk_refr(lens_shape(d[0], d[1], d[2], d[5], d[6], d[7], d[10], nc1 >= 0 ? &a1 : nullptr, nc2 >= 0 ? &a2 : nullptr), RI(ih[0])));
+    }
     if (k == "CylindricalLens")   // r1 d1 h1 md1 r2 d2 h2 md2 ct (r2 = Inf: RectangularFlatSurface)
         return reg_object(mk_refr(cyl_lens_shape(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8]), RI(ih[0])));
     if (k == "ThinLens") return reg_object(mk_refr(thin_lens_sdf(d[0], d[1], d[2]), RI(ih[0])));

@@ -17,7 +17,7 @@ _LIB_PATH = os.path.join(_HERE, "liboracle.so")
 
 def build(force=False):
     """Compile oracle/liboracle.so with the Makefile next to this file."""
-    srcs = [os.path.join(_HERE, f) for f in ("bmo_oracle.cpp", "orc_math.hpp", "orc_shapes.hpp", "orc_optics.hpp")]
+    srcs = [os.path.join(_HERE, f) for f in ("bmo_oracle.cpp", "orc_math.hpp", "orc_shapes.hpp", "orc_optics.hpp", "orc_asphere.hpp")]
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
