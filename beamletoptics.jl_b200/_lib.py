@@ -23,7 +23,8 @@ class BmoError(RuntimeError):
 
 
 class bmo_prim(C.Structure):
-    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("pos", C.c_double * 3), ("tdir", C.c_double * 9), ("par", C.c_double * 4)]
+    _fields_ = [("type", C.c_int32), ("reserved", C.c_int32), ("pos", C.c_double * 3), ("tdir", C.c_double * 9), ("par", C.c_double * 4),
+                ("ext_first", C.c_int32), ("ext_count", C.c_int32)]
 
 
 class bmo_part(C.Structure):
@@ -51,6 +52,7 @@ class bmo_tables(C.Structure):
                 ("n_lambda", C.c_int32), ("lambdas", C.POINTER(C.c_double)),
                 ("n_rows", C.c_int32), ("n_table", C.POINTER(C.c_double)),
                 ("n_system", C.c_double),
+                ("n_ext", C.c_int64), ("ext", C.POINTER(C.c_double)),
                 ("n_jones", C.c_int32), ("jones", C.POINTER(C.c_double)),
                 ("norm_zero_rule", C.c_int32), ("reserved", C.c_int32)]
 

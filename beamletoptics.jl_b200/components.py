@@ -382,17 +382,60 @@ def _meniscus(r1, d1, front, r2, d2, back, ct):   # MeniscusLensSDF.jl:122-189
     return sh.MeniscusLensSDF(cvx, cyl, ccv, ct)
 
 
-def lens_shape(r1, d1, md1, r2, d2, md2, ct):
-    """Lenses.jl:176-311 for SphericalSurface / CircularFlatSurface (r = Inf) pairs."""
+class SphericalSurface:
+    """SphericalLensSDF.jl:380-419: radius of curvature, clear aperture, mechanical diameter (r = Inf: flat)."""
+    def __init__(self, radius, diameter, mechanical_diameter=None):
+        self.radius, self.diameter = float(radius), float(diameter)
+        self.mechanical_diameter = float(diameter if mechanical_diameter is None else mechanical_diameter)
+
+    def sdf_forward(self): return _surf_forward(self.radius, self.diameter)
+    def sdf_backward(self): return _surf_backward(self.radius, self.diameter)
+
+
+def CircularFlatSurface(diameter):    # SphericalLensSDF.jl:456-466
+    return SphericalSurface(math.inf, diameter)
+
+
+class EvenAsphericalSurface(SphericalSurface):
+    """AsphericalLensSDF.jl:392-428: base sphere + conic constant + even coefficients (coefficients[i] multiplies r^(2i))."""
+    def __init__(self, radius, diameter, conic_constant, coefficients, mechanical_diameter=None):
+        super().__init__(radius, diameter, mechanical_diameter)
+        self.conic_constant, self.coefficients = float(conic_constant), [float(a) for a in coefficients]
+
+    def sdf_forward(self):      # :452-462
+        if math.isinf(self.radius):
+            return None
+        return sh.AsphericalSurfaceSDF(self.radius > 0, self.coefficients, self.radius, self.conic_constant, self.diameter)
+
+    def sdf_backward(self):     # :464-474 (no rotation: the distance functions read the sign of the curvature)
+        if math.isinf(self.radius):
+            return None
+        return sh.AsphericalSurfaceSDF(not (self.radius > 0), self.coefficients, self.radius, self.conic_constant, self.diameter)
+
+
+def LensFromSurfaces(front, back_or_ct, ct_or_n, n=None):
+    """Lens(front_surface, [back_surface,] center_thickness, n) for rotationally symmetric surfaces (Lenses.jl:176-311)."""
+    if n is None:
+        front_s, back_s, ct, n = front, CircularFlatSurface(front.diameter), back_or_ct, ct_or_n
+    else:
+        front_s, back_s, ct = front, back_or_ct, ct_or_n
+    return Lens(lens_shape(front_s.radius, front_s.diameter, front_s.mechanical_diameter, back_s.radius, back_s.diameter,
+                           back_s.mechanical_diameter, ct, front_s, back_s), n)
+
+
+def lens_shape(r1, d1, md1, r2, d2, md2, ct, front_surface=None, back_surface=None):
+    """Lenses.jl:176-311.  Without surface objects: SphericalSurface / CircularFlatSurface (r = Inf) pairs."""
     d_mid, md_mid = min(d1, d2), max(md1, md2)
     l0 = ct
-    front = _surf_forward(r1, d1)
+    front = front_surface.sdf_forward() if front_surface is not None else _surf_forward(r1, d1)
     l0 -= front.thickness() if front is not None else 0.0
-    back = _surf_backward(r2, d2)
+    back = back_surface.sdf_backward() if back_surface is not None else _surf_backward(r2, d2)
     l0 -= back.thickness() if back is not None else 0.0
     if front is None and back is None:
         return sh.PlanoSurfaceSDF(ct, d_mid)
     if l0 <= 0:
+        if isinstance(front, sh.AsphericalSurfaceSDF) or isinstance(back, sh.AsphericalSurfaceSDF):
+            raise ValueError("only spherical meniscus lenses are supported (Lenses.jl:188-190)")
         if _sign(r1) != _sign(r2):
             raise ValueError("Lens parameters lead to cylinder section length of <= 0, use ThinLens instead.")
         shape = _meniscus(r1, d1, front, r2, d2, back, ct)

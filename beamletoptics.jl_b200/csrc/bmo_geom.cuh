@@ -4,6 +4,8 @@
 #pragma once
 #include "../../include/bmo.h"
 #include "bmo_math.cuh"
+#include "bmo_asphere.cuh"
+#include <type_traits>
 
 namespace bmo {
 
@@ -39,6 +41,7 @@ struct SysView {
     const double* det_pose;  // [n_poses][n_objects][12] pos(3) dir(9 row-major)
     const double* lambdas;   // [n_lambda]
     const double* jones;     // [n_jones][10] PolarizationFilter: J (3x3 row-major), cutoff
+    const double* ext;       // parameter blocks of the aspheric primitives (bmo_asphere.cuh)
     int32_t n_prims, n_parts, n_objects, n_meshes, n_lambda, n_poses, zr, pad;
     int64_t n_vertices;
     double n_system;
@@ -66,9 +69,51 @@ template <class T> BMO_D P3<T> w2s(const bmo_prim& pr, P3<T> q) {
 template <class T> BMO_D T cyl_(T d1, T d2, int zr) {
     return min_(max_(d1, d2), 0.0) + norm2_(max_(d1, 0.0), max_(d2, 0.0), zr);
 }
-template <class T> BMO_NI T prim_eval(const bmo_prim& pr, P3<T> q, int zr, Stats& st) {
+// Aspheric primitives: bmo_system_upload stores the device address of the primitive's parameter block
+// (SysView::ext + ext_first) in par[0], bit for bit, so that every evaluation site reaches it through the record.
+BMO_D const double* asph_block(const bmo_prim& pr) { return reinterpret_cast<const double*>((unsigned long long)__double_as_longlong(pr.par[0])); }
+BMO_D bool is_asph(int type) { return type == BMO_PRIM_CONVEX_ASPH || type == BMO_PRIM_CONCAVE_ASPH; }
+// Cylindrical and aspheric surfaces, generic (value / dual) evaluation: out of line for the same reason as
+// prim_eval_rare below -- a noinline function saves every callee-saved register any of its cases needs.
+template <class T> BMO_NI T prim_eval_rare_t(const bmo_prim& pr, P3<T> p, int zr) {
+    const double a = pr.par[0], b = pr.par[1], c = pr.par[2], d = pr.par[3];
+    switch (pr.type) {
+        case BMO_PRIM_CONVEX_ASPH:
+        case BMO_PRIM_CONCAVE_ASPH:   // AsphericalLensSDF.jl:309-349: y is the optical axis, the 2-D distance is revolved about it
+            if constexpr (std::is_same<T, double>::value)
+                return aspheric_surface_distance(pr.type == BMO_PRIM_CONVEX_ASPH, sqrt(p.x * p.x + p.z * p.z) - 0.0, p.y, asph_block(pr));
+            else
+                return T{};   // no AD path: normal3d = numeric_gradient (:5)
+        case BMO_PRIM_CONVEX_CYL: {  // CylindricalSDF.jl:59-78: sdf_cut_disk in (y, z), op_extrude_x (AbstractSDF.jl:229-234)
+            const double r = a, h = b, w = c, hx = d;
+            T p1 = abs_(p.y), p2 = p.z;
+            T s = max_((h - r) * (p1 * p1) + (w * w) * (h + r - 2 * p2), h * p1 - w * p2);
+            T dd;
+            if (s < 0.0) dd = norm2_(p1, p2, zr) - r;
+            else if (p1 < w) dd = h - p2;
+            else dd = norm2_(p1 - w, p2 - h, zr);
+            return cyl_(dd, abs_(p.x) - hx, zr);
+        }
+        case BMO_PRIM_CONCAVE_CYL: {  // CylindricalSDF.jl:120-133
+            const double r = a, sg = d;
+            T psy = p.y + (-r);
+            T d1 = abs_(norm2_(p.z, psy, zr)) - fabs(r);
+            T d2 = abs_(p.x) - c / 2;
+            T cc = cyl_(d1, d2, zr);
+            T ppy = p.y + (-sg / 2 * (r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0)));
+            T qx = abs_(p.x) - c / 2, qy = abs_(ppy) - sg / 2, qz = abs_(p.z) - b / 2;
+            T l = norm3_(max_(qx, 0.0), max_(qy, 0.0), max_(qz, 0.0), zr) + min_(max_(qx, max_(qy, qz)), 0.0);
+            return max_(l, -cc);
+        }
+        default: break;
+    }
+    return T{};
+}
+// RK: the kernel was compiled for systems with cylindrical / aspheric primitives (chosen by the host per system)
+template <class T, bool RK> BMO_NI T prim_eval(const bmo_prim& pr, P3<T> q, int zr, Stats& st) {
     st.sdf++;
     P3<T> p = w2s(pr, q);
+    if (RK) { if (pr.type >= BMO_PRIM_CONVEX_CYL) return prim_eval_rare_t<T>(pr, p, zr); }
     const double a = pr.par[0], b = pr.par[1], c = pr.par[2], d = pr.par[3];
     switch (pr.type) {
         case BMO_PRIM_PLANO: {  // SphericalLensSDF.jl:60-65
@@ -124,39 +169,18 @@ template <class T> BMO_NI T prim_eval(const bmo_prim& pr, P3<T> q, int zr, Stats
             T pln = (p.x + p.y) / 1.4142135623730951;  // sqrt(2)
             return max_(box, pln);
         }
-        case BMO_PRIM_CONVEX_CYL: {  // CylindricalSDF.jl:59-78: sdf_cut_disk in (y, z), op_extrude_x (AbstractSDF.jl:229-234)
-            const double r = a, h = b, w = c, hx = d;
-            T p1 = abs_(p.y), p2 = p.z;
-            T s = max_((h - r) * (p1 * p1) + (w * w) * (h + r - 2 * p2), h * p1 - w * p2);
-            T dd;
-            if (s < 0.0) dd = norm2_(p1, p2, zr) - r;
-            else if (p1 < w) dd = h - p2;
-            else dd = norm2_(p1 - w, p2 - h, zr);
-            return cyl_(dd, abs_(p.x) - hx, zr);
-        }
-        case BMO_PRIM_CONCAVE_CYL: {  // CylindricalSDF.jl:120-133
-            const double r = a, sg = d;
-            T psy = p.y + (-r);
-            T d1 = abs_(norm2_(p.z, psy, zr)) - fabs(r);
-            T d2 = abs_(p.x) - c / 2;
-            T cc = cyl_(d1, d2, zr);
-            T ppy = p.y + (-sg / 2 * (r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0)));
-            T qx = abs_(p.x) - c / 2, qy = abs_(ppy) - sg / 2, qz = abs_(p.z) - b / 2;
-            T l = norm3_(max_(qx, 0.0), max_(qy, 0.0), max_(qz, 0.0), zr) + min_(max_(qx, max_(qy, qz)), 0.0);
-            return max_(l, -cc);
-        }
         default: break;
     }
     return T{};
 }
 // one member of a union: a primitive, or a meniscus frame + 3 children (MeniscusLensSDF.jl:42-46)
-template <class T> BMO_D T member_eval(const bmo_prim* prims, int i, P3<T> q, int zr, Stats& st) {
+template <class T, bool RK> BMO_D T member_eval(const bmo_prim* prims, int i, P3<T> q, int zr, Stats& st) {
     const bmo_prim& pr = prims[i];
-    if (pr.type != BMO_PRIM_MENISCUS) return prim_eval(pr, q, zr, st);
+    if (pr.type != BMO_PRIM_MENISCUS) return prim_eval<T, RK>(pr, q, zr, st);
     P3<T> p = w2s(pr, q);
-    T cv = prim_eval(prims[i + 1], p, zr, st);
-    T cy = prim_eval(prims[i + 2], p, zr, st);
-    T cc = prim_eval(prims[i + 3], p, zr, st);
+    T cv = prim_eval<T, RK>(prims[i + 1], p, zr, st);
+    T cy = prim_eval<T, RK>(prims[i + 2], p, zr, st);
+    T cc = prim_eval<T, RK>(prims[i + 3], p, zr, st);
     return max_(min_(cv, cy), -cc);
 }
 BMO_D int member_advance(const bmo_prim* prims, int i) { return prims[i].type == BMO_PRIM_MENISCUS ? 4 : 1; }
@@ -199,8 +223,40 @@ BMO_D V3 w2s_f(const bmo_prim& pr, V3 q) {
                pr.tdir[6] * dx + pr.tdir[7] * dy + pr.tdir[8] * dz);
 }
 BMO_D double cyl_f(double d1, double d2) { return neg_part(fmax_jl(d1, d2)) + pnorm2(d1, d2); }
-BMO_D double prim_eval_f(const bmo_prim& pr, V3 q) {
+// Less common primitives (cylindrical and aspheric lens surfaces) are kept out of line so that the marching
+// loop of the common spherical-lens path keeps its register budget.
+BMO_NI double prim_eval_rare(const bmo_prim& pr, V3 p) {
+    const double a = pr.par[0], b = pr.par[1], c = pr.par[2], d = pr.par[3];
+    switch (pr.type) {
+        case BMO_PRIM_CONVEX_ASPH:
+        case BMO_PRIM_CONCAVE_ASPH:
+            return aspheric_surface_distance(pr.type == BMO_PRIM_CONVEX_ASPH, sqrt(p.x * p.x + p.z * p.z) - 0.0, p.y, asph_block(pr));
+        case BMO_PRIM_CONVEX_CYL: {
+            const double r = a, h = b, w = c, hx = d;
+            const double p1 = fabs(p.y), p2 = p.z;
+            const double s = fmax_jl((h - r) * (p1 * p1) + (w * w) * (h + r - 2 * p2), h * p1 - w * p2);
+            double dd;
+            if (s < 0.0) dd = hyp2(p1, p2) - r;
+            else if (p1 < w) dd = h - p2;
+            else dd = hyp2(p1 - w, p2 - h);
+            return cyl_f(dd, fabs(p.x) - hx);
+        }
+        case BMO_PRIM_CONCAVE_CYL: {
+            const double r = a, sg = d;
+            const double psy = p.y + (-r);
+            const double cc = cyl_f(hyp2(p.z, psy) - fabs(r), fabs(p.x) - c / 2);
+            const double ppy = p.y + (-sg / 2 * (r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0)));
+            const double qx = fabs(p.x) - c / 2, qy = fabs(ppy) - sg / 2, qz = fabs(p.z) - b / 2;
+            const double l = pnorm3(qx, qy, qz) + neg_part(fmax_jl(qx, fmax_jl(qy, qz)));
+            return fmax_jl(l, -cc);
+        }
+        default: break;
+    }
+    return 0.0;
+}
+template <bool RARE> BMO_D double prim_eval_f(const bmo_prim& pr, V3 q) {
     const V3 p = w2s_f(pr, q);
+    if (RARE) { if (pr.type >= BMO_PRIM_CONVEX_CYL) return prim_eval_rare(pr, p); }
     const double a = pr.par[0], b = pr.par[1], c = pr.par[2], d = pr.par[3];
     switch (pr.type) {
         case BMO_PRIM_PLANO:
@@ -246,25 +302,6 @@ BMO_D double prim_eval_f(const bmo_prim& pr, V3 q) {
             const double pln = (p.x + p.y) / 1.4142135623730951;
             return fmax_jl(box, pln);
         }
-        case BMO_PRIM_CONVEX_CYL: {
-            const double r = a, h = b, w = c, hx = d;
-            const double p1 = fabs(p.y), p2 = p.z;
-            const double s = fmax_jl((h - r) * (p1 * p1) + (w * w) * (h + r - 2 * p2), h * p1 - w * p2);
-            double dd;
-            if (s < 0.0) dd = hyp2(p1, p2) - r;
-            else if (p1 < w) dd = h - p2;
-            else dd = hyp2(p1 - w, p2 - h);
-            return cyl_f(dd, fabs(p.x) - hx);
-        }
-        case BMO_PRIM_CONCAVE_CYL: {
-            const double r = a, sg = d;
-            const double psy = p.y + (-r);
-            const double cc = cyl_f(hyp2(p.z, psy) - fabs(r), fabs(p.x) - c / 2);
-            const double ppy = p.y + (-sg / 2 * (r > 0 ? 1.0 : (r < 0 ? -1.0 : 0.0)));
-            const double qx = fabs(p.x) - c / 2, qy = fabs(ppy) - sg / 2, qz = fabs(p.z) - b / 2;
-            const double l = pnorm3(qx, qy, qz) + neg_part(fmax_jl(qx, fmax_jl(qy, qz)));
-            return fmax_jl(l, -cc);
-        }
         default: break;
     }
     return 0.0;
@@ -301,7 +338,7 @@ struct MemberBounds {
 // over the prim records so that prim_eval_f is instantiated once (instruction-cache footprint).
 // The previous arg-min member is evaluated first (its value bounds the minimum from above), then the
 // others in order unless their lower bound rules them out; ties still go to the lowest member index.
-BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx, MemberBounds& lb) {
+template <bool RARE> BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx, MemberBounds& lb) {
     const int first = sh.first, end = sh.first + sh.count;
     double m = 0.0, acc = 0.0;
     V3 q = p;
@@ -315,9 +352,9 @@ BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx, Mem
         const bmo_prim& pr = sh.prims[i];
         if (pr.type == BMO_PRIM_MENISCUS) { q = w2s_f(pr, p); men = 3; start = i; continue; }
         const int k = i - first;
-        const bool tracked = men == 0 && k < 4;
+        const bool tracked = men == 0 && k < 4 && !(RARE && is_asph(pr.type));   // aspheric pseudo-distances are not 1-Lipschitz
         if (tracked && have && lb.get(k) > m_ub) continue;   // cannot be the minimum at this point
-        double v = prim_eval_f(pr, q);
+        double v = prim_eval_f<RARE>(pr, q);
         nsdf++;
         if (men) {
             if (men == 3) acc = v;                       // convex
@@ -335,22 +372,24 @@ BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx, Mem
 }
 // AbstractSDF.jl:79-95: ForwardDiff gradient of member idx; central differences (eps = 1e-8) if any
 // component of the normalised gradient is NaN.
-BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
-    P3<Dual> qd;
-    qd.x = mkd(p.x, 1, 0, 0); qd.y = mkd(p.y, 0, 1, 0); qd.z = mkd(p.z, 0, 0, 1);
-    Dual g = member_eval(prims, idx, qd, zr, st);
-    V3 n = normalize(mk3(g.p0, g.p1, g.p2));
-    if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
+template <bool RK> BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
+    if (!(RK && is_asph(prims[idx].type))) {   // aspheric surfaces: numeric_gradient only (AsphericalLensSDF.jl:3-5)
+        P3<Dual> qd;
+        qd.x = mkd(p.x, 1, 0, 0); qd.y = mkd(p.y, 0, 1, 0); qd.z = mkd(p.z, 0, 0, 1);
+        Dual g = member_eval<Dual, RK>(prims, idx, qd, zr, st);
+        V3 n = normalize(mk3(g.p0, g.p1, g.p2));
+        if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
+    }
     const double e = 1e-8;
     P3<double> q; q.x = p.x; q.y = p.y; q.z = p.z;
     P3<double> a, b;
     V3 gr;
     a = q; b = q; a.x = p.x + e; b.x = p.x - e;
-    gr.x = member_eval(prims, idx, a, zr, st) - member_eval(prims, idx, b, zr, st);
+    gr.x = member_eval<double, RK>(prims, idx, a, zr, st) - member_eval<double, RK>(prims, idx, b, zr, st);
     a = q; b = q; a.y = p.y + e; b.y = p.y - e;
-    gr.y = member_eval(prims, idx, a, zr, st) - member_eval(prims, idx, b, zr, st);
+    gr.y = member_eval<double, RK>(prims, idx, a, zr, st) - member_eval<double, RK>(prims, idx, b, zr, st);
     a = q; b = q; a.z = p.z + e; b.z = p.z - e;
-    gr.z = member_eval(prims, idx, a, zr, st) - member_eval(prims, idx, b, zr, st);
+    gr.z = member_eval<double, RK>(prims, idx, a, zr, st) - member_eval<double, RK>(prims, idx, b, zr, st);
     return normalize(gr);
 }
 
@@ -366,7 +405,9 @@ BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st)
 // eps_ray for the rest of the reference's 1000 iterations => miss.
 // `nsdf` counts primitive evaluations in a register; the out-of-line normal evaluation reports its
 // own count through a stack temporary that only lives around the call.
-BMO_D bool sdf_intersect_f(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, double& t, V3& n) {
+// RARE = true: the shape may contain cylindrical / aspheric members (flagged at upload); such shapes take an
+// out-of-line copy of this routine (sdf_intersect_rare) so that the common path keeps its register budget.
+template <bool RARE> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, double& t, V3& n) {
     {   // guaranteed miss: origin outside the bounding sphere and the line never enters it
         const V3 v = mk3(pos.x - sh.cx, pos.y - sh.cy, pos.z - sh.cz);
         const double cc = dot(v, v) - sh.R2;
@@ -386,7 +427,7 @@ BMO_D bool sdf_intersect_f(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, d
     const double dlen = fmax(1.0, dot(dir, dir)) * (1.0 + 1e-9);
     for (;;) {
         int idx;
-        const double dist = shape_sdf_f(sh, p, nsdf, idx, lb);
+        const double dist = shape_sdf_f<RARE>(sh, p, nsdf, idx, lb);
         if (mode == OUT) {
             t0 += dist;
             if (!(dist < eps_ray)) {
@@ -406,7 +447,7 @@ BMO_D bool sdf_intersect_f(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, d
         }
         {
             Stats tmp; tmp.sdf = 0; tmp.tri = 0;
-            n = member_normal(sh.prims, idx, p, sh.zr, tmp);
+            n = member_normal<RARE>(sh.prims, idx, p, sh.zr, tmp);
             nsdf += tmp.sdf;
         }
         if (mode == OUT) { t = back ? tin - t0 : t0; return true; }
@@ -414,6 +455,10 @@ BMO_D bool sdf_intersect_f(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, d
         mode = IN; it = 0;
         p = p + eps_ins * d; tin = eps_ins; lb.moved(eps_ins * dlen);
     }
+}
+
+BMO_NI bool sdf_intersect_rare(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, double& t, V3& n) {
+    return sdf_intersect_t<true>(sh, pos, dir, nsdf, t, n);
 }
 
 // ---- meshes -----------------------------------------------------------------------------------
@@ -531,14 +576,20 @@ struct TraceCtx {
     int pose;
 };
 // intersect3d(shape, ray)
-BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
+template <bool RK> BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
     const bmo_part& pt = C.parts[part];
     if (pt.shape_kind == BMO_SHAPE_SDF) {
         const double* bnd = C.bounds + NBOUND * part;
         SdfShape sh;
         sh.prims = C.prims; sh.first = pt.first; sh.count = pt.count; sh.zr = C.zr;
         sh.cx = bnd[0]; sh.cy = bnd[1]; sh.cz = bnd[2]; sh.R2 = bnd[3] * bnd[3];
-        return sdf_intersect_f(sh, pos, dir, st.sdf, t, n);
+        if (RK && (C.prims[pt.first].reserved & 2)) {       // bit 1: the union has cylindrical / aspheric members
+            unsigned ns = 0;
+            const bool hit = sdf_intersect_rare(sh, pos, dir, ns, t, n);
+            st.sdf += ns;
+            return hit;
+        }
+        return sdf_intersect_t<false>(sh, pos, dir, st.sdf, t, n);
     }
     Stats tmp; tmp.sdf = 0; tmp.tri = 0;
     const bool hit = mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, t, n);
@@ -574,7 +625,7 @@ BMO_D bool box_may_hit(const double* bx, V3 o, V3 d, double t_best) {
 // [lo, hi) is the range of parts that trace_all looks at: the whole system for tracing_step!, the parts
 // of one object (or one hinted shape) for retrace_system!'s `intersect3d(object(_intersection), ray)` /
 // `intersect3d(shape(_hint), ray)` (System.jl:209-218); hi < 0 means C.n_parts.
-BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st, const int lo = 0, const int hi = -1) {
+template <bool RK> BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st, const int lo = 0, const int hi = -1) {
     Hit res; res.part = -1; res.t = INFINITY; res.n = mk3(0, 0, 0);
     Hit ob; ob.part = -1; ob.t = INFINITY; ob.n = mk3(0, 0, 0);   // best of the current object
     int cur_obj = -1;
@@ -604,7 +655,7 @@ BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& 
                 if (res.part >= 0) t_best = res.t;
                 if (ob.part >= 0 && ob.t < t_best) t_best = ob.t;
             }
-            if (box_may_hit(bx, pos, dir, t_best)) hit = part_intersect(C, part, pos, dir, st, t, n);
+            if (box_may_hit(bx, pos, dir, t_best)) hit = part_intersect<RK>(C, part, pos, dir, st, t, n);
         }
         if (!all) {
             if (hit) { res.t = t; res.n = n; res.part = part; return res; }

@@ -53,11 +53,12 @@ struct bmo_sys {
     std::vector<bmo::MeshView> meshes;
     std::vector<double> lambdas;
     int64_t n_vertices = 0, n_faces = 0;
+    bool has_rare = false;       // some primitive is a cylindrical / aspheric surface: the trace kernels compiled with them are used
     // owned device buffers
     bmo_prim* d_prims = nullptr; bmo_part* d_parts = nullptr; bmo_object* d_objects = nullptr;
     bmo::MeshView* d_meshes = nullptr; double* d_vertices = nullptr; int32_t* d_faces = nullptr;
     bmo::BvhNode* d_nodes = nullptr; int32_t* d_bvh_faces = nullptr; double* d_ntable = nullptr;
-    double* d_bounds = nullptr; double* d_detpose = nullptr; double* d_lambdas = nullptr; double* d_jones = nullptr;
+    double* d_bounds = nullptr; double* d_detpose = nullptr; double* d_lambdas = nullptr; double* d_jones = nullptr; double* d_ext = nullptr;
     // pose-0 copies to restore after a sweep
     std::vector<double> h_vertices, h_bounds, h_detpose;
     // high-water marks of earlier branching traces, keyed by (mode, root beams): queue units, beams and scratch

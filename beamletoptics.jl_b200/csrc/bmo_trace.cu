@@ -102,7 +102,7 @@ BMO_D V3 shfl3(V3 v, int l) {
 constexpr int IBLOCK = 128;
 // STAGED: the small system tables (prims, parts, bounds) live in shared memory -- a compile-time fact,
 // so that the marching loop reads them with LDS instead of generic loads.
-template <int MINB, bool STAGED>
+template <int MINB, bool STAGED, bool RK>
 __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysView& S = P.S;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
             C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
         }
         Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
-        if (budget) h = tracing_step(C, pos, dir, hint, st);   // System.jl:100-110
+        if (budget) h = tracing_step<RK>(C, pos, dir, hint, st);   // System.jl:100-110
         const int64_t hs = P.hit.cap;
         P.hit.d[ri] = h.t; P.hit.d[hs + ri] = h.n.x; P.hit.d[2 * hs + ri] = h.n.y; P.hit.d[3 * hs + ri] = h.n.z;
         P.hit.part[ri] = h.part;
@@ -174,7 +174,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
 // first tracing_step! has no hint (:132-137): pass 1, the ordinary full trace, for exactly those beams and
 // for the beams that are not retracing.  flag: 0 ordinary step, 1 re-validated (K2 must not apply the
 // r_max test: retrace_system! has none), 2 stored path left in this wave.
-template <int MODE, bool STAGED>
+template <int MODE, bool STAGED, bool RK>
 __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(const StepParams P) {
     constexpr int R = Cfg<MODE>::R;
     constexpr int UNITS = Cfg<MODE>::UNITS;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(co
         int hp = -1, plo = lo, phi = hi;
         if (pass == 0) run = restricted;
         else { run = active && budget && !(in_phase && ok); hp = in_phase ? -1 : hint; plo = 0; phi = S.n_parts; }
-        if (run) h = tracing_step(C, pos, dir, hp, st, plo, phi);
+        if (run) h = tracing_step<RK>(C, pos, dir, hp, st, plo, phi);
         if (pass == 0) {
             ok = restricted && h.part >= 0;
             if (MODE == 2) {   // Gaussian.jl:171-180: all three rays must hit the same shape
@@ -630,7 +630,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, MODE == 0 ? KMINB0 : 1) inte
 // ---- K1+K2 fused: plain rays through a system without beamsplitters (the sequential lens-stack path) --
 // One thread per ray does tracing_step! and interact3d back to back: the hit record never leaves the
 // registers and the ray state is read once.  Needs IBLOCK == Cfg<0>::BLOCK == Cfg<0>::UNITS.
-template <int MINB, bool STAGED>
+template <int MINB, bool STAGED, bool RK>
 __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) {
     static_assert(IBLOCK == Cfg<0>::BLOCK && Cfg<0>::UNITS == IBLOCK, "fused_wave0 maps one thread to one ray like interact_wave<0>");
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -672,7 +672,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
             C.parts = S.parts;
             C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
         }
-        if (budget) h = tracing_step(C, pos, dir, hint, st);
+        if (budget) h = tracing_step<RK>(C, pos, dir, hint, st);
     }
     unsigned sd = st.sdf, tr = st.tri;
 #pragma unroll
@@ -1054,6 +1054,25 @@ static int32_t prim_flags(const bmo_prim& p) {
     return 1;
 }
 
+// aspheric primitives carry the device address of their parameter block in par[0] (see asph_block, bmo_geom.cuh)
+// bit 1 of the first prim record of an SDF part: the union has cylindrical / aspheric members (part_intersect, bmo_geom.cuh)
+static void flag_rare_parts(bmo_prim* p, size_t n_prims_per_pose, size_t n_poses, const std::vector<bmo_part>& parts) {
+    for (size_t q = 0; q < n_poses; q++)
+        for (const bmo_part& pt : parts) {
+            if (pt.shape_kind != BMO_SHAPE_SDF) continue;
+            bool rare = false;
+            for (int k = 0; k < pt.count; k++) rare |= p[q * n_prims_per_pose + pt.first + k].type >= BMO_PRIM_CONVEX_CYL;
+            if (rare) p[q * n_prims_per_pose + pt.first].reserved |= 2;
+        }
+}
+static void patch_asph(bmo_prim* p, size_t n, const double* d_ext) {
+    for (size_t i = 0; i < n; i++)
+        if (p[i].type == BMO_PRIM_CONVEX_ASPH || p[i].type == BMO_PRIM_CONCAVE_ASPH) {
+            const unsigned long long a = (unsigned long long)(uintptr_t)(d_ext + p[i].ext_first);
+            std::memcpy(&p[i].par[0], &a, sizeof(double));
+        }
+}
+
 template <class T> static int32_t upload(T** dptr, const T* h, size_t n) {
     BMO_CUDA(cudaMalloc((void**)dptr, std::max<size_t>(n, 1) * sizeof(T)));
     if (n) BMO_CUDA(cudaMemcpy(*dptr, h, n * sizeof(T), cudaMemcpyHostToDevice));
@@ -1102,6 +1121,14 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
     for (int p = 0; p < t->n_parts; p++)
         for (int k = 0; k < NBOUND; k++) s->h_bounds[NBOUND * p + k] = t->parts[p].bound[k];
     std::vector<double> ntab(t->n_table, t->n_table + (size_t)std::max(t->n_rows, 0) * t->n_lambda);
+    if (t->n_ext > 0 && (rc = upload(&s->d_ext, t->ext, (size_t)t->n_ext))) return rc;
+    for (const bmo_prim& pr : s->prims)
+        if ((pr.type == BMO_PRIM_CONVEX_ASPH || pr.type == BMO_PRIM_CONCAVE_ASPH) &&
+            (!t->ext || pr.ext_first < 0 || pr.ext_count < 7 || (int64_t)pr.ext_first + pr.ext_count > t->n_ext))
+            return fail(BMO_EINVAL, "aspheric primitive without a parameter block in tables.ext");
+    patch_asph(s->prims.data(), s->prims.size(), s->d_ext);
+    flag_rare_parts(s->prims.data(), s->prims.size(), 1, s->parts);
+    for (const bmo_prim& pr : s->prims) s->has_rare |= pr.type >= BMO_PRIM_CONVEX_CYL;
     if ((rc = upload(&s->d_prims, s->prims.data(), s->prims.size()))) return rc;
     if ((rc = upload(&s->d_parts, s->parts.data(), s->parts.size()))) return rc;
     if ((rc = upload(&s->d_objects, s->objects.data(), s->objects.size()))) return rc;
@@ -1118,7 +1145,7 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
     SysView& v = s->view;
     v.prims = s->d_prims; v.parts = s->d_parts; v.objects = s->d_objects; v.meshes = s->d_meshes;
     v.vertices = s->d_vertices; v.faces = s->d_faces; v.nodes = s->d_nodes; v.bvh_faces = s->d_bvh_faces;
-    v.n_table = s->d_ntable; v.bounds = s->d_bounds; v.det_pose = s->d_detpose; v.lambdas = s->d_lambdas; v.jones = s->d_jones;
+    v.n_table = s->d_ntable; v.bounds = s->d_bounds; v.det_pose = s->d_detpose; v.lambdas = s->d_lambdas; v.jones = s->d_jones; v.ext = s->d_ext;
     v.n_prims = t->n_prims; v.n_parts = t->n_parts; v.n_objects = t->n_objects; v.n_meshes = t->n_meshes;
     v.n_lambda = t->n_lambda; v.n_poses = 1; v.zr = t->norm_zero_rule; v.n_vertices = t->n_vertices;
     v.n_system = t->n_system;
@@ -1131,7 +1158,7 @@ int32_t bmo_system_free(bmo_sys* s) {
     cudaStreamSynchronize(s->ctx->stream);
     cudaFree(s->d_prims); cudaFree(s->d_parts); cudaFree(s->d_objects); cudaFree(s->d_meshes); cudaFree(s->d_vertices);
     cudaFree(s->d_faces); cudaFree(s->d_nodes); cudaFree(s->d_bvh_faces); cudaFree(s->d_ntable); cudaFree(s->d_bounds);
-    cudaFree(s->d_detpose); cudaFree(s->d_lambdas); cudaFree(s->d_jones);
+    cudaFree(s->d_detpose); cudaFree(s->d_lambdas); cudaFree(s->d_jones); cudaFree(s->d_ext);
     delete s;
     return BMO_OK;
 }
@@ -1156,6 +1183,8 @@ int32_t bmo_system_set_poses(bmo_sys* s, int32_t n_poses, const bmo_prim* prims,
         if (!prims || !bounds || (!vertices && s->n_vertices > 0) || !det_pos || !det_dir) return fail(BMO_EINVAL, "bmo_system_set_poses: NULL table");
         std::vector<bmo_prim> pp(prims, prims + np * s->prims.size());
         for (auto& pr : pp) pr.reserved = prim_flags(pr);
+        patch_asph(pp.data(), pp.size(), s->d_ext);
+        flag_rare_parts(pp.data(), s->prims.size(), np, s->parts);
         if ((rc = reup(&s->d_prims, pp.data(), pp.size()))) return rc;
         if ((rc = reup(&s->d_vertices, vertices, np * 3 * (size_t)s->n_vertices))) return rc;
         if ((rc = reup(&s->d_bounds, bounds, np * NBOUND * s->parts.size()))) return rc;
@@ -1409,20 +1438,32 @@ int32_t SubTrace::enqueue_chunk() {
         static const int fuse_policy = getenv("BMO_FUSE") ? atoi(getenv("BMO_FUSE")) : 1;
         const bool allow_fused = !rt.on && (fuse_policy == 2 || (fuse_policy == 1 && pipelined));
         const SysView& V = sys->view;
+        const bool rk = sys->has_rare;     // kernels compiled with the cylindrical / aspheric primitives
         const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
         BMO_CUDA(cudaEventRecord(ev[2 * c], st));
         if (mode == 0 && !has_splitter && allow_fused) {
             // sequential lens-stack path: intersect + interact in one kernel, hit records stay in registers
-            if (!staged) fused_wave0<4, false><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
-            else if (minb <= 4) fused_wave0<4, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
-            else fused_wave0<6, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+            if (rk) {
+                if (!staged) fused_wave0<4, false, true><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
+                else fused_wave0<6, true, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+            } else {
+                if (!staged) fused_wave0<4, false, false><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
+                else if (minb <= 4) fused_wave0<4, true, false><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+                else fused_wave0<6, true, false><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+            }
             BMO_LAUNCH(ctx, "fused_wave0");
             BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
         } else if (rt.on) {
             // retrace call: K1r re-validates the stored path where there is one, ordinary tracing_step! elsewhere
-            if (mode == 0) { if (staged) retrace_intersect_wave<0, true><<<(unsigned)nblocks, Cfg<0>::BLOCK, smem, st>>>(sp); else retrace_intersect_wave<0, false><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp); }
-            else if (mode == 1) { if (staged) retrace_intersect_wave<1, true><<<(unsigned)nblocks, Cfg<1>::BLOCK, smem, st>>>(sp); else retrace_intersect_wave<1, false><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp); }
-            else { if (staged) retrace_intersect_wave<2, true><<<(unsigned)nblocks, Cfg<2>::BLOCK, smem, st>>>(sp); else retrace_intersect_wave<2, false><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp); }
+#define BMO_RETRACE_LAUNCH(M, RKV)                                                                                         \
+    do {                                                                                                                   \
+        if (staged) retrace_intersect_wave<M, true, RKV><<<(unsigned)nblocks, Cfg<M>::BLOCK, smem, st>>>(sp);              \
+        else retrace_intersect_wave<M, false, RKV><<<(unsigned)nblocks, Cfg<M>::BLOCK, 0, st>>>(sp);                       \
+    } while (0)
+            if (mode == 0) { if (rk) BMO_RETRACE_LAUNCH(0, true); else BMO_RETRACE_LAUNCH(0, false); }
+            else if (mode == 1) { if (rk) BMO_RETRACE_LAUNCH(1, true); else BMO_RETRACE_LAUNCH(1, false); }
+            else { if (rk) BMO_RETRACE_LAUNCH(2, true); else BMO_RETRACE_LAUNCH(2, false); }
+#undef BMO_RETRACE_LAUNCH
             BMO_LAUNCH(ctx, "retrace_intersect_wave");
             BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
             if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
@@ -1434,12 +1475,15 @@ int32_t SubTrace::enqueue_chunk() {
             xp.S = sys->view; xp.cur = cur; xp.hit = hit; xp.n_rays = n_slots * R; xp.r_max = r_max;
             xp.counters = ctx->d_counters;
             const unsigned grid = (unsigned)((n_slots * R + IBLOCK - 1) / IBLOCK);
-            if (!staged) intersect_wave<4, false><<<grid, IBLOCK, 0, st>>>(xp);
-            else if (minb <= 3) intersect_wave<3, true><<<grid, IBLOCK, smem, st>>>(xp);
-            else if (minb == 4) intersect_wave<4, true><<<grid, IBLOCK, smem, st>>>(xp);
-            else if (minb == 5) intersect_wave<5, true><<<grid, IBLOCK, smem, st>>>(xp);
-            else if (minb <= 7) intersect_wave<6, true><<<grid, IBLOCK, smem, st>>>(xp);
-            else intersect_wave<8, true><<<grid, IBLOCK, smem, st>>>(xp);
+            if (rk) {
+                if (!staged) intersect_wave<4, false, true><<<grid, IBLOCK, 0, st>>>(xp);
+                else intersect_wave<6, true, true><<<grid, IBLOCK, smem, st>>>(xp);
+            } else {
+                if (!staged) intersect_wave<4, false, false><<<grid, IBLOCK, 0, st>>>(xp);
+                else if (minb <= 4) intersect_wave<4, true, false><<<grid, IBLOCK, smem, st>>>(xp);
+                else if (minb == 5) intersect_wave<5, true, false><<<grid, IBLOCK, smem, st>>>(xp);
+                else intersect_wave<6, true, false><<<grid, IBLOCK, smem, st>>>(xp);
+            }
             BMO_LAUNCH(ctx, "intersect_wave");
             BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
             if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);

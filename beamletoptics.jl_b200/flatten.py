@@ -27,26 +27,29 @@ _ROLES = {"plate_bs": (ROLE_SUBSTRATE, ROLE_COATING), "cube_bs": (ROLE_FRONT, RO
 BOUND_REL, BOUND_ABS = 1e-9, 1e-6   # inflation of the bounding spheres / boxes (see bmo_geom.cuh sdf_intersect_f, tracing_step)
 
 
-def _prim_record(s):
+def _prim_record(s, ext):
     p = L.bmo_prim()
     p.type = s.type if isinstance(s, sh.PrimSDF) else sh.MENISCUS
     p.pos[:] = s.pos
     p.tdir[:] = [s.tdir[i][j] for i in range(3) for j in range(3)]
     p.par[:] = s.par if isinstance(s, sh.PrimSDF) else (0.0, 0.0, 0.0, 0.0)
+    if isinstance(s, sh.AsphericalSurfaceSDF):      # parameter block in tables.ext
+        p.ext_first, p.ext_count = len(ext), len(s.ext)
+        ext.extend(s.ext)
     return p
 
 
-def _emit_sdf(shape, prims):
+def _emit_sdf(shape, prims, ext):
     """Append the prim records of one top-level SDF shape; returns (first, count)."""
     first = len(prims)
     members = shape.sdfs if isinstance(shape, sh.UnionSDF) else [shape]
     for m in members:
         if isinstance(m, sh.MeniscusLensSDF):
-            prims.append(_prim_record(m))
+            prims.append(_prim_record(m, ext))
             for child in (m.convex, m.cylinder, m.concave):
-                prims.append(_prim_record(child))
+                prims.append(_prim_record(child, ext))
         elif isinstance(m, sh.PrimSDF):
-            prims.append(_prim_record(m))
+            prims.append(_prim_record(m, ext))
         else:
             raise TypeError(f"unsupported SDF member {type(m).__name__}")
     return first, len(prims) - first
@@ -63,7 +66,7 @@ class FlatSystem:
         self.objects = leaves           # device object index -> host object
         self.part_owner = []            # device part index -> host sub-object (Lens of a doublet, coating, ...)
         prims, parts, objs, meshes = [], [], [], []
-        verts, faces, ntab, jones = [], [], [], []
+        verts, faces, ntab, jones, ext = [], [], [], [], []
         nv = nf = 0
         for oi, o in enumerate(leaves):
             kind = _KIND[o.kind]
@@ -89,7 +92,7 @@ class FlatSystem:
                 pr.transmittance = getattr(s_obj, "transmittance", 0.0)
                 if isinstance(shape, sh.AbstractSDF):
                     pr.shape_kind = SHAPE_SDF
-                    pr.first, pr.count = _emit_sdf(shape, prims)
+                    pr.first, pr.count = _emit_sdf(shape, prims, ext)
                 elif isinstance(shape, sh.Mesh):
                     pr.shape_kind = SHAPE_MESH
                     pr.first, pr.count = len(meshes), 1
@@ -134,6 +137,8 @@ class FlatSystem:
         t.n_rows, t.n_table = len(ntab), self._ntab.ctypes.data_as(C.POINTER(C.c_double))
         self._jones = np.array(jones, dtype=np.float64).reshape(len(jones), 10) if jones else np.zeros((0, 10))
         t.n_jones, t.jones = len(jones), self._jones.ctypes.data_as(C.POINTER(C.c_double))
+        self._ext = np.array(ext, dtype=np.float64) if ext else np.zeros(1)
+        t.n_ext, t.ext = len(ext), self._ext.ctypes.data_as(C.POINTER(C.c_double))
         t.n_system = float(system.n)
         t.norm_zero_rule = int(norm_zero_rule)
         self.tables = t

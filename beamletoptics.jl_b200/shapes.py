@@ -12,7 +12,7 @@ import numpy as np
 from . import linalg as la
 
 # bmo_prim_type (include/bmo.h)
-PLANO, CYLINDER, SPHERE, CONVEX, CONCAVE, CUTSPHERE, BOX, RING, RAPRISM, MENISCUS, CONVEX_CYL, CONCAVE_CYL = range(12)
+PLANO, CYLINDER, SPHERE, CONVEX, CONCAVE, CUTSPHERE, BOX, RING, RAPRISM, MENISCUS, CONVEX_CYL, CONCAVE_CYL, CONVEX_ASPH, CONCAVE_ASPH = range(14)
 
 
 def sag(r, l):
@@ -170,6 +170,53 @@ def ConvexSphericalSurfaceSDF(radius, diameter):   # SphericalLensSDF.jl:203-217
 def ConcaveSphericalSurfaceSDF(radius, diameter):  # :147-157
     check_sag(radius, diameter)
     return PrimSDF(CONCAVE, (radius, diameter, sag(radius, diameter)))
+
+
+class AsphericalSurfaceSDF(PrimSDF):
+    """Convex / ConcaveAsphericalSurfaceSDF (AsphericalLensSDF.jl:22-31, 88-98).  `ext` is the parameter block the
+    device reads (csrc/bmo_asphere.cuh): c, k, d, max_sag[1], sag(d/2), sag'(d/2), n, coefficients."""
+
+    def __init__(self, convex, coefficients, radius, conic_constant, diameter):
+        super().__init__(CONVEX_ASPH if convex else CONCAVE_ASPH, (0.0, 0.0, 0.0, 0.0))
+        from . import asphere as asp
+        self.coefficients = [float(a) for a in coefficients]
+        self.radius, self.conic_constant, self._diameter = float(radius), float(conic_constant), float(diameter)
+        c = 1 / self.radius
+        self.max_sag = asp.max_aspheric_value(c, self.conic_constant, self.coefficients, self._diameter)
+        self._edge = asp.aspheric_equation(self._diameter / 2, c, self.conic_constant, self.coefficients)
+        gzb = asp.gradient_aspheric_equation(self._diameter / 2, c, self.conic_constant, self.coefficients)
+        self.ext = [c, self.conic_constant, self._diameter, self.max_sag[0], self._edge, gzb, float(len(self.coefficients))] + self.coefficients
+
+    def has_thickness(self): return True
+
+    def thickness(self):          # :33-36, :100-103
+        sg, ms = self._edge, self.max_sag[0]
+        if self.type == CONVEX_ASPH:
+            return ms if (ms > 0 and sg < 0) else abs(sg)
+        return abs(sg) if (ms > 0 and sg < 0) else 0.0
+
+    def diameter(self): return self._diameter
+    def sag(self): return self._edge      # edge_sag(::EvenAsphericalSurface, sdf), :434-443
+
+    def local_box(self):
+        # everything with sdf <= 0 lies within the aperture, between the extreme sag values and the closing planes
+        h = self._diameter / 2
+        zs = (0.0, self._edge, self.max_sag[0])
+        return (-h, min(zs), -h), (h, max(zs), h)
+
+    def local_bound(self):
+        lo, hi = self.local_box()
+        cl = tuple((lo[k] + hi[k]) / 2 for k in range(3))
+        r = math.sqrt(sum(((hi[k] - lo[k]) / 2) ** 2 for k in range(3)))
+        return la.add(self.pos, la.matvec(self.dir, cl)), r
+
+
+def ConvexAsphericalSurfaceSDF(coefficients, radius, conic_constant, diameter):
+    return AsphericalSurfaceSDF(True, coefficients, radius, conic_constant, diameter)
+
+
+def ConcaveAsphericalSurfaceSDF(coefficients, radius, conic_constant, diameter):
+    return AsphericalSurfaceSDF(False, coefficients, radius, conic_constant, diameter)
 
 
 def ConvexCylinderSDF(radius, diameter, height):   # CylindricalSDF.jl:30-55: cut cylinder built along x, turned upright, vertex at the origin

@@ -43,6 +43,11 @@ enum bmo_prim_type {
                                  w = sqrt(r^2 - cut height^2), half extrusion height                  */
     BMO_PRIM_CONCAVE_CYL = 11,/* ConcaveCylinderSDF (CylindricalSDF.jl:92-133); par: radius (signed), diameter, height,
                                  sag(|radius|, diameter)                                            */
+    BMO_PRIM_CONVEX_ASPH = 12,/* ConvexAsphericalSurfaceSDF (AsphericalLensSDF.jl:22-31, 188-240, 309-328): parameters in
+                                 tables.ext[ext_first ...]: c = 1/radius, conic constant, diameter, max_sag[1],
+                                 aspheric_equation(d/2), gradient_aspheric_equation(d/2)[1], n coefficients, coefficients.
+                                 Normals by central differences only (:3-5).                        */
+    BMO_PRIM_CONCAVE_ASPH = 13,/* ConcaveAsphericalSurfaceSDF (:88-98, 242-307, 330-349), same parameter block */
     BMO_PRIM_MENISCUS = 9   /* frame only; followed by 3 child records: convex, cylinder, concave,
                                posed relative to this frame (MeniscusLensSDF.jl:42-46)            */
 };
@@ -52,6 +57,8 @@ typedef struct bmo_prim {
     double pos[3];   /* position(shape)                                   (AbstractSDF.jl:35-40) */
     double tdir[9];  /* transposed_orientation(shape), row-major: local = tdir * (P - pos)       */
     double par[4];
+    int32_t ext_first;   /* aspheric surfaces: first double of the parameter block in tables.ext, else 0        */
+    int32_t ext_count;   /* length of that block                                                             */
 } bmo_prim;
 
 /* ---- parts: one shape each.  A part is what `shape(intersection)` / `Hint.shape` identify
@@ -125,6 +132,7 @@ typedef struct bmo_tables {
     int32_t n_rows;     const double* n_table;   /* [n_rows][n_lambda] refractive_index(obj, lambda),
                                                     evaluated on the host (Lenses.jl:37-38)        */
     double n_system;                             /* refractive_index(system, lambda) = 1.0 (AbstractSystem.jl:21) */
+    int64_t n_ext;      const double* ext;       /* parameter blocks of the aspheric primitives (see bmo_prim_type)       */
     int32_t n_jones;    const double* jones;     /* [n_jones][10]: GlobalJonesBasis of a PolarizationFilter, 3x3 real row-major
                                                     (XZBasis(1,0,0,0) by default), then its cutoff (PolarizationFilter.jl:5-9) */
     int32_t norm_zero_rule;                      /* 1 (use this): zero-vector norm of duals is a clean zero -- pinned by test/runtests.jl:1309-1314; 0: NaN partials */

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(bmo):
 
 def test_struct_layouts_match_header(bmo):
     from bmo_b200 import _lib
-    assert C.sizeof(_lib.bmo_prim) == 8 + 8 * (3 + 9 + 4)
+    assert C.sizeof(_lib.bmo_prim) == 8 + 8 * (3 + 9 + 4) + 8
     assert C.sizeof(_lib.bmo_part) == 6 * 4 + 8 * (2 + 10)
     assert C.sizeof(_lib.bmo_object) == 4 * 4 + 8 * (3 + 9 + 2)
     assert C.sizeof(_lib.bmo_mesh) == 4 * 8 + 8

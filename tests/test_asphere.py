@@ -94,3 +94,65 @@ def test_oracle_aspherical_imaging_system(orc):
         r = orc.beam_export(sys_, b)[0]["rays"]
         f_pos = r["pos"][-1] + 0.12e-3 * r["dir"][-1]
         assert abs(f_pos[2]) <= 1e-7
+
+
+# ---- GPU ------------------------------------------------------------------------------------------
+def _surf(bmo, s):
+    return bmo.SphericalSurface(s[0], s[1]) if len(s) == 2 else bmo.EvenAsphericalSurface(s[0], s[1], s[2], s[3])
+
+
+def _compare_bundle(bmo, orc, sys_, osys, pos, d, lam, r_max):
+    res = bmo.solve_system_(sys_, bmo.RayBundle(pos, d, lam), r_max=r_max)
+    b, seg = res.beams(), res.segments()
+    ref = orc.bulk_trace_rays(osys, pos, d, lam, r_max=r_max, max_seg=64)
+    assert np.array_equal(b["nseg"], ref["nseg"])
+    worst = 0.0
+    for i in range(pos.shape[0]):
+        f0, k = int(b["first"][i]), int(b["nseg"][i])
+        got = np.concatenate([seg["pos"][f0:f0 + k], seg["dir"][f0:f0 + k]], axis=1)
+        worst = max(worst, float(np.abs(got - ref["seg"][i, :k, 0:6]).max()))
+        assert np.array_equal(seg["n"][f0:f0 + k], ref["seg"][i, :k, 6])
+    return worst, b
+
+
+@pytest.mark.gpu
+def test_gpu_al50100j_matches_oracle(bmo, orc):
+    L = AL50100J
+    s1, s2 = (L["R"], L["d"], L["k"], L["A"]), (INF, L["d"])
+    lens = bmo.LensFromSurfaces(_surf(bmo, s1), L["ct"], L["n"])
+    olens = _asph(orc, s1, s2, L["ct"], L["n"])
+    for x in (lens, olens):
+        x.xrotate3d_(0.05); x.zrotate3d_(-0.08); x.translate3d_([1e-3, 0.0, -2e-3])
+    rng = np.random.default_rng(2)
+    n = 256
+    pos = np.zeros((n, 3)); pos[:, 0] = rng.uniform(-0.03, 0.03, n); pos[:, 2] = rng.uniform(-0.03, 0.03, n); pos[:, 1] = -0.1
+    d = np.tile([0.0, 1.0, 0.0], (n, 1)) + 0.03 * rng.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    worst, b = _compare_bundle(bmo, orc, bmo.System([lens]), orc.system([olens]), pos, d, 1.31e-6, 40)
+    assert (b["nseg"] == 3).sum() > n // 3          # most rays go through both faces
+    assert worst <= POS_TOL, worst
+
+
+@pytest.mark.gpu
+def test_gpu_aspherical_imaging_system_matches_oracle(bmo, orc):
+    olenses = _imaging_system(lambda s1, s2, ct, n: _asph(orc, s1, s2, ct, n))
+    lenses = _imaging_system(lambda s1, s2, ct, n: bmo.LensFromSurfaces(_surf(bmo, s1), _surf(bmo, s2), ct, n))
+    _place(olenses, lambda l: float(l.eval("thickness_object", nout=1)[0]), lambda l: list(l.position()))
+    _place(lenses, lambda l: l.thickness(), lambda l: list(l.position()))
+    for a, t in zip(lenses, (0.72e-3, 0.55e-3, 0.7e-3, 0.15e-3, 0.5e-3)):
+        assert abs(a.thickness() - t) <= 1.5e-8 * t
+    sys_, osys = bmo.System(list(lenses)), orc.system(list(olenses))
+    # the reference's three on-axis-field rays focus on the axis (runtests.jl:1672-1683)
+    for z in (-1.3e-3 / 2, 0.0, 1.3e-3 / 2):
+        beam = bmo.Beam(bmo.Ray((0.0, -0.5e-3, z), (0.0, 1.0, 0.0), 0.5876e-6))
+        bmo.solve_system_(sys_, beam, r_max=50)
+        last = beam.rays[-1]
+        assert abs(last.pos[2] + 0.12e-3 * last.dir[2]) <= 1e-7
+    rng = np.random.default_rng(4)
+    n = 128
+    pos = np.zeros((n, 3)); pos[:, 0] = rng.uniform(-0.6e-3, 0.6e-3, n); pos[:, 2] = rng.uniform(-0.6e-3, 0.6e-3, n); pos[:, 1] = -0.5e-3
+    d = np.tile([0.0, 1.0, 0.0], (n, 1)) + 0.05 * rng.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    worst, b = _compare_bundle(bmo, orc, sys_, osys, pos, d, 0.5876e-6, 50)
+    assert (b["nseg"] >= 11).sum() > n // 4         # through all five elements
+    assert worst <= POS_TOL, worst
