@@ -158,10 +158,19 @@ SDF* lens_shape(double r1, double d1, double md1, double r2, double d2, double m
 }
 // OpticalComponents/Lenses.jl:331-379 Lens(front::AbstractCylindricalSurface, back, center_thickness, n) with
 // CylindricalSDF.jl:176-205 (surface -> SDF; r = Inf stands for RectangularFlatSurface / a flat side)
-SDF* cyl_lens_shape(double r1, double d1, double h1, double md1, double r2, double d2, double h2, double md2, double ct) {
+// edge_sag of a cylindric surface: thickness(sdf) (CylindricalSDF.jl:173-174) / the signed aspheric sag (AcylindricalSDF.jl:170-178)
+static double cyl_edge_sag(SDF* s) {
+    if (auto* a = dynamic_cast<AcylSDF*>(s)) return a->edge_sag();
+    return s->thickness();
+}
+SDF* cyl_lens_shape(double r1, double d1, double h1, double md1, double r2, double d2, double h2, double md2, double ct,
+                    const AsphDesc* a1 = nullptr, const AsphDesc* a2 = nullptr) {
     const bool flat1 = std::isinf(r1), flat2 = std::isinf(r2);
-    PrimSDF* front = flat1 ? nullptr : (r1 > 0 ? mk_convex_cyl(r1, d1, h1) : mk_concave_cyl(r1, d1, h1));
-    PrimSDF* back = flat2 ? nullptr : (r2 > 0 ? mk_concave_cyl(r2, d2, h2) : mk_convex_cyl(-r2, d2, h2));
+    SDF* front = flat1 ? nullptr : (a1 ? (SDF*)new AcylSDF(r1 > 0, r1, d1, h1, a1->k, a1->coeffs)     // AcylindricalSDF.jl:184-191
+                                       : (r1 > 0 ? (SDF*)mk_convex_cyl(r1, d1, h1) : (SDF*)mk_concave_cyl(r1, d1, h1)));
+    SDF* back = flat2 ? nullptr : (a2 ? (r2 > 0 ? (SDF*)new AcylSDF(false, r2, d2, h2, a2->k, a2->coeffs)
+                                                : (SDF*)new AcylSDF(true, -r2, d2, h2, a2->k, a2->coeffs))      // :192-199
+                                      : (r2 > 0 ? (SDF*)mk_concave_cyl(r2, d2, h2) : (SDF*)mk_convex_cyl(-r2, d2, h2)));
     double l0 = ct;
     l0 -= front ? front->thickness() : 0.0;
     l0 -= back ? back->thickness() : 0.0;
@@ -181,8 +190,8 @@ SDF* cyl_lens_shape(double r1, double d1, double h1, double md1, double r2, doub
     if (md_mid > d_mid) {
         double ring_thickness = mid->thickness();
         double ring_center = mid->pos.y + ring_thickness / 2;   // position(mid): of the box if there is no union, else 0
-        if (front) { double sg = front->thickness(); ring_thickness -= sg; ring_center += sg / 2; }   // edge_sag = thickness (CylindricalSDF.jl:173-174)
-        if (back) { double sg = back->thickness(); ring_thickness += sg; ring_center += sg / 2; }
+        if (front) { double sg = cyl_edge_sag(front); ring_thickness -= sg; ring_center += sg / 2; }
+        if (back) { double sg = cyl_edge_sag(back); ring_thickness += sg; ring_center += sg / 2; }
         SDF* ring = mk_ring(d_mid / 2, (md_mid - d_mid) / 2, ring_thickness);
         ring->translate(V3{0, ring_center, 0});
         shape = sdf_union(shape, ring);
@@ -296,6 +305,15 @@ int orc_new(const char* kind, const double* d, int nd, const int* ih, int ni) {
         if (nc1 >= 0) { a1.k = d[3]; a1.coeffs.assign(d + o, d + o + nc1); o += nc1; }
         if (nc2 >= 0) { a2.k = d[8]; a2.coeffs.assign(d + o, d + o + nc2); o += nc2; }
         return reg_object(mk_refr(lens_shape(d[0], d[1], d[2], d[5], d[6], d[7], d[10], nc1 >= 0 ? &a1 : nullptr, nc2 >= 0 ? &a2 : nullptr), RI(ih[0])));
+    }
+    if (k == "AcylindricalLens") {
+        // r1 d1 h1 md1 k1 nc1 | r2 d2 h2 md2 k2 nc2 | ct | coeffs1... coeffs2...   (nc < 0: CylindricalSurface; r2 = Inf: flat)
+        int nc1 = (int)d[5], nc2 = (int)d[11];
+        AsphDesc a1, a2;
+        int o = 13;
+        if (nc1 >= 0) { a1.k = d[4]; a1.coeffs.assign(d + o, d + o + nc1); o += nc1; }
+        if (nc2 >= 0) { a2.k = d[10]; a2.coeffs.assign(d + o, d + o + nc2); o += nc2; }
+        return reg_object(mk_refr(cyl_lens_shape(d[0], d[1], d[2], d[3], d[6], d[7], d[8], d[9], d[12], nc1 >= 0 ? &a1 : nullptr, nc2 >= 0 ? &a2 : nullptr), RI(ih[0])));
     }
     if (k == "CylindricalLens")   // r1 d1 h1 md1 r2 d2 h2 md2 ct (r2 = Inf: RectangularFlatSurface)
         return reg_object(mk_refr(cyl_lens_shape(d[0], d[1], d[2], d[3], d[4], d[5], d[6], d[7], d[8]), RI(ih[0])));

@@ -47,43 +47,64 @@ inline double jl_pow(double x, long n) {
     return (std::isfinite(x) && std::isfinite(err)) ? std::fma(x, y, err) : x * y;
 }
 
+// ---- helpers so that the surface functions can be written once for Float64 and for ForwardDiff duals -------------
+inline bool operator>(Dual a, Dual b) { return a.v > b.v; }
+inline Dual operator/(double a, Dual b) {   // ForwardDiff: divv = x / v; partials * -(divv / v)
+    double q = a / b.v, c = -(q / b.v);
+    return {q, {b.p[0] * c, b.p[1] * c, b.p[2] * c}};
+}
+inline Dual jl_pow(Dual x, long n) {        // d/dx x^n = n x^(n-1) (ForwardDiff's rule for Dual ^ Integer)
+    double v = jl_pow(x.v, n), dv = n == 0 ? 0.0 : (double)n * jl_pow(x.v, n - 1);
+    return {v, {x.p[0] * dv, x.p[1] * dv, x.p[2] * dv}};
+}
+inline bool isnan_(double a) { return std::isnan(a); }
+inline bool isnan_(Dual a) { return std::isnan(a.v); }
+inline double clamp_(double x, double lo, double hi) { return jl_clamp(x, lo, hi); }
+inline Dual clamp_(Dual x, double lo, double hi) { return x.v > hi ? mkdual(hi) : (x.v < lo ? mkdual(lo) : x); }
+inline double sign_(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); }   // Base.sign (keeps the signed zero / NaN)
+inline double sign_(Dual x) { return sign_(x.v); }
+inline double mkT(double, double c) { return c; }
+inline Dual mkT(Dual, double c) { return mkdual(c); }
+inline double nan_of(double) { return std::nan(""); }
+inline Dual nan_of(Dual) { return mkdual(std::nan("")); }
+template <class T> inline T min3(T a, T b, T c) { return min_(min_(a, b), c); }
+template <class T> inline T min4(T a, T b, T c, T d) { return min_(min_(min_(a, b), c), d); }
+
 // AsphericalLensSDF.jl:128-141
-inline double aspheric_equation(double r, double c, double k, const std::vector<double>& al) {
-    double r2 = r * r;
-    double sqrt_arg = 1 - (1 + k) * (c * c) * r2;
-    if (sqrt_arg < 0) return std::nan("");
-    double sum_a = 0.0;
+template <class T> inline T aspheric_equation(T r, double c, double k, const std::vector<double>& al) {
+    T r2 = r * r;
+    T sqrt_arg = 1 - (1 + k) * (c * c) * r2;
+    if (sqrt_arg < 0.0) return nan_of(r);
+    T sum_a = r2 * 0.0;
     for (size_t i = 0; i < al.size(); i++) {
-        double t = al[i] * jl_pow(r2, (long)i + 1);
+        T t = al[i] * jl_pow(r2, (long)i + 1);
         sum_a = (i == 0) ? t : sum_a + t;
     }
-    return c * r2 / (1 + std::sqrt(sqrt_arg)) + sum_a;
+    return c * r2 / (1 + sqrt_(sqrt_arg)) + sum_a;
 }
 // :147-157 first component of the returned Point2 (the second is 1); NaN when the square root argument is negative
-inline double gradient_aspheric_equation(double r, double c, double k, const std::vector<double>& al) {
+template <class T> inline T gradient_aspheric_equation(T r, double c, double k, const std::vector<double>& al) {
     double Ri = 1 / c;
-    double sqrt_arg = 1 - (r * r) * (1 + k) / (Ri * Ri);
-    if (sqrt_arg < 0) return std::nan("");
-    double sq = std::sqrt(sqrt_arg);
-    double gr = 2 * r / (Ri * (sq + 1)) + (r * r * r) * (1 + k) / ((Ri * Ri * Ri) * sq * ((sq + 1) * (sq + 1)));
-    double sum_r = 0.0;
+    T sqrt_arg = 1 - (r * r) * (1 + k) / (Ri * Ri);
+    if (sqrt_arg < 0.0) return nan_of(r);
+    T sq = sqrt_(sqrt_arg);
+    T gr = 2 * r / (Ri * (sq + 1)) + (r * r * r) * (1 + k) / ((Ri * Ri * Ri) * sq * ((sq + 1) * (sq + 1)));
+    T sum_r = r * 0.0;
     for (size_t i = 0; i < al.size(); i++) {
         long m = (long)i + 1;
-        double t = (double)(2 * m) * al[i] * jl_pow(r, 2 * (m - 1) + 1);
+        T t = (double)(2 * m) * al[i] * jl_pow(r, 2 * (m - 1) + 1);
         sum_r = (i == 0) ? t : sum_r + t;
     }
     return -sum_r - gr;
 }
 // :165-170  distance from p to the segment a-b (2-D)
-inline double sd_line_segment(double px, double py, double ax, double ay, double bx, double by) {
-    double pax = px - ax, pay = py - ay, bax = bx - ax, bay = by - ay;
-    double h = jl_clamp((pax * bax + pay * bay) / (bax * bax + bay * bay), 0.0, 1.0);
-    double ex = pax - h * bax, ey = pay - h * bay;
-    return std::sqrt(ex * ex + ey * ey);
+template <class T> inline T sd_line_segment(T px, T py, double ax, double ay, double bx, double by) {
+    T pax = px - ax, pay = py - ay;
+    double bax = bx - ax, bay = by - ay;
+    T h = clamp_((pax * bax + pay * bay) / (bax * bax + bay * bay), 0.0, 1.0);
+    T ex = pax - h * bax, ey = pay - h * bay;
+    return sqrt_(ex * ex + ey * ey);
 }
-inline double sign_(double x) { return x > 0 ? 1.0 : (x < 0 ? -1.0 : x); }   // Base.sign (keeps the signed zero / NaN)
-inline double min3(double a, double b, double c) { return jl_min(jl_min(a, b), c); }
-inline double min4(double a, double b, double c, double d) { return jl_min(jl_min(jl_min(a, b), c), d); }
 
 struct AsphParams {
     double c, k, d, max_sag;              // curvature 1/radius, conic constant, diameter, max_sag[1]
@@ -92,62 +113,65 @@ struct AsphParams {
 };
 
 // :188-240
-inline double convex_aspheric_surface_distance(double r, double z, const AsphParams& P) {
+template <class T> inline T convex_aspheric_surface_distance(T r, T z, const AsphParams& P) {
     const double c = P.c, d = P.d;
-    double r2 = r * r, r2_bound = (d / 2) * (d / 2);
-    double zv = aspheric_equation(r, c, P.k, P.al);
-    double g = gradient_aspheric_equation(r, c, P.k, P.al);
+    T r2 = r * r;
+    double r2_bound = (d / 2) * (d / 2);
+    T zv = aspheric_equation(r, c, P.k, P.al);
+    T g = gradient_aspheric_equation(r, c, P.k, P.al);
     double zb = P.zb, n_gzb = std::sqrt(P.gzb * P.gzb + 1.0 * 1.0);
-    if (std::isnan(zv) || std::isnan(g) || r2 > r2_bound) {
-        double rr = r - sign_(r) * d / 2, dist;
-        if (z < zb) dist = std::sqrt(rr * rr + (z - zb) * (z - zb));
-        else if (zb < z && z < 0) dist = std::sqrt(rr * rr);
-        else if (z > 0 && (sign_(c) == 1 && zb < 0)) dist = std::sqrt(rr * rr + z * z);
-        else dist = std::sqrt(rr * rr + (z - zb) * (z - zb));
+    if (isnan_(zv) || isnan_(g) || r2 > mkT(r, r2_bound)) {
+        T rr = r - sign_(r) * d / 2, dist;
+        if (z < zb) dist = sqrt_(rr * rr + (z - zb) * (z - zb));
+        else if (z > mkT(z, zb) && z < 0.0) dist = sqrt_(rr * rr);
+        else if (z > mkT(z, 0.0) && (sign_(c) == 1 && zb < 0)) dist = sqrt_(rr * rr + z * z);
+        else dist = sqrt_(rr * rr + (z - zb) * (z - zb));
         return dist / n_gzb;
     }
-    double da = std::fabs(z - zv) / std::sqrt(g * g + 1.0 * 1.0);
+    T da = abs_(z - zv) / sqrt_(g * g + 1.0 * 1.0);
     if (sign_(c) == 1 && zb < 0) {
         double ms = P.max_sag;
-        double s1 = sd_line_segment(r, z, d / 2, zb, d / 2, ms) / n_gzb;
-        double s2 = sd_line_segment(r, z, d / 2, ms, -d / 2, ms) / n_gzb;
-        double s3 = sd_line_segment(r, z, -d / 2, ms, -d / 2, zb) / n_gzb;
+        T s1 = sd_line_segment(r, z, d / 2, zb, d / 2, ms) / n_gzb;
+        T s2 = sd_line_segment(r, z, d / 2, ms, -d / 2, ms) / n_gzb;
+        T s3 = sd_line_segment(r, z, -d / 2, ms, -d / 2, zb) / n_gzb;
         if (zv < z && z < ms) return -min4(da, s1, s2, s3);
         return min4(da, s1, s2, s3);
     }
-    double sdl = sd_line_segment(r, z, d / 2, zb, -d / 2, zb) / n_gzb;
+    T sdl = sd_line_segment(r, z, d / 2, zb, -d / 2, zb) / n_gzb;
     double sc = sign_(c);
-    if (sc * zv < sc * z && sc * z < sc * zb) return -jl_min(sdl, da);
-    return jl_min(sdl, da);
+    if (sc * zv < sc * z && sc * z < sc * zb) return -min_(sdl, da);
+    return min_(sdl, da);
 }
 // :242-307
-inline double concave_aspheric_surface_distance(double r, double z, const AsphParams& P) {
+template <class T> inline T concave_aspheric_surface_distance(T r, T z, const AsphParams& P) {
     const double c = P.c, d = P.d;
-    double r2 = r * r, r2_bound = (d / 2) * (d / 2);
-    double zv = aspheric_equation(r, c, P.k, P.al);
-    double g = gradient_aspheric_equation(r, c, P.k, P.al);
+    T r2 = r * r;
+    double r2_bound = (d / 2) * (d / 2);
+    T zv = aspheric_equation(r, c, P.k, P.al);
+    T g = gradient_aspheric_equation(r, c, P.k, P.al);
     double zb = P.zb, n_gzb = std::sqrt(P.gzb * P.gzb + 1.0 * 1.0);
-    if (std::isnan(zv) || std::isnan(g)) {
-        double rr = r - sign_(r) * d / 2, dist;
-        if (z < 0) dist = std::sqrt(rr * rr + z * z);
-        else if (0 < z && z < zb) dist = std::sqrt(rr * rr);
-        else dist = std::sqrt(rr * rr + (z - zb) * (z - zb));
+    (void)c;
+    if (isnan_(zv) || isnan_(g)) {
+        T rr = r - sign_(r) * d / 2, dist;
+        if (z < 0.0) dist = sqrt_(rr * rr + z * z);
+        else if (z > mkT(z, 0.0) && z < zb) dist = sqrt_(rr * rr);
+        else dist = sqrt_(rr * rr + (z - zb) * (z - zb));
         return dist / n_gzb;
     }
-    double da = std::fabs(z - zv) / std::sqrt(g * g + 1.0 * 1.0);
+    T da = abs_(z - zv) / sqrt_(g * g + 1.0 * 1.0);
     if (P.max_sag > 0 && zb < 0) {
-        double sdl = sd_line_segment(r, z, d / 2, zb, -d / 2, zb) / n_gzb;
-        if (r2 > r2_bound) return sdl;
-        if (zb < z && z < zv) return -jl_min(da, sdl);
-        if (zb > 0 && (0.0 < z && z < zv)) return -jl_min(da, sdl);
-        return jl_min(da, sdl);
+        T sdl = sd_line_segment(r, z, d / 2, zb, -d / 2, zb) / n_gzb;
+        if (r2 > mkT(r, r2_bound)) return sdl;
+        if (z > mkT(z, zb) && z < zv) return -min_(da, sdl);
+        if (zb > 0 && (z > mkT(z, 0.0) && z < zv)) return -min_(da, sdl);
+        return min_(da, sdl);
     }
-    double s1 = sd_line_segment(r, z, d / 2, zb, d / 2, 0.0) / n_gzb;
-    double s2 = sd_line_segment(r, z, d / 2, 0.0, -d / 2, 0.0) / n_gzb;
-    double s3 = sd_line_segment(r, z, -d / 2, 0.0, -d / 2, zb) / n_gzb;
-    if (r2 > r2_bound) return min3(s1, s2, s3);
+    T s1 = sd_line_segment(r, z, d / 2, zb, d / 2, 0.0) / n_gzb;
+    T s2 = sd_line_segment(r, z, d / 2, 0.0, -d / 2, 0.0) / n_gzb;
+    T s3 = sd_line_segment(r, z, -d / 2, 0.0, -d / 2, zb) / n_gzb;
+    if (r2 > mkT(r, r2_bound)) return min3(s1, s2, s3);
     if (zb < 0 && (zv < z && z < 0.0)) return -min4(da, s1, s2, s3);
-    if (zb > 0 && (0.0 < z && z < zv)) return -min4(da, s1, s2, s3);
+    if (zb > 0 && (z > mkT(z, 0.0) && z < zv)) return -min4(da, s1, s2, s3);
     return min4(da, s1, s2, s3);
 }
 
@@ -200,6 +224,36 @@ struct AsphSDF : SDF {
     }
     Dual sdf(P3<Dual>) const override { throw std::runtime_error("aspheric surfaces have no AD path (normal3d = numeric_gradient)"); }
     V3 normal3d(V3 p) const override { return numeric_gradient(p); }
+};
+
+// Aconvex / AconcaveCylinderSDF (AcylindricalSDF.jl:14-113): the aspheric profile in (z, y), extruded along x
+// (AbstractSDF.jl:229-234).  Normals: the generic normal_fd (ForwardDiff, finite-difference fallback).
+struct AcylSDF : SDF {
+    bool convex;
+    double radius, diameter, height;
+    AsphParams P;
+    double max_sag_r = 0;
+    AcylSDF(bool cvx, double radius_, double d, double h, double k, const std::vector<double>& al)
+        : convex(cvx), radius(radius_), diameter(d), height(h) {
+        P.c = 1 / radius_; P.k = k; P.d = d; P.al = al;
+        max_aspheric_value(P.c, k, al, d, P.max_sag, max_sag_r);
+        P.zb = aspheric_equation(d / 2, P.c, k, al);
+        P.gzb = gradient_aspheric_equation(d / 2, P.c, k, al);
+    }
+    double edge_sag() const { return aspheric_equation(diameter / 2, 1 / radius, P.k, P.al); }   // AcylindricalSDF.jl:170-178
+    double thickness() const override {   // :52-54, :97-100
+        double sg = edge_sag();
+        if (convex) return std::fabs(sg);
+        return (P.max_sag > 0 && sg < 0) ? std::fabs(sg) : 0.0;
+    }
+    bool has_thickness() const override { return true; }
+    template <class T> T eval(P3<T> q) const {
+        P3<T> p = w2s(q);
+        T d2 = convex ? convex_aspheric_surface_distance(p.z, p.y, P) : concave_aspheric_surface_distance(p.z, p.y, P);
+        return cyl_(d2, abs_(p.x) - height / 2);
+    }
+    double sdf(V3 p) const override { return eval(P3<double>{p.x, p.y, p.z}); }
+    Dual sdf(P3<Dual> p) const override { return eval(p); }
 };
 
 }  // namespace orc

@@ -89,3 +89,22 @@ def test_gpu_cylindrical_lens_matches_oracle(bmo, orc, case):
         worst = max(worst, float(np.abs(got - ref["seg"][i, :k, 0:6]).max()))
         assert np.array_equal(seg["n"][f0:f0 + k], ref["seg"][i, :k, 6])
     assert worst <= POS_TOL, worst
+
+
+# ---- acylindrical lenses (src/SDFs/AcylindricalSDF.jl; test/runtests.jl:1745-1791) -------------------------------
+AYL2520 = dict(radius=15.538e-3, diameter=25e-3, height=50e-3, k=-1.0, ct=7.5e-3, n=1.777,
+               A=[0, 1.1926075e-5 * (1e3) ** 3, -2.9323497e-9 * (1e3) ** 5, -1.8718889e-11 * (1e3) ** 7, -1.7009961e-14 * (1e3) ** 9,
+                  3.5481542e-17 * (1e3) ** 11, 6.5241296e-20 * (1e3) ** 13])
+
+
+def _oacyl(orc, r, d, h, k, A, ct, n, r2=math.inf):
+    return orc.new("AcylindricalLens", [r, d, h, d, k, float(len(A)), r2, d, h, d, 0.0, -1.0, ct] + list(A), [orc.refindex(n)])
+
+
+def test_oracle_thorlabs_acylinder_lens(orc):
+    L = AYL2520
+    lens = _oacyl(orc, L["radius"], L["diameter"], L["height"], L["k"], L["A"], L["ct"], L["n"])
+    assert abs(lens.eval("thickness_object", nout=1)[0] - L["ct"]) <= 1.5e-8 * L["ct"]       # runtests.jl:1765
+    assert abs(_working_distance(orc, lens, 0.05 * L["diameter"] / 2) - 15.8e-3) <= 1e-4       # :1768
+    inv = _oacyl(orc, -L["radius"], L["diameter"], L["height"], L["k"], L["A"], L["ct"], L["n"])
+    assert abs(inv.eval("thickness_object", nout=1)[0] - L["ct"]) <= 1.5e-8 * L["ct"]         # :1790
