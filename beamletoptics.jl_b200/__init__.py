@@ -9,13 +9,13 @@ from . import linalg
 from ._lib import BmoError, counters, counters_reset, measure_fp64_peak
 from .beams import (Beam, BeamletBundle, CollimatedSource, GaussianBeamlet, Intersection, PointSource, PolarizedRay, Ray,
                     RayBundle, UniformDiscSource)
-from .components import (CircularFlatSurface, ConcaveSphericalMirror, CubeBeamsplitter, EvenAsphericalSurface, LensFromSurfaces, SphericalSurface, CylindricalLens, CylindricalSurface, RectangularFlatSurface, DiscreteRefractiveIndex, DoubletLens, IntersectableObject, Lens,
+from .components import (AcylindricalSurface, CircularFlatSurface, ConcaveSphericalMirror, CubeBeamsplitter, EvenAsphericalSurface, LensFromSurfaces, SphericalSurface, CylindricalLens, CylindricalSurface, RectangularFlatSurface, DiscreteRefractiveIndex, DoubletLens, IntersectableObject, Lens,
                          MeshDummy, Mirror, NonInteractableObject, ObjectGroup, PSFDetector, Photodetector, PolarizationFilter, Prism, RectangularCompensatorPlate,
                          RectangularPlanoMirror, RectangularPlateBeamsplitter, Retroreflector, RightAnglePrism, RightAnglePrismMirror,
                          RoundPlanoMirror, RoundPlateBeamsplitter, RoundThinBeamsplitter, SellmeierEquation, SphericalDoubletLens,
                          SphericalLens, Spotdetector, SquarePlanoMirror, SquarePlanoMirror2D, StaticSystem, System, ThinBeamsplitter,
                          ThinLens, XYBasis, XZBasis, YZBasis, inch, lens_shape)
-from .shapes import (AsphericalSurfaceSDF, BoxSDF, CircularFlatMesh, ConcaveAsphericalSurfaceSDF, ConvexAsphericalSurfaceSDF, ConcaveCylinderSDF, ConcaveSphericalSurfaceSDF, ConvexCylinderSDF, ConvexSphericalSurfaceSDF, CubeMesh, CuboidMesh, CutSphereSDF,
+from .shapes import (AcylindricalSurfaceSDF, AsphericalSurfaceSDF, BoxSDF, CircularFlatMesh, ConcaveAsphericalSurfaceSDF, ConvexAsphericalSurfaceSDF, ConcaveCylinderSDF, ConcaveSphericalSurfaceSDF, ConvexCylinderSDF, ConvexSphericalSurfaceSDF, CubeMesh, CuboidMesh, CutSphereSDF,
                      CylinderSDF, Mesh, MeniscusLensSDF, PlanoSurfaceSDF, QuadraticFlatMesh, RectangularFlatMesh, RetroMesh,
                      RightAnglePrismSDF, RingSDF, SphereSDF, ThinLensSDF, UnionSDF, load_stl)
 from .solver import DeviceSystem, TraceResult, pd_accumulate, retrace, solve_system_, trace_beamlets, trace_rays, trace_rays_spots, upload_system

@@ -490,6 +490,13 @@ class CylindricalSurface:
         self.mechanical_diameter = float(diameter if mechanical_diameter is None else mechanical_diameter)
 
 
+class AcylindricalSurface(CylindricalSurface):
+    """AcylindricalSDF.jl:136-168: a cylindric surface whose profile is an even asphere."""
+    def __init__(self, radius, diameter, height, conic_constant, coefficients, mechanical_diameter=None):
+        super().__init__(radius, diameter, height, mechanical_diameter)
+        self.conic_constant, self.coefficients = float(conic_constant), [float(a) for a in coefficients]
+
+
 class RectangularFlatSurface:   # CylindricalSDF.jl:218-223
     def __init__(self, size):
         self.size = self.diameter = float(size)
@@ -497,11 +504,25 @@ class RectangularFlatSurface:   # CylindricalSDF.jl:218-223
 
 def cylindric_lens_shape(front, back, ct):
     """Lenses.jl:331-379 with the surface -> SDF rules of CylindricalSDF.jl:176-205."""
-    f = None if math.isinf(front.radius) else (sh.ConvexCylinderSDF(front.radius, front.diameter, front.height) if front.radius > 0
-                                                 else sh.ConcaveCylinderSDF(front.radius, front.diameter, front.height))
-    flat_back = isinstance(back, RectangularFlatSurface) or math.isinf(back.radius)
-    b = None if flat_back else (sh.ConcaveCylinderSDF(back.radius, back.diameter, back.height) if back.radius > 0
-                                else sh.ConvexCylinderSDF(-back.radius, back.diameter, back.height))
+    def fwd(s):      # CylindricalSDF.jl:184-193, AcylindricalSDF.jl:184-191
+        if math.isinf(s.radius):
+            return None
+        if isinstance(s, AcylindricalSurface):
+            return sh.AcylindricalSurfaceSDF(s.radius > 0, s.radius, s.diameter, s.height, s.conic_constant, s.coefficients)
+        return sh.ConvexCylinderSDF(s.radius, s.diameter, s.height) if s.radius > 0 else sh.ConcaveCylinderSDF(s.radius, s.diameter, s.height)
+
+    def bwd(s):      # CylindricalSDF.jl:195-204, AcylindricalSDF.jl:192-199
+        if isinstance(s, RectangularFlatSurface) or math.isinf(s.radius):
+            return None
+        if isinstance(s, AcylindricalSurface):
+            if s.radius > 0:
+                return sh.AcylindricalSurfaceSDF(False, s.radius, s.diameter, s.height, s.conic_constant, s.coefficients)
+            return sh.AcylindricalSurfaceSDF(True, -s.radius, s.diameter, s.height, s.conic_constant, s.coefficients)
+        return sh.ConcaveCylinderSDF(s.radius, s.diameter, s.height) if s.radius > 0 else sh.ConvexCylinderSDF(-s.radius, s.diameter, s.height)
+
+    def edge_sag(sdf):   # thickness(sdf) for cylinders (CylindricalSDF.jl:173-174), the signed aspheric sag for acylinders (AcylindricalSDF.jl:170-178)
+        return sdf.sag() if isinstance(sdf, sh.AcylindricalSurfaceSDF) else sdf.thickness()
+    f, b = fwd(front), bwd(back)
     l0 = ct - (f.thickness() if f is not None else 0.0)
     l0 -= b.thickness() if b is not None else 0.0
     if isinstance(back, RectangularFlatSurface):
@@ -524,9 +545,9 @@ def cylindric_lens_shape(front, back, ct):
     if md_mid > d_mid:
         rt, rc = mid.thickness(), mid.pos[1] + mid.thickness() / 2
         if f is not None:
-            rt -= f.thickness(); rc += f.thickness() / 2        # edge_sag(::CylindricalSurface, sdf) = thickness(sdf), CylindricalSDF.jl:173-174
+            rt -= edge_sag(f); rc += edge_sag(f) / 2
         if b is not None:
-            rt += b.thickness(); rc += b.thickness() / 2
+            rt += edge_sag(b); rc += edge_sag(b) / 2
         ring = sh.RingSDF(d_mid / 2, (md_mid - d_mid) / 2, rt)
         ring.translate3d_((0.0, rc, 0.0))
         shape = shape + ring

@@ -73,6 +73,7 @@ template <class T> BMO_D T cyl_(T d1, T d2, int zr) {
 // (SysView::ext + ext_first) in par[0], bit for bit, so that every evaluation site reaches it through the record.
 BMO_D const double* asph_block(const bmo_prim& pr) { return reinterpret_cast<const double*>((unsigned long long)__double_as_longlong(pr.par[0])); }
 BMO_D bool is_asph(int type) { return type == BMO_PRIM_CONVEX_ASPH || type == BMO_PRIM_CONCAVE_ASPH; }
+BMO_D bool is_acyl(int type) { return type == BMO_PRIM_CONVEX_ACYL || type == BMO_PRIM_CONCAVE_ACYL; }
 // Cylindrical and aspheric surfaces, generic (value / dual) evaluation: out of line for the same reason as
 // prim_eval_rare below -- a noinline function saves every callee-saved register any of its cases needs.
 template <class T> BMO_NI T prim_eval_rare_t(const bmo_prim& pr, P3<T> p, int zr) {
@@ -81,9 +82,14 @@ template <class T> BMO_NI T prim_eval_rare_t(const bmo_prim& pr, P3<T> p, int zr
         case BMO_PRIM_CONVEX_ASPH:
         case BMO_PRIM_CONCAVE_ASPH:   // AsphericalLensSDF.jl:309-349: y is the optical axis, the 2-D distance is revolved about it
             if constexpr (std::is_same<T, double>::value)
-                return aspheric_surface_distance(pr.type == BMO_PRIM_CONVEX_ASPH, sqrt(p.x * p.x + p.z * p.z) - 0.0, p.y, asph_block(pr));
+                return aspheric_surface_distance<double>(pr.type == BMO_PRIM_CONVEX_ASPH, sqrt(p.x * p.x + p.z * p.z) - 0.0, p.y, asph_block(pr));
             else
                 return T{};   // no AD path: normal3d = numeric_gradient (:5)
+        case BMO_PRIM_CONVEX_ACYL:
+        case BMO_PRIM_CONCAVE_ACYL: {  // AcylindricalSDF.jl:55-72, 101-120: profile over (z, y), op_extrude_x (AbstractSDF.jl:229-234)
+            T d2 = aspheric_surface_distance<T>(pr.type == BMO_PRIM_CONVEX_ACYL, p.z, p.y, asph_block(pr));
+            return cyl_(d2, abs_(p.x) - b, zr);
+        }
         case BMO_PRIM_CONVEX_CYL: {  // CylindricalSDF.jl:59-78: sdf_cut_disk in (y, z), op_extrude_x (AbstractSDF.jl:229-234)
             const double r = a, h = b, w = c, hx = d;
             T p1 = abs_(p.y), p2 = p.z;
@@ -230,7 +236,10 @@ BMO_NI double prim_eval_rare(const bmo_prim& pr, V3 p) {
     switch (pr.type) {
         case BMO_PRIM_CONVEX_ASPH:
         case BMO_PRIM_CONCAVE_ASPH:
-            return aspheric_surface_distance(pr.type == BMO_PRIM_CONVEX_ASPH, sqrt(p.x * p.x + p.z * p.z) - 0.0, p.y, asph_block(pr));
+            return aspheric_surface_distance<double>(pr.type == BMO_PRIM_CONVEX_ASPH, sqrt(p.x * p.x + p.z * p.z) - 0.0, p.y, asph_block(pr));
+        case BMO_PRIM_CONVEX_ACYL:
+        case BMO_PRIM_CONCAVE_ACYL:
+            return cyl_f(aspheric_surface_distance<double>(pr.type == BMO_PRIM_CONVEX_ACYL, p.z, p.y, asph_block(pr)), fabs(p.x) - b);
         case BMO_PRIM_CONVEX_CYL: {
             const double r = a, h = b, w = c, hx = d;
             const double p1 = fabs(p.y), p2 = p.z;
@@ -352,7 +361,7 @@ template <bool RARE> BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned
         const bmo_prim& pr = sh.prims[i];
         if (pr.type == BMO_PRIM_MENISCUS) { q = w2s_f(pr, p); men = 3; start = i; continue; }
         const int k = i - first;
-        const bool tracked = men == 0 && k < 4 && !(RARE && is_asph(pr.type));   // aspheric pseudo-distances are not 1-Lipschitz
+        const bool tracked = men == 0 && k < 4 && !(RARE && (is_asph(pr.type) || is_acyl(pr.type)));   // aspheric pseudo-distances are not 1-Lipschitz
         if (tracked && have && lb.get(k) > m_ub) continue;   // cannot be the minimum at this point
         double v = prim_eval_f<RARE>(pr, q);
         nsdf++;

@@ -1067,7 +1067,7 @@ static void flag_rare_parts(bmo_prim* p, size_t n_prims_per_pose, size_t n_poses
 }
 static void patch_asph(bmo_prim* p, size_t n, const double* d_ext) {
     for (size_t i = 0; i < n; i++)
-        if (p[i].type == BMO_PRIM_CONVEX_ASPH || p[i].type == BMO_PRIM_CONCAVE_ASPH) {
+        if (p[i].type >= BMO_PRIM_CONVEX_ASPH && p[i].type <= BMO_PRIM_CONCAVE_ACYL) {
             const unsigned long long a = (unsigned long long)(uintptr_t)(d_ext + p[i].ext_first);
             std::memcpy(&p[i].par[0], &a, sizeof(double));
         }
@@ -1123,7 +1123,7 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
     std::vector<double> ntab(t->n_table, t->n_table + (size_t)std::max(t->n_rows, 0) * t->n_lambda);
     if (t->n_ext > 0 && (rc = upload(&s->d_ext, t->ext, (size_t)t->n_ext))) return rc;
     for (const bmo_prim& pr : s->prims)
-        if ((pr.type == BMO_PRIM_CONVEX_ASPH || pr.type == BMO_PRIM_CONCAVE_ASPH) &&
+        if ((pr.type >= BMO_PRIM_CONVEX_ASPH && pr.type <= BMO_PRIM_CONCAVE_ACYL) &&
             (!t->ext || pr.ext_first < 0 || pr.ext_count < 7 || (int64_t)pr.ext_first + pr.ext_count > t->n_ext))
             return fail(BMO_EINVAL, "aspheric primitive without a parameter block in tables.ext");
     patch_asph(s->prims.data(), s->prims.size(), s->d_ext);

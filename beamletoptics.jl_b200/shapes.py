@@ -12,7 +12,7 @@ import numpy as np
 from . import linalg as la
 
 # bmo_prim_type (include/bmo.h)
-PLANO, CYLINDER, SPHERE, CONVEX, CONCAVE, CUTSPHERE, BOX, RING, RAPRISM, MENISCUS, CONVEX_CYL, CONCAVE_CYL, CONVEX_ASPH, CONCAVE_ASPH = range(14)
+PLANO, CYLINDER, SPHERE, CONVEX, CONCAVE, CUTSPHERE, BOX, RING, RAPRISM, MENISCUS, CONVEX_CYL, CONCAVE_CYL, CONVEX_ASPH, CONCAVE_ASPH, CONVEX_ACYL, CONCAVE_ACYL = range(16)
 
 
 def sag(r, l):
@@ -209,6 +209,27 @@ class AsphericalSurfaceSDF(PrimSDF):
         cl = tuple((lo[k] + hi[k]) / 2 for k in range(3))
         r = math.sqrt(sum(((hi[k] - lo[k]) / 2) ** 2 for k in range(3)))
         return la.add(self.pos, la.matvec(self.dir, cl)), r
+
+
+class AcylindricalSurfaceSDF(AsphericalSurfaceSDF):
+    """Aconvex / AconcaveCylinderSDF (AcylindricalSDF.jl:14-120): the aspheric profile extruded along x over `height`."""
+
+    def __init__(self, convex, radius, diameter, height, conic_constant, coefficients):
+        super().__init__(convex, coefficients, radius, conic_constant, diameter)
+        self.type = CONVEX_ACYL if convex else CONCAVE_ACYL
+        self.height = float(height)
+        self.par = (0.0, self.height / 2, 0.0, 0.0)
+
+    def thickness(self):          # :52-54, :97-100
+        sg, ms = self._edge, self.max_sag[0]
+        if self.type == CONVEX_ACYL:
+            return abs(sg)
+        return abs(sg) if (ms > 0 and sg < 0) else 0.0
+
+    def local_box(self):
+        h = self._diameter / 2
+        zs = (0.0, self._edge, self.max_sag[0])
+        return (-self.height / 2, min(zs), -h), (self.height / 2, max(zs), h)
 
 
 def ConvexAsphericalSurfaceSDF(coefficients, radius, conic_constant, diameter):

@@ -48,6 +48,9 @@ enum bmo_prim_type {
                                  aspheric_equation(d/2), gradient_aspheric_equation(d/2)[1], n coefficients, coefficients.
                                  Normals by central differences only (:3-5).                        */
     BMO_PRIM_CONCAVE_ASPH = 13,/* ConcaveAsphericalSurfaceSDF (:88-98, 242-307, 330-349), same parameter block */
+    BMO_PRIM_CONVEX_ACYL = 14,/* AconvexCylinderSDF (AcylindricalSDF.jl:14-72): the aspheric profile in (z, y) extruded along x;
+                                 parameter block as for the aspheres, par[1] = half extrusion height; AD normals */
+    BMO_PRIM_CONCAVE_ACYL = 15,/* AconcaveCylinderSDF (:74-120)                                     */
     BMO_PRIM_MENISCUS = 9   /* frame only; followed by 3 child records: convex, cylinder, concave,
                                posed relative to this frame (MeniscusLensSDF.jl:42-46)            */
 };

@@ -108,3 +108,31 @@ def test_oracle_thorlabs_acylinder_lens(orc):
     assert abs(_working_distance(orc, lens, 0.05 * L["diameter"] / 2) - 15.8e-3) <= 1e-4       # :1768
     inv = _oacyl(orc, -L["radius"], L["diameter"], L["height"], L["k"], L["A"], L["ct"], L["n"])
     assert abs(inv.eval("thickness_object", nout=1)[0] - L["ct"]) <= 1.5e-8 * L["ct"]         # :1790
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sign", [1.0, -1.0])
+def test_gpu_acylindrical_lens_matches_oracle(bmo, orc, sign):
+    L = AYL2520
+    r = sign * L["radius"]
+    lens = bmo.CylindricalLens(bmo.AcylindricalSurface(r, L["diameter"], L["height"], L["k"], L["A"]), L["ct"], L["n"])
+    olens = _oacyl(orc, r, L["diameter"], L["height"], L["k"], L["A"], L["ct"], L["n"])
+    assert abs(lens.thickness() - L["ct"]) <= 1.5e-8 * L["ct"]
+    for x in (lens, olens):
+        x.zrotate3d_(-0.15); x.xrotate3d_(0.07); x.translate3d_([2e-3, 0.01, 1e-3])
+    rng = np.random.default_rng(21)
+    n = 256
+    pos = np.zeros((n, 3)); pos[:, 0] = rng.uniform(-0.02, 0.02, n); pos[:, 2] = rng.uniform(-0.014, 0.014, n); pos[:, 1] = -0.05
+    d = np.tile([0.0, 1.0, 0.0], (n, 1)) + 0.02 * rng.standard_normal((n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    res = bmo.solve_system_(bmo.System([lens]), bmo.RayBundle(pos, d, 1e-6))
+    b, seg = res.beams(), res.segments()
+    ref = orc.bulk_trace_rays(orc.system([olens]), pos, d, 1e-6, max_seg=128)
+    assert np.array_equal(b["nseg"], ref["nseg"])
+    assert (b["nseg"] >= 3).sum() > n // 4
+    worst = 0.0
+    for i in range(n):
+        f0, k = int(b["first"][i]), int(b["nseg"][i])
+        got = np.concatenate([seg["pos"][f0:f0 + k], seg["dir"][f0:f0 + k]], axis=1)
+        worst = max(worst, float(np.abs(got - ref["seg"][i, :k, 0:6]).max()))
+    assert worst <= POS_TOL, worst
