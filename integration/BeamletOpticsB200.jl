@@ -27,6 +27,7 @@ const libbmo = get(ENV, "LIBBMO", "libbmo.so")
 struct BmoPrim                      # bmo_prim
     type::Int32; reserved::Int32
     pos::NTuple{3,Float64}; tdir::NTuple{9,Float64}; par::NTuple{4,Float64}
+    ext_first::Int32; ext_count::Int32          # aspheric / acylindric surfaces: parameter block in BmoTables.ext
 end
 struct BmoPart                      # bmo_part
     object::Int32; role::Int32; shape_kind::Int32; first::Int32; count::Int32; n_row::Int32
@@ -49,6 +50,7 @@ struct BmoTables                    # bmo_tables
     n_lambda::Int32;   lambdas::Ptr{Float64}
     n_rows::Int32;     n_table::Ptr{Float64}
     n_system::Float64
+    n_ext::Int64;      ext::Ptr{Float64}        # c, k, d, max_sag[1], sag(d/2), sag'(d/2), n, coefficients... per aspheric primitive
     n_jones::Int32;    jones::Ptr{Float64}      # [n_jones][10]: GlobalJonesBasis (row-major) + cutoff of each PolarizationFilter
     norm_zero_rule::Int32; reserved::Int32
 end
@@ -58,7 +60,8 @@ struct BmoResultInfo
 end
 
 const PRIM = Dict(PlanoSurfaceSDF => 0, CylinderSDF => 1, SphereSDF => 2, ConvexSphericalSurfaceSDF => 3,
-    ConcaveSphericalSurfaceSDF => 4, CutSphereSDF => 5, BoxSDF => 6, RingSDF => 7, RightAnglePrismSDF => 8)
+    ConcaveSphericalSurfaceSDF => 4, CutSphereSDF => 5, BoxSDF => 6, RingSDF => 7, RightAnglePrismSDF => 8,
+    BeamletOptics.ConvexCylinderSDF => 10, BeamletOptics.ConcaveCylinderSDF => 11)
 const KEEP_SEGMENTS = UInt32(1)
 
 check(rc) = rc == 0 || error(unsafe_string(ccall((:bmo_last_error, libbmo), Cstring, ())))
@@ -77,16 +80,31 @@ params(s::RingSDF) = (s.inner_radius, s.hwidth, s.hthickness, 0.0)
 params(s::RightAnglePrismSDF) = (s.x / 2, s.y / 2, s.z / 2, 0.0)
 
 prim(s::AbstractSDF) = BmoPrim(PRIM[Base.typename(typeof(s)).wrapper], 0, Tuple(Float64.(position(s))),
-    rowmajor(transposed_orientation(s)), Float64.(params(s)))
+    rowmajor(transposed_orientation(s)), Float64.(params(s)), 0, 0)
+# cylindric surfaces (CylindricalSDF.jl): the constants each sdf call recomputes are passed precomputed
+params(s::BeamletOptics.ConvexCylinderSDF) = (h = sqrt(s.radius^2 - (s.diameter / 2)^2); (s.radius, h, sqrt(s.radius^2 - h^2), s.height / 2))
+params(s::BeamletOptics.ConcaveCylinderSDF) = (s.radius, s.diameter, s.height, BeamletOptics.sag(abs(s.radius), s.diameter))
+# aspheric / acylindric surfaces: parameter block appended to `ext` (see include/bmo.h, BMO_PRIM_CONVEX_ASPH)
+const ASPH = Dict(BeamletOptics.ConvexAsphericalSurfaceSDF => 12, BeamletOptics.ConcaveAsphericalSurfaceSDF => 13,
+    BeamletOptics.AconvexCylinderSDF => 14, BeamletOptics.AconcaveCylinderSDF => 15)
+function prim(s::Union{BeamletOptics.AbstractAsphericalSurfaceSDF,BeamletOptics.AbstractAcylindricalSurfaceSDF}, ext::Vector{Float64})
+    c, k, d, α = 1 / s.radius, s.conic_constant, s.diameter, s.coefficients
+    first = length(ext)
+    append!(ext, (c, k, d, s.max_sag[1], BeamletOptics.aspheric_equation(d / 2, c, k, α),
+        BeamletOptics.gradient_aspheric_equation(d / 2, c, k, α)[1], Float64(length(α)), α...))
+    hx = s isa BeamletOptics.AbstractAcylindricalSurfaceSDF ? s.height / 2 : 0.0
+    BmoPrim(ASPH[Base.typename(typeof(s)).wrapper], 0, Tuple(Float64.(position(s))), rowmajor(transposed_orientation(s)),
+        (0.0, hx, 0.0, 0.0), first, length(ext) - first)
+end
 
-function emit_sdf!(prims, s::AbstractSDF)
+function emit_sdf!(prims, s::AbstractSDF, ext::Vector{Float64})
     first = length(prims)
     for m in (s isa UnionSDF ? s.sdfs : (s,))
         if m isa MeniscusLensSDF        # frame + children posed relative to it (MeniscusLensSDF.jl:42-46)
-            push!(prims, BmoPrim(9, 0, Tuple(Float64.(position(m))), rowmajor(transposed_orientation(m)), (0.0, 0.0, 0.0, 0.0)))
+            push!(prims, BmoPrim(9, 0, Tuple(Float64.(position(m))), rowmajor(transposed_orientation(m)), (0.0, 0.0, 0.0, 0.0), 0, 0))
             push!(prims, prim(m.convex), prim(m.cylinder), prim(m.concave))
         else
-            push!(prims, prim(m))
+            push!(prims, haskey(ASPH, Base.typename(typeof(m)).wrapper) ? prim(m, ext) : prim(m))
         end
     end
     return first, length(prims) - first
@@ -125,7 +143,7 @@ kind_of(o::AbstractObject) = (0, (o,), (0,))                 # Lens, Prism: Abst
 """Leaves(system.objects) -> tables of include/bmo.h (same order: it is trace_all's tie-break order)."""
 function flatten(cs::CUDASystem, λs::Vector{Float64}; norm_zero_rule = 1)
     prims, parts, objs, meshes = BmoPrim[], BmoPart[], BmoObject[], BmoMesh[]
-    verts, fcs, ntab, owners, jones = Float64[], Int32[], Float64[], Any[], Float64[]
+    verts, fcs, ntab, owners, jones, ext = Float64[], Int32[], Float64[], Any[], Float64[], Float64[]
     leaves = [o for o in objects(cs) if !(o isa NonInteractableObject)]
     for (oi, o) in enumerate(leaves)
         kind, subs, roles = kind_of(o)
@@ -151,7 +169,7 @@ function flatten(cs::CUDASystem, λs::Vector{Float64}; norm_zero_rule = 1)
             bound = (c[1], c[2], c[3], rr, c[1] - rr, c[2] - rr, c[3] - rr, c[1] + rr, c[2] + rr, c[3] + rr)
             R = sub isa ThinBeamsplitter ? (sub.reflectance, sub.transmittance) : (0.0, 0.0)
             if sh isa AbstractSDF
-                first, count = emit_sdf!(prims, sh)
+                first, count = emit_sdf!(prims, sh, ext)
                 push!(parts, BmoPart(oi - 1, role, 0, first, count, n_row, R[1], R[2], bound))
             else
                 V, F = vertices(sh), faces(sh)
@@ -163,7 +181,7 @@ function flatten(cs::CUDASystem, λs::Vector{Float64}; norm_zero_rule = 1)
             push!(owners, sub)
         end
     end
-    return (; prims, parts, objs, meshes, verts, fcs, ntab, owners, leaves, λs, norm_zero_rule, jones)
+    return (; prims, parts, objs, meshes, verts, fcs, ntab, owners, leaves, λs, norm_zero_rule, jones, ext)
 end
 
 # conservative world-space bounding sphere of a shape (only used for result-identical early exits)
@@ -194,7 +212,7 @@ function upload(cs::CUDASystem, f)
         t = BmoTables(length(f.prims), pointer(f.prims), length(f.parts), pointer(f.parts), length(f.objs), pointer(f.objs),
             length(f.meshes), pointer(f.meshes), length(f.verts) ÷ 3, pointer(f.verts), length(f.fcs) ÷ 3, pointer(f.fcs),
             length(f.λs), pointer(f.λs), length(f.ntab) ÷ length(f.λs), pointer(f.ntab), 1.0,
-            length(f.jones) ÷ 10, pointer(f.jones), f.norm_zero_rule, 0)
+            length(f.ext), pointer(f.ext), length(f.jones) ÷ 10, pointer(f.jones), f.norm_zero_rule, 0)
         check(ccall((:bmo_system_upload, libbmo), Int32, (Ptr{Cvoid}, Ref{BmoTables}, Ref{Ptr{Cvoid}}), context(cs.device), t, sys))
     end
     return sys[]
