@@ -84,6 +84,7 @@ struct StepParams {
     unsigned long long* wave_totals;   // [2] units alive after this wave, spawn events of this wave
     DevCounters* counters;
     RetraceView rt;
+    int32_t n_waves, pad2;   // fused_wave0: waves traced by one launch (the queue is updated in place between them)
 };
 
 template <int MODE> struct Cfg {
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(co
 // The body is shared by the stand-alone kernel (hit records read from the buffer K1 wrote) and by the
 // fused kernel of splitter-free plain-ray systems (hit still in registers, FUSED = true).
 template <int MODE, bool FUSED>
-BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
+BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_off = 0) {
     constexpr int R = Cfg<MODE>::R;
     constexpr int UNITS = Cfg<MODE>::UNITS;
     constexpr int NWARP = Cfg<MODE>::NWARP;
@@ -563,8 +564,8 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg) {
         int a = 0, b = 0;
         for (int k = 0; k < NWARP; k++) { s_woff[k][1] = b; a += s_wcnt[k][0]; b += s_wcnt[k][1]; }
         P.blk_cnt[blockIdx.x] = b;
-        if (a) atomicAdd(P.wave_totals, (unsigned long long)a);        // units alive in the next wave
-        if (b) atomicAdd(P.wave_totals + 1, (unsigned long long)b);    // spawn events
+        if (a) atomicAdd(P.wave_totals + 2 * wave_off, (unsigned long long)a);        // units alive in the next wave
+        if (b) atomicAdd(P.wave_totals + 2 * wave_off + 1, (unsigned long long)b);    // spawn events
     }
     __syncthreads();
     if (MODE == 2) wsoff = __shfl_sync(full, wsoff, base);
@@ -651,30 +652,39 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
     }
     const int64_t ri = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
     const int64_t qs = P.cur.cap;
-    const bool active = ri < P.count && P.cur.i[I_BEAM * qs + ri] >= 0;
-    Stats st; st.sdf = 0; st.tri = 0;
-    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
-    if (active) {
-        const double* q = P.cur.d;
-        const V3 pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
-        const V3 dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
-        const int hint = P.cur.i[I_HINT * qs + ri];
-        const int pose = P.cur.i[I_POSE * qs + ri];
-        const bool budget = P.cur.i[I_SEG * qs + ri] + 1 < P.r_max;
-        TraceCtx C;
-        C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
-        C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
-        C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
-        C.pose = pose;
-        if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
-        else {
-            C.prims = S.prims + (int64_t)pose * S.n_prims;
-            C.parts = S.parts;
-            C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
+    // Splitter-free systems never grow the queue and every continuing ray overwrites its own slot, so one launch
+    // can run several waves back to back: the thread re-reads the slot it wrote (L1 / L2 hits), the hit record and
+    // the table staging are not repeated, and the host gets the per-wave totals exactly as from separate launches.
+    unsigned sd = 0, tr = 0;
+#pragma unroll 1
+    for (int w = 0; w < P.n_waves; w++) {
+        const bool active = ri < P.count && P.cur.i[I_BEAM * qs + ri] >= 0;
+        if (w > 0 && !__syncthreads_or(active)) break;      // the whole block is done
+        Stats st; st.sdf = 0; st.tri = 0;
+        Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+        if (active) {
+            const double* q = P.cur.d;
+            const V3 pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
+            const V3 dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
+            const int hint = P.cur.i[I_HINT * qs + ri];
+            const int pose = P.cur.i[I_POSE * qs + ri];
+            const bool budget = P.cur.i[I_SEG * qs + ri] + 1 < P.r_max;
+            TraceCtx C;
+            C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
+            C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
+            C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
+            C.pose = pose;
+            if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
+            else {
+                C.prims = S.prims + (int64_t)pose * S.n_prims;
+                C.parts = S.parts;
+                C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
+            }
+            if (budget) h = tracing_step<RK>(C, pos, dir, hint, st);
         }
-        if (budget) h = tracing_step<RK>(C, pos, dir, hint, st);
+        sd += st.sdf; tr += st.tri;
+        interact_body<0, true>(P, h, w);
     }
-    unsigned sd = st.sdf, tr = st.tri;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         sd += __shfl_xor_sync(0xffffffffu, sd, o);
@@ -684,7 +694,6 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
         if (sd) atomicAdd(&P.counters->sdf, (unsigned long long)sd);
         if (tr) atomicAdd(&P.counters->tri, (unsigned long long)tr);
     }
-    interact_body<0, true>(P, h);
 }
 
 // ---- K2: exclusive scan of int32 counts with stride (single block, chunked) -----------------------
@@ -1442,7 +1451,11 @@ int32_t SubTrace::enqueue_chunk() {
         const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
         BMO_CUDA(cudaEventRecord(ev[2 * c], st));
         if (mode == 0 && !has_splitter && allow_fused) {
-            // sequential lens-stack path: intersect + interact in one kernel, hit records stay in registers
+            // sequential lens-stack path: intersect + interact in one kernel, hit records stay in registers; without a
+            // segment table to fill, all waves of this chunk run inside one launch (BMO_MULTIWAVE=0: one launch per wave)
+            static const bool multiwave = !(getenv("BMO_MULTIWAVE") && atoi(getenv("BMO_MULTIWAVE")) == 0);
+            const int nw = (multiwave && !res->keep) ? chunk - c : 1;
+            sp.n_waves = nw;
             if (rk) {
                 if (!staged) fused_wave0<4, false, true><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
                 else fused_wave0<6, true, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
@@ -1453,6 +1466,11 @@ int32_t SubTrace::enqueue_chunk() {
             }
             BMO_LAUNCH(ctx, "fused_wave0");
             BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
+            for (int k = 1; k < nw; k++) {      // the waves folded into this launch: empty timing brackets, same bookkeeping
+                BMO_CUDA(cudaEventRecord(ev[2 * (c + k)], st));
+                BMO_CUDA(cudaEventRecord(ev[2 * (c + k) + 1], st));
+            }
+            wave += nw - 1; launched += nw - 1; c += nw - 1;
         } else if (rt.on) {
             // retrace call: K1r re-validates the stored path where there is one, ordinary tracing_step! elsewhere
 #define BMO_RETRACE_LAUNCH(M, RKV)                                                                                         \
