@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbmo.so")
+LIB_PATH = os.environ.get("BMO_LIB") or os.path.join(_HERE, "libbmo.so")   # BMO_LIB: another build of the same library (A/B timing)
 
 KEEP_SEGMENTS = 1
 INPUT_DEVICE = 2

@@ -65,6 +65,18 @@ template <class T> BMO_D P3<T> w2s(const bmo_prim& pr, P3<T> q) {
     p.z = pr.tdir[6] * dx + pr.tdir[7] * dy + pr.tdir[8] * dz;
     return p;
 }
+// The same transform of a point that carries ForwardDiff's seed partials (dq/dq = I), as member_normal passes it:
+// the generic dual arithmetic multiplies every tdir entry by the seeds 1 / 0 and adds the zeros, which leaves exactly
+// the rows of tdir (up to the sign of an exact zero, see the note at the fast double path below) -- written down directly.
+BMO_D P3<double> w2s_seeded(const bmo_prim& pr, P3<double> q) { return w2s(pr, q); }
+BMO_D P3<Dual> w2s_seeded(const bmo_prim& pr, P3<Dual> q) {
+    const double dx = q.x.v - pr.pos[0], dy = q.y.v - pr.pos[1], dz = q.z.v - pr.pos[2];
+    P3<Dual> p;
+    p.x = mkd(pr.tdir[0] * dx + pr.tdir[1] * dy + pr.tdir[2] * dz, pr.tdir[0], pr.tdir[1], pr.tdir[2]);
+    p.y = mkd(pr.tdir[3] * dx + pr.tdir[4] * dy + pr.tdir[5] * dz, pr.tdir[3], pr.tdir[4], pr.tdir[5]);
+    p.z = mkd(pr.tdir[6] * dx + pr.tdir[7] * dy + pr.tdir[8] * dz, pr.tdir[6], pr.tdir[7], pr.tdir[8]);
+    return p;
+}
 // min(maximum(d), 0) + norm(max.(d, 0))   (SphericalLensSDF.jl:64)
 template <class T> BMO_D T cyl_(T d1, T d2, int zr) {
     return min_(max_(d1, d2), 0.0) + norm2_(max_(d1, 0.0), max_(d2, 0.0), zr);
@@ -116,9 +128,10 @@ template <class T> BMO_NI T prim_eval_rare_t(const bmo_prim& pr, P3<T> p, int zr
     return T{};
 }
 // RK: the kernel was compiled for systems with cylindrical / aspheric primitives (chosen by the host per system)
-template <class T, bool RK> BMO_NI T prim_eval(const bmo_prim& pr, P3<T> q, int zr, Stats& st) {
+// seeded: q carries the identity partials (only meaningful for T = Dual)
+template <class T, bool RK> BMO_NI T prim_eval(const bmo_prim& pr, P3<T> q, int zr, Stats& st, bool seeded = false) {
     st.sdf++;
-    P3<T> p = w2s(pr, q);
+    P3<T> p = seeded ? w2s_seeded(pr, q) : w2s(pr, q);
     if (RK) { if (pr.type >= BMO_PRIM_CONVEX_CYL) return prim_eval_rare_t<T>(pr, p, zr); }
     const double a = pr.par[0], b = pr.par[1], c = pr.par[2], d = pr.par[3];
     switch (pr.type) {
@@ -180,10 +193,10 @@ template <class T, bool RK> BMO_NI T prim_eval(const bmo_prim& pr, P3<T> q, int 
     return T{};
 }
 // one member of a union: a primitive, or a meniscus frame + 3 children (MeniscusLensSDF.jl:42-46)
-template <class T, bool RK> BMO_D T member_eval(const bmo_prim* prims, int i, P3<T> q, int zr, Stats& st) {
+template <class T, bool RK> BMO_D T member_eval(const bmo_prim* prims, int i, P3<T> q, int zr, Stats& st, bool seeded = false) {
     const bmo_prim& pr = prims[i];
-    if (pr.type != BMO_PRIM_MENISCUS) return prim_eval<T, RK>(pr, q, zr, st);
-    P3<T> p = w2s(pr, q);
+    if (pr.type != BMO_PRIM_MENISCUS) return prim_eval<T, RK>(pr, q, zr, st, seeded);
+    P3<T> p = seeded ? w2s_seeded(pr, q) : w2s(pr, q);
     T cv = prim_eval<T, RK>(prims[i + 1], p, zr, st);
     T cy = prim_eval<T, RK>(prims[i + 2], p, zr, st);
     T cc = prim_eval<T, RK>(prims[i + 3], p, zr, st);
@@ -338,6 +351,10 @@ struct MemberBounds {
         const float s = __double2float_ru(step);
         b0 = __fsub_rd(b0, s); b1 = __fsub_rd(b1, s); b2 = __fsub_rd(b2, s); b3 = __fsub_rd(b3, s);
     }
+    BMO_D void moved_f(double step, float len) {   // the same with the path length per unit of step kept in binary32 (rounded up)
+        const float s = __fmul_ru(__double2float_ru(step), len);
+        b0 = __fsub_rd(b0, s); b1 = __fsub_rd(b1, s); b2 = __fsub_rd(b2, s); b3 = __fsub_rd(b3, s);
+    }
 };
 // UnionSDF.jl:53-56: minimum over the members (left fold); idx = first member attaining it, which
 // is the member normal3d(::UnionSDF) dispatches to (UnionSDF.jl:86-91) -- the reference evaluates the
@@ -385,7 +402,7 @@ template <bool RK> BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p,
     if (!(RK && is_asph(prims[idx].type))) {   // aspheric surfaces: numeric_gradient only (AsphericalLensSDF.jl:3-5)
         P3<Dual> qd;
         qd.x = mkd(p.x, 1, 0, 0); qd.y = mkd(p.y, 0, 1, 0); qd.z = mkd(p.z, 0, 0, 1);
-        Dual g = member_eval<Dual, RK>(prims, idx, qd, zr, st);
+        Dual g = member_eval<Dual, RK>(prims, idx, qd, zr, st, true);
         V3 n = normalize(mk3(g.p0, g.p1, g.p2));
         if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
     }
@@ -427,13 +444,16 @@ template <bool RARE> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 d
         }
     }
     enum { INIT = 0, IN = 1, OUT = 2 };
-    int mode = INIT, it = 0;
+    // Register diet (the loop state is what the 80-register budget has to hold): the backward march direction is
+    // -dir, so p + dist * (-dir) is formed as p + (-dist) * dir (negation is exact, the bits are the same) and the
+    // escape test's dot(v, -dir) > 0 as dot(v, dir) < 0; the inside steps are counted (tin = n_in * 1.0 exactly).
+    int mode = INIT, it = 0, n_in = 0;
     bool back = false;
-    V3 p = pos, d = dir;
-    double t0 = 0.0, tin = 0.0;
+    V3 p = pos;
+    double t0 = 0.0;
     MemberBounds lb; lb.reset();
     // |d| <= max(1, |d|^2): how far the march point moves per unit of step (directions are unit up to rounding)
-    const double dlen = fmax(1.0, dot(dir, dir)) * (1.0 + 1e-9);
+    const float dlen = __double2float_ru(fmax(1.0, dot(dir, dir)) * (1.0 + 1e-9));
     for (;;) {
         int idx;
         const double dist = shape_sdf_f<RARE>(sh, p, nsdf, idx, lb);
@@ -441,17 +461,18 @@ template <bool RARE> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 d
             t0 += dist;
             if (!(dist < eps_ray)) {
                 const V3 v = mk3(p.x - sh.cx, p.y - sh.cy, p.z - sh.cz);
-                if (dot(v, v) > sh.R2 && dot(v, d) > 0.0) return false;
+                const double vd = dot(v, dir);
+                if (dot(v, v) > sh.R2 && (back ? vd < 0.0 : vd > 0.0)) return false;
                 if (++it >= kMarchIter || !(dist == dist)) return false;   // NaN can never satisfy dist < eps_ray again
-                p = p + dist * d; lb.moved(dist * dlen);
+                p = p + (back ? -dist : dist) * dir; lb.moved_f(dist, dlen);
                 continue;
             }
         } else if (mode == INIT) {
-            if (dist > eps_srf) { mode = OUT; t0 = dist; p = p + dist * d; lb.moved(dist * dlen); continue; }
+            if (dist > eps_srf) { mode = OUT; t0 = dist; p = p + dist * dir; lb.moved_f(dist, dlen); continue; }
         } else {  // IN
-            if (dist > 0) { mode = OUT; back = true; d = -d; t0 = dist; it = 0; p = p + dist * d; lb.moved(dist * dlen); continue; }
+            if (dist > 0) { mode = OUT; back = true; t0 = dist; it = 0; p = p + (-dist) * dir; lb.moved_f(dist, dlen); continue; }
             if (++it >= kMarchIter) return false;
-            p = p + eps_ins * d; tin += eps_ins; lb.moved(eps_ins * dlen);
+            p = p + eps_ins * dir; n_in++; lb.moved_f(eps_ins, dlen);
             continue;
         }
         {
@@ -459,10 +480,10 @@ template <bool RARE> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 d
             n = member_normal<RARE>(sh.prims, idx, p, sh.zr, tmp);
             nsdf += tmp.sdf;
         }
-        if (mode == OUT) { t = back ? tin - t0 : t0; return true; }
-        if (!(dot(d, n) <= 0)) return false;   // on the surface, heading out
+        if (mode == OUT) { t = back ? (double)n_in - t0 : t0; return true; }
+        if (!(dot(dir, n) <= 0)) return false;   // on the surface, heading out
         mode = IN; it = 0;
-        p = p + eps_ins * d; tin = eps_ins; lb.moved(eps_ins * dlen);
+        p = p + eps_ins * dir; n_in = 1; lb.moved_f(eps_ins, dlen);
     }
 }
 

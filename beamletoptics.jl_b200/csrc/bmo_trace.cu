@@ -15,6 +15,7 @@
 // beam-major order at the end (K4 gather_segments).
 #include <chrono>
 #include <cstdlib>
+#include <cooperative_groups.h>
 #include "bmo_host.cuh"
 #include "bmo_interact.cuh"
 
@@ -107,6 +108,16 @@ template <int MINB, bool STAGED, bool RK>
 __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysView& S = P.S;
+    // The ray state is requested first, every load at once and from a clamped slot so that none of them sits
+    // behind a branch on another one's value: the DRAM round trip then overlaps the table staging below instead of
+    // being paid three times in a row (alive? -> segment budget? -> position / direction).
+    const int64_t ri = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
+    const int64_t qs = P.cur.cap;
+    const int64_t rl = ri < P.n_rays ? ri : 0;   // slot 0 exists whenever the kernel is launched
+    const int q_beam = P.cur.i[I_BEAM * qs + rl], q_seg = P.cur.i[I_SEG * qs + rl];
+    const int q_hint = P.cur.i[I_HINT * qs + rl], q_pose = P.cur.i[I_POSE * qs + rl];
+    const double q_px = P.cur.d[F_PX * qs + rl], q_py = P.cur.d[F_PY * qs + rl], q_pz = P.cur.d[F_PZ * qs + rl];
+    const double q_dx = P.cur.d[F_DX * qs + rl], q_dy = P.cur.d[F_DY * qs + rl], q_dz = P.cur.d[F_DZ * qs + rl];
     // shared-memory copies of the small system tables: prims | parts | bounds
     bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
     bmo_part* s_parts = reinterpret_cast<bmo_part*>(smem_raw + (size_t)S.n_prims * sizeof(bmo_prim));
@@ -123,17 +134,14 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
         __syncthreads();
     }
 
-    const int64_t ri = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
-    const bool active = ri < P.n_rays && P.cur.i[I_BEAM * P.cur.cap + ri] >= 0;
+    const bool active = ri < P.n_rays && q_beam >= 0;
     Stats st; st.sdf = 0; st.tri = 0;
     if (active) {
-        const int64_t qs = P.cur.cap;
-        const double* q = P.cur.d;
-        const V3 pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
-        const V3 dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
-        const int hint = P.cur.i[I_HINT * qs + ri];
-        const int pose = P.cur.i[I_POSE * qs + ri];
-        const bool budget = P.cur.i[I_SEG * qs + ri] + 1 < P.r_max;   // `while length(rays) < r_max` (System.jl:133)
+        const V3 pos = mk3(q_px, q_py, q_pz);
+        const V3 dir = mk3(q_dx, q_dy, q_dz);
+        const int hint = q_hint;
+        const int pose = q_pose;
+        const bool budget = q_seg + 1 < P.r_max;   // `while length(rays) < r_max` (System.jl:133)
         TraceCtx C;
         C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
         C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
@@ -304,35 +312,38 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
     const bool in_queue = lane_ok && unit < P.count;
     const int64_t ri = unit * R + r;
     const int64_t qs = P.cur.cap;
-    const bool active = in_queue && P.cur.i[I_BEAM * qs + ri] >= 0;   // dead slots wait for the next compaction
-    const bool leader = active && r == 0;
-
-    V3 pos = mk3(0, 0, 0), dir = mk3(0, 1, 0);
-    double rn = 1.0;
-    int lam = 0, beam = 0, seg = 0, pose = 0;
+    // All loads of the unit's state are issued at once from a clamped slot (slot 0 exists whenever the kernel runs):
+    // behind `if (active)` they would wait for the alive flag's own DRAM round trip first.
+    const int64_t rl = in_queue ? ri : 0;
+    const int32_t* qi = P.cur.i;
+    const double* q = P.cur.d;
+    const int q_beam = qi[I_BEAM * qs + rl];
+    int lam = qi[I_LAM * qs + rl], seg = qi[I_SEG * qs + rl], pose = qi[I_POSE * qs + rl];
+    V3 pos = mk3(q[F_PX * qs + rl], q[F_PY * qs + rl], q[F_PZ * qs + rl]);
+    V3 dir = mk3(q[F_DX * qs + rl], q[F_DY * qs + rl], q[F_DZ * qs + rl]);
+    double rn = q[F_N * qs + rl];
     Cx E0[3];
     E0[0] = E0[1] = E0[2] = mkc(0, 0);
-    double acc_lsum = 0, acc_lpar = 0, acc_opl = 0;
-    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
-    if (active) {
-        const double* q = P.cur.d;
-        pos = mk3(q[F_PX * qs + ri], q[F_PY * qs + ri], q[F_PZ * qs + ri]);
-        dir = mk3(q[F_DX * qs + ri], q[F_DY * qs + ri], q[F_DZ * qs + ri]);
-        rn = q[F_N * qs + ri];
-        if (MODE == 1) {
+    if (MODE == 1) {
 #pragma unroll
-            for (int k = 0; k < 3; k++) E0[k] = mkc(q[(F_X0 + 2 * k) * qs + ri], q[(F_X0 + 2 * k + 1) * qs + ri]);
-        }
-        if (MODE == 2) { acc_lsum = q[F_X0 * qs + ri]; acc_lpar = q[(F_X0 + 1) * qs + ri]; acc_opl = q[(F_X0 + 2) * qs + ri]; }
-        const int32_t* qi = P.cur.i;
-        lam = qi[I_LAM * qs + ri]; beam = qi[I_BEAM * qs + ri];
-        seg = qi[I_SEG * qs + ri]; pose = qi[I_POSE * qs + ri];
-        if (FUSED) h = h_reg;
-        else {
-            const int64_t hs = P.hit.cap;
-            h.t = P.hit.d[ri]; h.n = mk3(P.hit.d[hs + ri], P.hit.d[2 * hs + ri], P.hit.d[3 * hs + ri]);
-            h.part = P.hit.part[ri];
-        }
+        for (int k = 0; k < 3; k++) E0[k] = mkc(q[(F_X0 + 2 * k) * qs + rl], q[(F_X0 + 2 * k + 1) * qs + rl]);
+    }
+    double acc_lsum = 0, acc_lpar = 0, acc_opl = 0;
+    if (MODE == 2) { acc_lsum = q[F_X0 * qs + rl]; acc_lpar = q[(F_X0 + 1) * qs + rl]; acc_opl = q[(F_X0 + 2) * qs + rl]; }
+    Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
+    if (FUSED) h = h_reg;
+    else {
+        const int64_t hs = P.hit.cap;
+        h.t = P.hit.d[rl]; h.n = mk3(P.hit.d[hs + rl], P.hit.d[2 * hs + rl], P.hit.d[3 * hs + rl]);
+        h.part = P.hit.part[rl];
+    }
+    const bool active = in_queue && q_beam >= 0;   // dead slots wait for the next compaction
+    const bool leader = active && r == 0;
+    int beam = q_beam;
+    if (!active) {   // the values a dead / absent lane carried before (they reach other lanes through the Gaussian shuffles)
+        pos = mk3(0, 0, 0); dir = mk3(0, 1, 0); rn = 1.0; lam = 0; beam = 0; seg = 0; pose = 0;
+        E0[0] = E0[1] = E0[2] = mkc(0, 0); acc_lsum = acc_lpar = acc_opl = 0;
+        h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
     }
     // retrace calls (K1r): how this wave's intersection was obtained, and the beam's retrace cursor
     int rflag = 0, pb = -1;
@@ -540,9 +551,12 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
     if (leader) {
         P.B.nseg[beam] = seg + 1;
         // bit 8: the reference's E0-orthogonality check (atol 1e-14) failed somewhere along this beam
-        const int old = P.B.status[beam];
-        const int wbit = (old & 0x100) | (((o1.valid && o1.warn) || (o2.valid && o2.warn)) ? 0x100 : 0);
-        P.B.status[beam] = ((nsucc != 1) ? status : (old & 0xff)) | wbit;
+        const bool warn = (o1.valid && o1.warn) || (o2.valid && o2.warn);
+        if (nsucc != 1 || warn) {   // a continuing beam without a new warning keeps its word: no read-modify-write
+            const int old = P.B.status[beam];
+            const int wbit = (old & 0x100) | (warn ? 0x100 : 0);
+            P.B.status[beam] = ((nsucc != 1) ? status : (old & 0xff)) | wbit;
+        }
     }
 
     // ---- successors ----
@@ -852,6 +866,70 @@ __global__ void __launch_bounds__(CBLOCK) compact_scatter(Queue src, Queue dst, 
         for (int f = 0; f < nf; f++) dst.d[f * ds + di] = src.d[f * ss + si];
 #pragma unroll
         for (int f = 0; f < NI_Q; f++) dst.i[f * ds + di] = src.i[f * ss + si];
+    }
+}
+
+// K3 in one launch (cooperative grid, one CTA slice per resident block): count the live units of the block's
+// contiguous slice, grid-wide barrier, own offset = sum of the lower blocks' counts (a few hundred values, L2
+// hits), then the order-preserving scatter row by row with warp ballots.  The alive flags are read twice (the
+// second time from L2), every surviving ray is read and written once: the same algorithmic traffic as the
+// three-kernel version without its two launch gaps and the single-block scan in between.
+__global__ void __launch_bounds__(CBLOCK) compact_fused(Queue src, Queue dst, int64_t n_slots, int64_t per, int R, int nf, int32_t* blk_cnt) {
+    namespace cg = cooperative_groups;
+    __shared__ int s_w[CBLOCK / 32];
+    __shared__ long long s_red[CBLOCK / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t ss = src.cap, ds = dst.cap;
+    const int64_t lo = (int64_t)blockIdx.x * per, hi = min(lo + per, n_slots);
+    const int32_t* alive = src.i + I_BEAM * ss;
+    int cnt = 0;
+    for (int64_t u = lo + threadIdx.x; u < hi; u += CBLOCK) cnt += alive[u * R] >= 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) s_w[warp] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int a = 0;
+        for (int k = 0; k < CBLOCK / 32; k++) a += s_w[k];
+        blk_cnt[blockIdx.x] = a;
+    }
+    cg::this_grid().sync();
+    long long part = 0;
+    for (int k = threadIdx.x; k < (int)blockIdx.x; k += CBLOCK) part += __ldcg(blk_cnt + k);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) s_red[warp] = part;
+    __syncthreads();
+    long long off = 0;
+    for (int k = 0; k < CBLOCK / 32; k++) off += s_red[k];
+    for (int64_t base = lo; base < hi; base += CBLOCK) {
+        const int64_t u = base + threadIdx.x;
+        const bool live = u < hi && alive[u * R] >= 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, live);
+        __syncthreads();                       // s_w of the previous row has been consumed
+        if (lane == 0) s_w[warp] = __popc(bal);
+        __syncthreads();
+        int woff = 0, row = 0;
+        for (int k = 0; k < CBLOCK / 32; k++) { if (k < warp) woff += s_w[k]; row += s_w[k]; }
+        if (live) {
+            const int64_t du = off + woff + __popc(bal & lanemask_lt());
+            for (int r = 0; r < R; r++) {
+                const int64_t si = u * R + r, di = du * R + r;
+                for (int f0 = 0; f0 < nf; f0 += 8) {
+                    double v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (f0 + k < nf) v[k] = src.d[(f0 + k) * ss + si];
+#pragma unroll
+                    for (int k = 0; k < 8; k++) if (f0 + k < nf) dst.d[(f0 + k) * ds + di] = v[k];
+                }
+                int w[NI_Q];
+#pragma unroll
+                for (int f = 0; f < NI_Q; f++) w[f] = src.i[f * ss + si];
+#pragma unroll
+                for (int f = 0; f < NI_Q; f++) dst.i[f * ds + di] = w[f];
+            }
+        }
+        off += row;
     }
 }
 
@@ -1440,7 +1518,7 @@ int32_t SubTrace::enqueue_chunk() {
         sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
         sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
         sp.rt = rt;
-        static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 6;   // tuning knob: resident blocks per SM the kernel is compiled for
+        static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 7;   // tuning knob: resident blocks per SM K1 is compiled for (C2: 4..8 measured, 7 = 72 registers is the fastest)
         // tuning knob: 0 never fuse, 1 fuse in pipelined (launch-bound) calls [default], 2 always fuse.  Measured on C2:
         // the fused kernel carries the interaction's registers through the march (0.282 vs 0.209 + 0.058 ms per
         // wave), so it only pays where the number of launches is what limits the call.
@@ -1500,6 +1578,8 @@ int32_t SubTrace::enqueue_chunk() {
                 if (!staged) intersect_wave<4, false, false><<<grid, IBLOCK, 0, st>>>(xp);
                 else if (minb <= 4) intersect_wave<4, true, false><<<grid, IBLOCK, smem, st>>>(xp);
                 else if (minb == 5) intersect_wave<5, true, false><<<grid, IBLOCK, smem, st>>>(xp);
+                else if (minb == 7) intersect_wave<7, true, false><<<grid, IBLOCK, smem, st>>>(xp);
+                else if (minb >= 8) intersect_wave<8, true, false><<<grid, IBLOCK, smem, st>>>(xp);
                 else intersect_wave<6, true, false><<<grid, IBLOCK, smem, st>>>(xp);
             }
             BMO_LAUNCH(ctx, "intersect_wave");
@@ -1559,12 +1639,35 @@ int32_t SubTrace::finish_chunk() {
         const int64_t want = has_splitter ? 2 * alive * R : alive * R;
         if (next.cap < want) { free_queue(next, st); if ((rc = alloc_queue(next, want, nfq, NI_Q, st))) return rc; }
         BMO_CUDA(cudaEventRecord(evs0, st));
-        compact_count<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur.i, cur.cap, n_slots, R, blk_cnt);
-        BMO_LAUNCH(ctx, "compact_count");
-        scan_counts<<<1, 1024, 0, st>>>(blk_cnt, cblocks, 1, 1, blk_off, d_scan_tot);
-        BMO_LAUNCH(ctx, "scan_counts");
-        compact_scatter<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur, next, n_slots, R, nfq, blk_off);
-        BMO_LAUNCH(ctx, "compact_scatter");
+        // one cooperative launch (BMO_COMPACT=0: the three-kernel version, also the fallback if the device refuses)
+        static const bool fused_ok = !(getenv("BMO_COMPACT") && atoi(getenv("BMO_COMPACT")) == 0);
+        static int coop_blocks = -1;   // blocks of compact_fused that are resident at once on this device
+        if (coop_blocks < 0) {
+            int per_sm = 0, sms = 0, coop = 0;
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, compact_fused, CBLOCK, 0);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+            cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device);
+            coop_blocks = coop ? per_sm * sms : 0;
+        }
+        bool done = false;
+        if (fused_ok && coop_blocks > 0) {
+            int64_t nb = std::min<int64_t>(coop_blocks, cblocks);
+            int64_t per = ((n_slots + nb - 1) / nb + CBLOCK - 1) / CBLOCK * CBLOCK;   // slots per block, whole rows
+            nb = (n_slots + per - 1) / per;
+            int R_ = R, nf_ = nfq;
+            int64_t ns_ = n_slots;
+            void* args[] = {&cur, &next, &ns_, &per, &R_, &nf_, &blk_cnt};
+            if (cudaLaunchCooperativeKernel((const void*)compact_fused, dim3((unsigned)nb), dim3(CBLOCK), args, 0, st) == cudaSuccess) done = true;
+            else cudaGetLastError();
+        }
+        if (!done) {
+            compact_count<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur.i, cur.cap, n_slots, R, blk_cnt);
+            BMO_LAUNCH(ctx, "compact_count");
+            scan_counts<<<1, 1024, 0, st>>>(blk_cnt, cblocks, 1, 1, blk_off, d_scan_tot);
+            BMO_LAUNCH(ctx, "scan_counts");
+            compact_scatter<<<(unsigned)cblocks, CBLOCK, 0, st>>>(cur, next, n_slots, R, nfq, blk_off);
+            BMO_LAUNCH(ctx, "compact_scatter");
+        } else BMO_LAUNCH(ctx, "compact_fused");
         BMO_CUDA(cudaEventRecord(evs1, st));
         BMO_CUDA(cudaStreamSynchronize(st));
         float sms = 0;

@@ -460,7 +460,7 @@ def bench_compaction(m, L, dev, dsys, n, hbm_peak):
         if it and c["scatter_ms"] > 0:
             gbs = c["scatter_bytes"] / (c["scatter_ms"] * 1e-3) / 1e9
             best = gbs if best is None else max(best, gbs)
-    return {"bound": "hbm", "kernel": "compact_count + scan_counts + compact_scatter", "achieved": best, "peak": hbm_peak, "unit": "GB/s",
+    return {"bound": "hbm", "kernel": "compact_fused (one cooperative launch: count, grid barrier, offsets, scatter)", "achieved": best, "peak": hbm_peak, "unit": "GB/s",
             "frac": (best / hbm_peak) if best else None, "peak_source": "MEASURED_PEAKS.json hbm_gbs",
             "workload": "C2 doublet with an overfilled pupil (40 mm disc): one compaction of the 2^20-slot queue to the ~40 % live rays"}
 
