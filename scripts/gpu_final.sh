@@ -8,7 +8,9 @@ python bench.py --steps 10 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_o
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/${TAG}_ncu1.log 2>&1; echo "launch list rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"intersect_wave|interact_wave" -s 24 -c 8 -f -o /tmp/${TAG}_trace python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-detector --no-extras > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu trace rc=$?"
 python scripts/ncu_summary.py /tmp/${TAG}_trace.ncu-rep gpurun_out/${TAG}_ncu_trace_kernels.txt > /dev/null
-ncu --set full --clock-control none -k regex:"pd_field_fast|compact_scatter|psf_intensity_kernel|retrace_intersect_wave" -c 8 -f -o /tmp/${TAG}_pd python bench.py --steps 2 --warmup 3 --no-cpu-baseline --c3-side 16 > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu pd/psf/retrace rc=$?"
+ncu --set full --clock-control none -k regex:"pd_field_fast|psf_intensity_kernel|retrace_intersect_wave" -c 8 -f -o /tmp/${TAG}_pd python bench.py --steps 2 --warmup 3 --no-cpu-baseline --c3-side 16 > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu pd/psf/retrace rc=$?"
 python scripts/ncu_summary.py /tmp/${TAG}_pd.ncu-rep gpurun_out/${TAG}_ncu_pd_psf_retrace.txt > /dev/null
+ncu --set full --clock-control none -k regex:"compact_fused" -c 8 -f -o /tmp/${TAG}_k3 python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-detector --no-extras > gpurun_out/${TAG}_ncu4.log 2>&1; echo "ncu compaction rc=$?"
+python scripts/ncu_summary.py /tmp/${TAG}_k3.ncu-rep gpurun_out/${TAG}_ncu_compaction.txt > /dev/null
 ls -la /tmp/${TAG}_*.ncu-rep
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm --format=csv,noheader; nproc
