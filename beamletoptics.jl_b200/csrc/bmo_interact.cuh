@@ -100,6 +100,30 @@ struct RayOut {
     Cx E0[3];
 };
 
+// Lenses.jl:46-77 for a plain Ray, inlined: the out-of-line interact_refractive below takes its result by reference,
+// which pins the caller's RayOut (and the E0 array it is handed) to local memory; plain rays and Gaussian triples
+// (K2 MODE 0 / 2) keep everything in registers with this copy of its non-polarised branch (same operations, same order).
+BMO_D void interact_refractive_plain(V3 rpos, V3 rdir, double rn, double t, V3 nrm, double n_opt, double n_sys, int self_part, RayOut& o) {
+    V3 normal = nrm;
+    double n1, n2;
+    o.hint = -1;
+    o.err = false; o.warn = false;
+    o.valid = true;
+    o.pos = rpos + t * rdir;
+    if (dot(rdir, nrm) < 0) { n1 = rn; n2 = n_opt; o.hint = self_part; }
+    else { n1 = n_opt; n2 = n_sys; normal = -normal; }
+    bool tir;
+    o.dir = refraction3d(rdir, normal, n1, n2, tir, o.err);
+    if (tir) { o.hint = self_part; n2 = n_opt; }
+    o.n = n2;
+}
+// Mirrors.jl:39-48 for a plain Ray, inlined for the same reason
+BMO_D void interact_mirror_plain(V3 rpos, V3 rdir, double rn, double t, V3 nrm, RayOut& o) {
+    o.valid = true; o.err = false; o.warn = false; o.hint = -1;
+    o.pos = rpos + t * rdir;
+    o.dir = reflection3d(rdir, nrm);
+    o.n = rn;
+}
 // OpticalComponents/Lenses.jl:46-126  (n_opt = refractive_index(optic, lambda))
 BMO_NI void interact_refractive(V3 rpos, V3 rdir, double rn, const Cx* rE0, bool polarized, double t, V3 nrm, double n_opt,
                                double n_sys, int self_part, RayOut& o) {

@@ -399,29 +399,40 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
         const bool pol = MODE == 1;
         const double t = h.t;
         bool split = false;
+        // Plain rays and Gaussian triples (MODE 0 / 2) take the inlined interactions; whatever is out of line writes into
+        // temporaries, so that o1 / o2 / E0 never have their address taken on this path and stay in registers.
+        const auto n_of_hit = [&]() { return S.n_table[pt.n_row * S.n_lambda + lam]; };   // only refractive parts have a row
+        RayOut ta, tb;
+        ta.valid = tb.valid = false; ta.err = tb.err = false; ta.warn = tb.warn = false; ta.hint = tb.hint = -1;
+        Cx Et[3];
+        if (pol) { Et[0] = E0[0]; Et[1] = E0[1]; Et[2] = E0[2]; }
         switch (ob.kind) {
             case BMO_OBJ_REFRACTIVE:
-                interact_refractive(pos, dir, rn, E0, pol, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                if (pol) { interact_refractive(pos, dir, rn, Et, true, t, h.n, n_of_hit(), S.n_system, hit_part, ta); o1 = ta; }
+                else interact_refractive_plain(pos, dir, rn, t, h.n, n_of_hit(), S.n_system, hit_part, o1);
                 break;
             case BMO_OBJ_DOUBLET:      // DoubletLenses.jl:66-76 (Ray only; a PolarizedRay has no method -> nothing)
                 if (pol) break;
-                interact_refractive(pos, dir, rn, E0, false, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                interact_refractive_plain(pos, dir, rn, t, h.n, n_of_hit(), S.n_system, hit_part, o1);
                 o1.hint = ob.first_part + (1 - (hit_part - ob.first_part));
                 break;
             case BMO_OBJ_MIRROR:
-                interact_mirror(pos, dir, rn, E0, pol, t, h.n, o1);
+                if (pol) { interact_mirror(pos, dir, rn, Et, true, t, h.n, ta); o1 = ta; }
+                else interact_mirror_plain(pos, dir, rn, t, h.n, o1);
                 break;
             case BMO_OBJ_CUBE_BS:      // CubeBeamsplitter.jl:63-121
                 if (pt.role == BMO_ROLE_COATING) split = true;
                 else {
-                    interact_refractive(pos, dir, rn, E0, pol, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                    if (pol) { interact_refractive(pos, dir, rn, Et, true, t, h.n, n_of_hit(), S.n_system, hit_part, ta); o1 = ta; }
+                    else interact_refractive_plain(pos, dir, rn, t, h.n, n_of_hit(), S.n_system, hit_part, o1);
                     o1.hint = ob.first_part + 2;
                 }
                 break;
             case BMO_OBJ_PLATE_BS:     // PlateBeamsplitter.jl:189-275
                 if (pt.role == BMO_ROLE_COATING) split = true;
                 else {
-                    interact_refractive(pos, dir, rn, E0, pol, t, h.n, S.n_table[pt.n_row * S.n_lambda + lam], S.n_system, hit_part, o1);
+                    if (pol) { interact_refractive(pos, dir, rn, Et, true, t, h.n, n_of_hit(), S.n_system, hit_part, ta); o1 = ta; }
+                    else interact_refractive_plain(pos, dir, rn, t, h.n, n_of_hit(), S.n_system, hit_part, o1);
                     o1.hint = ob.first_part + 1;
                 }
                 break;
@@ -431,7 +442,8 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
             case BMO_OBJ_POLFILTER: {   // PolarizationFilter.jl:31-47 (PolarizedRay only; other beams: no method -> nothing)
                 if (!pol) break;
                 const double* dp = S.det_pose + 12 * ((int64_t)pose * S.n_objects + pt.object);
-                interact_polfilter(pos, dir, rn, E0, t, dp + 3, S.jones + 10 * (int64_t)ob.pd_n, o1);
+                interact_polfilter(pos, dir, rn, Et, t, dp + 3, S.jones + 10 * (int64_t)ob.pd_n, ta);
+                o1 = ta;
                 break;
             }
             case BMO_OBJ_SPOTDETECTOR: {  // Spotdetector.jl:50-61
@@ -447,7 +459,8 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
             default: break;  // Photodetector (field added by bmo_pd_accumulate), IntersectableObject
         }
         if (split) {
-            bs_children(pos, dir, E0, pol, t, h.n, pt.reflectance, pt.transmittance, o1, o2);
+            bs_children(pos, dir, Et, pol, t, h.n, pt.reflectance, pt.transmittance, ta, tb);
+            o1 = ta; o2 = tb;
             if (ob.kind == BMO_OBJ_CUBE_BS) {          // CubeBeamsplitter.jl:80-82,110-112
                 const double ng = S.n_table[S.parts[ob.first_part].n_row * S.n_lambda + lam];
                 o1.n = ng; o2.n = ng;
