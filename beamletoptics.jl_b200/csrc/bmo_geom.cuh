@@ -615,15 +615,21 @@ template <bool RK> BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos
         sh.cx = bnd[0]; sh.cy = bnd[1]; sh.cz = bnd[2]; sh.R2 = bnd[3] * bnd[3];
         if (RK && (C.prims[pt.first].reserved & 2)) {       // bit 1: the union has cylindrical / aspheric members
             unsigned ns = 0;
-            const bool hit = sdf_intersect_rare(sh, pos, dir, ns, t, n);
+            double tm = 0.0; V3 nm = mk3(0, 0, 0);
+            const bool hit = sdf_intersect_rare(sh, pos, dir, ns, tm, nm);
             st.sdf += ns;
+            t = tm; n = nm;
             return hit;
         }
         return sdf_intersect_t<false>(sh, pos, dir, st.sdf, t, n);
     }
+    // results through temporaries: the out-of-line callee takes references, and t / n of the caller (shared with the
+    // SDF path) must not have their address taken or they live in local memory for every part
     Stats tmp; tmp.sdf = 0; tmp.tri = 0;
-    const bool hit = mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, t, n);
+    double tm = 0.0; V3 nm = mk3(0, 0, 0);
+    const bool hit = mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, tm, nm);
     st.tri += tmp.tri;
+    t = tm; n = nm;
     return hit;
 }
 // slab test of the ray (t >= 0) against an axis-aligned box, entry distance compared with t_best
