@@ -64,7 +64,9 @@ struct bmo_sys {
     // high-water marks of earlier branching traces, keyed by (mode, root beams): queue units, beams and scratch
     // units the call ended with.  The next call of the same shape allocates them up front (no growth copies,
     // identical request sizes for the pool).
-    struct TraceHint { int64_t slots = 0, beams = 0, scr = 0; };
+    // first_chunk (splitter-free systems): waves to enqueue before the first look at the device -- 1 until a call of this
+    // shape has shown that (almost) nobody dies on the first wave, then 4 (no early compaction decision to take).
+    struct TraceHint { int64_t slots = 0, beams = 0, scr = 0; int first_chunk = 1; };
     std::map<std::pair<int, int64_t>, TraceHint> hints;
 };
 

@@ -1433,6 +1433,8 @@ struct SubTrace {
     cudaEvent_t evs0 = nullptr, evs1 = nullptr;
     int64_t n_slots = 0, alive = 0, n_beams = 0;
     int wave = 0, waves_done = 0, launched = 0, slot = 0;
+    int first_chunk = 1;                   // waves before the first look (bmo_sys::TraceHint)
+    int64_t alive_after_w0 = -1;           // units alive after the first wave (feeds the hint)
     int32_t* spot_obj_out = nullptr; double* spot_xz_out = nullptr;   // host destinations of the Spotdetector hits (optional)
     double host_wait_ms = 0;
     RetraceView rt;                        // retrace calls: the previous solution
@@ -1493,7 +1495,7 @@ int32_t SubTrace::enqueue_chunk() {
     // waves per look at the device: 1 (most rays that miss everything die on the first wave, so the
     // compaction decision is worth an early look), then 3, then 4, 4, ...
     // (pipelined sub-batches enqueue 4 at once: an idle stream costs more than a late compaction)
-    const int chunk = has_splitter ? 1 : (pipelined ? 4 : (wave == 0 ? 1 : (wave == 1 ? 3 : 4)));
+    const int chunk = has_splitter ? 1 : (pipelined ? 4 : (wave == 0 ? first_chunk : (wave == 1 ? 3 : 4)));
     for (int c = 0; c < chunk; c++) {
         const int64_t nblocks = (n_slots + units - 1) / units;
         if (has_splitter) {
@@ -1617,6 +1619,7 @@ int32_t SubTrace::finish_chunk() {
     BMO_CUDA(cudaStreamSynchronize(st));
     host_wait_ms += tnow_ms() - tw0;
     int64_t prev_alive = alive;
+    if (wave == launched) alive_after_w0 = (int64_t)h_wtot[0];   // this chunk began with wave 0
     for (int c = 0; c < launched; c++) {
         if (prev_alive > 0) {       // waves launched on an already empty queue are no-ops and not counted
             float kms = 0;
@@ -1764,6 +1767,10 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         s.spot_obj_out = spot_obj_out; s.spot_xz_out = spot_xz_out;
         if (prev_rt) s.rt = *prev_rt;
         if (k > 0) BMO_CUDA(cudaStreamWaitEvent(s.st, ev_fork, 0));
+        if (!has_splitter && n_sub == 1 && !prev_rt) {
+            auto it = sys->hints.find({mode, n});
+            if (it != sys->hints.end()) s.first_chunk = it->second.first_chunk;
+        }
         if ((rc = s.begin(in_h))) return rc;
         s.n_beams = n;
         if (has_splitter) {     // sizes the previous call of this shape ended with (see bmo_sys::hints)
@@ -1802,6 +1809,8 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     ctx->waves += wave;
     res->n_beams = has_splitter ? subs[0].n_beams : n;
     res->waves = wave;
+    if (!has_splitter && n_sub == 1 && !prev_rt && subs[0].alive_after_w0 >= 0)   // would the look after wave 0 have compacted?
+        sys->hints[{mode, n}].first_chunk = (2 * subs[0].alive_after_w0 > n || n < 4096) ? 4 : 1;
     if (has_splitter) {
         bmo_sys::TraceHint& hh = sys->hints[{mode, n}];
         hh.slots = std::max(hh.slots, subs[0].cur.cap / R); hh.scr = std::max(hh.scr, subs[0].scr.cap); hh.beams = std::max(hh.beams, res->cap_beams);

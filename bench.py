@@ -131,6 +131,10 @@ def main():
         run_reference(args, rank)
         return
 
+    # stdout carries exactly one JSON line: native libraries that print to fd 1 (NCCL's version banner) go to stderr
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -271,7 +275,8 @@ def main():
             out.update(extras)
         if not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(out))
+        print(json.dumps(out), file=json_out)
+        json_out.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
