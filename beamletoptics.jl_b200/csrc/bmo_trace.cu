@@ -1072,7 +1072,7 @@ int32_t bmo_init(int32_t device, bmo_ctx** out) {
     BMO_CUDA(cudaMalloc((void**)&c->d_counters, sizeof(DevCounters)));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     BMO_CUDA(cudaMalloc((void**)&c->d_totals, 4 * sizeof(long long)));
-    BMO_CUDA(cudaMallocHost((void**)&c->h_totals, 8 * 9 * sizeof(long long)));   // scans + 8 sub-batch slots
+    BMO_CUDA(cudaMallocHost((void**)&c->h_totals, 8 * 10 * sizeof(long long)));   // scans + 8 sub-batch slots + the device counters
     cudaMemPool_t pool;
     BMO_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t thr = UINT64_MAX;  // keep freed blocks cached: the wave loop reuses them every call
@@ -1609,6 +1609,8 @@ int32_t SubTrace::enqueue_chunk() {
         if (wave > r_max + 1) break;
     }
     BMO_CUDA(cudaMemcpyAsync(h_wtot, d_wtot + 2 * (wave - launched), (size_t)2 * launched * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+    // single-stream calls: the cumulative counters ride along, so that the call needs no blocking read-back at its end
+    if (!pipelined) BMO_CUDA(cudaMemcpyAsync(ctx->h_totals + 72, ctx->d_counters, sizeof(DevCounters), cudaMemcpyDeviceToHost, st));
     return BMO_OK;
 }
 
@@ -1845,7 +1847,8 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     ctx->trace_ms = ms;
     {
         DevCounters h;
-        BMO_CUDA(cudaMemcpy(&h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
+        if (n_sub == 1) memcpy(&h, ctx->h_totals + 72, sizeof(h));   // copied behind the last chunk of waves (enqueue_chunk), stream synchronised since
+        else BMO_CUDA(cudaMemcpy(&h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
         res->interactions = (int64_t)h.interactions - ctx->interactions_seen;  // the counter is cumulative since the last reset
         ctx->interactions_seen = (int64_t)h.interactions;
     }
