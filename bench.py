@@ -32,8 +32,9 @@ CPU_SAMPLE = 1 << 14
 # algorithmic FP64 work per unit (SURVEY 8(d) cost table): primitive SDF eval 45, triangle test 40, interaction 60
 FLOP_SDF, FLOP_TRI, FLOP_INT = 45.0, 40.0, 60.0
 # intersect_wave, 2^20 rays per launch: dram__bytes_read.sum + dram__bytes_write.sum, mean over the 4 waves of one C2 solve
-# (ncu --set full, profiles/r01r_ncu_intersect_wave_after_member_skipping.txt): 70.6 MB read + 71.2 MB written
-K1_DRAM_BYTES_PER_LAUNCH = 141.8e6
+# (ncu --set full, profiles/r01s4_ncu_trace_kernels.txt): 68.1 MB read + 89.0 MB written (the excess over the algorithmic 36 MB of
+# writes is register-spill lines evicted from L1)
+K1_DRAM_BYTES_PER_LAUNCH = 157.0e6
 
 
 def rays_for_rank(rank, n=N_RAYS):
@@ -259,9 +260,9 @@ def main():
             "roofline": {"bound": "fp64", "kernel": "intersect_wave", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 waves of one solve, from the
-                         # ncu --set full capture summarised in profiles/r01r_ncu_intersect_wave_after_member_skipping.txt
+                         # ncu --set full capture summarised in profiles/r01s4_ncu_trace_kernels.txt
                          "traffic": K1_DRAM_BYTES_PER_LAUNCH * n / N_RAYS, "traffic_algorithmic": 100.0 * n,
-                         "traffic_source": "profiles/r01r_ncu_intersect_wave_after_member_skipping.txt (2^20 rays per launch; algorithmic = 64 B ray state read + 36 B hit record written per ray)",
+                         "traffic_source": "profiles/r01s4_ncu_trace_kernels.txt (mean of the 4 waves, 2^20 rays per launch; algorithmic = 64 B ray state read + 36 B hit record written per ray)",
                          "peak_source": "measured here: DFMA probe (bmo_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": flops / k1_n, "ms_per_launch": k1_ms / k1_n,
                          "share_of_step": k1_ms / n_total_steps / (tot_ms / args.steps) if tot_ms else None,
