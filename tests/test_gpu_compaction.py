@@ -54,3 +54,31 @@ def test_compaction_gaussian_triples_field(bmo, orc):
     assert np.abs(ref).max() > 0
     err = float(np.linalg.norm((sc["pd"].field - ref).ravel()) / np.linalg.norm(ref.ravel()))
     assert err <= FIELD_TOL, err
+
+
+@pytest.mark.gpu
+def test_late_look_after_a_full_bundle_is_result_identical(bmo, orc):
+    """A splitter-free system that saw a bundle in which nobody died enqueues 4 waves before its first look at the device
+    (bmo_sys::TraceHint::first_chunk, kept with the uploaded system).  A later bundle of the same size that does lose most
+    of its rays on the first wave is then compacted late or not at all: the hit points must not depend on that."""
+    n = 8192
+    sc, osc = scenes.doublet_spot(bmo), scenes.doublet_spot_oracle()
+    dsys = bmo.upload_system(sc["system"], [707e-9])
+    lam = np.zeros(n, dtype=np.int32)
+    pos, d = scenes.fibonacci_disc(n)                          # fills 20 of the 25.4 mm: every ray reaches the detector
+    res0 = bmo.trace_rays(dsys, pos, d, lam)
+    assert res0.interactions == 4 * n
+    res0.free()
+    pos2, _ = scenes.fibonacci_disc(n, diameter=40e-3)
+    pos2 = np.ascontiguousarray(pos2[np.random.default_rng(11).permutation(n)])
+    ref = orc.bulk_trace_rays(osc["system"], pos2, d, 707e-9, max_seg=8, spot=osc["spot"])
+    rsel = np.concatenate([ref["seg"][i, :ref["nseg"][i]] for i in range(n)])
+    for _ in range(2):                                         # with the hint left by res0, then with the hint this call leaves
+        res = bmo.trace_rays(dsys, pos2, d, lam)
+        beams, seg = res.beams(), res.segments()
+        assert res.interactions == ref["interactions"]
+        assert np.array_equal(beams["nseg"], ref["nseg"])
+        rows = np.concatenate([beams["first"][i] + np.arange(beams["nseg"][i]) for i in range(n)])
+        assert np.array_equal(seg["pos"][rows], rsel[:, 0:3])
+        assert np.array_equal(seg["t"][rows], rsel[:, 7])
+        res.free()
