@@ -294,7 +294,9 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(co
 // ---- K2: interact + block-local compaction ----------------------------------------------------------
 // The body is shared by the stand-alone kernel (hit records read from the buffer K1 wrote) and by the
 // fused kernel of splitter-free plain-ray systems (hit still in registers, FUSED = true).
-template <int MODE, bool FUSED>
+// NS: the system has no beamsplitter (host-side fact): no spawn events, so the block-level numbering of children, its two
+// barriers and the scratch queue are compiled out and the units alive after the wave are counted per warp.
+template <int MODE, bool FUSED, bool NS = false>
 BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_off = 0) {
     constexpr int R = Cfg<MODE>::R;
     constexpr int UNITS = Cfg<MODE>::UNITS;
@@ -458,7 +460,7 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
             }
             default: break;  // Photodetector (field added by bmo_pd_accumulate), IntersectableObject
         }
-        if (split) {
+        if (!NS && split) {
             bs_children(pos, dir, Et, pol, t, h.n, pt.reflectance, pt.transmittance, ta, tb);
             o1 = ta; o2 = tb;
             if (ob.kind == BMO_OBJ_CUBE_BS) {          // CubeBeamsplitter.jl:80-82,110-112
@@ -579,22 +581,32 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
     //             prefix sums), spawn_children numbers them deterministically and puts the transmitted
     //             child into the parent's slot, the reflected child at the tail of the queue.
     const unsigned full = 0xffffffffu;
-    const unsigned b2 = __ballot_sync(full, leader && nsucc == 2);
-    const unsigned lt = lanemask_lt();
-    int wsoff = __popc(b2 & lt);                     // spawn events of lower lanes
-    const unsigned alive = __popc(__ballot_sync(full, leader && nsucc >= 1)) + __popc(b2);
-    if (lane == 0) { s_wcnt[warp][0] = (int)alive; s_wcnt[warp][1] = __popc(b2); }
-    const unsigned ia = __popc(__ballot_sync(full, interacted));
-    if (lane == 0 && ia) atomicAdd(&P.counters->interactions, (unsigned long long)ia);
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int a = 0, b = 0;
-        for (int k = 0; k < NWARP; k++) { s_woff[k][1] = b; a += s_wcnt[k][0]; b += s_wcnt[k][1]; }
-        P.blk_cnt[blockIdx.x] = b;
-        if (a) atomicAdd(P.wave_totals + 2 * wave_off, (unsigned long long)a);        // units alive in the next wave
-        if (b) atomicAdd(P.wave_totals + 2 * wave_off + 1, (unsigned long long)b);    // spawn events
+    int wsoff = 0;
+    if (NS) {
+        const unsigned alive = __popc(__ballot_sync(full, leader && nsucc >= 1));
+        const unsigned ia = __popc(__ballot_sync(full, interacted));
+        if (lane == 0) {
+            if (ia) atomicAdd(&P.counters->interactions, (unsigned long long)ia);
+            if (alive) atomicAdd(P.wave_totals + 2 * wave_off, (unsigned long long)alive);   // units alive in the next wave
+        }
+    } else {
+        const unsigned b2 = __ballot_sync(full, leader && nsucc == 2);
+        const unsigned lt = lanemask_lt();
+        wsoff = __popc(b2 & lt);                     // spawn events of lower lanes
+        const unsigned alive = __popc(__ballot_sync(full, leader && nsucc >= 1)) + __popc(b2);
+        if (lane == 0) { s_wcnt[warp][0] = (int)alive; s_wcnt[warp][1] = __popc(b2); }
+        const unsigned ia = __popc(__ballot_sync(full, interacted));
+        if (lane == 0 && ia) atomicAdd(&P.counters->interactions, (unsigned long long)ia);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int a = 0, b = 0;
+            for (int k = 0; k < NWARP; k++) { s_woff[k][1] = b; a += s_wcnt[k][0]; b += s_wcnt[k][1]; }
+            P.blk_cnt[blockIdx.x] = b;
+            if (a) atomicAdd(P.wave_totals + 2 * wave_off, (unsigned long long)a);        // units alive in the next wave
+            if (b) atomicAdd(P.wave_totals + 2 * wave_off + 1, (unsigned long long)b);    // spawn events
+        }
+        __syncthreads();
     }
-    __syncthreads();
     if (MODE == 2) wsoff = __shfl_sync(full, wsoff, base);
     if (active) {
         int32_t* qi = P.cur.i;
@@ -614,7 +626,7 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
         } else {
             qi[I_BEAM * qs + ri] = -1;
         }
-        if (nsucc == 2) {
+        if (!NS && nsucc == 2) {
             const int64_t ss = P.scr.cap;
             const int lspawn = s_woff[warp][1] + wsoff;
             for (int k = 0; k < 2; k++) {
@@ -649,10 +661,10 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
 #ifndef KMINB0
 #define KMINB0 6
 #endif
-template <int MODE>
+template <int MODE, bool NS = false>
 __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, MODE == 0 ? KMINB0 : 1) interact_wave(const StepParams P) {
     Hit none; none.part = -1; none.t = INFINITY; none.n = mk3(0, 0, 0);
-    interact_body<MODE, false>(P, none);
+    interact_body<MODE, false, NS>(P, none);
 }
 
 // ---- K1+K2 fused: plain rays through a system without beamsplitters (the sequential lens-stack path) --
@@ -710,7 +722,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
             if (budget) h = tracing_step<RK>(C, pos, dir, hint, st);
         }
         sd += st.sdf; tr += st.tri;
-        interact_body<0, true>(P, h, w);
+        interact_body<0, true, true>(P, h, w);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
@@ -1577,7 +1589,11 @@ int32_t SubTrace::enqueue_chunk() {
 #undef BMO_RETRACE_LAUNCH
             BMO_LAUNCH(ctx, "retrace_intersect_wave");
             BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
-            if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+            if (!has_splitter) {
+                if (mode == 0) interact_wave<0, true><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+                else if (mode == 1) interact_wave<1, true><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
+                else interact_wave<2, true><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
+            } else if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
             else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
             else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
             BMO_LAUNCH(ctx, "interact_wave");
@@ -1599,7 +1615,11 @@ int32_t SubTrace::enqueue_chunk() {
             }
             BMO_LAUNCH(ctx, "intersect_wave");
             BMO_CUDA(cudaEventRecord(ev[2 * c + 1], st));
-            if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+            if (!has_splitter) {
+                if (mode == 0) interact_wave<0, true><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
+                else if (mode == 1) interact_wave<1, true><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
+                else interact_wave<2, true><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
+            } else if (mode == 0) interact_wave<0><<<(unsigned)nblocks, Cfg<0>::BLOCK, 0, st>>>(sp);
             else if (mode == 1) interact_wave<1><<<(unsigned)nblocks, Cfg<1>::BLOCK, 0, st>>>(sp);
             else interact_wave<2><<<(unsigned)nblocks, Cfg<2>::BLOCK, 0, st>>>(sp);
             BMO_LAUNCH(ctx, "interact_wave");
