@@ -40,6 +40,7 @@ struct bmo_ctx {
     int64_t waves = 0, launches = 0, px_beamlets = 0, psf_pairs = 0;
     double psf_ms = 0;
     double trace_ms = 0, pd_ms = 0;
+    int64_t pool_slack = 0;   // bytes by which bmo_retrace has grown the stream-ordered pool beyond its own needs (see there)
     int sm_count = 148;
 };
 
@@ -92,6 +93,7 @@ struct bmo_result {
     bool keep = false;
     // per-beam tables (device), capacity cap_beams
     int64_t cap_beams = 0;
+    void* beam_slab = nullptr;    // splitter-free traces: the per-beam tables below are carved out of one allocation
     int32_t *parent = nullptr, *slot = nullptr, *nseg = nullptr, *status = nullptr, *lam = nullptr, *pose = nullptr;
     double *w0 = nullptr, *e0 = nullptr, *plen = nullptr, *popl = nullptr;
     int32_t* spot_obj = nullptr;  // [cap_beams * R]

@@ -1350,8 +1350,28 @@ template <class T> static int32_t grow(T*& p, int64_t old_n, int64_t new_n, cuda
     p = np_;
     return BMO_OK;
 }
+// Per-beam tables of a trace that cannot add beams (no beamsplitter in the system): one allocation instead of 8-12.
+static int32_t alloc_beams_slab(bmo_result* r, int64_t n, cudaStream_t st) {
+    const int64_t R = r->R;
+    auto pad = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t b_xz = pad((size_t)n * R * 2 * 8), b_d = r->mode == 2 ? pad((size_t)n * 8) : 0, b_i = pad((size_t)n * 4), b_so = pad((size_t)n * R * 4);
+    const size_t total = b_xz + (r->mode == 2 ? 3 * b_d + pad((size_t)n * 16) : 0) + 6 * b_i + b_so;
+    unsigned char* p = nullptr;
+    BMO_CUDA(dev_alloc(&p, total, st));
+    r->beam_slab = p;
+    auto take = [&](size_t b) { unsigned char* q = p; p += b; return q; };
+    r->spot_xz = (double*)take(b_xz);
+    if (r->mode == 2) {
+        r->w0 = (double*)take(b_d); r->plen = (double*)take(b_d); r->popl = (double*)take(b_d); r->e0 = (double*)take(pad((size_t)n * 16));
+    }
+    r->parent = (int32_t*)take(b_i); r->slot = (int32_t*)take(b_i); r->nseg = (int32_t*)take(b_i); r->status = (int32_t*)take(b_i);
+    r->lam = (int32_t*)take(b_i); r->pose = (int32_t*)take(b_i); r->spot_obj = (int32_t*)take(b_so);
+    r->cap_beams = n;
+    return BMO_OK;
+}
 static int32_t ensure_beams(bmo_result* r, int64_t need, cudaStream_t st) {
     if (need <= r->cap_beams) return BMO_OK;
+    if (r->beam_slab) return fail(BMO_ESTATE, "trace: a splitter-free trace asked for more beams than it started with");
     int64_t nc = std::max<int64_t>(need, r->cap_beams + r->cap_beams / 2);
     const int64_t oc = r->cap_beams, R = r->R;
     int32_t rc;
@@ -1753,13 +1773,12 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     const double tp0 = tnow_ms();
     BMO_CUDA(cudaEventRecord(ctx->ev0, st));
     int32_t rc;
-    if ((rc = ensure_beams(res, n, st))) return rc;
-
     // Beamsplitters are the only objects that add beams: without them the queue never grows, the
     // continuing rays are updated in place and the host only looks at the device every few waves.
     bool has_splitter = false;
     for (const bmo_object& ob : sys->objects)
         has_splitter |= ob.kind == BMO_OBJ_THIN_BS || ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_CUBE_BS;
+    if ((rc = has_splitter ? ensure_beams(res, n, st) : alloc_beams_slab(res, n, st))) return rc;
     const SysView& V = sys->view;
     const size_t table_bytes = (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double));
     const bool staged = V.n_poses == 1 && table_bytes <= 40 * 1024;
@@ -1919,6 +1938,20 @@ int32_t bmo_retrace(bmo_sys* sys, bmo_result* prev, int32_t r_max, uint32_t flag
     if ((rc = ensure_first_seg(prev))) return rc;
     const int mode = prev->mode, R = prev->R;
     const int64_t n = prev->n_roots;
+    // A retrace allocates the same buffers as a fresh trace plus its own temporaries (root rays, child table) while the
+    // previous solution is still alive.  In a pool that holds just enough memory for the fresh trace these extra requests
+    // shift every later one onto blocks that have to be split / remapped: cudaMallocAsync then takes milliseconds, erratically
+    // (measured: 3.5 - 22 ms per call against 2.5 ms, pool size constant).  Growing the pool once by the footprint of a
+    // call (allocate + free; the release threshold keeps it) gives the allocator the slack it needs.
+    {
+        const int64_t want = (int64_t)n * R * 1024;
+        if (ctx->pool_slack < want) {
+            void* w = nullptr;
+            if (cudaMallocAsync(&w, (size_t)want, st) == cudaSuccess) cudaFreeAsync(w, st);
+            else cudaGetLastError();
+            ctx->pool_slack = want;
+        }
+    }
     PrevRoots pr{};
     pr.seg_d = prev->seg_d; pr.first_seg = prev->first_seg; pr.rows = prev->seg_rows; pr.lam = prev->lam; pr.pose = prev->pose;
     pr.w0 = prev->w0; pr.e0 = prev->e0; pr.n = n; pr.mode = mode;
@@ -2039,9 +2072,13 @@ int32_t bmo_result_free(bmo_result* r) {
     if (!r) return BMO_OK;
     cudaSetDevice(r->ctx->device);
     cudaStream_t st = r->ctx->stream;
-    dev_free(r->parent, st); dev_free(r->slot, st); dev_free(r->nseg, st); dev_free(r->status, st); dev_free(r->lam, st); dev_free(r->pose, st);
-    dev_free(r->w0, st); dev_free(r->e0, st); dev_free(r->plen, st); dev_free(r->popl, st);
-    dev_free(r->spot_obj, st); dev_free(r->spot_xz, st); dev_free(r->first_seg, st);
+    if (r->beam_slab) dev_free(r->beam_slab, st);
+    else {
+        dev_free(r->parent, st); dev_free(r->slot, st); dev_free(r->nseg, st); dev_free(r->status, st); dev_free(r->lam, st); dev_free(r->pose, st);
+        dev_free(r->w0, st); dev_free(r->e0, st); dev_free(r->plen, st); dev_free(r->popl, st);
+        dev_free(r->spot_obj, st); dev_free(r->spot_xz, st);
+    }
+    dev_free(r->first_seg, st);
     dev_free(r->seg_d, st); dev_free(r->seg_part, st);
     for (auto& wb : r->wavebufs) { dev_free(wb.d, st); dev_free(wb.part, st); dev_free(wb.beam, st); dev_free(wb.seg, st); }
     delete r;

@@ -227,13 +227,16 @@ def main():
     inter_all, inter_all_e = float(it[0].item()), float(it[1].item())
 
     peak = L.measure_fp64_peak(dev)
+    # the retrace leg runs before the detector leg: after the detector's 64 MiB fields have gone through the stream-ordered pool
+    # the retrace's wave buffers (4 x 100 MB per call) hit a fragmented pool and its timings scatter between 6 and 30 ms
+    extras = None
+    if rank == 0 and not args.no_extras:
+        extras = {"retrace": bench_retrace(m, L, dev, stream, dsys, sc, pos_d, dir_d, lam_d, n, flush)}
     det = None
     if not args.no_detector:
         det = bench_detector(m, L, dev, stream, args.c3_side, args.c3_pixels, max(2, min(args.steps, 3)), 1, flush, peak, rank, world)
-    extras = None
-    if rank == 0 and not args.no_extras:
-        extras = {"retrace": bench_retrace(m, L, dev, stream, dsys, sc, pos_d, dir_d, lam_d, n, flush),
-                  "psf": bench_psf(m, L, dev, stream, flush, peak)}
+    if extras is not None:
+        extras["psf"] = bench_psf(m, L, dev, stream, flush, peak)
     if rank == 0:
         value = inter_all * args.steps / (tot_ms * 1e-3)
         e2e = inter_all_e * args.steps / (tot_ms_e * 1e-3)
