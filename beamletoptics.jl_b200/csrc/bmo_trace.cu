@@ -3,16 +3,21 @@
 // One wave = one `tracing_step!` + `interact3d` of every live beam (System.jl:100-154, 274-318).
 // Kernels per wave:
 //   K1 intersect_wave     one thread per ray: trace_one / trace_all (SDF sphere tracing, Moeller-
-//                         Trumbore behind the BVH) -> hit record (t, normal, part).  Register-lean on
-//                         purpose: the FP64 marching loop is latency bound, occupancy is what feeds it.
-//   K2 interact_wave<MODE> one thread per ray (Gaussian beamlets: chief/waist/divergence in adjacent
-//                         lanes, 10 triples per warp): interact3d -> block-local queue compaction
-//                         with warp ballots + prefix sums, successors written to scratch.
-//      scan_counts        exclusive scan of the per-block successor / spawn counts.
-//   K3 scatter_queue      HBM-bound copy of the compacted successors into the next queue and
-//                         numbering of beamsplitter children (deterministic: queue order).
-// With BMO_KEEP_SEGMENTS the segment records are written wave-major by K1 and gathered into
-// beam-major order at the end (K4 gather_segments).
+//                         Trumbore behind the BVH) -> hit record (t, normal, part).  Bound by the issue rate of
+//                         its non-FP64 instructions (profiles/r01s4_ncu_k1_instruction_mix.txt); 72 registers,
+//                         7 blocks per SM.
+//   K2 interact_wave<MODE, NS> one thread per ray (Gaussian beamlets: chief/waist/divergence in adjacent
+//                         lanes, 10 triples per warp): interact3d; the continuing ray overwrites its own queue
+//                         slot, a dead one is flagged.  Systems with beamsplitters (NS = false): the children go
+//                         to a scratch area in queue order (warp ballots + prefix sums), scan_counts + spawn_children
+//                         number them deterministically and append the reflected ones to the queue.
+//   K1+K2 fused_wave0     plain rays through a splitter-free system, all waves of a chunk in one launch (used by
+//                         pipelined host-input calls, where the number of launches is what limits).
+//   K1r retrace_intersect_wave   K1 of a retrace call (stored path re-validated per beam).
+//   K3 compact_fused      queue compaction in one cooperative launch once the dead slots are the majority
+//                         (compact_count + scan_counts + compact_scatter as the fallback).
+// With BMO_KEEP_SEGMENTS the segment records are written wave-major by K2 and gathered into
+// beam-major order at the end (gather_segments).
 #include <chrono>
 #include <cstdlib>
 #include <cooperative_groups.h>
