@@ -19,7 +19,7 @@ from .shapes import (AcylindricalSurfaceSDF, AsphericalSurfaceSDF, BoxSDF, Circu
                      CylinderSDF, Mesh, MeniscusLensSDF, PlanoSurfaceSDF, QuadraticFlatMesh, RectangularFlatMesh, RetroMesh,
                      RightAnglePrismSDF, RingSDF, SphereSDF, ThinLensSDF, UnionSDF, load_stl)
 from .solver import DeviceSystem, TraceResult, pd_accumulate, retrace, solve_system_, trace_beamlets, trace_rays, trace_rays_spots, upload_system
-from .sweep import flatten_poses, solve_pose_sweep
+from .sweep import flatten_poses, solve_pose_sweep, KinProgram, get_pose_tables, solve_pose_sweep_device
 from . import parallel
 from .parallel import solve_system_sharded
 

@@ -14,6 +14,9 @@ LIB_PATH = os.environ.get("BMO_LIB") or os.path.join(_HERE, "libbmo.so")   # BMO
 KEEP_SEGMENTS = 1
 INPUT_DEVICE = 2
 PD_REFERENCE_ORDER = 4
+UNIFORM_DIR = 8
+COMM_SYNC = 16
+COMM_ID_BYTES = 128
 
 STATUS_NAMES = ["ACTIVE", "MISS", "ABSORBED", "RMAX", "SPLIT", "CLIPPED", "TORN", "ERROR"]
 
@@ -57,6 +60,15 @@ class bmo_tables(C.Structure):
                 ("norm_zero_rule", C.c_int32), ("reserved", C.c_int32)]
 
 
+class bmo_kin_node(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("size", C.c_int32), ("pos_ref", C.c_int32), ("index", C.c_int32), ("flags", C.c_int32),
+                ("object", C.c_int32), ("pos", C.c_double * 3), ("dir", C.c_double * 9)]
+
+
+class bmo_kin_op(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("node", C.c_int32), ("pivot", C.c_int32), ("param", C.c_int32)]
+
+
 class bmo_counters(C.Structure):
     _fields_ = [("interactions", C.c_int64), ("sdf_evals", C.c_int64), ("tri_tests", C.c_int64), ("waves", C.c_int64),
                 ("kernel_launches", C.c_int64), ("px_beamlets", C.c_int64), ("trace_ms", C.c_double), ("pd_ms", C.c_double),
@@ -77,6 +89,8 @@ EXPORTS = [
     "bmo_retrace", "bmo_psf_collect", "bmo_psf_count", "bmo_psf_data", "bmo_psf_lims", "bmo_psf_intensity", "bmo_psf_free",
     "bmo_result_get_info", "bmo_result_beams", "bmo_result_segments", "bmo_result_spots", "bmo_result_spots_device",
     "bmo_result_free", "bmo_pd_accumulate", "bmo_pd_accumulate_poses", "bmo_pd_power", "bmo_pd_sweep", "bmo_measure_fp64_peak",
+    "bmo_system_set_kinematics", "bmo_system_apply_poses", "bmo_system_get_pose",
+    "bmo_comm_unique_id", "bmo_comm_init", "bmo_comm_init_local", "bmo_comm_info", "bmo_pd_allreduce", "bmo_pd_allreduce_local", "bmo_comm_free",
 ]
 
 _lib = None
@@ -119,6 +133,16 @@ def lib():
         L.bmo_psf_intensity.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_double, C.c_double, _vp, C.c_uint32]
         L.bmo_psf_free.argtypes = [_vp]
         L.bmo_measure_fp64_peak.argtypes = [_vp, _dp]
+        L.bmo_system_set_kinematics.argtypes = [_vp, C.c_int32, _vp, _vp]
+        L.bmo_system_apply_poses.argtypes = [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, _vp]
+        L.bmo_system_get_pose.argtypes = [_vp, C.c_int32, _vp, _vp, _vp, _vp]
+        L.bmo_comm_unique_id.argtypes = [_vp]
+        L.bmo_comm_init.argtypes = [_vp, C.c_int32, C.c_int32, _vp, C.POINTER(_vp)]
+        L.bmo_comm_init_local.argtypes = [C.c_int32, C.POINTER(_vp), C.POINTER(_vp)]
+        L.bmo_comm_info.argtypes = [_vp, _ip, _ip, _ip]
+        L.bmo_pd_allreduce.argtypes = [_vp, _vp, C.c_int64, C.c_uint32]
+        L.bmo_pd_allreduce_local.argtypes = [C.c_int32, C.POINTER(_vp), C.POINTER(_vp), C.c_int64, C.c_uint32]
+        L.bmo_comm_free.argtypes = [_vp]
         _lib = L
     return _lib
 

@@ -151,6 +151,7 @@ class RayBundle:
     def __init__(self, pos, dir, lam=1000e-9, E0=None, normalize=True):
         self.pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(-1, 3)
         d = np.ascontiguousarray(dir, dtype=np.float64)
+        self.uniform_dir = d.ndim == 1      # one direction for the whole bundle (collimated sources): shipped once (BMO_UNIFORM_DIR)
         if d.ndim == 1:
             d = np.broadcast_to(d, self.pos.shape)
         d = np.array(d, dtype=np.float64)
@@ -158,6 +159,7 @@ class RayBundle:
             inv = 1.0 / np.sqrt(d[:, 0] * d[:, 0] + d[:, 1] * d[:, 1] + d[:, 2] * d[:, 2])
             d = d * inv[:, None]
         self.dir = np.ascontiguousarray(d)
+        self.uniform_lam = np.ndim(lam) == 0
         self.lam = np.ascontiguousarray(np.broadcast_to(np.asarray(lam, dtype=np.float64), (self.pos.shape[0],)))
         self.E0 = None
         if E0 is not None:

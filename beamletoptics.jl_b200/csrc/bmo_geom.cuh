@@ -42,7 +42,8 @@ struct SysView {
     const double* lambdas;   // [n_lambda]
     const double* jones;     // [n_jones][10] PolarizationFilter: J (3x3 row-major), cutoff
     const double* ext;       // parameter blocks of the aspheric primitives (bmo_asphere.cuh)
-    int32_t n_prims, n_parts, n_objects, n_meshes, n_lambda, n_poses, zr, pad;
+    int32_t n_prims, n_parts, n_objects, n_meshes, n_lambda, n_poses, zr;
+    int32_t bvh_ok;          // 1: the vertex table is the one the BVH was built from (upload / restore); 0 after a pose update
     int64_t n_vertices;
     double n_system;
 };
@@ -551,7 +552,7 @@ BMO_D bool box_hit(const BvhNode& nd, V3 o, V3 d, double tbest) {
 // the compiler copy it to local memory.
 struct MeshTabs {
     const MeshView* meshes; const double* vertices; const int32_t* faces; const BvhNode* nodes; const int32_t* bvh_faces;
-    int64_t n_vertices; int32_t n_poses, pad;
+    int64_t n_vertices; int32_t n_poses, bvh_ok;
 };
 BMO_NI bool mesh_intersect(const MeshTabs S, int mesh_id, int pose, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
     const MeshView mv = S.meshes[mesh_id];
@@ -559,7 +560,7 @@ BMO_NI bool mesh_intersect(const MeshTabs S, int mesh_id, int pose, V3 pos, V3 d
     const int32_t* faces = S.faces + 3 * mv.first_face;
     double t0 = INFINITY;
     int64_t fid = -1;
-    if (mv.n_nodes == 0 || S.n_poses > 1) {  // small meshes (and posed sweeps): reference order
+    if (mv.n_nodes == 0 || !S.bvh_ok) {  // small meshes, and vertex tables that are not the ones the BVH was built from (pose updates): reference order
         for (int64_t i = 0; i < mv.n_faces; i++) {
             st.tri++;
             double tt = moeller_trumbore(load_vertex(verts, __ldg(faces + 3 * i)), load_vertex(verts, __ldg(faces + 3 * i + 1)),

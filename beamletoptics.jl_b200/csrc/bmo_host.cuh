@@ -22,7 +22,7 @@ inline int32_t fail(int32_t code, const std::string& msg) { g_last_error = msg; 
             return fail(BMO_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
     } while (0)
 
-struct DevCounters { unsigned long long interactions, sdf, tri; };
+struct DevCounters { unsigned long long interactions, sdf, tri, bad_ids; };   // bad_ids: rays whose lambda_id / pose_id was out of range (init_queue)
 
 }  // namespace bmo
 
@@ -33,7 +33,7 @@ struct bmo_ctx {
     std::vector<cudaEvent_t> ev_pool;        // 10 events per sub-batch slot
     std::vector<cudaStream_t> aux_streams;   // streams of the sub-batches of a pipelined trace call (created on demand)
     double k1_ms = 0, k3_ms = 0, k3_bytes = 0, k4_ms = 0;  // accumulated device time of trace_step / scatter_queue / pd_field
-    int64_t k1_launches = 0, interactions_seen = 0;
+    int64_t k1_launches = 0, interactions_seen = 0, bad_ids_seen = 0;
     bmo::DevCounters* d_counters = nullptr;
     long long* d_totals = nullptr;   // [4] scratch for scans
     long long* h_totals = nullptr;   // pinned, 8 entries for the scans + 8 per sub-batch slot
@@ -62,6 +62,10 @@ struct bmo_sys {
     double* d_bounds = nullptr; double* d_detpose = nullptr; double* d_lambdas = nullptr; double* d_jones = nullptr; double* d_ext = nullptr;
     // pose-0 copies to restore after a sweep
     std::vector<double> h_vertices, h_bounds, h_detpose;
+    // K5 (bmo_pose.cu): kinematic tree + the uploaded tables every pose starts from
+    std::vector<bmo_kin_node> kin_nodes;
+    bmo_kin_node* d_kin_nodes = nullptr; double* d_prim_bounds = nullptr;
+    bmo_prim* d_prims0 = nullptr; double* d_vertices0 = nullptr; double* d_detpose0 = nullptr;
     // high-water marks of earlier branching traces, keyed by (mode, root beams): queue units, beams and scratch
     // units the call ended with.  The next call of the same shape allocates them up front (no growth copies,
     // identical request sizes for the pool).

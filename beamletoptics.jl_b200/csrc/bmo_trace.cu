@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
         const bool budget = q_seg + 1 < P.r_max;   // `while length(rays) < r_max` (System.jl:133)
         TraceCtx C;
         C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
-        C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
+        C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.bvh_ok = S.bvh_ok;
         C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
         C.pose = pose;
         if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(co
     const bool budget = seg + 1 < P.r_max;   // `while length(rays) < r_max` (System.jl:133), trace_system! only
     TraceCtx C;
     C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
-    C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
+    C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.bvh_ok = S.bvh_ok;
     C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
     C.pose = pose;
     if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
@@ -549,6 +549,11 @@ BMO_D void interact_body(const StepParams& P, const Hit& h_reg, const int wave_o
         } else if (nsucc == 2 && seg + 1 == np) {
             retr_child0 = P.rt.child[2 * pb]; retr_child1 = P.rt.child[2 * pb + 1];
         }
+        // replace! (Beam.jl:81-95) and _modify_beam_head! (Beam.jl:97-112) write through direction!, which
+        // normalises (AbstractRay.jl:83-86); push! of a fresh ray does not
+        if (retr_next >= 0) o1.dir = normalize(o1.dir);
+        if (retr_child0 >= 0) o1.dir = normalize(o1.dir);
+        if (retr_child1 >= 0) o2.dir = normalize(o2.dir);
     }
 
     // ---- bookkeeping: counters, segment record, per-beam state ----
@@ -715,7 +720,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
             const bool budget = P.cur.i[I_SEG * qs + ri] + 1 < P.r_max;
             TraceCtx C;
             C.M.meshes = S.meshes; C.M.vertices = S.vertices; C.M.faces = S.faces; C.M.nodes = S.nodes; C.M.bvh_faces = S.bvh_faces;
-            C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.pad = 0;
+            C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.bvh_ok = S.bvh_ok;
             C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
             C.pose = pose;
             if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
@@ -850,6 +855,7 @@ __global__ void __launch_bounds__(256) spawn_children(const SpawnParams P) {
             }
         }
         P.B.spot_obj[(int64_t)beam * R + r] = -1;
+        P.B.spot_xz[2 * ((int64_t)beam * R + r)] = P.B.spot_xz[2 * ((int64_t)beam * R + r) + 1] = __longlong_as_double(0x7ff8000000000000ll);
         int32_t* nq = P.q.i;
         nq[I_LAM * qs + di] = lam;
         nq[I_HINT * qs + di] = -1;
@@ -972,6 +978,9 @@ struct InitParams {
     const int32_t *lam, *pose;
     BeamTab B;
     int32_t retrace, pad;   // retrace: root beam g re-validates beam g of the previous solution
+    int32_t n_lambda, n_poses;   // valid ranges of lambda_id / pose_id
+    DevCounters* counters;
+    int32_t dir_uniform, pad2;   // BMO_UNIFORM_DIR: dir holds one direction shared by every ray of the bundle
 };
 __global__ void init_queue(const InitParams P) {
     const int R = P.mode == 2 ? 3 : 1;
@@ -988,19 +997,25 @@ __global__ void init_queue(const InitParams P) {
         d[F_X0 * s + i] = 0; d[(F_X0 + 1) * s + i] = 0; d[(F_X0 + 2) * s + i] = 0;
     } else {
         d[F_PX * s + i] = P.pos[3 * u]; d[F_PY * s + i] = P.pos[3 * u + 1]; d[F_PZ * s + i] = P.pos[3 * u + 2];
-        d[F_DX * s + i] = P.dir[3 * u]; d[F_DY * s + i] = P.dir[3 * u + 1]; d[F_DZ * s + i] = P.dir[3 * u + 2];
+        const int64_t du = P.dir_uniform ? 0 : u;
+        d[F_DX * s + i] = P.dir[3 * du]; d[F_DY * s + i] = P.dir[3 * du + 1]; d[F_DZ * s + i] = P.dir[3 * du + 2];
         if (P.mode == 1)
             for (int k = 0; k < 6; k++) d[(F_X0 + k) * s + i] = P.E0[6 * u + k];
     }
     d[F_N * s + i] = 1.0;  // Ray(pos, dir, lambda): n = 1 (Rays.jl:32-42)
     int32_t* q = P.q.i;
-    const int lam = P.lam ? P.lam[u] : 0, pose = P.pose ? P.pose[u] : 0;
+    int lam = P.lam ? P.lam[u] : 0, pose = P.pose ? P.pose[u] : 0;
     const int64_t g = P.beam0 + u;   // global beam id; inputs are this sub-batch's slices, tables are global
-    q[I_LAM * s + i] = lam; q[I_HINT * s + i] = -1; q[I_BEAM * s + i] = (int)g; q[I_SEG * s + i] = 0; q[I_POSE * s + i] = pose;
+    // An id outside the tables would index n_table / lambdas / the pose-stacked tables out of bounds: the ray is parked
+    // (dead slot, status ERROR) and counted; the trace call then returns BMO_EINVAL instead of faulting the context.
+    const bool bad = (unsigned)lam >= (unsigned)P.n_lambda || (unsigned)pose >= (unsigned)P.n_poses;
+    if (bad) { lam = 0; pose = 0; if (r == 0) atomicAdd(&P.counters->bad_ids, 1ull); }
+    q[I_LAM * s + i] = lam; q[I_HINT * s + i] = -1; q[I_BEAM * s + i] = bad ? -1 : (int)g; q[I_SEG * s + i] = 0; q[I_POSE * s + i] = pose;
     q[I_RETR * s + i] = P.retrace ? (int)g : -1;
     P.B.spot_obj[g * R + r] = -1;
+    P.B.spot_xz[2 * (g * R + r)] = P.B.spot_xz[2 * (g * R + r) + 1] = __longlong_as_double(0x7ff8000000000000ll);   // NaN until a Spotdetector is hit
     if (r == 0) {
-        P.B.parent[g] = -1; P.B.slot[g] = -1; P.B.nseg[g] = 0; P.B.status[g] = BMO_ST_ACTIVE; P.B.lam[g] = lam; P.B.pose[g] = pose;
+        P.B.parent[g] = -1; P.B.slot[g] = -1; P.B.nseg[g] = 0; P.B.status[g] = bad ? BMO_ST_ERROR : BMO_ST_ACTIVE; P.B.lam[g] = lam; P.B.pose[g] = pose;
         if (P.mode == 2) { P.B.w0[g] = P.w0[u]; P.B.e0[2 * g] = P.ge0[2 * u]; P.B.e0[2 * g + 1] = P.ge0[2 * u + 1]; P.B.plen[g] = 0; P.B.popl[g] = 0; }
     }
 }
@@ -1127,7 +1142,7 @@ int32_t bmo_counters_reset(bmo_ctx* c) {
     BMO_CUDA(cudaStreamSynchronize(c->stream));
     BMO_CUDA(cudaMemset(c->d_counters, 0, sizeof(DevCounters)));
     c->waves = c->launches = c->px_beamlets = 0; c->psf_pairs = 0; c->psf_ms = 0;
-    c->k1_ms = c->k3_ms = c->k3_bytes = c->k4_ms = 0; c->k1_launches = 0; c->interactions_seen = 0;
+    c->k1_ms = c->k3_ms = c->k3_bytes = c->k4_ms = 0; c->k1_launches = 0; c->interactions_seen = 0; c->bad_ids_seen = 0;
     return BMO_OK;
 }
 
@@ -1145,13 +1160,24 @@ static int32_t validate_tables(const bmo_tables* t) {
             if (pt.first < 0 || pt.first >= t->n_meshes) return fail(BMO_EINVAL, "part mesh index out of range");
         } else return fail(BMO_EINVAL, "unknown shape kind");
         if (pt.n_row >= t->n_rows) return fail(BMO_EINVAL, "part.n_row out of range");
+        if (pt.n_row >= 0 && !t->n_table) return fail(BMO_EINVAL, "part.n_row set but n_table is NULL");
+        if (pt.role < BMO_ROLE_SINGLE || pt.role > BMO_ROLE_COATING) return fail(BMO_EINVAL, "unknown part role");
+    }
+    for (int p = 0; p < t->n_prims; p++) {
+        const int ty = t->prims[p].type;
+        if (ty < BMO_PRIM_PLANO || ty > BMO_PRIM_CONCAVE_ACYL) return fail(BMO_EINVAL, "unknown primitive type");
     }
     for (int o = 0; o < t->n_objects; o++) {
         const bmo_object& ob = t->objects[o];
         if (ob.first_part < 0 || ob.n_parts <= 0 || ob.first_part + ob.n_parts > t->n_parts) return fail(BMO_EINVAL, "object part range out of bounds");
         const int need = ob.kind == BMO_OBJ_CUBE_BS ? 3 : ((ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_DOUBLET) ? 2 : 1);
         if (ob.n_parts != need) return fail(BMO_EINVAL, "object has the wrong number of parts for its kind");
-        if ((ob.kind == BMO_OBJ_REFRACTIVE) && t->parts[ob.first_part].n_row < 0) return fail(BMO_EINVAL, "refractive object without n_row");
+        if (ob.kind < BMO_OBJ_REFRACTIVE || ob.kind > BMO_OBJ_POLFILTER) return fail(BMO_EINVAL, "unknown object kind");
+        // every part whose interaction reads n_table needs a row: lens / prism, both lenses of a doublet, the substrate of a
+        // plate splitter, both prisms of a cube splitter (interact_wave: n_of_hit, the children's n of CUBE_BS / PLATE_BS)
+        const int n_refr = ob.kind == BMO_OBJ_REFRACTIVE ? 1 : (ob.kind == BMO_OBJ_DOUBLET || ob.kind == BMO_OBJ_CUBE_BS) ? 2 : (ob.kind == BMO_OBJ_PLATE_BS ? 1 : 0);
+        for (int k = 0; k < n_refr; k++)
+            if (t->parts[ob.first_part + k].n_row < 0) return fail(BMO_EINVAL, "refractive part without a row of n_table (n_row < 0)");
         if (ob.kind == BMO_OBJ_POLFILTER && (!t->jones || ob.pd_n < 0 || ob.pd_n >= t->n_jones)) return fail(BMO_EINVAL, "PolarizationFilter without a row of tables.jones");
     }
     for (int m = 0; m < t->n_meshes; m++) {
@@ -1264,7 +1290,7 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
     v.vertices = s->d_vertices; v.faces = s->d_faces; v.nodes = s->d_nodes; v.bvh_faces = s->d_bvh_faces;
     v.n_table = s->d_ntable; v.bounds = s->d_bounds; v.det_pose = s->d_detpose; v.lambdas = s->d_lambdas; v.jones = s->d_jones; v.ext = s->d_ext;
     v.n_prims = t->n_prims; v.n_parts = t->n_parts; v.n_objects = t->n_objects; v.n_meshes = t->n_meshes;
-    v.n_lambda = t->n_lambda; v.n_poses = 1; v.zr = t->norm_zero_rule; v.n_vertices = t->n_vertices;
+    v.n_lambda = t->n_lambda; v.n_poses = 1; v.bvh_ok = 1; v.zr = t->norm_zero_rule; v.n_vertices = t->n_vertices;
     v.n_system = t->n_system;
     *out = s;
     return BMO_OK;
@@ -1276,6 +1302,7 @@ int32_t bmo_system_free(bmo_sys* s) {
     cudaFree(s->d_prims); cudaFree(s->d_parts); cudaFree(s->d_objects); cudaFree(s->d_meshes); cudaFree(s->d_vertices);
     cudaFree(s->d_faces); cudaFree(s->d_nodes); cudaFree(s->d_bvh_faces); cudaFree(s->d_ntable); cudaFree(s->d_bounds);
     cudaFree(s->d_detpose); cudaFree(s->d_lambdas); cudaFree(s->d_jones); cudaFree(s->d_ext);
+    cudaFree(s->d_kin_nodes); cudaFree(s->d_prim_bounds); cudaFree(s->d_prims0); cudaFree(s->d_vertices0); cudaFree(s->d_detpose0);
     delete s;
     return BMO_OK;
 }
@@ -1314,6 +1341,7 @@ int32_t bmo_system_set_poses(bmo_sys* s, int32_t n_poses, const bmo_prim* prims,
     }
     v.prims = s->d_prims; v.vertices = s->d_vertices; v.bounds = s->d_bounds; v.det_pose = s->d_detpose;
     v.n_poses = n_poses;
+    v.bvh_ok = (n_poses == 1 && !prims) ? 1 : 0;   // moved vertices: the BVH boxes are stale, meshes fall back to the face loop
     return BMO_OK;
 }
 
@@ -1432,6 +1460,7 @@ struct TraceInputs {
     int64_t n;
     const double *pos, *dir, *E0, *grays, *w0, *ge0;
     const int32_t *lam, *pose;
+    bool dir_uniform = false;   // BMO_UNIFORM_DIR
 };
 
 template <class T> static int32_t stage_in(const T* h, size_t n, bool on_device, cudaStream_t st, const T** out, std::vector<void*>& tmp) {
@@ -1494,7 +1523,7 @@ int32_t SubTrace::begin(const TraceInputs& in_h) {
         if ((rc = stage_in(in_h.ge0 ? in_h.ge0 + o * 2 : nullptr, (size_t)n * 2, on_dev, st, &in.ge0, tmp))) return rc;
     } else {
         if ((rc = stage_in(in_h.pos + o * 3, (size_t)n * 3, on_dev, st, &in.pos, tmp))) return rc;
-        if ((rc = stage_in(in_h.dir + o * 3, (size_t)n * 3, on_dev, st, &in.dir, tmp))) return rc;
+        if ((rc = stage_in(in_h.dir_uniform ? in_h.dir : in_h.dir + o * 3, in_h.dir_uniform ? 3 : (size_t)n * 3, on_dev, st, &in.dir, tmp))) return rc;
         if (mode == 1 && (rc = stage_in(in_h.E0 + o * 6, (size_t)n * 6, on_dev, st, &in.E0, tmp))) return rc;
     }
     if ((rc = stage_in(in_h.lam ? in_h.lam + o : nullptr, (size_t)n, on_dev, st, &in.lam, tmp))) return rc;
@@ -1503,6 +1532,7 @@ int32_t SubTrace::begin(const TraceInputs& in_h) {
     InitParams ip{};
     ip.q = cur; ip.n = n; ip.beam0 = beam0; ip.mode = mode; ip.pos = in.pos; ip.dir = in.dir; ip.E0 = in.E0; ip.grays = in.grays;
     ip.w0 = in.w0; ip.ge0 = in.ge0; ip.lam = in.lam; ip.pose = in.pose; ip.B = beamtab(res); ip.retrace = rt.on;
+    ip.n_lambda = sys->view.n_lambda; ip.n_poses = sys->view.n_poses; ip.counters = ctx->d_counters; ip.dir_uniform = in.dir_uniform;
     const int64_t tot = n * R;
     init_queue<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(ip);
     BMO_LAUNCH(ctx, "init_queue");
@@ -1895,6 +1925,12 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
         else BMO_CUDA(cudaMemcpy(&h, ctx->d_counters, sizeof(h), cudaMemcpyDeviceToHost));
         res->interactions = (int64_t)h.interactions - ctx->interactions_seen;  // the counter is cumulative since the last reset
         ctx->interactions_seen = (int64_t)h.interactions;
+        const int64_t bad = (int64_t)h.bad_ids - ctx->bad_ids_seen;
+        ctx->bad_ids_seen = (int64_t)h.bad_ids;
+        if (bad > 0) {
+            bmo_result_free(res);
+            return fail(BMO_EINVAL, "trace: " + std::to_string(bad) + " beam(s) carry a lambda_id outside [0, n_lambda) or a pose_id outside [0, n_poses)");
+        }
     }
     if (prof) fprintf(stderr, "[bmo] trace n=%lld waves=%d sub-batches=%d: setup %.3f ms, wave loop %.3f ms (of which waiting %.3f), finalize %.3f ms\n",
                       (long long)n, wave, n_sub, tp1 - tp0, tp2 - tp1, tp_wave_sync, tnow_ms() - tp2);
@@ -1907,7 +1943,7 @@ int32_t bmo_trace_rays(bmo_sys* sys, int64_t n, const double* pos, const double*
                        const int32_t* pose_id, int32_t r_max, uint32_t flags, bmo_result** out) {
     if (!pos || !dir) return fail(BMO_EINVAL, "bmo_trace_rays: pos/dir NULL");
     TraceInputs in{};
-    in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id;
+    in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id; in.dir_uniform = (flags & BMO_UNIFORM_DIR) != 0;
     if (!sys) return fail(BMO_EINVAL, "sys NULL");
     return trace_common(sys, E0 ? 1 : 0, in, r_max, flags, out);
 }
@@ -1920,7 +1956,7 @@ int32_t bmo_trace_rays_spots(bmo_sys* sys, int64_t n, const double* pos, const d
         if (ob.kind == BMO_OBJ_THIN_BS || ob.kind == BMO_OBJ_PLATE_BS || ob.kind == BMO_OBJ_CUBE_BS)
             return fail(BMO_EINVAL, "bmo_trace_rays_spots: the system has beamsplitters (beams != rays); use bmo_trace_rays + bmo_result_spots");
     TraceInputs in{};
-    in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id;
+    in.n = n; in.pos = pos; in.dir = dir; in.E0 = E0; in.lam = lambda_id; in.pose = pose_id; in.dir_uniform = (flags & BMO_UNIFORM_DIR) != 0;
     return trace_common(sys, E0 ? 1 : 0, in, r_max, flags & ~BMO_KEEP_SEGMENTS, out, det_object, xz);
 }
 // solve_system!(system, beam; retrace = true) on beams that already hold a solution (System.jl:444-461 with

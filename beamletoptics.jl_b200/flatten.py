@@ -39,11 +39,13 @@ def _prim_record(s, ext):
     return p
 
 
-def _emit_sdf(shape, prims, ext):
-    """Append the prim records of one top-level SDF shape; returns (first, count)."""
+def _emit_sdf(shape, prims, ext, index_of=None):
+    """Append the prim records of one top-level SDF shape; returns (first, count).  index_of: id(member) -> prim record."""
     first = len(prims)
     members = shape.sdfs if isinstance(shape, sh.UnionSDF) else [shape]
     for m in members:
+        if index_of is not None:
+            index_of[id(m)] = len(prims)
         if isinstance(m, sh.MeniscusLensSDF):
             prims.append(_prim_record(m, ext))
             for child in (m.convex, m.cylinder, m.concave):
@@ -60,6 +62,8 @@ class FlatSystem:
 
     def __init__(self, system, lambdas, norm_zero_rule=1):
         self.lambdas = [float(x) for x in lambdas]
+        self.system = system
+        self.prim_index, self.mesh_index = {}, {}     # id(host shape) -> prim record / mesh index (kinematic tree)
         leaves = [o for o in system.leaves() if not isinstance(o, co.NonInteractableObject)]
         if not leaves:
             raise ValueError("system has no traceable objects")
@@ -92,10 +96,11 @@ class FlatSystem:
                 pr.transmittance = getattr(s_obj, "transmittance", 0.0)
                 if isinstance(shape, sh.AbstractSDF):
                     pr.shape_kind = SHAPE_SDF
-                    pr.first, pr.count = _emit_sdf(shape, prims, ext)
+                    pr.first, pr.count = _emit_sdf(shape, prims, ext, self.prim_index)
                 elif isinstance(shape, sh.Mesh):
                     pr.shape_kind = SHAPE_MESH
                     pr.first, pr.count = len(meshes), 1
+                    self.mesh_index[id(shape)] = len(meshes)
                     m = L.bmo_mesh()
                     m.first_vertex, m.n_vertices = nv, shape.vertices.shape[0]
                     m.first_face, m.n_faces = nf, shape.faces.shape[0]
@@ -150,6 +155,79 @@ class FlatSystem:
         det_pos = np.array([list(o.pos) for o in self._objs], dtype=np.float64)
         det_dir = np.array([list(o.dir) for o in self._objs], dtype=np.float64)
         return prims[:self.n_prims * C.sizeof(L.bmo_prim)], self._verts.copy(), bounds, det_pos, det_dir
+
+    # ---- K5: kinematic tree of the system for batched pose updates on the device (bmo_system_set_kinematics) ----
+    def kinematics(self):
+        """(nodes, prim_bounds, node_of): bmo_kin_node array in pre-order, [n_prims][10] local bounds of the top-level prim
+        records, and id(host object / group / shape) -> node index.  Mirrors who owns a pose in the reference:
+        ObjectGroup (center, dir), MultiShape objects (position = position of a pivot part), UnionSDF (own pose + members
+        with world poses), primitives, meshes."""
+        nodes, node_of = [], {}
+        obj_index = {id(o): i for i, o in enumerate(self.objects)}
+
+        def new(kind, host, pos=(0.0, 0.0, 0.0), dirm=la.IDENTITY, index=-1, flags=0, obj=-1):
+            nd = L.bmo_kin_node()
+            nd.kind, nd.size, nd.pos_ref, nd.index, nd.flags, nd.object = kind, 1, len(nodes), index, flags, obj
+            nd.pos[:] = [float(x) for x in pos]
+            nd.dir[:] = [float(dirm[i][j]) for i in range(3) for j in range(3)]
+            node_of[id(host)] = len(nodes)
+            nodes.append(nd)
+            return len(nodes) - 1
+
+        def emit_shape(shape, obj=-1):
+            if isinstance(shape, sh.UnionSDF):
+                i = new(2, shape, shape.pos, shape.dir, obj=obj)
+                for m in shape.sdfs:
+                    emit_shape(m)
+                nodes[i].size = len(nodes) - i
+                return i
+            if isinstance(shape, sh.Mesh):
+                return new(4, shape, shape.pos, shape.dir, index=self.mesh_index[id(shape)], obj=obj)
+            if isinstance(shape, (sh.PrimSDF, sh.MeniscusLensSDF)):
+                sphere = isinstance(shape, sh.PrimSDF) and shape.type == sh.SPHERE
+                return new(3, shape, shape.pos, shape.dir, index=self.prim_index[id(shape)], flags=1 if sphere else 0, obj=obj)
+            raise TypeError(f"unsupported shape {type(shape).__name__}")
+
+        def emit(o):
+            if isinstance(o, co.NonInteractableObject):
+                return None
+            if isinstance(o, co.ObjectGroup):
+                i = new(0, o, o.center, o.dir)
+                for c in o.parts:
+                    emit(c)
+                nodes[i].size = len(nodes) - i
+                return i
+            if o.multi:
+                i = new(1, o)
+                kids = [emit(c) for c in o.parts]
+                nodes[i].size = len(nodes) - i
+                # position(object): the part whose position the object reports (first part; the coating of a plate splitter)
+                pivot = 1 if o.kind == "plate_bs" else 0
+                nodes[i].pos_ref = nodes[kids[pivot]].pos_ref
+                return i
+            j = emit_shape(o.shape, obj_index.get(id(o), -1))
+            node_of[id(o)] = j
+            return j
+
+        for o in self.system.objects:
+            emit(o)
+        bounds = np.zeros((max(self.n_prims, 1), 10))
+        for part_i in range(self.n_parts):
+            shape = self.part_owner[part_i].shape
+            if not isinstance(shape, sh.AbstractSDF):
+                continue
+            for m in (shape.sdfs if isinstance(shape, sh.UnionSDF) else [shape]):
+                # bounds in the member's own frame: evaluate them with the member moved to the origin frame
+                pos, dirm, tdir = m.pos, m.dir, m.tdir
+                m.pos, m.dir, m.tdir = (0.0, 0.0, 0.0), la.IDENTITY, la.IDENTITY
+                try:
+                    c, r = m.local_bound()
+                    lo, hi = sh._box_of(m.box_points())
+                finally:
+                    m.pos, m.dir, m.tdir = pos, dirm, tdir
+                bounds[self.prim_index[id(m)]] = [c[0], c[1], c[2], r, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]]
+        arr = (L.bmo_kin_node * len(nodes))(*nodes)
+        return arr, np.ascontiguousarray(bounds), node_of
 
     def object_index(self, obj):
         for i, o in enumerate(self.objects):

@@ -8,11 +8,72 @@ rank accumulates *its* beamlets onto a full n x n complex128 partial field and t
 are summed with one all-reduce of 2 n^2 doubles (the reference adds the beamlet fields serially into
 `pd.field`, Photodetector.jl:103; addition order across ranks changes the sum at the 1e-16 level).
 """
+import ctypes as C
 import os
 
 import numpy as np
 
+from . import _lib as L
 from . import beams as bm
+
+
+class FieldComm:
+    """bmo_comm (include/bmo.h): the NCCL communicator behind the C ABI, one per process and GPU.  The 128-byte id
+    made by rank 0 (`FieldComm.unique_id()`) has to reach every rank by some host transport; `from_torch` uses the
+    process group torchrun set up, a Julia host would use Distributed / MPI / a file."""
+
+    def __init__(self, rank, world_size, id_bytes, device=0):
+        self.rank, self.world_size, self.device = int(rank), int(world_size), int(device)
+        buf = (C.c_uint8 * L.COMM_ID_BYTES).from_buffer_copy(bytes(id_bytes))
+        h = C.c_void_p()
+        L.check(L.lib().bmo_comm_init(L.context(device), self.world_size, self.rank, buf, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id():
+        buf = (C.c_uint8 * L.COMM_ID_BYTES)()
+        L.check(L.lib().bmo_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def from_torch(cls, device=None, group=None):
+        import torch.distributed as dist
+        rank, ws = dist.get_rank(group), dist.get_world_size(group)
+        box = [cls.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        return cls(rank, ws, box[0], world()[2] if device is None else device)
+
+    def nccl_version(self):
+        v = C.c_int32(0)
+        L.check(L.lib().bmo_comm_info(self.h, None, None, C.byref(v)))
+        return int(v.value)
+
+    def allreduce(self, field, n_complex=None, sync=True):
+        """Sum `field` over all ranks in place (bmo_pd_allreduce).  field: complex128 / float64 numpy array (host, staged
+        through the GPU by the library), or an integer device pointer together with n_complex."""
+        if isinstance(field, int):
+            L.check(L.lib().bmo_pd_allreduce(self.h, C.c_void_p(field), int(n_complex), L.INPUT_DEVICE | (L.COMM_SYNC if sync else 0)))
+            return field
+        assert field.dtype in (np.complex128, np.float64) and (field.flags["C_CONTIGUOUS"] or field.flags["F_CONTIGUOUS"])
+        n = field.size if field.dtype == np.complex128 else field.size // 2
+        L.check(L.lib().bmo_pd_allreduce(self.h, L.ptr(field), int(n), 0))
+        return field
+
+    def free(self):
+        if self.h:
+            L.lib().bmo_comm_free(self.h)
+            self.h = None
+
+
+_default_comm = None
+
+
+def default_comm(group=None):
+    """The process-wide FieldComm (created on first use from the torch.distributed group; NCCL backends only)."""
+    global _default_comm
+    if _default_comm is None:
+        _default_comm = FieldComm.from_torch(group=group)
+    return _default_comm
 
 
 def world():
@@ -47,12 +108,23 @@ def shard_bundle(bundle, rank, world_size, interleaved=False):
     return part, idx
 
 
-def allreduce_field(field, group=None):
-    """Sum the ranks' partial Photodetector fields in place.  `field`: complex128 numpy array (host;
-    gloo, or staged through the GPU for NCCL) or a torch tensor (float64 view of re/im pairs, or
-    complex128) that already lives where the backend wants it."""
+def allreduce_field(field, group=None, comm=None):
+    """Sum the ranks' partial Photodetector fields in place.  With a FieldComm (or an NCCL process group, for which the
+    process-wide FieldComm is used) the sum runs through the C ABI (bmo_pd_allreduce: NCCL inside libbmo.so); the
+    torch.distributed path remains for gloo (CPU tests).  `field`: complex128 numpy array or a torch tensor (float64 view
+    of re/im pairs, or complex128) that lives where the backend wants it."""
     import torch
     import torch.distributed as dist
+    if comm is None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1 and dist.get_backend(group) == "nccl":
+        comm = default_comm(group)
+    if comm is not None:
+        if isinstance(field, np.ndarray):
+            return comm.allreduce(field)
+        t = torch.view_as_real(field) if field.is_complex() else field
+        assert t.is_cuda and t.is_contiguous() and t.dtype == torch.float64
+        torch.cuda.current_stream(t.device).synchronize()      # the library reduces on its own stream
+        comm.allreduce(int(t.data_ptr()), t.numel() // 2, sync=True)
+        return field
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return field
     if isinstance(field, np.ndarray):
@@ -87,7 +159,7 @@ def gather_rows(local, idx, n_total, group=None):
     return out
 
 
-def solve_system_sharded(system, bundle, r_max=100, interleaved=False, keep_segments=False, group=None):
+def solve_system_sharded(system, bundle, r_max=100, interleaved=False, keep_segments=False, group=None, comm=None):
     """solve_system! of a bundle across all ranks: this rank traces its shard on GPU LOCAL_RANK; every
     Photodetector of `system` ends up with the field of the *whole* bundle on every rank (all-reduce);
     Spotdetector data stay rank-local (disjoint slices).  Returns (TraceResult of the shard, indices)."""
@@ -101,6 +173,6 @@ def solve_system_sharded(system, bundle, r_max=100, interleaved=False, keep_segm
         pd.field[...] = 0
     res = solve_system_(system, part, r_max=r_max, device=local, keep_segments=keep_segments) if len(part) else None
     for pd, old in zip(pds, before):
-        allreduce_field(pd.field, group)
+        allreduce_field(pd.field, group, comm)
         pd.field += old                  # the reference's `+=` onto whatever the detector already held
     return res, idx

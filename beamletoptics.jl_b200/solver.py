@@ -28,6 +28,7 @@ class DeviceSystem:
         h = C.c_void_p()
         L.check(L.lib().bmo_system_upload(self.ctx, C.byref(flat.tables), C.byref(h)))
         self.h = h
+        self.n_poses = 1
         self._results = weakref.WeakSet()    # results traced through this system
 
     def free(self):
@@ -144,6 +145,44 @@ def upload_system(system, lambdas, device=0, norm_zero_rule=1):
     return DeviceSystem(FlatSystem(system, lambdas, norm_zero_rule), device)
 
 
+def _tables_key(flat, device):
+    """Everything bmo_system_upload reads, as bytes: two flattenings with the same key are the same device system."""
+    t = flat.tables
+    parts = [bytes(memoryview(flat._prims)) if flat.n_prims else b"", bytes(memoryview(flat._parts)), bytes(memoryview(flat._objs)),
+             bytes(memoryview(flat._meshes)) if flat.n_meshes else b"", flat._verts.tobytes(), flat._faces.tobytes(), flat._lams.tobytes(),
+             flat._ntab.tobytes(), flat._jones.tobytes(), flat._ext.tobytes() if t.n_ext else b"",
+             np.array([t.n_system, float(t.norm_zero_rule), float(device)]).tobytes()]
+    import hashlib
+    h = hashlib.blake2b(digest_size=16)
+    for b in parts:
+        h.update(len(b).to_bytes(8, "little")); h.update(b)
+    return h.digest()
+
+
+def cached_system(system, lambdas, device=0, norm_zero_rule=1):
+    """upload_system with a one-entry cache on the System: poses are static during a trace and usually between the solves
+    of a loop as well (the reference keeps its objects; a Michelson scan moves one mirror per step), so the flattened tables
+    are hashed and the uploaded copy -- BVH included -- is reused while they do not change.  Moving an object changes the
+    key and triggers a fresh upload."""
+    flat = FlatSystem(system, lambdas, norm_zero_rule)
+    key = _tables_key(flat, device)
+    hit = getattr(system, "_device", None)
+    if hit is not None and hit[0] == key and hit[1].h:
+        dsys = hit[1]
+        # the host objects the ids map back to are those of this flattening (same objects unless the list was rebuilt)
+        dsys.flat.objects, dsys.flat.part_owner = flat.objects, flat.part_owner
+        if dsys.n_poses != 1:     # a sweep left stacked pose tables behind: restore the uploaded ones
+            L.check(L.lib().bmo_system_set_poses(dsys.h, 1, None, None, None, None, None))
+            dsys.n_poses = 1
+        return dsys
+    dsys = DeviceSystem(flat, device)
+    try:
+        system._device = (key, dsys)
+    except AttributeError:
+        pass
+    return dsys
+
+
 def trace_rays(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100, keep_segments=True, device_inputs=False):
     """Thin wrapper of bmo_trace_rays.  With device_inputs=True pos/dir/lam_id/E0/pose_id are integer
     device pointers (e.g. torch tensors' data_ptr()) and `n` must be given as pos=(ptr, n)."""
@@ -156,7 +195,9 @@ def trace_rays(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100, keep_se
     else:
         pos = np.ascontiguousarray(pos, dtype=np.float64)
         dir = np.ascontiguousarray(dir, dtype=np.float64)
-        lam_id = np.ascontiguousarray(lam_id, dtype=np.int32)
+        if dir.ndim == 1:
+            flags |= L.UNIFORM_DIR
+        lam_id = None if lam_id is None else np.ascontiguousarray(lam_id, dtype=np.int32)
         e = None
         if E0 is not None:
             ec = np.ascontiguousarray(E0, dtype=np.complex128)
@@ -168,21 +209,24 @@ def trace_rays(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100, keep_se
     return res
 
 
-def trace_rays_spots(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100):
+def trace_rays_spots(dsys, pos, dir, lam_id, E0=None, pose_id=None, r_max=100, want_objects=True):
     """bmo_trace_rays_spots: trace a bundle through a splitter-free system and return the Spotdetector
-    hits (det_object (n,), xz (n, 2)) and the TraceResult -- host copies pipelined with the waves."""
+    hits (det_object (n,), xz (n, 2)) and the TraceResult -- host copies pipelined with the waves.
+    `dir` of shape (3,) is one direction for the whole bundle (BMO_UNIFORM_DIR), `lam_id=None` means lambdas[0] for
+    every ray; with want_objects=False only xz comes back (NaN where no Spotdetector was reached)."""
     pos = np.ascontiguousarray(pos, dtype=np.float64)
     dir = np.ascontiguousarray(dir, dtype=np.float64)
-    lam_id = np.ascontiguousarray(lam_id, dtype=np.int32)
+    flags = L.UNIFORM_DIR if dir.ndim == 1 else 0
+    lam_id = None if lam_id is None else np.ascontiguousarray(lam_id, dtype=np.int32)
     n = pos.shape[0]
     e = None
     if E0 is not None:
         ec = np.ascontiguousarray(E0, dtype=np.complex128)
         e = np.ascontiguousarray(np.stack([ec.real, ec.imag], axis=-1).reshape(n, 6))
     pid = None if pose_id is None else np.ascontiguousarray(pose_id, dtype=np.int32)
-    obj, xz = np.zeros(n, np.int32), np.zeros((n, 2))
+    obj, xz = (np.zeros(n, np.int32) if want_objects else None), np.zeros((n, 2))
     h = C.c_void_p()
-    L.check(L.lib().bmo_trace_rays_spots(dsys.h, n, L.ptr(pos), L.ptr(dir), L.ptr(lam_id), L.ptr(e), L.ptr(pid), r_max, 0,
+    L.check(L.lib().bmo_trace_rays_spots(dsys.h, n, L.ptr(pos), L.ptr(dir), L.ptr(lam_id), L.ptr(e), L.ptr(pid), r_max, flags,
                                          L.ptr(obj), L.ptr(xz), C.byref(h)))
     return obj, xz, TraceResult(dsys, h)
 
@@ -324,7 +368,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
     if isinstance(beam, bm.Beam):
         r0 = beam.rays[0]
         lams, lam_id = _lambda_ids([r0.lam])
-        dsys = upload_system(system, lams, device, norm_zero_rule)
+        dsys = cached_system(system, lams, device, norm_zero_rule)
         prev = _previous_solution(beam, dsys, lams) if retrace else None
         if prev is not None:
             res = globals()["retrace"](dsys, prev, r_max)
@@ -339,7 +383,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         return res
     if isinstance(beam, bm.GaussianBeamlet):
         lams, lam_id = _lambda_ids([beam.lam])
-        dsys = upload_system(system, lams, device, norm_zero_rule)
+        dsys = cached_system(system, lams, device, norm_zero_rule)
         prev = _previous_solution(beam, dsys, lams) if retrace else None
         if prev is not None:
             res = globals()["retrace"](dsys, prev, r_max)
@@ -353,18 +397,21 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         return res
     if isinstance(beam, bm.RayBundle):
         lams, lam_id = _lambda_ids(beam.lam)
-        dsys = upload_system(system, lams, device, norm_zero_rule)
+        dsys = cached_system(system, lams, device, norm_zero_rule)
         splitters = any(o.kind in ("thin_bs", "plate_bs", "cube_bs") for o in dsys.flat.objects)
         has_psf = any(isinstance(o, co.PSFDetector) for o in dsys.flat.objects)
         keep_segments = keep_segments or has_psf       # the PSF records are rebuilt from the segment table
+        # collimated single-wavelength bundles ship one direction and no wavelength ids (24 B per ray instead of 52)
+        bdir = beam.dir[0] if getattr(beam, "uniform_dir", False) and len(beam) else beam.dir
+        blam = None if len(lams) == 1 else lam_id
         prev = _previous_solution(beam, dsys, lams) if retrace else None
         if prev is not None:
             res = globals()["retrace"](dsys, prev, r_max, keep_segments)
         elif not keep_segments and not splitters:      # one beam per ray: fused trace + Spotdetector read-back (pipelined copies)
-            obj, xz, res = trace_rays_spots(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max)
+            obj, xz, res = trace_rays_spots(dsys, beam.pos, bdir, blam, beam.E0, None, r_max)
             res._spots = (obj, xz)
         else:
-            res = trace_rays(dsys, beam.pos, beam.dir, lam_id, beam.E0, None, r_max, keep_segments)
+            res = trace_rays(dsys, beam.pos, bdir, blam, beam.E0, None, r_max, keep_segments)
         res.lams = lams
         beam.result = beam._solution = res
         _collect_spots(dsys.flat, res)
@@ -373,7 +420,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
         return res
     if isinstance(beam, bm.BeamletBundle):
         lams, lam_id = _lambda_ids(beam.lam)
-        dsys = upload_system(system, lams, device, norm_zero_rule)
+        dsys = cached_system(system, lams, device, norm_zero_rule)
         prev = _previous_solution(beam, dsys, lams) if retrace else None
         if prev is not None:
             res = globals()["retrace"](dsys, prev, r_max)

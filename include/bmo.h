@@ -25,6 +25,7 @@ extern "C" {
 #define BMO_ECUDA (-2)    /* CUDA runtime error */
 #define BMO_ENOMEM (-3)
 #define BMO_ESTATE (-4)   /* call order / handle misuse */
+#define BMO_ENCCL (-5)    /* NCCL missing (dlopen failed) or an NCCL call failed */
 
 /* ---- SDF primitives: replaces the `sdf(shape, point)` methods of
  * src/SDFs/SphericalLensSDF.jl:60-65,86-89,159-170,219-232, src/SDFs/PrimitiveSDF.jl:41-46,71-76,
@@ -152,6 +153,10 @@ typedef struct bmo_result bmo_result;  /* device-resident result of one trace ca
 /* flag of bmo_pd_accumulate*: evaluate every pixel-beamlet pair in the reference's operation order
  * (slower; the default kernel is algebraically identical, strength-reduced, within 1e-8 rel. L2)   */
 #define BMO_PD_REFERENCE_ORDER 4u
+/* flag of bmo_trace_rays / bmo_trace_rays_spots: `dir` holds ONE direction [3] shared by every ray of the bundle (a
+ * collimated source, BeamGroups.jl:51-120 / :232-243: every beam of the group is built with the same `dir`), so a
+ * host bundle ships 24 B per ray instead of 48.  lambda_id == NULL already means "all rays use lambdas[0]".     */
+#define BMO_UNIFORM_DIR 8u
 
 typedef struct bmo_counters {
     int64_t interactions;   /* hits that reached interact3d (a Gaussian triple counts 3)           */
@@ -188,6 +193,52 @@ int32_t bmo_system_set_poses(bmo_sys* sys, int32_t n_poses, const bmo_prim* prim
                              const double* bounds, const double* det_pos /* [n_poses][n_objects][3] */,
                              const double* det_dir /* [n_poses][n_objects][9] */);
 
+/* ---- K5: batched kinematics on the device ----------------------------------------------------------------
+ * replaces: the loop `translate3d!(obj, ...) / rotate3d!(obj, axis, theta)` over many poses of one system
+ * (AbstractShape.jl:56-94, AbstractShapeTrait.jl:88-128, UnionSDF.jl:63-82, Mesh.jl:78-96, ObjectGroups.jl:21-47,
+ * rotate3d LinearAlgebraUtils.jl:55-65; pose sweeps: test/runtests.jl:2092-2120) followed by re-flattening.
+ * The flattener uploads the kinematic tree of the system once (bmo_system_set_kinematics); a sweep is a short program of
+ * micro-ops, the same for every pose, whose numeric operands (offset vectors, rotation matrices) vary per pose.  One CUDA
+ * block per pose replays the program on the tree with the reference's operation order (`pos + offset`, `R * dir`, pivot
+ * rule `v = (R * v) - v`, mesh `(V - p) * R' + p`, no FMA contraction) and writes that pose's prim records, vertices,
+ * detector poses and part bounds -- the tables bmo_system_set_poses would have been handed.
+ * Nodes are laid out in pre-order, so a subtree is the index range [i, i + size).                                   */
+enum bmo_kin_kind {
+    BMO_KIN_GROUP = 0,   /* ObjectGroup: own center + dir (ObjectGroups.jl:21-35)                                       */
+    BMO_KIN_MULTI = 1,   /* MultiShape object: no own pose; position = position of its pivot child (AbstractShapeTrait.jl:77-84;
+                            PlateBeamsplitter: the coating)                                                          */
+    BMO_KIN_UNION = 2,   /* UnionSDF: own pos + dir, members keep world poses (UnionSDF.jl:63-82)                     */
+    BMO_KIN_PRIM = 3,    /* one prim record (a primitive, or a meniscus frame whose children are posed relative to it) */
+    BMO_KIN_MESH = 4     /* Mesh: pos, dir and world-space vertices (Mesh.jl:78-96)                                   */
+};
+typedef struct bmo_kin_node {
+    int32_t kind;
+    int32_t size;      /* nodes of the subtree rooted here, this one included                                          */
+    int32_t pos_ref;   /* node whose stored position is position(node): itself, or (MULTI) the pivot child's pos_ref    */
+    int32_t index;     /* PRIM: prim record; MESH: mesh index; else -1                                                 */
+    int32_t flags;     /* bit 0: SphereSDF -- orientation!(::SphereSDF) is a no-op (SphericalLensSDF.jl:82-84)          */
+    int32_t object;    /* object whose detector pose (bmo_object.pos / .dir) follows this node, else -1               */
+    double pos[3];     /* position(node) at upload                                                                    */
+    double dir[9];     /* orientation(node) at upload, row-major                                                      */
+} bmo_kin_node;
+enum bmo_kin_op_kind {
+    BMO_KIN_TRANSLATE = 0,     /* every node of subtree(node): pos = pos + param[0..2]; mesh vertices likewise          */
+    BMO_KIN_TRANSLATE_TO = 1,  /* offset = param[0..2] - position(node), then as TRANSLATE (translate_to3d!)            */
+    BMO_KIN_ROT_FRAME = 2,     /* dir(node) = R * dir(node), R = param[0..8] row-major (GROUP, UNION)                    */
+    BMO_KIN_ROT_LEAF = 3,      /* PRIM: dir = R * dir (unless SphereSDF); MESH: V = (V - pos) * R' + pos, dir = R * dir   */
+    BMO_KIN_PIVOT = 4          /* v = position(node) - position(pivot); v = (R * v) - v; TRANSLATE subtree(node) by v    */
+};
+typedef struct bmo_kin_op { int32_t kind, node, pivot, param; } bmo_kin_op;
+/* prim_bounds: [n_prims][10] = bounding sphere (centre xyz, radius) and box (lo xyz, hi xyz) of every top-level prim record
+ * in its own frame (meniscus: in the frame of the meniscus record; entries of meniscus children are ignored).          */
+int32_t bmo_system_set_kinematics(bmo_sys* sys, int32_t n_nodes, const bmo_kin_node* nodes, const double* prim_bounds);
+/* params: [n_poses][n_params][9] doubles.  Starts from the uploaded tables (pose 0 of bmo_system_upload) for every pose;
+ * afterwards the system holds n_poses poses exactly as after bmo_system_set_poses.                                   */
+int32_t bmo_system_apply_poses(bmo_sys* sys, int32_t n_poses, int32_t n_ops, const bmo_kin_op* ops, int32_t n_params, const double* params);
+/* read back the tables of one pose (tests / debugging): any pointer may be NULL.  prims: [n_prims] records,
+ * vertices: [n_vertices][3], bounds: [n_parts][10], det_pose: [n_objects][12] (pos, dir row-major).                    */
+int32_t bmo_system_get_pose(bmo_sys* sys, int32_t pose, bmo_prim* prims, double* vertices, double* bounds, double* det_pose);
+
 /* replaces: solve_system!(system, beams(bg)) for Beam{Ray} / Beam{PolarizedRay}
  * (System.jl:130-154, 444-475).  pos/dir: [n][3]; lambda_id: [n] index into tables.lambdas;
  * E0: NULL or [n][6] (re,im x 3) -> PolarizedRay; pose_id: NULL or [n].                          */
@@ -196,7 +247,8 @@ int32_t bmo_trace_rays(bmo_sys* sys, int64_t n, const double* pos, const double*
 
 /* bmo_trace_rays + bmo_result_spots in one call, for systems without beamsplitters (one beam per ray):
  * replaces `solve_system!(system, beams(bg))` followed by reading `Spotdetector.data`
- * (System.jl:463-468, Spotdetector.jl:50-61).  det_object (NULL ok) / xz: [n] / [n][2] host arrays.
+ * (System.jl:463-468, Spotdetector.jl:50-61).  det_object (NULL ok) / xz: [n] / [n][2] host arrays; xz of a ray that
+ * reached no Spotdetector is (NaN, NaN), so det_object is only needed to tell several detectors apart.
  * With host inputs the rays are traced in sub-batches on separate streams, so that the host->device
  * copy of one sub-batch and the device->host copy of the hits of another overlap the waves of a
  * third (pinned host memory makes the copies truly asynchronous).  out may be NULL.              */
@@ -296,6 +348,28 @@ int32_t bmo_psf_free(bmo_psf* psf);   /* empty!(psf) */
  * fields[pose] start from zero on the device, power[pose] = optical_power of each; fields (host, [n_poses][n*n*2]) and
  * power (host, [n_poses]) may each be NULL -- with fields == NULL only n_poses doubles leave the device.        */
 int32_t bmo_pd_sweep(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_poses, double* fields, double* power, uint32_t flags);
+
+/* ---- multi-GPU: the one exchange step of the path ---------------------------------------------------------
+ * replaces: the serial `for beam in beams(bg)` of solve_system!(system, ::AbstractBeamGroup) (System.jl:463-468) once the
+ * host shards the beams of a group over several GPUs -- every GPU accumulates its beamlets onto a full n x n partial field
+ * (bmo_pd_accumulate) and the partial fields are summed, which is what the reference's `pd.field[i, j] += ...`
+ * (Photodetector.jl:103) does serially.  One complex128 all-reduce over NVLink (NCCL, bound at run time: dlopen of
+ * libnccl.so.2, or BMO_NCCL_LIB).  Tracing itself needs no communication (rays / beamlets are independent).
+ *   one process per GPU: rank 0 calls bmo_comm_unique_id, ships the 128 bytes to the other ranks, all call bmo_comm_init;
+ *   one process, n GPUs: bmo_comm_init_local over the n contexts + bmo_pd_allreduce_local (grouped).                  */
+#define BMO_COMM_ID_BYTES 128
+#define BMO_COMM_SYNC 16u   /* flag: synchronise the context's stream before returning (device fields; host fields always do) */
+typedef struct bmo_comm bmo_comm;
+int32_t bmo_comm_unique_id(uint8_t* id /* [BMO_COMM_ID_BYTES] */);
+int32_t bmo_comm_init(bmo_ctx* ctx, int32_t n_ranks, int32_t rank, const uint8_t* id, bmo_comm** comm);
+int32_t bmo_comm_init_local(int32_t n, bmo_ctx* const* ctxs, bmo_comm** comms /* [n] out */);
+int32_t bmo_comm_info(bmo_comm* comm, int32_t* rank, int32_t* n_ranks, int32_t* nccl_version);
+/* field: n_complex complex128 values (re, im interleaved; a Photodetector field has n_complex = n * n), summed in place over
+ * all ranks.  Host pointer (staged through the device), or device pointer with BMO_INPUT_DEVICE (enqueued on the context's
+ * stream; add BMO_COMM_SYNC to wait for it).                                                                    */
+int32_t bmo_pd_allreduce(bmo_comm* comm, double* field, int64_t n_complex, uint32_t flags);
+int32_t bmo_pd_allreduce_local(int32_t n, bmo_comm* const* comms, double* const* fields, int64_t n_complex, uint32_t flags);
+int32_t bmo_comm_free(bmo_comm* comm);
 
 /* FP64 DFMA micro-benchmark used as the roofline denominator of the FP64-bound kernels.          */
 int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops);

@@ -437,6 +437,34 @@ int orc_new(const char* kind, const double* d, int nd, const int* ih, int ni) {
 }
 
 // sub-handles: part i of a multi-shape object / shape of an object (registered on demand)
+// Mesh(load(path)) for a binary STL (Mesh.jl:48-70 on top of MeshIO's binary STL reader): 80-byte header, uint32 triangle
+// count, per triangle 12 little-endian Float32 (normal, 3 vertices) + uint16; vertex 3(i-1)+j = j-th corner of triangle i,
+// faces are the consecutive triples, everything scaled by Float32(1e-3) in Float32 arithmetic.
+int orc_load_stl(const char* path) {
+    ORC_TRY
+    FILE* f = fopen(path, "rb");
+    if (!f) throw std::runtime_error(std::string("orc_load_stl: cannot open ") + path);
+    unsigned char hdr[84];
+    if (fread(hdr, 1, 84, f) != 84) { fclose(f); throw std::runtime_error("orc_load_stl: short file"); }
+    uint32_t n = (uint32_t)hdr[80] | ((uint32_t)hdr[81] << 8) | ((uint32_t)hdr[82] << 16) | ((uint32_t)hdr[83] << 24);
+    auto* m = new Mesh();
+    m->f32 = true;
+    const float sc = 1e-3f;
+    m->scale = (double)sc;
+    std::vector<unsigned char> rec(50);
+    for (uint32_t i = 0; i < n; i++) {
+        if (fread(rec.data(), 1, 50, f) != 50) { fclose(f); delete m; throw std::runtime_error("orc_load_stl: truncated triangle record"); }
+        for (int j = 0; j < 3; j++) {
+            float c[3];
+            std::memcpy(c, rec.data() + 12 + 12 * j, 12);
+            m->vertices.push_back({(double)(c[0] * sc), (double)(c[1] * sc), (double)(c[2] * sc)});
+        }
+        m->faces.push_back({(int)(3 * i), (int)(3 * i + 1), (int)(3 * i + 2)});
+    }
+    fclose(f);
+    return reg_shape(m);
+    ORC_CATCH(-1)
+}
 int orc_part(int h, int i) { ORC_TRY return reg_object(O(h)->parts.at(i)); ORC_CATCH(-1) }
 int orc_shape_of(int h) { ORC_TRY return reg_shape(O(h)->shape); ORC_CATCH(-1) }
 
@@ -827,6 +855,8 @@ int orc_eval(const char* fn, const int* ih, int ni, const double* a, int na, dou
         out[0] = h.valid; out[1] = h.t; out[2] = h.n.x; out[3] = h.n.y; out[4] = h.n.z; out[5] = part_index(o, h.shape); return 6;
     }
     if (k == "moeller_trumbore") { out[0] = Mesh::moeller_trumbore(V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}, V3{a[6], a[7], a[8]}, V3{a[9], a[10], a[11]}, V3{a[12], a[13], a[14]}); return 1; }
+    if (k == "mesh_counts") { Mesh* m = M(ih[0]); out[0] = (double)m->vertices.size(); out[1] = (double)m->faces.size(); out[2] = m->f32; out[3] = m->scale; return 4; }
+    if (k == "mesh_faces") { Mesh* m = M(ih[0]); for (size_t i = 0; i < m->faces.size(); i++) for (int j = 0; j < 3; j++) out[3 * i + j] = m->faces[i][j]; return 3 * (int)m->faces.size(); }
     if (k == "mesh_vertices") { Mesh* m = M(ih[0]); for (size_t i = 0; i < m->vertices.size(); i++) { out[3 * i] = m->vertices[i].x; out[3 * i + 1] = m->vertices[i].y; out[3 * i + 2] = m->vertices[i].z; } return 3 * (int)m->vertices.size(); }
     if (k == "thickness_shape") { out[0] = S(ih[0])->thickness(); return 1; }
     if (k == "thickness_object") { out[0] = O(ih[0])->thickness(); return 1; }

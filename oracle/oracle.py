@@ -204,6 +204,12 @@ def mesh(vertices, faces, f32=False):
     return new("Mesh", v.ravel(), [v.shape[0], f.shape[0], int(f32)] + list(f.ravel()))
 
 
+def load_stl(path):
+    """Mesh(load(path)) of a binary STL (Mesh.jl:48-70): Mesh{Float32} scaled by 1e-3."""
+    lib().orc_load_stl.argtypes = [C.c_char_p]
+    return Handle(_chk(lib().orc_load_stl(os.fsencode(path))))
+
+
 def system(objects):
     return new("System", ih=objects)
 

@@ -479,7 +479,7 @@ inline Beam* bs_reflected_beam(Object* bs, Ray& ray) {
 // wavelength, refractive index (and polarisation) of the freshly computed child; its stored path stays.
 inline void modify_beam_head(Beam& old_, const Beam& new_) {
     Ray& o = old_.rays.front(); const Ray& n = new_.rays.front();
-    o.pos = n.pos; o.dir = n.dir; o.lambda = n.lambda; o.n = n.n;
+    o.pos = n.pos; o.dir = normalize(n.dir) /* direction! normalises, AbstractRay.jl:83-86 */; o.lambda = n.lambda; o.n = n.n;
     if (o.polarized) for (int k = 0; k < 3; k++) o.E0[k] = n.E0[k];
 }
 // AbstractBeam.jl:59-76 children!(beam, [t, r]): a childless beam adopts the children; a beam that
@@ -820,7 +820,7 @@ inline void retrace_system(System& sys, Beam& beam) {
         }
         if (i < beam.rays.size()) {   // Beam.jl:82-95 replace!
             Ray& nx = beam.rays[i];
-            nx.pos = in.ray.pos; nx.dir = in.ray.dir; nx.lambda = in.ray.lambda; nx.n = in.ray.n;
+            nx.pos = in.ray.pos; nx.dir = normalize(in.ray.dir) /* direction!, AbstractRay.jl:83-86 */; nx.lambda = in.ray.lambda; nx.n = in.ray.n;
             if (nx.polarized) for (int k = 0; k < 3; k++) nx.E0[k] = in.ray.E0[k];
         } else {
             cleanup_children = true;
@@ -864,7 +864,7 @@ inline void retrace_system(System& sys, Gauss& g) {
             const BeamInteraction* is[3] = {&in.c, &in.w, &in.d};
             for (int k = 0; k < 3; k++) {
                 Ray& nx = bs[k]->rays[i];
-                nx.pos = is[k]->ray.pos; nx.dir = is[k]->ray.dir; nx.lambda = is[k]->ray.lambda; nx.n = is[k]->ray.n;
+                nx.pos = is[k]->ray.pos; nx.dir = normalize(is[k]->ray.dir); nx.lambda = is[k]->ray.lambda; nx.n = is[k]->ray.n;
             }
         } else {
             cleanup_children = true;

@@ -12,12 +12,14 @@ class OracleFactory2(_OracleFactory):
     def MirrorFromMesh(self, mesh): return self.orc.new("Mirror", ih=[mesh])
     def CuboidMesh(self, x, y, z, th=math.pi / 2): return self.orc.new("CuboidMesh", [x, y, z, th])
     def MeshF32(self, v, f): return self.orc.mesh(v, f, f32=True)
+    def LoadSTL(self, path): return self.orc.load_stl(path)
 
 
 class ProductFactory2(_ProductFactory):
     def LensFromMesh(self, mesh, n): return self.m.Lens(mesh, n)
     def MirrorFromMesh(self, mesh): return self.m.Mirror(mesh)
     def MeshF32(self, v, f): return self.m.Mesh(v, f, scale=float(np.float32(1e-3)), f32=True)
+    def LoadSTL(self, path): return self.m.load_stl(path)
 
 
 # ---- C3: Keplerian expander (docs/src/tutorials/expander.md:25-66) + Photodetector ---------------------
@@ -87,6 +89,40 @@ def _mesh_scene(F, nu=96, nv=96):
 
 def mesh_scene(m, **kw): return _mesh_scene(ProductFactory2(m), **kw)
 def mesh_scene_oracle(**kw): return _mesh_scene(OracleFactory2(), **kw)
+
+
+# BASELINE config 4 as SURVEY 8(d) specifies it: the Fresnel rhomb of test/runtests.jl:2339-2349 at full size (CuboidMesh
+# 0.5 x 1.25 x 0.5 m, 53.3 deg, n = 1.5, turned by 135 deg about y), a ThinBeamsplitter (R = 0.5), Retroreflector(25e-3)
+# (Misc.jl:49) and the reference's own STL asset as a mirror: Mirror(Mesh(load("Mirror_Post.stl"))), 18 196 triangles.
+# A ray entering at the origin along +y leaves the rhomb at x = z = RHOMB_EXIT, y = 1.25, still along +y.
+RHOMB_EXIT = -0.52102107
+C4_HALF, C4_Y0 = 0.006, -1.0      # the bundle: jittered lattice of half-width 6 mm (inside the retroreflector's aperture)
+
+
+def _mesh_scene_c4(F, stl_path):
+    s1 = F.CuboidMesh(0.5, 1.25, 0.5, math.radians(53.3))
+    rhomb = F.LensFromMesh(s1, 1.5)
+    rhomb.translate3d_([-0.25, 0.0, -0.25])
+    s1.set_new_origin3d_()
+    rhomb.yrotate3d_(math.radians(135))
+    c = RHOMB_EXIT
+    bs = F.ThinBeamsplitter(0.1, reflectance=0.5)
+    bs.zrotate3d_(math.radians(45))
+    bs.translate3d_([c, 1.5, c])
+    retro = F.Retroreflector(25e-3)
+    a = np.array([1.0, 1.0, 1.0]) / math.sqrt(3)
+    b = np.array([0.0, -1.0, 0.0])
+    ax = np.cross(a, b); ax /= np.linalg.norm(ax)
+    retro.rotate3d_([float(x) for x in ax], math.acos(float(a @ b)))      # open corner towards -y
+    retro.translate3d_([c, 1.8 + 25e-3 / math.sqrt(3), c])                 # apex on the beam axis, aperture plane at y = 1.8
+    post = F.MirrorFromMesh(F.LoadSTL(stl_path))
+    post.zrotate3d_(math.radians(20))
+    post.translate3d_([c + 0.3, 1.49, c - 0.03])                            # in the reflected arm (+x from the splitter)
+    return dict(system=F.System([rhomb, bs, retro, post]), rhomb=rhomb, bs=bs, retro=retro, post=post)
+
+
+def mesh_scene_c4(m, stl_path): return _mesh_scene_c4(ProductFactory2(m), stl_path)
+def mesh_scene_c4_oracle(stl_path): return _mesh_scene_c4(OracleFactory2(), stl_path)
 
 
 def jittered_lattice(n, seed=0, half=0.012, y0=-0.6):

@@ -54,6 +54,9 @@ def _fold(F):
     return dict(system=F.System([lens, fold, bs, e1, e2, blocker]), lens=lens, fold=fold, bs=bs, e1=e1, e2=e2, blocker=blocker)
 
 
+RETRACE_ULP = 1e-13     # normalize() of an already (almost) unit direction moves it by an ulp or two; hit points follow
+
+
 def _tree_equal(a, b, tol=0.0):
     assert [(x["parent"], len(x["rays"]["t"])) for x in a] == [(x["parent"], len(x["rays"]["t"])) for x in b]
     for x, y in zip(a, b):
@@ -63,7 +66,7 @@ def _tree_equal(a, b, tol=0.0):
             assert np.array_equal(np.isfinite(u), fin)
             if tol == 0.0:
                 assert np.array_equal(u[fin], v[fin]), k
-            else:
+            elif fin.any():
                 assert np.abs(u[fin] - v[fin]).max() <= tol * max(1.0, np.abs(v[fin]).max()), k
         assert np.array_equal(x["rays"]["obj"], y["rays"]["obj"])
 
@@ -76,7 +79,9 @@ def test_oracle_retrace_reproduces_solved_ring(orc):
     first = orc.beam_export(sc["system"], b)
     assert len(first[0]["rays"]["t"]) == 21 + 1            # runtests.jl:1055: n_mirrors + 1 rays
     orc.solve_system_(sc["system"], b, r_max=1000, retrace=True)
-    _tree_equal(orc.beam_export(sc["system"], b), first)
+    # replace! writes the re-validated successor rays through direction!, which normalises (Beam.jl:81-95, AbstractRay.jl:83-86):
+    # a retraced path equals the solved one up to that rounding, not to the bit
+    _tree_equal(orc.beam_export(sc["system"], b), first, tol=RETRACE_ULP)
 
 
 def test_oracle_retrace_follows_moved_mirror_and_matches_fresh_trace(orc):
@@ -91,7 +96,7 @@ def test_oracle_retrace_follows_moved_mirror_and_matches_fresh_trace(orc):
     orc.solve_system_(sc["system"], b, retrace=True)
     fresh = orc.beam([0.0, -0.1, 0.0], [0.0, 1.0, 0.0], 1e-6)
     orc.solve_system_(sc["system"], fresh)
-    _tree_equal(orc.beam_export(sc["system"], b), orc.beam_export(sc["system"], fresh))
+    _tree_equal(orc.beam_export(sc["system"], b), orc.beam_export(sc["system"], fresh), tol=RETRACE_ULP)
 
 
 def test_oracle_retrace_drops_tail_when_path_breaks(orc):
@@ -105,7 +110,7 @@ def test_oracle_retrace_drops_tail_when_path_breaks(orc):
     orc.solve_system_(sc["system"], fresh)
     t = orc.beam_export(sc["system"], b)
     assert len(t) == 1                                       # children dropped (System.jl:249)
-    _tree_equal(t, orc.beam_export(sc["system"], fresh))
+    _tree_equal(t, orc.beam_export(sc["system"], fresh), tol=RETRACE_ULP)
 
 
 def test_oracle_retrace_is_blind_to_new_occluder(orc):
@@ -117,7 +122,7 @@ def test_oracle_retrace_is_blind_to_new_occluder(orc):
     t0 = orc.beam_export(sc["system"], b)
     sc["blocker"].translate3d_([0.0, 0.0, -1.0])             # now between lens and fold mirror
     orc.solve_system_(sc["system"], b, retrace=True)
-    _tree_equal(orc.beam_export(sc["system"], b), t0)        # unchanged: the blocker is not seen
+    _tree_equal(orc.beam_export(sc["system"], b), t0, tol=RETRACE_ULP)        # unchanged: the blocker is not seen
     fresh = orc.beam([0.0, -0.1, 0.0], [0.0, 1.0, 0.0], 1e-6)
     orc.solve_system_(sc["system"], fresh)
     assert len(orc.beam_export(sc["system"], fresh)) == 1    # a fresh trace is stopped... reflected by it
