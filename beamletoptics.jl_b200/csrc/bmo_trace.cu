@@ -1492,7 +1492,7 @@ struct SubTrace {
     Queue cur, next, scr;
     HitBuf hit;
     int32_t* blk_cnt = nullptr; long long* blk_off = nullptr; int64_t blk_cap = 0;
-    unsigned long long* d_wtot = nullptr;  // [r_max + 8][2]: units alive after wave w, spawn events of wave w
+    unsigned long long* d_wtot = nullptr;  // [max_waves() + 8][2]: units alive after wave w, spawn events of wave w
     unsigned long long* h_wtot = nullptr;  // pinned, 2 * 4 entries
     long long* d_scan_tot = nullptr;       // scratch total of scan_counts
     std::vector<cudaEvent_t> ev;           // (start, stop) of intersect_wave for each wave of a chunk
@@ -1505,6 +1505,10 @@ struct SubTrace {
     double host_wait_ms = 0;
     RetraceView rt;                        // retrace calls: the previous solution
 
+    // A beam holds at most r_max rays (`while length(rays) < r_max`, System.jl:133), but the children of a beamsplitter
+    // start counting afresh (System.jl:141-150): a tree of g generations needs up to g * r_max waves.  The host gives up
+    // after 64 generations' worth (the reference would recurse as deep as the tree is).
+    int64_t max_waves() const { return has_splitter ? (int64_t)64 * (r_max + 1) : (int64_t)r_max + 1; }
     int32_t begin(const TraceInputs& in_h);
     int32_t enqueue_chunk();
     int32_t finish_chunk();
@@ -1546,7 +1550,7 @@ int32_t SubTrace::begin(const TraceInputs& in_h) {
     }
     ev.assign(ctx->ev_pool.begin() + e0, ctx->ev_pool.begin() + e0 + 2 * max_chunk);
     evs0 = ctx->ev_pool[e0 + 8]; evs1 = ctx->ev_pool[e0 + 9];
-    const size_t n_wtot = (size_t)2 * (r_max + 8);
+    const size_t n_wtot = (size_t)2 * (max_waves() + 8);
     BMO_CUDA(dev_alloc(&d_wtot, n_wtot, st));
     BMO_CUDA(cudaMemsetAsync(d_wtot, 0, n_wtot * sizeof(unsigned long long), st));
     BMO_CUDA(dev_alloc(&d_scan_tot, 4, st));
@@ -1681,7 +1685,7 @@ int32_t SubTrace::enqueue_chunk() {
         }
         wave++;
         launched++;
-        if (wave > r_max + 1) break;
+        if (wave > max_waves()) break;
     }
     BMO_CUDA(cudaMemcpyAsync(h_wtot, d_wtot + 2 * (wave - launched), (size_t)2 * launched * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
     // single-stream calls: the cumulative counters ride along, so that the call needs no blocking read-back at its end
@@ -1872,7 +1876,7 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
             s.launched = 0;
             if (prof) fprintf(stderr, "[bmo]   sub-batch %d: chunk done at %.3f ms (waited %.3f), alive %lld\n", s.slot, tnow_ms() - tp0, s.host_wait_ms, (long long)s.alive);
             if (s.alive > 0) {
-                if (s.wave > r_max + 1) return fail(BMO_ESTATE, "trace: wave loop did not terminate");
+                if (s.wave > s.max_waves()) return fail(BMO_ESTATE, "trace: wave loop did not terminate (more than 64 generations of r_max rays)");
                 if ((rc = s.enqueue_chunk())) return rc;
                 any = true;
             }

@@ -35,6 +35,8 @@ FLOP_SDF, FLOP_TRI, FLOP_INT = 45.0, 40.0, 60.0
 # (ncu --set full, profiles/r01s4_ncu_trace_kernels.txt): 68.1 MB read + 89.0 MB written (the excess over the algorithmic 36 MB of
 # writes is register-spill lines evicted from L1)
 K1_DRAM_BYTES_PER_LAUNCH = 157.0e6
+K1_TRAFFIC_SOURCE = ("profiles/r01s4_ncu_trace_kernels.txt (mean of the 4 waves, 2^20 rays per launch; algorithmic = 64 B ray state read "
+                     "+ 36 B hit record written per ray)")
 
 
 def rays_for_rank(rank, n=N_RAYS):
@@ -49,31 +51,96 @@ def rays_for_rank(rank, n=N_RAYS):
     return np.ascontiguousarray(pos), np.ascontiguousarray(d)
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process (and the threads it starts later) to the CPUs of the NUMA node the rank's GPU hangs off, before
+    anything allocates pinned host memory: Linux places the pages of cudaHostAlloc on the node of the allocating CPU, and
+    a rank whose staging buffers sit on the other socket pays the inter-socket link on every host<->device copy.
+    Returns a description for the JSON line (None: topology unknown, nothing changed)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        bus = bus.lower()
+        if len(bus.split(":")[0]) == 8:          # NVML prints an 8-digit PCI domain, sysfs a 4-digit one
+            bus = bus[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if not use:
+            return {"numa_node": node, "bound": False, "why": "no allowed CPU on the GPU's node"}
+        os.sched_setaffinity(0, use)
+        return {"numa_node": node, "bound": True, "cpus": len(use)}
+    except Exception as e:      # no NVML / no sysfs topology: leave the affinity alone
+        return {"bound": False, "why": type(e).__name__}
+
+
 class ClockSampler(threading.Thread):
+    """SM clock and throttle reasons of the rank's GPU, sampled through NVML every 5 ms for as long as the bench runs
+    (nvidia-smi, one process per sample, is the fallback)."""
     Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.sm_max = index, [], False, None
+        self.marks = {}          # name -> (first sample, one past the last sample) of a timed region
+
+    def mark(self, name, begin):
+        lo, hi = self.marks.get(name, (len(self.samples), len(self.samples)))
+        self.marks[name] = (len(self.samples), hi) if begin else (lo, len(self.samples))
 
     def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            bits = [getattr(pynvml, n, 0) for n in ("nvmlClocksEventReasonHwSlowdown", "nvmlClocksEventReasonHwThermalSlowdown",
+                                                    "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksEventReasonSwPowerCap")]
+            fallback = [0x8, 0x40, 0x20, 0x4]
+            bits = [b or f for b, f in zip(bits, fallback)]
+            get_reasons = getattr(pynvml, "nvmlDeviceGetCurrentClocksEventReasons", None) or pynvml.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                mhz = float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                r = int(get_reasons(h))
+                self.samples.append((mhz, [bool(r & b) for b in bits]))
+                time.sleep(0.005)
+            return
+        except Exception:
+            pass
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
                                      capture_output=True, text=True, timeout=5).stdout.strip()
                 if out:
-                    self.samples.append([x.strip() for x in out.split(",")])
+                    f = [x.strip() for x in out.split(",")]
+                    self.sm_max = float(f[1])
+                    self.samples.append((float(f[0]), [x.lower().startswith("active") for x in f[2:6]]))
             except Exception:
                 pass
             time.sleep(0.1)
 
     def summary(self):
         if not self.samples:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        mhz = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for k, n in enumerate(names) if any(s[2 + k].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": mhz[len(mhz) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons, "samples": len(mhz)}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        def part(lo, hi):
+            sel = self.samples[lo:hi] or self.samples
+            mhz = sorted(x[0] for x in sel)
+            return {"sm_mhz": mhz[len(mhz) // 2], "sm_mhz_min": mhz[0], "samples": len(sel),
+                    "reasons": [n for k, n in enumerate(self.NAMES) if any(x[1][k] for x in sel)]}
+        out = part(0, len(self.samples))
+        out["sm_max_mhz"] = self.sm_max
+        out["how"] = "NVML every 5 ms over the whole run; per-leg medians under `legs`"
+        out["legs"] = {k: part(lo, hi) for k, (lo, hi) in self.marks.items() if hi > lo}
+        return out
 
 
 def run_reference(args, rank):
@@ -120,9 +187,11 @@ def main():
     ap.add_argument("--rays", type=int, default=N_RAYS)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-detector", action="store_true", help="skip the secondary Photodetector (C3) measurement")
-    ap.add_argument("--c3-side", type=int, default=64, help="beamlets per side of the C3 lattice block (256 = the full 65536-beamlet config)")
+    ap.add_argument("--c3-side", type=int, default=256, help="beamlets per side of the C3 lattice (256 = the full 65536-beamlet config), split over the ranks")
     ap.add_argument("--c3-pixels", type=int, default=2048)
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary retrace (a4) and PSFDetector (N2) measurements")
+    ap.add_argument("--no-numa", action="store_true", help="leave the CPU affinity of the rank alone")
+    ap.add_argument("--full-inputs", action="store_true", help="e2e ships a direction and a wavelength id per ray (52 B/ray) instead of one of each per bundle")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))
@@ -136,6 +205,7 @@ def main():
     sys.stdout.flush()
     json_out = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
+    numa = None if args.no_numa else bind_to_gpu_numa(local_rank)     # before torch starts threads / pins memory
     import torch
     import torch.distributed as dist
     if not torch.cuda.is_available():
@@ -156,6 +226,7 @@ def main():
     n = args.rays
     stream = torch.cuda.current_stream()
     L.set_stream(stream.cuda_stream, dev)
+    comm = m.parallel.FieldComm.from_torch(device=dev) if world > 1 else None     # NCCL behind the C ABI (bmo_comm_init)
 
     sc = scenes.doublet_spot(m)
     dsys = m.upload_system(sc["system"], [LAMBDA], device=dev)       # system upload: outside the timed region
@@ -164,6 +235,7 @@ def main():
     # pinned host buffers (e2e) and resident device copies (value)
     pin = lambda a: torch.from_numpy(a).pin_memory()
     pos_p, dir_p, lam_p = pin(pos_h), pin(dir_h), pin(lam_h)
+    dir1_p = pin(np.ascontiguousarray(dir_h[0]))                      # the one direction of the collimated bundle
     pos_d, dir_d, lam_d = pos_p.cuda(non_blocking=True), dir_p.cuda(non_blocking=True), lam_p.cuda(non_blocking=True)
     spot_obj_p = torch.empty(n, dtype=torch.int32).pin_memory()
     spot_xz_p = torch.empty((n, 2), dtype=torch.float64).pin_memory()
@@ -177,26 +249,40 @@ def main():
         res.free()
         return inter
 
+    import ctypes as C
+    if args.full_inputs:
+        e2e_args = (C.c_void_p(dir_p.data_ptr()), C.c_void_p(lam_p.data_ptr()), 0, C.c_void_p(spot_obj_p.data_ptr()))
+        h2d, d2h = int(pos_h.nbytes + dir_h.nbytes + lam_h.nbytes), int(n * 4 + n * 16)
+        e2e_inputs = "pos, dir [n][3] f64 + lambda id [n] i32 in; detector id [n] i32 + spot (x,z) [n][2] f64 out"
+    else:
+        # a collimated bundle: one direction and one wavelength for all rays (BMO_UNIFORM_DIR, lambda_id = NULL); the spot of a
+        # ray that reached no detector comes back as NaN, so the per-ray detector id is not requested
+        e2e_args = (C.c_void_p(dir1_p.data_ptr()), None, L.UNIFORM_DIR, None)
+        h2d, d2h = int(pos_h.nbytes + 24), int(n * 16)
+        e2e_inputs = "pos [n][3] f64 + one direction [3] (BMO_UNIFORM_DIR) in; spot (x,z) [n][2] f64 out (NaN = no detector reached)"
+
     def step_e2e():
-        import ctypes as C
         h = C.c_void_p()
         # solve_system! + Spotdetector.data in one C-ABI call: host buffers in, host buffers out
-        L.check(L.lib().bmo_trace_rays_spots(dsys.h, n, C.c_void_p(pos_p.data_ptr()), C.c_void_p(dir_p.data_ptr()), C.c_void_p(lam_p.data_ptr()),
-                                             None, None, 100, 0, C.c_void_p(spot_obj_p.data_ptr()), C.c_void_p(spot_xz_p.data_ptr()), C.byref(h)))
+        L.check(L.lib().bmo_trace_rays_spots(dsys.h, n, C.c_void_p(pos_p.data_ptr()), e2e_args[0], e2e_args[1],
+                                             None, None, 100, e2e_args[2], e2e_args[3], C.c_void_p(spot_xz_p.data_ptr()), C.byref(h)))
         info = L.bmo_result_info()
         L.check(L.lib().bmo_result_get_info(h, C.byref(info)))
         L.lib().bmo_result_free(h)
         return info.interactions
 
-    def timed(fn, steps, warmup):
+    sampler = ClockSampler(dev)
+
+    def timed(fn, steps, warmup, leg, together=True):
         for _ in range(warmup):
             fn()
         L.counters_reset(dev)                    # per-kernel counters cover the timed steps only
         times, inter = [], 0
+        sampler.mark(leg, True)
         for _ in range(steps):
             flush.fill_(1)                       # evict inputs from L2 between timed iterations
             torch.cuda.synchronize()
-            if world > 1:
+            if world > 1 and together:
                 dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -204,16 +290,22 @@ def main():
             e1.record(stream)
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
+        sampler.mark(leg, False)
         return times, inter
 
-    sampler = ClockSampler(dev)
     if rank == 0:
         sampler.start()
-    times, inter = timed(step_device, args.steps, args.warmup)
+    times, inter = timed(step_device, args.steps, args.warmup, "trace_resident")
     c = L.counters(dev)
     n_total_steps = args.steps
-    times_e, inter_e = timed(step_e2e, args.steps, args.warmup)
-    sampler.stop_flag = True
+    solo_ms = None
+    if world > 1:
+        # the same end-to-end step on rank 0 alone, the other ranks idle: the denominator of the weak-scaling efficiency of e2e
+        if rank == 0:
+            t_solo, _ = timed(step_e2e, args.steps, args.warmup, "trace_e2e_solo", together=False)
+            solo_ms = sum(t_solo) / len(t_solo)
+        dist.barrier()
+    times_e, inter_e = timed(step_e2e, args.steps, args.warmup, "trace_e2e")
 
     def agg(times):
         t = torch.tensor([sum(times)], dtype=torch.float64, device="cuda")
@@ -227,6 +319,7 @@ def main():
     inter_all, inter_all_e = float(it[0].item()), float(it[1].item())
 
     peak = L.measure_fp64_peak(dev)
+    parity = multi_gpu_parity(m, L, dev, comm, rank, world) if world > 1 else None
     # the retrace leg runs before the detector leg: after the detector's 64 MiB fields have gone through the stream-ordered pool
     # the retrace's wave buffers (4 x 100 MB per call) hit a fragmented pool and its timings scatter between 6 and 30 ms
     extras = None
@@ -234,7 +327,9 @@ def main():
         extras = {"retrace": bench_retrace(m, L, dev, stream, dsys, sc, pos_d, dir_d, lam_d, n, flush)}
     det = None
     if not args.no_detector:
-        det = bench_detector(m, L, dev, stream, args.c3_side, args.c3_pixels, max(2, min(args.steps, 3)), 1, flush, peak, rank, world)
+        sampler.mark("detector", True)
+        det = bench_detector(m, L, dev, stream, args.c3_side, args.c3_pixels, 2, 1, flush, peak, rank, world, comm)
+        sampler.mark("detector", False)
     if extras is not None:
         extras["psf"] = bench_psf(m, L, dev, stream, flush, peak)
     if rank == 0:
@@ -250,29 +345,36 @@ def main():
         except Exception:
             hbm_peak = 6650.0
         comp = bench_compaction(m, L, dev, dsys, n, hbm_peak)
+        sampler.stop_flag = True
+        e2e_ms = tot_ms_e / args.steps
         out = {
             "metric": "ray-surface interactions/s", "value": value, "unit": "interactions/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD, "rays_per_gpu": n, "r_max": 100, "l2": "flushed with a 256 MiB write between timed iterations",
                        "outputs": "spot (x,z) per ray; segment table not kept"},
-            "e2e": {"value": e2e, "unit": "interactions/s", "ms_per_step": tot_ms_e / args.steps,
-                    "h2d_bytes_per_step": int(pos_h.nbytes + dir_h.nbytes + lam_h.nbytes),
-                    "d2h_bytes_per_step": int(spot_obj_p.numel() * 4 + spot_xz_p.numel() * 8)},
+            "e2e": {"value": e2e, "unit": "interactions/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "buffers": e2e_inputs,
+                    "solo_ms_per_step": solo_ms,
+                    "weak_scaling_efficiency": (solo_ms / e2e_ms) if solo_ms else None,
+                    "efficiency_note": "rank 0's e2e step alone on the box / the same step with all ranks running (max over ranks)" if solo_ms else None},
             "gpu_launches": int(c["kernel_launches"] * args.steps / n_total_steps),
             "roofline": {"bound": "fp64", "kernel": "intersect_wave", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the 4 waves of one solve, from the
-                         # ncu --set full capture summarised in profiles/r01s4_ncu_trace_kernels.txt
+                         # ncu --set full capture named in traffic_source
                          "traffic": K1_DRAM_BYTES_PER_LAUNCH * n / N_RAYS, "traffic_algorithmic": 100.0 * n,
-                         "traffic_source": "profiles/r01s4_ncu_trace_kernels.txt (mean of the 4 waves, 2^20 rays per launch; algorithmic = 64 B ray state read + 36 B hit record written per ray)",
+                         "traffic_source": K1_TRAFFIC_SOURCE,
                          "peak_source": "measured here: DFMA probe (bmo_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry",
                          "flops_per_launch": flops / k1_n, "ms_per_launch": k1_ms / k1_n,
                          "share_of_step": k1_ms / n_total_steps / (tot_ms / args.steps) if tot_ms else None,
                          "counted": {"sdf_evals_per_step": c["sdf_evals"] / n_total_steps, "interactions_per_step": c["interactions"] / n_total_steps}},
             "roofline_compaction": comp,
             "clocks": sampler.summary(),
+            "numa": numa,
         }
+        if parity is not None:
+            out.update(parity)
         if det is not None:
             out["detector"] = det
         if extras is not None:
@@ -281,9 +383,47 @@ def main():
             out["cpu_baseline"] = cpu_baseline()
         print(json.dumps(out), file=json_out)
         json_out.flush()
+    if comm is not None:
+        comm.free()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def multi_gpu_parity(m, L, dev, comm, rank, world, k=16, pd_n=256):
+    """N > 1: the field of a small C3 lattice (k^2 beamlets, pd_n^2 pixels) sharded over the ranks and summed with
+    bmo_pd_allreduce, against the same lattice traced and accumulated by rank 0 alone.  Relative L2 of the difference."""
+    import ctypes as C
+    import torch
+    import torch.distributed as dist
+    from tests import scenes2 as s2
+    sc = s2.expander(m, pd_n)
+    lat = s2.beamlet_lattice(k, aperture=8e-3 * k / 256)
+    bundle = m.BeamletBundle.from_params(lat["pos"], lat["dir"], lat["lam"], lat["w0"], M2=lat["M2"], P0=1e-3 / 65536, support=lat["support"])
+    dsys = m.upload_system(sc["system"], [lat["lam"]], device=dev)
+    pd_index = dsys.flat.object_index(sc["pd"])
+    nb = k * k
+
+    def field_of(idx):
+        f = torch.zeros(pd_n * pd_n * 2, dtype=torch.float64, device="cuda")
+        if len(idx):
+            res = m.trace_beamlets(dsys, np.ascontiguousarray(bundle.rays[idx]), np.zeros(len(idx), np.int32), np.ascontiguousarray(bundle.w0[idx]),
+                                   np.ascontiguousarray(bundle.E0[idx]))
+            L.check(L.lib().bmo_pd_accumulate(dsys.h, res.h, pd_index, 0, C.c_void_p(f.data_ptr()), L.INPUT_DEVICE))
+            res.free()
+        torch.cuda.synchronize()
+        return f
+    mine = np.arange(rank, nb, world)                 # interleaved shards
+    f = field_of(mine)
+    comm.allreduce(int(f.data_ptr()), pd_n * pd_n, sync=True)
+    rel = torch.zeros(1, dtype=torch.float64, device="cuda")
+    if rank == 0:
+        ref = field_of(np.arange(nb))
+        rel[0] = torch.linalg.norm(f - ref) / torch.linalg.norm(ref)
+    dist.all_reduce(rel, op=dist.ReduceOp.MAX)
+    return {"multi_gpu_parity_rel_l2": float(rel.item()),
+            "multi_gpu_parity": f"{nb}-beamlet C3 lattice on a {pd_n}^2 Photodetector: field of the interleaved shards summed by bmo_pd_allreduce (NCCL {comm.nccl_version()} inside libbmo.so) "
+                                f"vs the whole lattice on rank 0 alone; tolerance 1e-8 (addition order across ranks differs)"}
 
 
 FLOP_PAIR_REF = 760.0   # flop-equivalents per pixel-beamlet pair in the reference's operation sequence (SURVEY 8(d))
@@ -291,37 +431,47 @@ FLOP_PAIR = 226.0       # the same weights (add/mul 1, sqrt/div 8, transcendenta
                         # pd_field_fast, counted op by op in DESIGN.md "K4" -- the work the kernel actually has to do
 
 
-def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_tflops, rank=0, world=1):
-    """Metric 2 (Photodetector px-beamlets/s) on the C3 workload: Keplerian expander + Photodetector(40 mm, pd_n),
-    k_side^2 beamlets of the C3 lattice (pitch 8 mm / 256, w0 = 1.5 pitch, lambda = 1 um).  The default run uses the central
-    64 x 64 block of the 256 x 256 lattice (bounded so that bench.py stays within minutes); the pair rate does not depend on it."""
+def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_tflops, rank=0, world=1, comm=None):
+    """Metric 2 (Photodetector px-beamlets/s) on the C3 workload: Keplerian expander + Photodetector(40 mm, pd_n), the
+    k_side x k_side beamlet lattice (pitch 8 mm / 256, w0 = 1.5 pitch, lambda = 1 um; k_side = 256 is BASELINE's 65536-beamlet
+    config).  STRONG scaling: the lattice is cut into `world` bands of rows, rank r traces and accumulates band r onto a full
+    partial field, and the partial fields are summed by bmo_pd_allreduce (NCCL inside libbmo.so) inside the timed region."""
     import ctypes as C
     import torch
     from tests import scenes2 as s2
     sc = s2.expander(m, pd_n)
     import torch.distributed as dist
     lat = s2.beamlet_lattice(k_side, aperture=8e-3 * k_side / 256)
-    pitch = 8e-3 / 256
-    lat["pos"][:, 0] += (rank - (world - 1) / 2) * k_side * pitch      # rank r holds the r-th block of the lattice (along x)
-    nb = k_side * k_side
-    bundle = m.BeamletBundle.from_params(lat["pos"], lat["dir"], lat["lam"], lat["w0"], M2=lat["M2"], P0=1e-3 / 65536, support=lat["support"])
+    nb_all = k_side * k_side
+    lo, hi = rank * nb_all // world, (rank + 1) * nb_all // world
+    nb = hi - lo
+    sel = slice(lo, hi)
+    bundle = m.BeamletBundle.from_params(lat["pos"][sel], lat["dir"][sel], lat["lam"], lat["w0"], M2=lat["M2"], P0=1e-3 / 65536, support=lat["support"])
     dsys = m.upload_system(sc["system"], [lat["lam"]], device=dev)
     res = m.trace_beamlets(dsys, bundle.rays, np.zeros(nb, np.int32), bundle.w0, bundle.E0)
     pd_index = dsys.flat.object_index(sc["pd"])
     field_d = torch.zeros(pd_n * pd_n * 2, dtype=torch.float64, device="cuda")
     field_h = torch.zeros(pd_n * pd_n * 2, dtype=torch.float64).pin_memory()
 
-    def run(ptr, flags):
-        if flags & L.INPUT_DEVICE:
-            field_d.zero_()                      # partial field of this rank
-        L.check(L.lib().bmo_pd_accumulate(dsys.h, res.h, pd_index, 0, C.c_void_p(ptr), flags))
-        if world > 1 and (flags & L.INPUT_DEVICE):
-            dist.all_reduce(field_d, op=dist.ReduceOp.SUM)
+    def run_device():
+        field_d.zero_()                      # partial field of this rank
+        L.check(L.lib().bmo_pd_accumulate(dsys.h, res.h, pd_index, 0, C.c_void_p(field_d.data_ptr()), L.INPUT_DEVICE))
+        if world > 1:
+            stream.synchronize()             # the library reduces on its context stream (= this stream); keep the order explicit
+            comm.allreduce(int(field_d.data_ptr()), pd_n * pd_n, sync=False)
+
+    def run_e2e():
+        if world == 1:
+            # pd.field (host) += field of the bundle: the C-ABI call with a host field copies it in, accumulates, copies it out
+            L.check(L.lib().bmo_pd_accumulate(dsys.h, res.h, pd_index, 0, C.c_void_p(field_h.data_ptr()), 0))
+        else:
+            run_device()
+            field_h.copy_(field_d, non_blocking=True)   # every rank ends with the whole field in host memory
 
     out = {}
-    for name, ptr, flags in (("device", field_d.data_ptr(), L.INPUT_DEVICE), ("e2e", field_h.data_ptr(), 0)):
+    for name, fn in (("device", run_device), ("e2e", run_e2e)):
         for _ in range(warmup):
-            run(ptr, flags)
+            fn()
         L.counters_reset(dev)
         times = []
         for _ in range(steps):
@@ -331,7 +481,7 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
                 dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            run(ptr, flags)
+            fn()
             e1.record(stream)
             torch.cuda.synchronize()
             times.append(e0.elapsed_time(e1))
@@ -343,22 +493,21 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
             dist.all_reduce(pr, op=dist.ReduceOp.SUM)        # whole-job pairs
         out[name] = dict(ms=float(tot.item()), pairs=float(pr.item()), k4_ms=c["pd_field_ms"] / steps, launches=c["kernel_launches"] / steps,
                          pairs_rank=c["px_beamlets"] / steps)
-        if name == "device" and world > 1:       # the e2e leg (host field) is a single-GPU notion: rank-local, no collective
-            break
-    if "e2e" not in out:
-        out["e2e"] = dict(out["device"])
     pairs = out["device"]["pairs"]
     ach = FLOP_PAIR * out["device"]["pairs_rank"] / (out["device"]["k4_ms"] * 1e-3) / 1e12
     res.free()
+    nbytes = int(field_h.numel() * 8)
     return {
         "metric": "Photodetector px-beamlets/s", "unit": "px-beamlets/s",
         "value": pairs / (out["device"]["ms"] * 1e-3), "ms_per_step": out["device"]["ms"],
-        "e2e": {"value": pairs / (out["e2e"]["ms"] * 1e-3), "ms_per_step": out["e2e"]["ms"],
-                "h2d_bytes_per_step": int(field_h.numel() * 8), "d2h_bytes_per_step": int(field_h.numel() * 8)},
-        "config": {"workload": f"C3: Keplerian beam expander, {nb} of 65536 GaussianBeamlets per GPU (a {k_side}x{k_side} block of the 256x256 lattice) onto a {pd_n}^2 Photodetector, coherent field sum"
-                               + (f", all-reduce of the {pd_n}^2 complex128 field over {world} GPUs inside the timed region" if world > 1 else ""),
-                   "beamlets_per_gpu": nb, "pixels": pd_n * pd_n, "pairs_per_step": pairs},
-        "n_gpus": world, "scaling": "weak",
+        "e2e": {"value": out["e2e"]["pairs"] / (out["e2e"]["ms"] * 1e-3), "ms_per_step": out["e2e"]["ms"],
+                "h2d_bytes_per_step": nbytes if world == 1 else 0, "d2h_bytes_per_step": nbytes,
+                "what": "bmo_pd_accumulate onto a pinned host field (copied in, accumulated, copied out)" if world == 1 else
+                        "partial field on the device, bmo_pd_allreduce, whole field copied to pinned host memory on every rank"},
+        "config": {"workload": f"C3: Keplerian beam expander, {nb_all} GaussianBeamlets ({k_side}x{k_side} lattice) onto a {pd_n}^2 Photodetector, coherent field sum"
+                               + (f"; {nb} beamlets per GPU, all-reduce of the {pd_n}^2 complex128 field over {world} GPUs inside the timed region" if world > 1 else ""),
+                   "beamlets": nb_all, "beamlets_per_gpu": nb, "pixels": pd_n * pd_n, "pairs_per_step": pairs},
+        "n_gpus": world, "scaling": "strong",
         "gpu_launches": out["device"]["launches"],
         "roofline": {"bound": "fp64", "kernel": "pd_field_fast", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s (FP64 flop-equivalents)",
                      "frac": ach / peak_tflops if peak_tflops else None, "ms_per_launch": out["device"]["k4_ms"],
