@@ -446,7 +446,7 @@ def bench_detector(m, L, dev, stream, k_side, pd_n, steps, warmup, flush, peak_t
     lo, hi = rank * nb_all // world, (rank + 1) * nb_all // world
     nb = hi - lo
     sel = slice(lo, hi)
-    bundle = m.BeamletBundle.from_params(lat["pos"][sel], lat["dir"][sel], lat["lam"], lat["w0"], M2=lat["M2"], P0=1e-3 / 65536, support=lat["support"])
+    bundle = m.BeamletBundle.from_params(lat["pos"][sel], lat["dir"], lat["lam"], lat["w0"], M2=lat["M2"], P0=1e-3 / 65536, support=lat["support"])
     dsys = m.upload_system(sc["system"], [lat["lam"]], device=dev)
     res = m.trace_beamlets(dsys, bundle.rays, np.zeros(nb, np.int32), bundle.w0, bundle.E0)
     pd_index = dsys.flat.object_index(sc["pd"])
