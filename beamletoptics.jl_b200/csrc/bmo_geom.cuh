@@ -397,6 +397,58 @@ template <bool RARE> BMO_D double shape_sdf_f(const SdfShape& sh, V3 p, unsigned
     lb.pred = (idx - first < 4 && sh.prims[idx].type != BMO_PRIM_MENISCUS) ? idx : -1;
     return m;
 }
+// ---- lean union evaluation ------------------------------------------------------------------------
+// The same result-identical member skipping for the common shape: a union of at most 4 plain primitives (no meniscus
+// frame, no aspheric pseudo-distance) -- flagged at upload (bit 2 of the first prim record).  The bookkeeping of
+// shape_sdf_f costs more instructions than the primitives it skips (ncu source page, profiles/r02e_*), so here
+//   * the bounds live in shared memory ([4][128] floats per block, one column per thread) and are indexed by the member
+//     number: one LDS / STS instead of select chains over four registers;
+//   * a bound is stored as B_k = v_k (+) S with S = the path length marched so far, both rounded so that
+//     B_k (-) S_now <= v_k - (distance moved since member k was evaluated): moving the march point is one add on S
+//     instead of four subtractions;
+//   * the evaluation order (previous arg-min first, then ascending) is a nibble-packed word.
+// Value and arg-min (lowest index on ties) are those of the plain left fold, as in shape_sdf_f.
+constexpr int LB_STRIDE = 128;    // threads per block of every kernel that marches (IBLOCK, Cfg::BLOCK)
+BMO_D float lds_f32(unsigned a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+BMO_D void sts_f32(unsigned a, float v) { asm volatile("st.shared.f32 [%0], %1;" :: "r"(a), "f"(v)); }
+struct LeanBounds {
+    unsigned addr;   // shared-memory address of this thread's column
+    float S;         // upper bound of the path length marched since reset()
+    int pred;        // member number of the previous arg-min, -1: none
+    BMO_D void reset() {
+        S = 0.0f; pred = -1;
+#pragma unroll
+        for (int k = 0; k < 4; k++) sts_f32(addr + 4u * LB_STRIDE * k, -INFINITY);
+    }
+    BMO_D void moved_f(double step, float len) { S = __fadd_ru(S, __fmul_ru(__double2float_ru(step), len)); }
+};
+template <bool RARE> BMO_D double shape_eval(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx_out, LeanBounds& lb) {
+    const int cnt = sh.count;
+    const bmo_prim* base = sh.prims + sh.first;
+    // evaluation order, low nibble first: the previous arg-min, then the others ascending
+    unsigned ord = lb.pred <= 0 ? 0x3210u : (lb.pred == 1 ? 0x3201u : (lb.pred == 2 ? 0x3102u : 0x2103u));
+    double m = 0.0;
+    int idx = 0;
+    float m_ub = INFINITY;
+    for (int j = 0; j < cnt; j++, ord >>= 4) {
+        const int k = ord & 3;
+        const unsigned a = lb.addr + 4u * LB_STRIDE * k;
+        if (j > 0 && __fsub_rd(lds_f32(a), lb.S) > m_ub) continue;   // cannot be (or tie with) the minimum at this point
+        const double v = prim_eval_f<RARE>(base[k], p);
+        nsdf++;
+        sts_f32(a, __fadd_rd(__double2float_rd(v), lb.S));
+        if (j == 0) { m = v; idx = k; }
+        else { if (v < m || (v == m && k < idx)) idx = k; m = fmin_jl(m, v); }
+        m_ub = __fadd_ru(__double2float_ru(m), 1e-7f);
+    }
+    lb.pred = idx;
+    idx_out = sh.first + idx;
+    return m;
+}
+template <bool RARE> BMO_D double shape_eval(const SdfShape& sh, V3 p, unsigned& nsdf, int& idx, MemberBounds& lb) {
+    return shape_sdf_f<RARE>(sh, p, nsdf, idx, lb);
+}
+
 // AbstractSDF.jl:79-95: ForwardDiff gradient of member idx; central differences (eps = 1e-8) if any
 // component of the normalised gradient is NaN.
 template <bool RK> BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
@@ -434,7 +486,7 @@ template <bool RK> BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p,
 // own count through a stack temporary that only lives around the call.
 // RARE = true: the shape may contain cylindrical / aspheric members (flagged at upload); such shapes take an
 // out-of-line copy of this routine (sdf_intersect_rare) so that the common path keeps its register budget.
-template <bool RARE> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, double& t, V3& n) {
+template <bool RARE, class LB> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, double& t, V3& n, LB lb) {
     {   // guaranteed miss: origin outside the bounding sphere and the line never enters it
         const V3 v = mk3(pos.x - sh.cx, pos.y - sh.cy, pos.z - sh.cz);
         const double cc = dot(v, v) - sh.R2;
@@ -452,12 +504,12 @@ template <bool RARE> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 d
     bool back = false;
     V3 p = pos;
     double t0 = 0.0;
-    MemberBounds lb; lb.reset();
+    lb.reset();
     // |d| <= max(1, |d|^2): how far the march point moves per unit of step (directions are unit up to rounding)
     const float dlen = __double2float_ru(fmax(1.0, dot(dir, dir)) * (1.0 + 1e-9));
     for (;;) {
         int idx;
-        const double dist = shape_sdf_f<RARE>(sh, p, nsdf, idx, lb);
+        const double dist = shape_eval<RARE>(sh, p, nsdf, idx, lb);
         if (mode == OUT) {
             t0 += dist;
             if (!(dist < eps_ray)) {
@@ -489,7 +541,7 @@ template <bool RARE> BMO_D bool sdf_intersect_t(const SdfShape& sh, V3 pos, V3 d
 }
 
 BMO_NI bool sdf_intersect_rare(const SdfShape& sh, V3 pos, V3 dir, unsigned& nsdf, double& t, V3& n) {
-    return sdf_intersect_t<true>(sh, pos, dir, nsdf, t, n);
+    return sdf_intersect_t<true, MemberBounds>(sh, pos, dir, nsdf, t, n, MemberBounds());
 }
 
 // ---- meshes -----------------------------------------------------------------------------------
@@ -596,6 +648,27 @@ BMO_NI bool mesh_intersect(const MeshTabs S, int mesh_id, int pose, V3 pos, V3 d
     return true;
 }
 
+// The same for kernels that only ever see small meshes (detector quads, cuboids, retroreflectors: at most 16 faces, no
+// BVH was built): the face loop in reference order, no traversal stack.
+BMO_NI bool mesh_intersect_small(const MeshTabs S, int mesh_id, int pose, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
+    const MeshView mv = S.meshes[mesh_id];
+    const double* verts = S.vertices + 3 * ((int64_t)pose * S.n_vertices + mv.first_vertex);
+    const int32_t* faces = S.faces + 3 * mv.first_face;
+    double t0 = INFINITY;
+    int fid = -1;
+    const int nf = (int)mv.n_faces;
+    for (int i = 0; i < nf; i++) {
+        const double tt = moeller_trumbore(load_vertex(verts, __ldg(faces + 3 * i)), load_vertex(verts, __ldg(faces + 3 * i + 1)),
+                                           load_vertex(verts, __ldg(faces + 3 * i + 2)), pos, dir, mv.f32);
+        if (tt < t0) { t0 = tt; fid = i; }
+    }
+    st.tri += nf;
+    if (fid < 0) return false;
+    t = t0;
+    n = face_normal(load_vertex(verts, __ldg(faces + 3 * fid)), load_vertex(verts, __ldg(faces + 3 * fid + 1)), load_vertex(verts, __ldg(faces + 3 * fid + 2)), mv.f32);
+    return true;
+}
+
 // ---- shapes, objects, system --------------------------------------------------------------------
 struct TraceCtx {
     MeshTabs M;
@@ -605,9 +678,11 @@ struct TraceCtx {
     const bmo_part* parts;   // part table (shared-memory copy when staged)
     const double* bounds;    // [n_parts][NBOUND] bounds of this ray's pose
     int pose;
+    unsigned lb_addr;        // LEAN kernels: shared-memory address of this thread's column of member bounds (LeanBounds)
 };
 // intersect3d(shape, ray)
-template <bool RK> BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
+// LEAN: every SDF part of the system is a lean union (shape_eval with LeanBounds) and every mesh is small (host-side facts)
+template <bool RK, bool LEAN> BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
     const bmo_part& pt = C.parts[part];
     if (pt.shape_kind == BMO_SHAPE_SDF) {
         const double* bnd = C.bounds + NBOUND * part;
@@ -622,27 +697,29 @@ template <bool RK> BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos
             t = tm; n = nm;
             return hit;
         }
-        return sdf_intersect_t<false>(sh, pos, dir, st.sdf, t, n);
+        if (LEAN) { LeanBounds lb; lb.addr = C.lb_addr; return sdf_intersect_t<false, LeanBounds>(sh, pos, dir, st.sdf, t, n, lb); }
+        return sdf_intersect_t<false, MemberBounds>(sh, pos, dir, st.sdf, t, n, MemberBounds());
     }
     // results through temporaries: the out-of-line callee takes references, and t / n of the caller (shared with the
     // SDF path) must not have their address taken or they live in local memory for every part
     Stats tmp; tmp.sdf = 0; tmp.tri = 0;
     double tm = 0.0; V3 nm = mk3(0, 0, 0);
-    const bool hit = mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, tm, nm);
+    const bool hit = LEAN ? mesh_intersect_small(C.M, pt.first, C.pose, pos, dir, tmp, tm, nm) : mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, tm, nm);
     st.tri += tmp.tri;
     t = tm; n = nm;
     return hit;
 }
 // slab test of the ray (t >= 0) against an axis-aligned box, entry distance compared with t_best
-BMO_D bool box_may_hit(const double* bx, V3 o, V3 d, double t_best) {
+// inv = 1 / d per component, formed once per tracing_step (unused where d is 0)
+BMO_D bool box_may_hit(const double* bx, V3 o, V3 d, V3 iv, double t_best) {
     double tmin = 0.0, tmax = INFINITY;
-    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z};
+    const double oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, ii[3] = {iv.x, iv.y, iv.z};
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         if (dd[k] == 0.0) {
             if (oo[k] < bx[k] || oo[k] > bx[3 + k]) return false;
         } else {
-            const double inv = 1.0 / dd[k];
+            const double inv = ii[k];
             double t1 = (bx[k] - oo[k]) * inv, t2 = (bx[3 + k] - oo[k]) * inv;
             if (t1 > t2) { const double tt = t1; t1 = t2; t2 = tt; }
             if (t1 > tmin) tmin = t1;
@@ -662,7 +739,8 @@ BMO_D bool box_may_hit(const double* bx, V3 o, V3 d, double t_best) {
 // [lo, hi) is the range of parts that trace_all looks at: the whole system for tracing_step!, the parts
 // of one object (or one hinted shape) for retrace_system!'s `intersect3d(object(_intersection), ray)` /
 // `intersect3d(shape(_hint), ray)` (System.jl:209-218); hi < 0 means C.n_parts.
-template <bool RK> BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st, const int lo = 0, const int hi = -1) {
+template <bool RK, bool LEAN = false> BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st, const int lo = 0, const int hi = -1) {
+    const V3 inv_dir = mk3(1.0 / dir.x, 1.0 / dir.y, 1.0 / dir.z);
     Hit res; res.part = -1; res.t = INFINITY; res.n = mk3(0, 0, 0);
     Hit ob; ob.part = -1; ob.t = INFINITY; ob.n = mk3(0, 0, 0);   // best of the current object
     int cur_obj = -1;
@@ -692,7 +770,7 @@ template <bool RK> BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int
                 if (res.part >= 0) t_best = res.t;
                 if (ob.part >= 0 && ob.t < t_best) t_best = ob.t;
             }
-            if (box_may_hit(bx, pos, dir, t_best)) hit = part_intersect<RK>(C, part, pos, dir, st, t, n);
+            if (box_may_hit(bx, pos, dir, inv_dir, t_best)) hit = part_intersect<RK, LEAN>(C, part, pos, dir, st, t, n);
         }
         if (!all) {
             if (hit) { res.t = t; res.n = n; res.part = part; return res; }

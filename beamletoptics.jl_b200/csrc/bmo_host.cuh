@@ -55,6 +55,7 @@ struct bmo_sys {
     std::vector<double> lambdas;
     int64_t n_vertices = 0, n_faces = 0;
     bool has_rare = false;       // some primitive is a cylindrical / aspheric surface: the trace kernels compiled with them are used
+    bool all_lean = false;       // every SDF part is a union of <= 4 plain primitives and no mesh has a BVH: the LEAN trace kernels are used
     // owned device buffers
     bmo_prim* d_prims = nullptr; bmo_part* d_parts = nullptr; bmo_object* d_objects = nullptr;
     bmo::MeshView* d_meshes = nullptr; double* d_vertices = nullptr; int32_t* d_faces = nullptr;

@@ -109,9 +109,12 @@ BMO_D V3 shfl3(V3 v, int l) {
 constexpr int IBLOCK = 128;
 // STAGED: the small system tables (prims, parts, bounds) live in shared memory -- a compile-time fact,
 // so that the marching loop reads them with LDS instead of generic loads.
-template <int MINB, bool STAGED, bool RK>
+// LEAN: every SDF part is a union of at most 4 plain primitives and every mesh is small (bmo_sys::all_lean): the union loop keeps
+// its member bounds in shared memory (LeanBounds, bmo_geom.cuh) and the BVH traversal is compiled out.
+template <int MINB, bool STAGED, bool RK, bool LEAN = false>
 __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_lb[LEAN ? 4 * LB_STRIDE : 1];
     const SysView& S = P.S;
     // The ray state is requested first, every load at once and from a clamped slot so that none of them sits
     // behind a branch on another one's value: the DRAM round trip then overlaps the table staging below instead of
@@ -158,8 +161,9 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
             C.parts = S.parts;
             C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
         }
+        C.lb_addr = LEAN ? (unsigned)__cvta_generic_to_shared(s_lb + threadIdx.x) : 0u;
         Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
-        if (budget) h = tracing_step<RK>(C, pos, dir, hint, st);   // System.jl:100-110
+        if (budget) h = tracing_step<RK, LEAN>(C, pos, dir, hint, st);   // System.jl:100-110
         const int64_t hs = P.hit.cap;
         P.hit.d[ri] = h.t; P.hit.d[hs + ri] = h.n.x; P.hit.d[2 * hs + ri] = h.n.y; P.hit.d[3 * hs + ri] = h.n.z;
         P.hit.part[ri] = h.part;
@@ -237,6 +241,7 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(co
     C.M.n_vertices = S.n_vertices; C.M.n_poses = S.n_poses; C.M.bvh_ok = S.bvh_ok;
     C.objects = S.objects; C.n_parts = S.n_parts; C.zr = S.zr;
     C.pose = pose;
+    C.lb_addr = 0u;
     if (STAGED) { C.prims = s_prims; C.parts = s_parts; C.bounds = s_bounds; }
     else {
         C.prims = S.prims + (int64_t)pose * S.n_prims;
@@ -680,9 +685,10 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, MODE == 0 ? KMINB0 : 1) inte
 // ---- K1+K2 fused: plain rays through a system without beamsplitters (the sequential lens-stack path) --
 // One thread per ray does tracing_step! and interact3d back to back: the hit record never leaves the
 // registers and the ray state is read once.  Needs IBLOCK == Cfg<0>::BLOCK == Cfg<0>::UNITS.
-template <int MINB, bool STAGED, bool RK>
+template <int MINB, bool STAGED, bool RK, bool LEAN = false>
 __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) {
     static_assert(IBLOCK == Cfg<0>::BLOCK && Cfg<0>::UNITS == IBLOCK, "fused_wave0 maps one thread to one ray like interact_wave<0>");
+    __shared__ float s_lb[LEAN ? 4 * LB_STRIDE : 1];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysView& S = P.S;
     bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
@@ -729,7 +735,8 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
                 C.parts = S.parts;
                 C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
             }
-            if (budget) h = tracing_step<RK>(C, pos, dir, hint, st);
+            C.lb_addr = LEAN ? (unsigned)__cvta_generic_to_shared(s_lb + threadIdx.x) : 0u;
+            if (budget) h = tracing_step<RK, LEAN>(C, pos, dir, hint, st);
         }
         sd += st.sdf; tr += st.tri;
         interact_body<0, true, true>(P, h, w);
@@ -1208,6 +1215,20 @@ static void flag_rare_parts(bmo_prim* p, size_t n_prims_per_pose, size_t n_poses
             if (rare) p[q * n_prims_per_pose + pt.first].reserved |= 2;
         }
 }
+// every SDF part is a union of at most 4 plain primitives (no meniscus frame, no cylindrical / aspheric member) and every mesh
+// is small enough to have no BVH: the LEAN builds of the trace kernels apply (bmo_geom.cuh: LeanBounds, mesh_intersect_small)
+static bool system_is_lean(const std::vector<bmo_prim>& prims, const std::vector<bmo_part>& parts, const std::vector<MeshView>& meshes) {
+    for (const bmo_part& pt : parts) {
+        if (pt.shape_kind != BMO_SHAPE_SDF) continue;
+        if (pt.count < 1 || pt.count > 4) return false;
+        for (int k = 0; k < pt.count; k++) {
+            const int ty = prims[pt.first + k].type;
+            if (ty == BMO_PRIM_MENISCUS || ty >= BMO_PRIM_CONVEX_CYL) return false;
+        }
+    }
+    for (const MeshView& mv : meshes) if (mv.n_nodes != 0) return false;
+    return true;
+}
 static void patch_asph(bmo_prim* p, size_t n, const double* d_ext) {
     for (size_t i = 0; i < n; i++)
         if (p[i].type >= BMO_PRIM_CONVEX_ASPH && p[i].type <= BMO_PRIM_CONCAVE_ACYL) {
@@ -1272,6 +1293,7 @@ int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
     patch_asph(s->prims.data(), s->prims.size(), s->d_ext);
     flag_rare_parts(s->prims.data(), s->prims.size(), 1, s->parts);
     for (const bmo_prim& pr : s->prims) s->has_rare |= pr.type >= BMO_PRIM_CONVEX_CYL;
+    s->all_lean = system_is_lean(s->prims, s->parts, s->meshes);
     if ((rc = upload(&s->d_prims, s->prims.data(), s->prims.size()))) return rc;
     if ((rc = upload(&s->d_parts, s->parts.data(), s->parts.size()))) return rc;
     if ((rc = upload(&s->d_objects, s->objects.data(), s->objects.size()))) return rc;
@@ -1612,6 +1634,8 @@ int32_t SubTrace::enqueue_chunk() {
         const bool allow_fused = !rt.on && (fuse_policy == 2 || (fuse_policy == 1 && pipelined));
         const SysView& V = sys->view;
         const bool rk = sys->has_rare;     // kernels compiled with the cylindrical / aspheric primitives
+        static const bool lean_ok = !(getenv("BMO_LEAN") && atoi(getenv("BMO_LEAN")) == 0);   // tuning knob: BMO_LEAN=0 uses the general kernels everywhere
+        const bool lean = lean_ok && sys->all_lean && !rk;   // kernels compiled for lean unions + small meshes only
         const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
         BMO_CUDA(cudaEventRecord(ev[2 * c], st));
         if (mode == 0 && !has_splitter && allow_fused) {
@@ -1623,6 +1647,9 @@ int32_t SubTrace::enqueue_chunk() {
             if (rk) {
                 if (!staged) fused_wave0<4, false, true><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
                 else fused_wave0<6, true, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+            } else if (lean) {
+                if (!staged) fused_wave0<4, false, false, true><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
+                else fused_wave0<6, true, false, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
             } else {
                 if (!staged) fused_wave0<4, false, false><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
                 else if (minb <= 4) fused_wave0<4, true, false><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
@@ -1664,6 +1691,11 @@ int32_t SubTrace::enqueue_chunk() {
             if (rk) {
                 if (!staged) intersect_wave<4, false, true><<<grid, IBLOCK, 0, st>>>(xp);
                 else intersect_wave<6, true, true><<<grid, IBLOCK, smem, st>>>(xp);
+            } else if (lean) {
+                if (!staged) intersect_wave<4, false, false, true><<<grid, IBLOCK, 0, st>>>(xp);
+                else if (minb <= 6) intersect_wave<6, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
+                else if (minb >= 8) intersect_wave<8, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
+                else intersect_wave<7, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
             } else {
                 if (!staged) intersect_wave<4, false, false><<<grid, IBLOCK, 0, st>>>(xp);
                 else if (minb <= 4) intersect_wave<4, true, false><<<grid, IBLOCK, smem, st>>>(xp);
