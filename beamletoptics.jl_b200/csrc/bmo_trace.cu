@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 #include "bmo_host.cuh"
 #include "bmo_interact.cuh"
+#include "bmo_lean.cuh"
 
 namespace bmo {
 thread_local std::string g_last_error;
@@ -114,7 +115,8 @@ constexpr int IBLOCK = 128;
 template <int MINB, bool STAGED, bool RK, bool LEAN = false>
 __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ float s_lb[LEAN ? 4 * LB_STRIDE : 1];
+    __shared__ float s_lb[LEAN ? LB_ROWS * LB_STRIDE : 1];
+    __shared__ double s_ls[LEAN ? LS_SLOTS * LB_STRIDE : 1];
     const SysView& S = P.S;
     // The ray state is requested first, every load at once and from a clamped slot so that none of them sits
     // behind a branch on another one's value: the DRAM round trip then overlaps the table staging below instead of
@@ -161,9 +163,12 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
             C.parts = S.parts;
             C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
         }
-        C.lb_addr = LEAN ? (unsigned)__cvta_generic_to_shared(s_lb + threadIdx.x) : 0u;
+        C.lb_addr = LEAN ? smem_u32(s_lb + threadIdx.x) : 0u;
         Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
-        if (budget) h = tracing_step<RK, LEAN>(C, pos, dir, hint, st);   // System.jl:100-110
+        if (budget) {   // System.jl:100-110
+            if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, pos, dir, hint, st);
+            else h = tracing_step<RK, false>(C, pos, dir, hint, st);
+        }
         const int64_t hs = P.hit.cap;
         P.hit.d[ri] = h.t; P.hit.d[hs + ri] = h.n.x; P.hit.d[2 * hs + ri] = h.n.y; P.hit.d[3 * hs + ri] = h.n.z;
         P.hit.part[ri] = h.part;
@@ -688,7 +693,8 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, MODE == 0 ? KMINB0 : 1) inte
 template <int MINB, bool STAGED, bool RK, bool LEAN = false>
 __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) {
     static_assert(IBLOCK == Cfg<0>::BLOCK && Cfg<0>::UNITS == IBLOCK, "fused_wave0 maps one thread to one ray like interact_wave<0>");
-    __shared__ float s_lb[LEAN ? 4 * LB_STRIDE : 1];
+    __shared__ float s_lb[LEAN ? LB_ROWS * LB_STRIDE : 1];
+    __shared__ double s_ls[LEAN ? LS_SLOTS * LB_STRIDE : 1];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysView& S = P.S;
     bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
@@ -735,8 +741,11 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
                 C.parts = S.parts;
                 C.bounds = S.bounds + NBOUND * (int64_t)pose * S.n_parts;
             }
-            C.lb_addr = LEAN ? (unsigned)__cvta_generic_to_shared(s_lb + threadIdx.x) : 0u;
-            if (budget) h = tracing_step<RK, LEAN>(C, pos, dir, hint, st);
+            C.lb_addr = LEAN ? smem_u32(s_lb + threadIdx.x) : 0u;
+            if (budget) {
+                if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, pos, dir, hint, st);
+                else h = tracing_step<RK, false>(C, pos, dir, hint, st);
+            }
         }
         sd += st.sdf; tr += st.tri;
         interact_body<0, true, true>(P, h, w);
