@@ -449,15 +449,117 @@ template <bool RARE> BMO_D double shape_eval(const SdfShape& sh, V3 p, unsigned&
     return shape_sdf_f<RARE>(sh, p, nsdf, idx, lb);
 }
 
+// ---- gradients of the lens primitives with identity orientation -----------------------------------------
+// prim_eval<Dual> with the seeds of an unrotated primitive (transposed_dir == I: p.x = (x; 1,0,0), p.y = (y; 0,1,0),
+// p.z = (z; 0,0,1)), written out: every product of a partial with an exact 0 or 1 and every sum with an exact 0 is dropped,
+// every other operation is kept in ForwardDiff's order, so the gradient has the same bits as the generic evaluation (up to the
+// sign of an exact zero, which no later comparison looks at).  All operands are finite here (the caller checks), so the
+// NaN-propagating branches of max / min cannot trigger.  Rule 1 for the norm of a zero vector (bmo_tables.norm_zero_rule).
+// Returns false where the generic evaluation has to decide (unknown type, zero vector under the outer square root).
+// tests/test_gpu_normals.py compares both evaluations bit for bit on random, on-axis, face and edge points.
+BMO_D void radial_dual(double x, double z, double& r, double& gx, double& gz) {   // norm2_(p.x, p.z)
+    const double sv = x * x + z * z;
+    if (sv == 0.0) { r = 0.0; gx = 0.0; gz = 0.0; return; }
+    r = sqrt(sv);
+    const double d = 1.0 / (2 * r);
+    gx = (x + x) * d; gz = (z + z) * d;
+}
+// cyl_(d1, d2) for d1 = (v1; gx, 0, gz), d2 = (v2; 0, sg, 0): value and gradient
+BMO_D double cyl_dual(double v1, double gx, double gz, double v2, double sg, V3& g) {
+    const bool pick2 = (v2 > v1) | ((int)signbit(v2) < (int)signbit(v1));   // max_w: d2 is the maximum
+    const double Mv = jl_max(v1, v2);
+    const bool keep = !(Mv > 0.0);                                          // min_(M, 0.0) keeps M's partials
+    V3 N = mk3(0.0, 0.0, 0.0);
+    if (keep) N = pick2 ? mk3(0.0, sg, 0.0) : mk3(gx, 0.0, gz);
+    const double Nv = jl_min(Mv, 0.0);
+    const bool z1 = signbit(v1), z2 = signbit(v2);                          // max_(d, 0.0) is the constant 0
+    const double A1 = z1 ? 0.0 : v1, A2 = z2 ? 0.0 : v2;
+    const double a0 = z1 ? 0.0 : gx, a2 = z1 ? 0.0 : gz, b1 = z2 ? 0.0 : sg;
+    const double sv = A1 * A1 + A2 * A2;
+    if (sv == 0.0) { g = N; return Nv + 0.0; }
+    const double rr = sqrt(sv);
+    const double dd = 1.0 / (2 * rr);
+    const double s0 = a0 * A1 + a0 * A1, s1 = b1 * A2 + b1 * A2, s2 = a2 * A1 + a2 * A1;
+    g = mk3(N.x + s0 * dd, N.y + s1 * dd, N.z + s2 * dd);
+    return Nv + rr;
+}
+BMO_D bool identity_gradient(const bmo_prim& pr, V3 q, V3& g) {
+    const double x = q.x - pr.pos[0], y = q.y - pr.pos[1], z = q.z - pr.pos[2];
+    if (!(fabs(x) < 1e150 && fabs(y) < 1e150 && fabs(z) < 1e150)) return false;   // non-finite or absurd input: generic path
+    const double a = pr.par[0], b = pr.par[1], c = pr.par[2], d = pr.par[3];
+    double r, gx, gz;
+    switch (pr.type) {
+        case BMO_PRIM_PLANO: {
+            radial_dual(x, z, r, gx, gz);
+            const double t = y - a / 2;
+            cyl_dual(r - b / 2, gx, gz, fabs(t) - a / 2, signbit(t) ? -1.0 : 1.0, g);
+            return true;
+        }
+        case BMO_PRIM_CYLINDER: {
+            radial_dual(x, z, r, gx, gz);
+            cyl_dual(r - a, gx, gz, fabs(y) - b, signbit(y) ? -1.0 : 1.0, g);
+            return true;
+        }
+        case BMO_PRIM_SPHERE: {
+            const double sv = x * x + y * y + z * z;
+            if (sv == 0.0) return false;
+            const double dd = 1.0 / (2 * sqrt(sv));
+            g = mk3((x + x) * dd, (y + y) * dd, (z + z) * dd);
+            return true;
+        }
+        case BMO_PRIM_CONVEX: {
+            radial_dual(x, z, r, gx, gz);
+            const double q2 = -y + a;
+            const double h = d, R = a, hd = b / 2;
+            const double s = jl_max((h - R) * (r * r) + (hd * hd) * (h + R - 2 * q2), h * r - hd * q2);
+            double A, B;
+            if (s < 0.0) { A = r; B = q2; }
+            else if (r < hd) { g = mk3(0.0, 1.0, 0.0); return true; }
+            else { A = r - hd; B = q2 - h; }
+            const double sv = A * A + B * B;
+            if (sv == 0.0) return false;
+            const double dd = 1.0 / (2 * sqrt(sv));
+            const double s0 = gx * A + gx * A, s1 = -B - B, s2 = gz * A + gz * A;
+            g = mk3(s0 * dd, s1 * dd, s2 * dd);
+            return true;
+        }
+        case BMO_PRIM_CONCAVE: {
+            radial_dual(x, z, r, gx, gz);
+            const double t = y + c / 2;
+            V3 g1;
+            const double v1 = cyl_dual(r - b / 2, gx, gz, fabs(t) - c / 2, signbit(t) ? -1.0 : 1.0, g1);
+            const double Y = y + a;
+            const double sv = x * x + Y * Y + z * z;
+            if (sv == 0.0) return false;
+            const double r3 = sqrt(sv);
+            const double d3 = 1.0 / (2 * r3);
+            const double nv = -(r3 - a);
+            const bool pick2 = (nv > v1) | ((int)signbit(nv) < (int)signbit(v1));   // max_(sdf1, -sdf2)
+            g = pick2 ? mk3(-((x + x) * d3), -((Y + Y) * d3), -((z + z) * d3)) : g1;
+            return true;
+        }
+        default: break;
+    }
+    return false;
+}
+
 // AbstractSDF.jl:79-95: ForwardDiff gradient of member idx; central differences (eps = 1e-8) if any
 // component of the normalised gradient is NaN.
-template <bool RK> BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
+// FAST: unrotated lens primitives take identity_gradient instead of the generic dual evaluation (same bits)
+template <bool RK, bool FAST = true> BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
     if (!(RK && is_asph(prims[idx].type))) {   // aspheric surfaces: numeric_gradient only (AsphericalLensSDF.jl:3-5)
+        V3 gf;
+        if (FAST && zr == 1 && (prims[idx].reserved & 1) && identity_gradient(prims[idx], p, gf)) {
+            st.sdf++;
+            const V3 n = normalize(gf);
+            if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
+        } else {
         P3<Dual> qd;
         qd.x = mkd(p.x, 1, 0, 0); qd.y = mkd(p.y, 0, 1, 0); qd.z = mkd(p.z, 0, 0, 1);
         Dual g = member_eval<Dual, RK>(prims, idx, qd, zr, st, true);
         V3 n = normalize(mk3(g.p0, g.p1, g.p2));
         if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
+        }
     }
     const double e = 1e-8;
     P3<double> q; q.x = p.x; q.y = p.y; q.z = p.z;

@@ -2202,4 +2202,40 @@ int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops) {
     return BMO_OK;
 }
 
+// ---- self-check of the normal evaluations --------------------------------------------------------------
+// normal3d (AbstractSDF.jl:79-95) of member prim_idx[i] at points[i], evaluated twice: with the written-out gradients of the
+// unrotated lens primitives (identity_gradient, bmo_geom.cuh) where they apply, and with the generic dual-number evaluation.
+// The two must agree bit for bit (tests/test_gpu_normals.py).
+__global__ void debug_normals_kernel(const SysView S, int64_t n, const double* pts, const int32_t* prim, double* out_fast, double* out_gen) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const V3 p = mk3(pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]);
+    Stats st; st.sdf = 0; st.tri = 0;
+    const V3 a = member_normal<true, true>(S.prims, prim[i], p, S.zr, st);
+    const V3 b = member_normal<true, false>(S.prims, prim[i], p, S.zr, st);
+    out_fast[3 * i] = a.x; out_fast[3 * i + 1] = a.y; out_fast[3 * i + 2] = a.z;
+    out_gen[3 * i] = b.x; out_gen[3 * i + 1] = b.y; out_gen[3 * i + 2] = b.z;
+}
+int32_t bmo_debug_normals(bmo_sys* sys, int64_t n, const double* points, const int32_t* prim_idx, double* out_fast, double* out_generic) {
+    if (!sys || !points || !prim_idx || !out_fast || !out_generic || n < 0) return fail(BMO_EINVAL, "bmo_debug_normals: bad argument");
+    for (int64_t i = 0; i < n; i++)
+        if (prim_idx[i] < 0 || prim_idx[i] >= sys->view.n_prims) return fail(BMO_EINVAL, "bmo_debug_normals: prim index out of range");
+    if (n == 0) return BMO_OK;
+    bmo_ctx* ctx = sys->ctx;
+    BMO_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    double *d_pts = nullptr, *d_a = nullptr, *d_b = nullptr; int32_t* d_idx = nullptr;
+    BMO_CUDA(dev_alloc(&d_pts, (size_t)3 * n, st)); BMO_CUDA(dev_alloc(&d_a, (size_t)3 * n, st)); BMO_CUDA(dev_alloc(&d_b, (size_t)3 * n, st));
+    BMO_CUDA(dev_alloc(&d_idx, (size_t)n, st));
+    BMO_CUDA(cudaMemcpyAsync(d_pts, points, (size_t)3 * n * sizeof(double), cudaMemcpyHostToDevice, st));
+    BMO_CUDA(cudaMemcpyAsync(d_idx, prim_idx, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    debug_normals_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(sys->view, n, d_pts, d_idx, d_a, d_b);
+    BMO_LAUNCH(ctx, "debug_normals_kernel");
+    BMO_CUDA(cudaMemcpyAsync(out_fast, d_a, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaMemcpyAsync(out_generic, d_b, (size_t)3 * n * sizeof(double), cudaMemcpyDeviceToHost, st));
+    BMO_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_pts, st); dev_free(d_a, st); dev_free(d_b, st); dev_free(d_idx, st);
+    return BMO_OK;
+}
+
 

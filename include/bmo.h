@@ -374,6 +374,11 @@ int32_t bmo_comm_free(bmo_comm* comm);
 /* FP64 DFMA micro-benchmark used as the roofline denominator of the FP64-bound kernels.          */
 int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops);
 
+/* Self-check (tests): normal3d(shape, point) (AbstractSDF.jl:79-95) of the primitive record prim_idx[i] at points[i] ([n][3], world
+ * coordinates), once through the written-out gradients the tracer uses for unrotated lens primitives and once through the generic
+ * dual-number evaluation (ForwardDiff's rules).  out_fast / out_generic: [n][3]; they must agree bit for bit.                    */
+int32_t bmo_debug_normals(bmo_sys* sys, int64_t n, const double* points, const int32_t* prim_idx, double* out_fast, double* out_generic);
+
 #ifdef __cplusplus
 }
 #endif
