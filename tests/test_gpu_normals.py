@@ -19,8 +19,9 @@ def _system(bmo):
     bcc = bmo.SphericalLens(-0.06, 0.08, 3e-3, INCH, 1.5); bcc.translate3d_([-0.04, 0.01, 0.0])   # concave + plano + concave(rotated)
     mir = bmo.RoundPlanoMirror(INCH, 5e-3); mir.translate3d_([0.0, 0.08, 0.02])
     ball = bmo.Prism(bmo.SphereSDF(4e-3), 1.5); ball.translate3d_([0.02, -0.03, 0.01])
+    rod = bmo.Mirror(bmo.CylinderSDF(7e-3, 5e-3)); rod.translate3d_([-0.03, -0.04, 0.02])
     rot = bmo.SphericalLens(0.05, -0.07, 6e-3, INCH, 1.5); rot.translate3d_([0.0, 0.15, 0.0]); rot.xrotate3d_(0.3)
-    return bmo.System([dl, pcx, bcc, mir, ball, rot])
+    return bmo.System([dl, pcx, bcc, mir, ball, rod, rot])
 
 
 def _points(rng, prim, n):
