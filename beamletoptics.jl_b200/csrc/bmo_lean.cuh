@@ -156,9 +156,23 @@ BMO_D bool box_may_hit_ls(const double* bx, unsigned sc, V3 d, double t_best) {
     return tmin <= tmax * (1 + 1e-9) + 1e-12 && tmin * (1 - 1e-9) - 1e-9 <= t_best;
 }
 
+// One 64-bit word per part, made at staging time from bmo_part / bmo_object so that the part loop needs one shared-memory load
+// where it used to chase parts[part].object -> objects[obj].kind through global memory:
+//   low word:  bits 0-15 object, bit 16 the object is a plate beamsplitter, bit 17 the part is its coating,
+//              bit 18 SDF shape (else mesh), bits 20-23 members of the union
+//   high word: first prim record (SDF) or mesh id
+BMO_D unsigned long long lean_part_info(const bmo_part& pt, const bmo_object& ob) {
+    const unsigned lo = ((unsigned)pt.object & 0xffffu) | (ob.kind == BMO_OBJ_PLATE_BS ? 1u << 16 : 0u) |
+                        ((pt.role == BMO_ROLE_COATING && ob.kind == BMO_OBJ_PLATE_BS) ? 1u << 17 : 0u) |
+                        (pt.shape_kind == BMO_SHAPE_SDF ? 1u << 18 : 0u) | (((unsigned)pt.count & 15u) << 20);
+    return ((unsigned long long)(unsigned)pt.first << 32) | lo;
+}
+BMO_D unsigned long long lds_u64(unsigned a) { unsigned long long v; asm volatile("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+
 // tracing_step! (System.jl:57-110) for LEAN systems; see tracing_step (bmo_geom.cuh) for the rules it follows.
-// sc / lb_addr: shared-memory addresses of this thread's scratch column and member-bounds column.
-BMO_D Hit tracing_step_lean(const TraceCtx& C, unsigned sc, unsigned lb_addr, V3 pos, V3 dir, int hint_part, Stats& st) {
+// sc / lb_addr: shared-memory addresses of this thread's scratch column and member-bounds column; pinfo: shared-memory
+// address of the part words.
+BMO_D Hit tracing_step_lean(const TraceCtx& C, unsigned sc, unsigned lb_addr, unsigned pinfo, V3 pos, V3 dir, int hint_part, Stats& st) {
     ls_store3(sc, LS_POS, pos);
     ls_store3(sc, LS_DIR, dir);
     ls_store3(sc, LS_INV, mk3(1.0 / dir.x, 1.0 / dir.y, 1.0 / dir.z));
@@ -168,7 +182,10 @@ BMO_D Hit tracing_step_lean(const TraceCtx& C, unsigned sc, unsigned lb_addr, V3
     for (int it = hint_part >= 0 ? -1 : 0; it <= n_parts; it++) {
         const bool all = it >= 0;                    // false: the trace_one iteration on the hinted part
         const int part = all ? it : hint_part;
-        const int obj = (all && it < n_parts) ? C.parts[part].object : -1;
+        const bool last = it == n_parts;
+        const unsigned long long w = last ? 0ull : lds_u64(pinfo + 8u * (unsigned)part);
+        const unsigned wl = (unsigned)w;
+        const int obj = (all && !last) ? (int)(wl & 0xffffu) : -1;
         if (all && obj != cur_obj) {       // object boundary: trace_all's comparison (System.jl:62-67)
             if (ob_part >= 0 && (res_part < 0 || ob_t < res_t)) {
                 res_t = ob_t; res_part = ob_part; res_idx = ob_idx;
@@ -176,49 +193,42 @@ BMO_D Hit tracing_step_lean(const TraceCtx& C, unsigned sc, unsigned lb_addr, V3
             }
             ob_part = -1; ob_t = INFINITY;
             cur_obj = obj;
-            if (it == n_parts) break;
         }
-        double t = 0.0;
-        int hidx = 0;
-        bool hit = false, is_sdf = false;
-        if (!(all && part == hint_part)) {
-            const double* bx = C.bounds + NBOUND * part + 4;
-            const bool plate = all && C.objects[obj].kind == BMO_OBJ_PLATE_BS;
-            double t_best = INFINITY;
-            if (all && !plate) {
+        if (last) break;
+        if (all && part == hint_part) continue;      // trace_one has just missed this shape: the same ray misses it again
+        const bool is_sdf = (wl >> 18) & 1u;
+        {
+            double t_best = INFINITY;      // a plate beamsplitter prefers its coating on approximate equality: never culled against the best hit
+            if (all && !((wl >> 16) & 1u)) {
                 if (res_part >= 0) t_best = res_t;
                 if (ob_part >= 0 && ob_t < t_best) t_best = ob_t;
             }
-            if (box_may_hit_ls(bx, sc, dir, t_best)) {
-                const bmo_part& pt = C.parts[part];
-                if (pt.shape_kind == BMO_SHAPE_SDF) {
-                    is_sdf = true;
-                    const unsigned r = lean_march(C.prims, pt.first, pt.count, C.zr, C.bounds + NBOUND * part, sc, lb_addr);
-                    st.sdf += r >> 4;
-                    hit = (r & 15u) != 0;
-                    if (hit) { t = lds_f64(ls_slot(sc, LS_T)); hidx = pt.first + (int)(r & 15u) - 1; }
-                } else {
-                    unsigned ntri = 0;
-                    double tm = 0.0;
-                    int fid = 0;
-                    hit = mesh_hit_small(C.M, pt.first, C.pose, ls_load3(sc, LS_POS), dir, tm, fid, ntri);
-                    st.tri += ntri;
-                    t = tm; hidx = fid;
-                }
-            }
+            if (!box_may_hit_ls(C.bounds + NBOUND * part + 4, sc, dir, t_best)) continue;
         }
-        if (!all) {
-            if (hit) {
-                res_t = t; res_part = part; res_idx = hidx;
-                if (is_sdf) ls_store3(sc, LS_RES, ls_load3(sc, LS_CAND));
-                break;
-            }
-            continue;
+        double t;
+        int hidx;
+        const int first = (int)(w >> 32);
+        if (is_sdf) {
+            const unsigned r = lean_march(C.prims, first, (int)((wl >> 20) & 15u), C.zr, C.bounds + NBOUND * part, sc, lb_addr);
+            st.sdf += r >> 4;
+            if (!(r & 15u)) continue;
+            t = lds_f64(ls_slot(sc, LS_T)); hidx = first + (int)(r & 15u) - 1;
+        } else {
+            unsigned ntri = 0;
+            double tm = 0.0;
+            int fid = 0;
+            const bool hit = mesh_hit_small(C.M, first, C.pose, ls_load3(sc, LS_POS), dir, tm, fid, ntri);
+            st.tri += ntri;
+            if (!hit) continue;
+            t = tm; hidx = fid;
         }
-        if (!hit) continue;
+        if (!all) {                        // trace_one: the hinted shape is accepted without looking at anything else
+            res_t = t; res_part = part; res_idx = hidx;
+            if (is_sdf) ls_store3(sc, LS_RES, ls_load3(sc, LS_CAND));
+            break;
+        }
         bool take = ob_part < 0 || t < ob_t;
-        if (C.parts[part].role == BMO_ROLE_COATING && C.objects[obj].kind == BMO_OBJ_PLATE_BS && ob_part >= 0)
-            take = jl_isapprox(t, ob_t) ? true : (t < ob_t);   // parts = (substrate, coating)
+        if (((wl >> 17) & 1u) && ob_part >= 0) take = jl_isapprox(t, ob_t) ? true : (t < ob_t);   // parts = (substrate, coating)
         if (take) {
             ob_t = t; ob_part = part; ob_idx = hidx;
             if (is_sdf) ls_store3(sc, LS_OB, ls_load3(sc, LS_CAND));
@@ -226,13 +236,13 @@ BMO_D Hit tracing_step_lean(const TraceCtx& C, unsigned sc, unsigned lb_addr, V3
     }
     Hit res; res.part = res_part; res.t = res_t; res.n = mk3(0, 0, 0);
     if (res_part >= 0) {   // normal3d of the one hit that is returned
-        const bmo_part& pt = C.parts[res_part];
-        if (pt.shape_kind == BMO_SHAPE_SDF) {
+        const unsigned long long w = lds_u64(pinfo + 8u * (unsigned)res_part);
+        if (((unsigned)w >> 18) & 1u) {
             Stats tmp; tmp.sdf = 0; tmp.tri = 0;
             res.n = member_normal<false>(C.prims, res_idx, ls_load3(sc, LS_RES), C.zr, tmp);
             st.sdf += tmp.sdf;
         } else {
-            res.n = mesh_face_normal(C.M, pt.first, C.pose, res_idx);
+            res.n = mesh_face_normal(C.M, (int)(w >> 32), C.pose, res_idx);
         }
     }
     return res;

@@ -141,6 +141,10 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
         dst = reinterpret_cast<double*>(s_parts);
         for (int k = threadIdx.x; k < nq; k += IBLOCK) dst[k] = src[k];
         for (int k = threadIdx.x; k < NBOUND * S.n_parts; k += IBLOCK) s_bounds[k] = S.bounds[k];
+        if (LEAN) {
+            unsigned long long* s_pinfo = reinterpret_cast<unsigned long long*>(s_bounds + NBOUND * S.n_parts);
+            for (int k = threadIdx.x; k < S.n_parts; k += IBLOCK) s_pinfo[k] = lean_part_info(S.parts[k], S.objects[S.parts[k].object]);
+        }
         __syncthreads();
     }
 
@@ -166,7 +170,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
         C.lb_addr = LEAN ? smem_u32(s_lb + threadIdx.x) : 0u;
         Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
         if (budget) {   // System.jl:100-110
-            if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, pos, dir, hint, st);
+            if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, smem_u32(s_bounds + NBOUND * S.n_parts), pos, dir, hint, st);
             else h = tracing_step<RK, false>(C, pos, dir, hint, st);
         }
         const int64_t hs = P.hit.cap;
@@ -709,6 +713,10 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
         dst = reinterpret_cast<double*>(s_parts);
         for (int k = threadIdx.x; k < nq; k += IBLOCK) dst[k] = src[k];
         for (int k = threadIdx.x; k < NBOUND * S.n_parts; k += IBLOCK) s_bounds[k] = S.bounds[k];
+        if (LEAN) {
+            unsigned long long* s_pinfo = reinterpret_cast<unsigned long long*>(s_bounds + NBOUND * S.n_parts);
+            for (int k = threadIdx.x; k < S.n_parts; k += IBLOCK) s_pinfo[k] = lean_part_info(S.parts[k], S.objects[S.parts[k].object]);
+        }
         __syncthreads();
     }
     const int64_t ri = (int64_t)blockIdx.x * IBLOCK + threadIdx.x;
@@ -743,7 +751,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
             }
             C.lb_addr = LEAN ? smem_u32(s_lb + threadIdx.x) : 0u;
             if (budget) {
-                if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, pos, dir, hint, st);
+                if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, smem_u32(s_bounds + NBOUND * S.n_parts), pos, dir, hint, st);
                 else h = tracing_step<RK, false>(C, pos, dir, hint, st);
             }
         }
@@ -1635,7 +1643,8 @@ int32_t SubTrace::enqueue_chunk() {
         sp.S = sys->view; sp.cur = cur; sp.scr = scr; sp.hit = hit; sp.count = n_slots; sp.r_max = r_max; sp.keep = res->keep;
         sp.wave = wb; sp.B = beamtab(res); sp.blk_cnt = blk_cnt; sp.wave_totals = d_wtot + 2 * wave; sp.counters = ctx->d_counters;
         sp.rt = rt;
-        static const int minb = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 7;   // tuning knob: resident blocks per SM K1 is compiled for (C2: 4..8 measured, 7 = 72 registers is the fastest)
+        static const int minb_env = getenv("BMO_IMINB") ? atoi(getenv("BMO_IMINB")) : 0;
+        static const int minb = minb_env ? minb_env : 7;   // tuning knob: resident blocks per SM K1 is compiled for (C2: 4..8 measured, 7 = 72 registers is the fastest)
         // tuning knob: 0 never fuse, 1 fuse in pipelined (launch-bound) calls [default], 2 always fuse.  Measured on C2:
         // the fused kernel carries the interaction's registers through the march (0.282 vs 0.209 + 0.058 ms per
         // wave), so it only pays where the number of launches is what limits the call.
@@ -1644,8 +1653,11 @@ int32_t SubTrace::enqueue_chunk() {
         const SysView& V = sys->view;
         const bool rk = sys->has_rare;     // kernels compiled with the cylindrical / aspheric primitives
         static const bool lean_ok = !(getenv("BMO_LEAN") && atoi(getenv("BMO_LEAN")) == 0);   // tuning knob: BMO_LEAN=0 uses the general kernels everywhere
-        const bool lean = lean_ok && sys->all_lean && !rk;   // kernels compiled for lean unions + small meshes only
-        const size_t smem = staged ? (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double)) : 0;
+        const size_t tab_bytes = (size_t)V.n_prims * sizeof(bmo_prim) + (size_t)V.n_parts * (sizeof(bmo_part) + NBOUND * sizeof(double));
+        // kernels compiled for lean unions + small meshes only; their tables live in shared memory next to 22 KB of per-thread
+        // scratch (static), so the tables + part words have to fit in what is left of the 48 KB a block gets without opting in
+        const bool lean = lean_ok && sys->all_lean && !rk && staged && tab_bytes + (size_t)V.n_parts * 8 <= 24 * 1024;
+        const size_t smem = staged ? tab_bytes + (lean ? (size_t)V.n_parts * 8 : 0) : 0;
         BMO_CUDA(cudaEventRecord(ev[2 * c], st));
         if (mode == 0 && !has_splitter && allow_fused) {
             // sequential lens-stack path: intersect + interact in one kernel, hit records stay in registers; without a
@@ -1657,7 +1669,9 @@ int32_t SubTrace::enqueue_chunk() {
                 if (!staged) fused_wave0<4, false, true><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
                 else fused_wave0<6, true, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
             } else if (lean) {
-                if (!staged) fused_wave0<4, false, false, true><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
+                static const int fminb = getenv("BMO_FMINB") ? atoi(getenv("BMO_FMINB")) : 6;   // tuning knob: resident blocks per SM of the fused lean kernel
+                if (fminb >= 8) fused_wave0<8, true, false, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
+                else if (fminb == 7) fused_wave0<7, true, false, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
                 else fused_wave0<6, true, false, true><<<(unsigned)nblocks, IBLOCK, smem, st>>>(sp);
             } else {
                 if (!staged) fused_wave0<4, false, false><<<(unsigned)nblocks, IBLOCK, 0, st>>>(sp);
@@ -1701,10 +1715,10 @@ int32_t SubTrace::enqueue_chunk() {
                 if (!staged) intersect_wave<4, false, true><<<grid, IBLOCK, 0, st>>>(xp);
                 else intersect_wave<6, true, true><<<grid, IBLOCK, smem, st>>>(xp);
             } else if (lean) {
-                if (!staged) intersect_wave<4, false, false, true><<<grid, IBLOCK, 0, st>>>(xp);
-                else if (minb <= 6) intersect_wave<6, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
-                else if (minb >= 8) intersect_wave<8, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
-                else intersect_wave<7, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
+                // 8 blocks per SM (64 registers) is the fastest for the lean build (C2: 6 / 7 / 8 measured); BMO_IMINB=6 / 7 select the others
+                if (minb_env == 6) intersect_wave<6, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
+                else if (minb_env == 7) intersect_wave<7, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
+                else intersect_wave<8, true, false, true><<<grid, IBLOCK, smem, st>>>(xp);
             } else {
                 if (!staged) intersect_wave<4, false, false><<<grid, IBLOCK, 0, st>>>(xp);
                 else if (minb <= 4) intersect_wave<4, true, false><<<grid, IBLOCK, smem, st>>>(xp);
