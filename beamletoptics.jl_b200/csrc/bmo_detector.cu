@@ -60,7 +60,7 @@ struct PdFast {
 static_assert(sizeof(PdFast) % 8 == 0, "PdFast must be a whole number of doubles");
 
 struct ResView {
-    const double* seg_d; const int32_t* seg_part; int64_t rows;
+    const double* seg_d; const int32_t* seg_part; int64_t rows; int nsd;   // segment table: row records [rows][nsd]
     const int32_t *nseg, *status, *lam, *pose;
     const long long* first_seg;
     const double *w0, *e0, *plen, *popl;
@@ -85,23 +85,23 @@ __global__ void pd_build(ResView R, SysView S, const int32_t* flags, const long 
     PdRec rc;
     const int n = R.nseg[b];
     const int64_t f = R.first_seg[b];
-    const int64_t rows = R.rows;
+    const int nsd = R.nsd;
     const double plen = R.plen[b], popl = R.popl[b];
     // running sums with the reference's association (Beam.jl:125-205)
     double lsum = 0.0, lpar = plen, opl = popl;
     for (int s = 0; s < n - 1; s++) {
         const int64_t row = (f + s) * 3;
-        const double t = R.seg_d[S_T * rows + row], nn = R.seg_d[S_N * rows + row];
+        const double t = R.seg_d[(size_t)(row) * nsd + S_T], nn = R.seg_d[(size_t)(row) * nsd + S_N];
         lsum += t; lpar += t; opl += t * nn;
     }
     const int64_t rc_ = (f + n - 1) * 3, rw = rc_ + 1, rd = rc_ + 2;
     const double* d = R.seg_d;
-    const double t_last = d[S_T * rows + rc_];
-    rc.cn = d[S_N * rows + rc_];
+    const double t_last = d[(size_t)(rc_) * nsd + S_T];
+    rc.cn = d[(size_t)(rc_) * nsd + S_N];
     for (int k = 0; k < 3; k++) {
-        rc.p0[k] = d[(S_PX + k) * rows + rc_]; rc.d0[k] = d[(S_DX + k) * rows + rc_];
-        rc.wp[k] = d[(S_PX + k) * rows + rw]; rc.wd[k] = d[(S_DX + k) * rows + rw];
-        rc.dp[k] = d[(S_PX + k) * rows + rd]; rc.dd[k] = d[(S_DX + k) * rows + rd];
+        rc.p0[k] = d[(size_t)(rc_) * nsd + (S_PX + k)]; rc.d0[k] = d[(size_t)(rc_) * nsd + (S_DX + k)];
+        rc.wp[k] = d[(size_t)(rw) * nsd + (S_PX + k)]; rc.wd[k] = d[(size_t)(rw) * nsd + (S_DX + k)];
+        rc.dp[k] = d[(size_t)(rd) * nsd + (S_PX + k)]; rc.dd[k] = d[(size_t)(rd) * nsd + (S_DX + k)];
     }
     const double L = (lsum + t_last) + plen;          // length(gauss) = l + l0
     const double OPL = opl + t_last * rc.cn;           // optical_path_length(gauss)
@@ -115,7 +115,7 @@ __global__ void pd_build(ResView R, SysView S, const int32_t* flags, const long 
     const double ref_phi = dl / rc.lambda * kTwoPi;
     Cx c = cis(ref_phi);
     rc.cr = c.re; rc.ci = c.im;
-    V3 nrm = mk3(d[S_NX * rows + rc_], d[S_NY * rows + rc_], d[S_NZ * rows + rc_]);
+    V3 nrm = mk3(d[(size_t)(rc_) * nsd + S_NX], d[(size_t)(rc_) * nsd + S_NY], d[(size_t)(rc_) * nsd + S_NZ]);
     rc.sq = sqrt(fabs(dot(mk3(rc.d0[0], rc.d0[1], rc.d0[2]), nrm)));
     rc.first_row = (double)f; rc.nseg = (double)n; rc.pose = (double)R.pose[b]; rc.pad = 0;
     recs[offs[b]] = rc;
@@ -172,7 +172,7 @@ BMO_D double lin_coord(int i, int n, double lo, double hi) {
 
 // One pixel-beamlet pair in the reference's operation order (Photodetector.jl:98-103, Beam.jl:177-205,
 // Gaussian.jl:298-353, 381-392, OpticUtils.jl:87-89)
-BMO_NI Cx pd_pair_reference(const PdRec& rc, V3 p1, const double* seg_d, int64_t rows) {
+BMO_NI Cx pd_pair_reference(const PdRec& rc, V3 p1, const double* seg_d, int nsd) {
     const V3 p0 = mk3(rc.p0[0], rc.p0[1], rc.p0[2]), d0 = mk3(rc.d0[0], rc.d0[1], rc.d0[2]);
     // projection of the pixel onto the beamlet axis (Photodetector.jl:98-101)
     const double l1 = dot(p1 - p0, d0);
@@ -191,18 +191,18 @@ BMO_NI Cx pd_pair_reference(const PdRec& rc, V3 p1, const double* seg_d, int64_t
         double temp = rc.plen;
         for (int s = 0; s < ns - 1; s++) {
             const int64_t row = (f + s) * 3;
-            const double len = d[S_T * rows + row];
+            const double len = d[(size_t)(row) * nsd + S_T];
             temp += len;
             if (z < temp) {
                 const double b = temp - z;
-                const V3 sp = mk3(d[S_PX * rows + row], d[S_PY * rows + row], d[S_PZ * rows + row]);
-                c_dir = mk3(d[S_DX * rows + row], d[S_DY * rows + row], d[S_DZ * rows + row]);
+                const V3 sp = mk3(d[(size_t)(row) * nsd + S_PX], d[(size_t)(row) * nsd + S_PY], d[(size_t)(row) * nsd + S_PZ]);
+                c_dir = mk3(d[(size_t)(row) * nsd + S_DX], d[(size_t)(row) * nsd + S_DY], d[(size_t)(row) * nsd + S_DZ]);
                 point = sp + (len - b) * c_dir;
-                c_n = d[S_N * rows + row];
-                w_pos = mk3(d[S_PX * rows + row + 1], d[S_PY * rows + row + 1], d[S_PZ * rows + row + 1]);
-                w_dir = mk3(d[S_DX * rows + row + 1], d[S_DY * rows + row + 1], d[S_DZ * rows + row + 1]);
-                d_pos = mk3(d[S_PX * rows + row + 2], d[S_PY * rows + row + 2], d[S_PZ * rows + row + 2]);
-                d_dir = mk3(d[S_DX * rows + row + 2], d[S_DY * rows + row + 2], d[S_DZ * rows + row + 2]);
+                c_n = d[(size_t)(row) * nsd + S_N];
+                w_pos = mk3(d[(size_t)(row + 1) * nsd + S_PX], d[(size_t)(row + 1) * nsd + S_PY], d[(size_t)(row + 1) * nsd + S_PZ]);
+                w_dir = mk3(d[(size_t)(row + 1) * nsd + S_DX], d[(size_t)(row + 1) * nsd + S_DY], d[(size_t)(row + 1) * nsd + S_DZ]);
+                d_pos = mk3(d[(size_t)(row + 2) * nsd + S_PX], d[(size_t)(row + 2) * nsd + S_PY], d[(size_t)(row + 2) * nsd + S_PZ]);
+                d_dir = mk3(d[(size_t)(row + 2) * nsd + S_DX], d[(size_t)(row + 2) * nsd + S_DY], d[(size_t)(row + 2) * nsd + S_DZ]);
                 found = true;
                 break;
             }
@@ -250,7 +250,7 @@ __global__ void __launch_bounds__(PD_TILE* PD_TILE) pd_field(const PdParams P) {
         }
         __syncthreads();
         if (!inside) continue;
-        for (int q = 0; q < nb; q++) acc = acc + pd_pair_reference(s_rec[q], p1, P.R.seg_d, P.R.rows);
+        for (int q = 0; q < nb; q++) acc = acc + pd_pair_reference(s_rec[q], p1, P.R.seg_d, P.R.nsd);
     }
     if (inside) {
         double* f = P.field + ((int64_t)fld * P.n * P.n + (int64_t)i + (int64_t)P.n * j) * 2;
@@ -336,7 +336,7 @@ __global__ void __launch_bounds__(PDF_TX* PDF_TY, MINB) pd_field_fast(const PdPa
             for (int u = 0; u < PDF_PX; u++) {
                 bool slow;
                 Cx e = pd_pair_fast(s_rec[q], p1[u], slow);
-                if (slow) e = pd_pair_reference(P.recs[base + q], p1[u], P.R.seg_d, P.R.rows);
+                if (slow) e = pd_pair_reference(P.recs[base + q], p1[u], P.R.seg_d, P.R.nsd);
                 acc[u] = acc[u] + e;
             }
         }
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(1024) bmo::scan_flags(const int32_t* in, int64
 
 static ResView res_view(bmo_result* r) {
     ResView v;
-    v.seg_d = r->seg_d; v.seg_part = r->seg_part; v.rows = r->seg_rows; v.nseg = r->nseg; v.status = r->status; v.lam = r->lam;
+    v.seg_d = r->seg_d; v.seg_part = r->seg_part; v.rows = r->seg_rows; v.nsd = r->nsd; v.nseg = r->nseg; v.status = r->status; v.lam = r->lam;
     v.pose = r->pose; v.first_seg = r->first_seg; v.w0 = r->w0; v.e0 = r->e0; v.plen = r->plen; v.popl = r->popl; v.n_beams = r->n_beams;
     return v;
 }

@@ -105,7 +105,7 @@ struct bmo_result {
     double* spot_xz = nullptr;    // [cap_beams * R * 2]
     long long* first_seg = nullptr;  // [n_beams + 1] after finalisation
     // beam-major segment table (device): rows = n_segments * R
-    double* seg_d = nullptr;      // [nsd][rows]
+    double* seg_d = nullptr;      // [rows][nsd]: one record per row
     int32_t* seg_part = nullptr;  // [rows]
     int64_t seg_rows = 0;
     std::vector<WaveBuf> wavebufs;
@@ -187,11 +187,64 @@ inline size_t size_class(size_t bytes) {
     const size_t step = (size_t)1 << (lg - 3);
     return (bytes + step - 1) & ~(step - 1);
 }
+// Blocks of 64 MiB and more (wave buffers and segment tables of large traces, queues of 10^7 rays) bypass the driver's pool:
+// a pool that holds free blocks of other sizes satisfies a 25 GB request by remapping physical memory, which costs ~6 ms per
+// gigabyte on every call (C4 with its segment table kept: 140 of 200 ms).  They are cudaMalloc'ed once and parked in a
+// per-device free list when released; a request takes the smallest parked block that is large enough (and at most 25 % larger)
+// and was released on the same stream (so that reuse is ordered behind the last user without an event).
+struct BigBlocks {
+    struct Blk { void* p; size_t bytes; cudaStream_t stream; };
+    std::vector<Blk> parked;
+    std::map<void*, size_t> live;
+    static constexpr size_t kMin = (size_t)64 << 20;
+    static BigBlocks& of_device() {
+        static BigBlocks per_dev[64];
+        int d = 0;
+        cudaGetDevice(&d);
+        return per_dev[d & 63];
+    }
+    void drop_parked() {
+        for (auto& b : parked) cudaFree(b.p);
+        parked.clear();
+    }
+    cudaError_t get(void** out, size_t bytes, cudaStream_t s) {
+        size_t best = parked.size();
+        for (size_t i = 0; i < parked.size(); i++)
+            if (parked[i].stream == s && parked[i].bytes >= bytes && parked[i].bytes <= bytes + bytes / 4 &&
+                (best == parked.size() || parked[i].bytes < parked[best].bytes)) best = i;
+        if (best < parked.size()) {
+            *out = parked[best].p;
+            live[*out] = parked[best].bytes;
+            parked.erase(parked.begin() + best);
+            return cudaSuccess;
+        }
+        cudaError_t e = cudaMalloc(out, bytes);
+        if (e != cudaSuccess) {          // make room: parked blocks of other sizes, then whatever the stream-ordered pool caches
+            cudaGetLastError();
+            drop_parked();
+            int d = 0; cudaGetDevice(&d);
+            cudaMemPool_t pool;
+            if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
+            e = cudaMalloc(out, bytes);
+        }
+        if (e == cudaSuccess) live[*out] = bytes;
+        return e;
+    }
+    bool put(void* p, cudaStream_t s) {
+        auto it = live.find(p);
+        if (it == live.end()) return false;
+        parked.push_back({p, it->second, s});
+        live.erase(it);
+        return true;
+    }
+};
 template <class T> inline cudaError_t dev_alloc(T** p, size_t n, cudaStream_t s) {
-    return cudaMallocAsync((void**)p, size_class(std::max<size_t>(n, 1) * sizeof(T)), s);
+    const size_t bytes = size_class(std::max<size_t>(n, 1) * sizeof(T));
+    if (bytes >= BigBlocks::kMin) return BigBlocks::of_device().get((void**)p, bytes, s);
+    return cudaMallocAsync((void**)p, bytes, s);
 }
 template <class T> inline void dev_free(T*& p, cudaStream_t s) {
-    if (p) cudaFreeAsync((void*)p, s);
+    if (p && !BigBlocks::of_device().put((void*)p, s)) cudaFreeAsync((void*)p, s);
     p = nullptr;
 }
 

@@ -19,7 +19,7 @@ constexpr int PSF_NREC = 9;    // hit xyz, dir xyz, opl, proj, k
 constexpr int PSF_NFAST = 5;   // c0 = k (opl - hit . dir), k dir xyz, proj
 
 struct PsfView {
-    const double* seg_d; const int32_t* seg_part; int64_t rows;
+    const double* seg_d; const int32_t* seg_part; int64_t rows; int nsd;   // segment table: row records [rows][nsd]
     const int32_t *nseg, *status, *lam, *parent;
     const long long* first_seg;
     int64_t n_beams;
@@ -46,9 +46,9 @@ __device__ double beam_opl(const PsfView& R, int b) {
         const int c = chain[d];
         const int64_t f = R.first_seg[c];
         for (int s = 0; s < R.nseg[c]; s++) {
-            const double t = R.seg_d[S_T * R.rows + f + s];
+            const double t = R.seg_d[(size_t)(f + s) * R.nsd + S_T];
             if (isinf(t)) break;
-            l0 += t * R.seg_d[S_N * R.rows + f + s];
+            l0 += t * R.seg_d[(size_t)(f + s) * R.nsd + S_N];
         }
     }
     return l0;
@@ -59,10 +59,10 @@ __global__ void psf_build(PsfView R, SysView S, const int32_t* flags, const long
     const int64_t row = R.first_seg[b] + R.nseg[b] - 1;
     const double* d = R.seg_d;
     const int64_t rows = R.rows;
-    const V3 pos = mk3(d[S_PX * rows + row], d[S_PY * rows + row], d[S_PZ * rows + row]);
-    const V3 dir = mk3(d[S_DX * rows + row], d[S_DY * rows + row], d[S_DZ * rows + row]);
-    const V3 nrm = mk3(d[S_NX * rows + row], d[S_NY * rows + row], d[S_NZ * rows + row]);
-    const double t = d[S_T * rows + row];
+    const V3 pos = mk3(d[(size_t)(row) * R.nsd + S_PX], d[(size_t)(row) * R.nsd + S_PY], d[(size_t)(row) * R.nsd + S_PZ]);
+    const V3 dir = mk3(d[(size_t)(row) * R.nsd + S_DX], d[(size_t)(row) * R.nsd + S_DY], d[(size_t)(row) * R.nsd + S_DZ]);
+    const V3 nrm = mk3(d[(size_t)(row) * R.nsd + S_NX], d[(size_t)(row) * R.nsd + S_NY], d[(size_t)(row) * R.nsd + S_NZ]);
+    const double t = d[(size_t)(row) * R.nsd + S_T];
     const V3 hit = pos + t * dir;
     const double opl = beam_opl(R, (int)b);
     const double proj = fabs(dot(dir, nrm));
@@ -211,7 +211,7 @@ int32_t bmo_psf_collect(bmo_sys* sys, bmo_result* r, int32_t psf_object, bmo_psf
     BMO_CUDA(dev_alloc(&d_flags, (size_t)nb, st));
     BMO_CUDA(dev_alloc(&d_offs, (size_t)nb, st));
     PsfView v;
-    v.seg_d = r->seg_d; v.seg_part = r->seg_part; v.rows = r->seg_rows; v.nseg = r->nseg; v.status = r->status; v.lam = r->lam;
+    v.seg_d = r->seg_d; v.seg_part = r->seg_part; v.rows = r->seg_rows; v.nsd = r->nsd; v.nseg = r->nseg; v.status = r->status; v.lam = r->lam;
     v.parent = r->parent; v.first_seg = r->first_seg; v.n_beams = nb;
     psf_flag<<<(unsigned)((nb + 255) / 256), 256, 0, st>>>(v, sys->view, psf_object, d_flags);
     scan_flags<<<1, 1024, 0, st>>>(d_flags, nb, d_offs, ctx->d_totals);

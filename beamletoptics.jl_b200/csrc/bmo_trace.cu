@@ -1047,7 +1047,7 @@ __global__ void init_queue(const InitParams P) {
 // The root beams of a retrace call start from the first stored ray of the previous solution's roots
 // (retrace_system! keeps ray 1 as it is, System.jl:198).
 struct PrevRoots {
-    const double* seg_d; const long long* first_seg; int64_t rows;   // previous segment table [nsd][rows]
+    const double* seg_d; const long long* first_seg; int64_t rows; int nsd;   // previous segment table, row records [rows][nsd]
     const int32_t *lam, *pose; const double *w0, *e0;
     int64_t n; int mode;
     double *pos, *dir, *E0, *grays, *ow0, *oe0; int32_t *olam, *opose;
@@ -1060,11 +1060,11 @@ __global__ void gather_prev_roots(const PrevRoots P) {
     const int r = (int)(i % R);
     const int64_t row = P.first_seg[b] * R + r;
     double v[6];
-    for (int k = 0; k < 6; k++) v[k] = P.seg_d[(S_PX + k) * P.rows + row];
+    for (int k = 0; k < 6; k++) v[k] = P.seg_d[(size_t)row * P.nsd + (S_PX + k)];
     if (P.mode == 2) { for (int k = 0; k < 6; k++) P.grays[i * 6 + k] = v[k]; }
     else {
         for (int k = 0; k < 3; k++) { P.pos[3 * b + k] = v[k]; P.dir[3 * b + k] = v[3 + k]; }
-        if (P.mode == 1) for (int k = 0; k < 6; k++) P.E0[6 * b + k] = P.seg_d[(S_E0 + k) * P.rows + row];
+        if (P.mode == 1) for (int k = 0; k < 6; k++) P.E0[6 * b + k] = P.seg_d[(size_t)row * P.nsd + (S_E0 + k)];
     }
     if (r == 0) {
         P.olam[b] = P.lam[b]; P.opose[b] = P.pose[b];
@@ -1079,13 +1079,31 @@ __global__ void build_child_table(const int32_t* parent, const int32_t* slot, in
     if (p >= 0 && (k == 0 || k == 1)) child[2 * (int64_t)p + k] = (int32_t)i;
 }
 
-__global__ void gather_segments(WaveBuf w, int R, int nsd, const long long* first_seg, double* seg_d, int32_t* seg_part, int64_t rows) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= w.count || w.beam[i] < 0) return;
-    const int r = (int)(i % R);
-    const int64_t row = (first_seg[w.beam[i]] + w.seg[i]) * R + r;
-    for (int f = 0; f < nsd; f++) seg_d[f * rows + row] = w.d[f * w.count + i];
-    seg_part[row] = w.part[i];
+// wave-major records -> row records of the beam-major table.  A warp takes 32 consecutive slots of the wave: the fields are read
+// plane by plane (coalesced), transposed through shared memory, and written so that consecutive lanes store consecutive doubles
+// of a row record (runs of NSD doubles): ~3 rows per store instruction instead of one 8-byte piece of 32 different rows.
+template <int NSD>
+__global__ void __launch_bounds__(256) gather_segments(WaveBuf w, int R, const long long* first_seg, double* seg_d, int32_t* seg_part) {
+    __shared__ double s_val[8][32 * NSD];
+    __shared__ long long s_row[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x;
+    const bool valid = i < w.count && w.beam[i] >= 0;
+    long long row = -1;
+    if (valid) {
+        row = (first_seg[w.beam[i]] + w.seg[i]) * R + (int)(i % R);
+        seg_part[row] = w.part[i];
+#pragma unroll
+        for (int f = 0; f < NSD; f++) s_val[warp][lane * NSD + f] = w.d[(size_t)f * w.count + i];
+    }
+    s_row[warp][lane] = row;
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < NSD; k++) {
+        const int flat = k * 32 + lane, ray = flat / NSD, field = flat - ray * NSD;
+        const long long rr = s_row[warp][ray];
+        if (rr >= 0) seg_d[(size_t)rr * NSD + field] = s_val[warp][flat];
+    }
 }
 
 }  // namespace bmo
@@ -1140,6 +1158,7 @@ int32_t bmo_shutdown(bmo_ctx* c) {
     if (!c) return BMO_OK;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    BigBlocks::of_device().drop_parked();
     cudaFree(c->d_counters); cudaFree(c->d_totals); cudaFreeHost(c->h_totals);
     cudaEventDestroy(c->ev0); cudaEventDestroy(c->ev1);
     delete c;
@@ -1843,7 +1862,7 @@ void SubTrace::release() {
     dev_free(hit.d, st); dev_free(hit.part, st); dev_free(hit.flag, st);
     dev_free(blk_cnt, st); dev_free(blk_off, st);
     dev_free(d_wtot, st); dev_free(d_scan_tot, st);
-    for (void* p : tmp) cudaFreeAsync(p, st);
+    for (void* p : tmp) dev_free(p, st);
     tmp.clear();
     ev.clear();
 }
@@ -1962,16 +1981,21 @@ static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int
     // segment table: first_seg = exclusive scan of nseg, then gather wave-major -> beam-major
     // (spot-only traces compute first_seg lazily, see ensure_first_seg)
     if (res->keep) {
+        const double tf0 = tnow_ms();
         if ((rc = ensure_first_seg(res))) return rc;
+        if (prof) { cudaStreamSynchronize(st); fprintf(stderr, "[bmo]   finalize: first_seg scan %.3f ms\n", tnow_ms() - tf0); }
         res->seg_rows = res->n_segments * R;
         BMO_CUDA(dev_alloc(&res->seg_d, (size_t)nsd * res->seg_rows, st));
         BMO_CUDA(dev_alloc(&res->seg_part, (size_t)res->seg_rows, st));
+        if (prof) { cudaStreamSynchronize(st); fprintf(stderr, "[bmo]   finalize: + table allocation (%.1f MB) %.3f ms\n", nsd * res->seg_rows * 8e-6, tnow_ms() - tf0); }
         for (auto& wb : res->wavebufs) {
-            gather_segments<<<(unsigned)((wb.count + 255) / 256), 256, 0, st>>>(wb, R, nsd, res->first_seg, res->seg_d, res->seg_part, res->seg_rows);
+            if (nsd == 17) gather_segments<17><<<(unsigned)((wb.count + 255) / 256), 256, 0, st>>>(wb, R, res->first_seg, res->seg_d, res->seg_part);
+            else gather_segments<11><<<(unsigned)((wb.count + 255) / 256), 256, 0, st>>>(wb, R, res->first_seg, res->seg_d, res->seg_part);
             BMO_LAUNCH(ctx, "gather_segments");
             dev_free(wb.d, st); dev_free(wb.part, st); dev_free(wb.beam, st); dev_free(wb.seg, st);
         }
         res->wavebufs.clear();
+        if (prof) { cudaStreamSynchronize(st); fprintf(stderr, "[bmo]   finalize: + gather %.3f ms\n", tnow_ms() - tf0); }
     }
     BMO_CUDA(cudaEventRecord(ctx->ev1, st));
     BMO_CUDA(cudaStreamSynchronize(st));
@@ -2053,7 +2077,7 @@ int32_t bmo_retrace(bmo_sys* sys, bmo_result* prev, int32_t r_max, uint32_t flag
         }
     }
     PrevRoots pr{};
-    pr.seg_d = prev->seg_d; pr.first_seg = prev->first_seg; pr.rows = prev->seg_rows; pr.lam = prev->lam; pr.pose = prev->pose;
+    pr.seg_d = prev->seg_d; pr.first_seg = prev->first_seg; pr.rows = prev->seg_rows; pr.nsd = prev->nsd; pr.lam = prev->lam; pr.pose = prev->pose;
     pr.w0 = prev->w0; pr.e0 = prev->e0; pr.n = n; pr.mode = mode;
     if (mode == 2) {
         BMO_CUDA(dev_alloc(&pr.grays, (size_t)n * 18, st)); BMO_CUDA(dev_alloc(&pr.ow0, (size_t)n, st)); BMO_CUDA(dev_alloc(&pr.oe0, (size_t)n * 2, st));
@@ -2132,22 +2156,24 @@ int32_t bmo_result_segments(bmo_result* r, double* pos, double* dir, double* n, 
     cudaStream_t st = r->ctx->stream;
     const size_t rows = (size_t)r->seg_rows;
     if (rows == 0) return BMO_OK;
-    // device table is SoA [field][row]; the ABI hands out [row][3] arrays -> stage through a host buffer
-    std::vector<double> h((size_t)r->nsd * rows);
+    // the device table holds one record of nsd doubles per row; the ABI hands out one array per quantity -> stage through a host buffer
+    const size_t nsd = (size_t)r->nsd;
+    std::vector<double> h(nsd * rows);
     std::vector<int32_t> hp(rows);
     BMO_CUDA(cudaMemcpyAsync(h.data(), r->seg_d, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st));
     BMO_CUDA(cudaMemcpyAsync(hp.data(), r->seg_part, rows * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     BMO_CUDA(cudaStreamSynchronize(st));
     const std::vector<int32_t>& part_object = r->part_object;
     for (size_t i = 0; i < rows; i++) {
-        if (pos) { pos[3 * i] = h[S_PX * rows + i]; pos[3 * i + 1] = h[S_PY * rows + i]; pos[3 * i + 2] = h[S_PZ * rows + i]; }
-        if (dir) { dir[3 * i] = h[S_DX * rows + i]; dir[3 * i + 1] = h[S_DY * rows + i]; dir[3 * i + 2] = h[S_DZ * rows + i]; }
-        if (n) n[i] = h[S_N * rows + i];
-        if (t) t[i] = h[S_T * rows + i];
-        if (nrm) { nrm[3 * i] = h[S_NX * rows + i]; nrm[3 * i + 1] = h[S_NY * rows + i]; nrm[3 * i + 2] = h[S_NZ * rows + i]; }
+        const double* q = h.data() + i * nsd;
+        if (pos) { pos[3 * i] = q[S_PX]; pos[3 * i + 1] = q[S_PY]; pos[3 * i + 2] = q[S_PZ]; }
+        if (dir) { dir[3 * i] = q[S_DX]; dir[3 * i + 1] = q[S_DY]; dir[3 * i + 2] = q[S_DZ]; }
+        if (n) n[i] = q[S_N];
+        if (t) t[i] = q[S_T];
+        if (nrm) { nrm[3 * i] = q[S_NX]; nrm[3 * i + 1] = q[S_NY]; nrm[3 * i + 2] = q[S_NZ]; }
         if (part) part[i] = hp[i];
         if (object) object[i] = hp[i] >= 0 ? part_object[hp[i]] : -1;
-        if (E0 && r->mode == 1) for (int k = 0; k < 6; k++) E0[6 * i + k] = h[(S_E0 + k) * rows + i];
+        if (E0 && r->mode == 1) for (int k = 0; k < 6; k++) E0[6 * i + k] = q[S_E0 + k];
     }
     return BMO_OK;
 }

@@ -18,7 +18,7 @@ dd = np.ascontiguousarray(np.broadcast_to(d, (nr, 3)))
 for it in range(reps):
     L.counters_reset()
     t0 = time.perf_counter()
-    r = m.trace_rays(dsys, pos, dd, lam, Ef, None, 100, keep_segments=False)
+    r = m.trace_rays(dsys, pos, dd, lam, Ef, None, 100, keep_segments=bool(int(os.environ.get("KEEP", "0"))))
     wall = time.perf_counter() - t0
     c = L.counters()
     print(f"rep {it}: rays {nr} beams {r.n_beams} interactions {r.interactions} waves {r.waves} trace_ms {c['trace_ms']:.1f} wall {wall*1e3:.1f} ms "
