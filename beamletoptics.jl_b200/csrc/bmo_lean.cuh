@@ -172,15 +172,17 @@ BMO_D unsigned long long lds_u64(unsigned a) { unsigned long long v; asm volatil
 // tracing_step! (System.jl:57-110) for LEAN systems; see tracing_step (bmo_geom.cuh) for the rules it follows.
 // sc / lb_addr: shared-memory addresses of this thread's scratch column and member-bounds column; pinfo: shared-memory
 // address of the part words.
-BMO_D Hit tracing_step_lean(const TraceCtx& C, unsigned sc, unsigned lb_addr, unsigned pinfo, V3 pos, V3 dir, int hint_part, Stats& st) {
+// [lo, hi): the parts trace_all looks at (retrace_system! restricts them, see tracing_step); hi < 0 means all parts.
+BMO_D Hit tracing_step_lean(const TraceCtx& C, unsigned sc, unsigned lb_addr, unsigned pinfo, V3 pos, V3 dir, int hint_part, Stats& st,
+                            const int lo = 0, const int hi = -1) {
     ls_store3(sc, LS_POS, pos);
     ls_store3(sc, LS_DIR, dir);
     ls_store3(sc, LS_INV, mk3(1.0 / dir.x, 1.0 / dir.y, 1.0 / dir.z));
     double res_t = INFINITY, ob_t = INFINITY;
     int res_part = -1, ob_part = -1, res_idx = 0, ob_idx = 0, cur_obj = -1;
-    const int n_parts = C.n_parts;
-    for (int it = hint_part >= 0 ? -1 : 0; it <= n_parts; it++) {
-        const bool all = it >= 0;                    // false: the trace_one iteration on the hinted part
+    const int n_parts = hi < 0 ? C.n_parts : hi;
+    for (int it = hint_part >= 0 ? lo - 1 : lo; it <= n_parts; it++) {
+        const bool all = it >= lo;                   // false: the trace_one iteration on the hinted part
         const int part = all ? it : hint_part;
         const bool last = it == n_parts;
         const unsigned long long w = last ? 0ull : lds_u64(pinfo + 8u * (unsigned)part);

@@ -201,10 +201,13 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
 // first tracing_step! has no hint (:132-137): pass 1, the ordinary full trace, for exactly those beams and
 // for the beams that are not retracing.  flag: 0 ordinary step, 1 re-validated (K2 must not apply the
 // r_max test: retrace_system! has none), 2 stored path left in this wave.
-template <int MODE, bool STAGED, bool RK>
+template <int MODE, bool STAGED, bool RK, bool LEAN = false>
 __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(const StepParams P) {
     constexpr int R = Cfg<MODE>::R;
     constexpr int UNITS = Cfg<MODE>::UNITS;
+    static_assert(Cfg<MODE>::BLOCK == LB_STRIDE, "the lean scratch columns are laid out for 128 threads per block");
+    __shared__ float s_lb[LEAN ? LB_ROWS * LB_STRIDE : 1];
+    __shared__ double s_ls[LEAN ? LS_SLOTS * LB_STRIDE : 1];
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const SysView& S = P.S;
     bmo_prim* s_prims = reinterpret_cast<bmo_prim*>(smem_raw);
@@ -219,6 +222,10 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(co
         dst = reinterpret_cast<double*>(s_parts);
         for (int k = threadIdx.x; k < nq; k += Cfg<MODE>::BLOCK) dst[k] = src[k];
         for (int k = threadIdx.x; k < NBOUND * S.n_parts; k += Cfg<MODE>::BLOCK) s_bounds[k] = S.bounds[k];
+        if (LEAN) {
+            unsigned long long* s_pinfo = reinterpret_cast<unsigned long long*>(s_bounds + NBOUND * S.n_parts);
+            for (int k = threadIdx.x; k < S.n_parts; k += Cfg<MODE>::BLOCK) s_pinfo[k] = lean_part_info(S.parts[k], S.objects[S.parts[k].object]);
+        }
         __syncthreads();
     }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -276,7 +283,10 @@ __global__ void __launch_bounds__(Cfg<MODE>::BLOCK, 6) retrace_intersect_wave(co
         int hp = -1, plo = lo, phi = hi;
         if (pass == 0) run = restricted;
         else { run = active && budget && !(in_phase && ok); hp = in_phase ? -1 : hint; plo = 0; phi = S.n_parts; }
-        if (run) h = tracing_step<RK>(C, pos, dir, hp, st, plo, phi);
+        if (run) {
+            if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), smem_u32(s_lb + threadIdx.x), smem_u32(s_bounds + NBOUND * S.n_parts), pos, dir, hp, st, plo, phi);
+            else h = tracing_step<RK>(C, pos, dir, hp, st, plo, phi);
+        }
         if (pass == 0) {
             ok = restricted && h.part >= 0;
             if (MODE == 2) {   // Gaussian.jl:171-180: all three rays must hit the same shape
@@ -1708,7 +1718,8 @@ int32_t SubTrace::enqueue_chunk() {
             // retrace call: K1r re-validates the stored path where there is one, ordinary tracing_step! elsewhere
 #define BMO_RETRACE_LAUNCH(M, RKV)                                                                                         \
     do {                                                                                                                   \
-        if (staged) retrace_intersect_wave<M, true, RKV><<<(unsigned)nblocks, Cfg<M>::BLOCK, smem, st>>>(sp);              \
+        if (lean) retrace_intersect_wave<M, true, false, true><<<(unsigned)nblocks, Cfg<M>::BLOCK, smem, st>>>(sp);        \
+        else if (staged) retrace_intersect_wave<M, true, RKV><<<(unsigned)nblocks, Cfg<M>::BLOCK, smem, st>>>(sp);         \
         else retrace_intersect_wave<M, false, RKV><<<(unsigned)nblocks, Cfg<M>::BLOCK, 0, st>>>(sp);                       \
     } while (0)
             if (mode == 0) { if (rk) BMO_RETRACE_LAUNCH(0, true); else BMO_RETRACE_LAUNCH(0, false); }
