@@ -939,28 +939,46 @@ __global__ void __launch_bounds__(CBLOCK) compact_scatter(Queue src, Queue dst, 
     }
 }
 
-// K3 in one launch (cooperative grid, one CTA slice per resident block): count the live units of the block's
-// contiguous slice, grid-wide barrier, own offset = sum of the lower blocks' counts (a few hundred values, L2
-// hits), then the order-preserving scatter row by row with warp ballots.  The alive flags are read twice (the
-// second time from L2), every surviving ray is read and written once: the same algorithmic traffic as the
-// three-kernel version without its two launch gaps and the single-block scan in between.
+// K3 in one launch (cooperative grid, one CTA slice per resident block, one contiguous sub-slice per warp): every warp counts
+// the live units of its sub-slice, grid-wide barrier, own offset = sum of the lower blocks' counts (a few hundred values, L2
+// hits) + the lower warps of the block, then every warp scatters its sub-slice on its own, two 32-slot rows per step, all loads
+// of both rows issued before the first store -- no block barrier inside the copy loop, so the 8 warps of a block and the two
+// rows of a step keep independent DRAM requests in flight (the previous version walked 256-slot rows between two barriers and was
+// bound by the latency of one row at a time: 36 % of the HBM peak).  The alive flags are read twice (the second time from L2),
+// every surviving ray is read and written once; order is preserved (sub-slices are contiguous and ordered).
+template <int NF>
+BMO_D void compact_copy_unit(const Queue& src, const Queue& dst, int64_t ss, int64_t ds, int64_t si, int64_t di) {
+    double v[NF];
+    int w[NI_Q];
+#pragma unroll
+    for (int k = 0; k < NF; k++) v[k] = src.d[k * ss + si];
+#pragma unroll
+    for (int f = 0; f < NI_Q; f++) w[f] = src.i[f * ss + si];
+#pragma unroll
+    for (int k = 0; k < NF; k++) dst.d[k * ds + di] = v[k];
+#pragma unroll
+    for (int f = 0; f < NI_Q; f++) dst.i[f * ds + di] = w[f];
+}
 __global__ void __launch_bounds__(CBLOCK) compact_fused(Queue src, Queue dst, int64_t n_slots, int64_t per, int R, int nf, int32_t* blk_cnt) {
     namespace cg = cooperative_groups;
-    __shared__ int s_w[CBLOCK / 32];
-    __shared__ long long s_red[CBLOCK / 32];
+    constexpr int NW = CBLOCK / 32;
+    __shared__ int s_w[NW];
+    __shared__ long long s_red[NW];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t ss = src.cap, ds = dst.cap;
     const int64_t lo = (int64_t)blockIdx.x * per, hi = min(lo + per, n_slots);
+    const int64_t wper = per / NW;                         // per is a multiple of CBLOCK: whole 32-slot rows per warp
+    const int64_t wlo = min(lo + warp * wper, hi), whi = min(wlo + wper, hi);
     const int32_t* alive = src.i + I_BEAM * ss;
     int cnt = 0;
-    for (int64_t u = lo + threadIdx.x; u < hi; u += CBLOCK) cnt += alive[u * R] >= 0;
+    for (int64_t u = wlo + lane; u < whi; u += 32) cnt += alive[u * R] >= 0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     if (lane == 0) s_w[warp] = cnt;
     __syncthreads();
     if (threadIdx.x == 0) {
         int a = 0;
-        for (int k = 0; k < CBLOCK / 32; k++) a += s_w[k];
+        for (int k = 0; k < NW; k++) a += s_w[k];
         blk_cnt[blockIdx.x] = a;
     }
     cg::this_grid().sync();
@@ -971,35 +989,55 @@ __global__ void __launch_bounds__(CBLOCK) compact_fused(Queue src, Queue dst, in
     if (lane == 0) s_red[warp] = part;
     __syncthreads();
     long long off = 0;
-    for (int k = 0; k < CBLOCK / 32; k++) off += s_red[k];
-    for (int64_t base = lo; base < hi; base += CBLOCK) {
-        const int64_t u = base + threadIdx.x;
-        const bool live = u < hi && alive[u * R] >= 0;
-        const unsigned bal = __ballot_sync(0xffffffffu, live);
-        __syncthreads();                       // s_w of the previous row has been consumed
-        if (lane == 0) s_w[warp] = __popc(bal);
-        __syncthreads();
-        int woff = 0, row = 0;
-        for (int k = 0; k < CBLOCK / 32; k++) { if (k < warp) woff += s_w[k]; row += s_w[k]; }
-        if (live) {
-            const int64_t du = off + woff + __popc(bal & lanemask_lt());
+    for (int k = 0; k < NW; k++) off += s_red[k];
+    for (int k = 0; k < warp; k++) off += s_w[k];
+    for (int64_t base = wlo; base < whi; base += 64) {
+        const int64_t u0 = base + lane, u1 = base + 32 + lane;
+        const bool l0 = u0 < whi && alive[u0 * R] >= 0, l1 = u1 < whi && alive[u1 * R] >= 0;
+        const unsigned b0 = __ballot_sync(0xffffffffu, l0), b1 = __ballot_sync(0xffffffffu, l1);
+        const int64_t d0 = off + __popc(b0 & lanemask_lt()), d1 = off + __popc(b0) + __popc(b1 & lanemask_lt());
+        off += __popc(b0) + __popc(b1);
+        if (R == 1 && nf == 7) {                            // plain rays: both rows' loads in flight before the stores
+            double v0[7], v1[7];
+            int w0[NI_Q], w1[NI_Q];
+            if (l0) {
+#pragma unroll
+                for (int k = 0; k < 7; k++) v0[k] = src.d[k * ss + u0];
+#pragma unroll
+                for (int f = 0; f < NI_Q; f++) w0[f] = src.i[f * ss + u0];
+            }
+            if (l1) {
+#pragma unroll
+                for (int k = 0; k < 7; k++) v1[k] = src.d[k * ss + u1];
+#pragma unroll
+                for (int f = 0; f < NI_Q; f++) w1[f] = src.i[f * ss + u1];
+            }
+            if (l0) {
+#pragma unroll
+                for (int k = 0; k < 7; k++) dst.d[k * ds + d0] = v0[k];
+#pragma unroll
+                for (int f = 0; f < NI_Q; f++) dst.i[f * ds + d0] = w0[f];
+            }
+            if (l1) {
+#pragma unroll
+                for (int k = 0; k < 7; k++) dst.d[k * ds + d1] = v1[k];
+#pragma unroll
+                for (int f = 0; f < NI_Q; f++) dst.i[f * ds + d1] = w1[f];
+            }
+        } else {
             for (int r = 0; r < R; r++) {
-                const int64_t si = u * R + r, di = du * R + r;
-                for (int f0 = 0; f0 < nf; f0 += 8) {
-                    double v[8];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) if (f0 + k < nf) v[k] = src.d[(f0 + k) * ss + si];
-#pragma unroll
-                    for (int k = 0; k < 8; k++) if (f0 + k < nf) dst.d[(f0 + k) * ds + di] = v[k];
+                if (nf == 13) {
+                    if (l0) compact_copy_unit<13>(src, dst, ss, ds, u0 * R + r, d0 * R + r);
+                    if (l1) compact_copy_unit<13>(src, dst, ss, ds, u1 * R + r, d1 * R + r);
+                } else if (nf == 10) {
+                    if (l0) compact_copy_unit<10>(src, dst, ss, ds, u0 * R + r, d0 * R + r);
+                    if (l1) compact_copy_unit<10>(src, dst, ss, ds, u1 * R + r, d1 * R + r);
+                } else {
+                    if (l0) compact_copy_unit<7>(src, dst, ss, ds, u0 * R + r, d0 * R + r);
+                    if (l1) compact_copy_unit<7>(src, dst, ss, ds, u1 * R + r, d1 * R + r);
                 }
-                int w[NI_Q];
-#pragma unroll
-                for (int f = 0; f < NI_Q; f++) w[f] = src.i[f * ss + si];
-#pragma unroll
-                for (int f = 0; f < NI_Q; f++) dst.i[f * ds + di] = w[f];
             }
         }
-        off += row;
     }
 }
 
