@@ -262,6 +262,25 @@ __global__ void __launch_bounds__(PD_TILE* PD_TILE) pd_field(const PdParams P) {
 constexpr int PDF_TX = 32, PDF_TY = 8;   // 256 threads; each thread owns PX pixels (rows j, j + 8, ...) of a 32 x (8 PX) tile
 constexpr int PDF_BATCH = 48;                        // beamlet records per shared-memory tile
 
+// Reciprocal, reciprocal square root and square root for the detector kernel: the hardware approximation (MUFU, 2^-22)
+// followed by ONE Newton step in FMAs -- relative error < 1e-13, four to six FP64 instructions instead of the ten to fourteen
+// of the correctly rounded library routines (which add a second Newton step and a fix-up).  The field is held to 1e-8 relative
+// L2; arguments are positive and far from the subnormal range (squared lengths in metres, 1 - cos^2).  0 -> NaN (the library
+// returns Inf): the waist-plane guards below treat both alike (Gaussian.jl:348-351).
+BMO_D double rcp13(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x, y, 1.0);
+    return fma(y, e, y);
+}
+BMO_D double rsqrt13(double x) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+BMO_D double sqrt13(double x) { return x > 0.0 ? x * rsqrt13(x) : (x == 0.0 ? 0.0 : NAN); }
+
 BMO_D Cx pd_pair_fast(const PdFast& rc, V3 p1, bool& slow) {
     const double vx = p1.x - rc.p0[0], vy = p1.y - rc.p0[1], vz = p1.z - rc.p0[2];
     const double l1 = vx * rc.d0[0] + vy * rc.d0[1] + vz * rc.d0[2];
@@ -277,19 +296,19 @@ BMO_D Cx pd_pair_fast(const PdFast& rc, V3 p1, bool& slow) {
     const double nd = rc.alpd + s * rc.betd, nw = rc.alpw + s * rc.betw;
     // cos^2 of the angle between height vector and ray, c_r^2 = n_r^2 / y_r^2: one reciprocal serves both
     // (NaN at y = 0, like the reference's y0 / 0)
-    const double ip = 1.0 / (y2d * y2w);
+    const double ip = rcp13(y2d * y2w);
     double c2d = (nd * nd) * (y2w * ip), c2w = (nw * nw) * (y2d * ip);
     c2d = c2d > 1.0 ? 1.0 : c2d; c2w = c2w > 1.0 ? 1.0 : c2w;  // clamp of angle3d (LinearAlgebraUtils.jl:103-108)
-    const double id = rsqrt(1.0 - c2d), iw = rsqrt(1.0 - c2w);
+    const double id = rsqrt13(1.0 - c2d), iw = rsqrt13(1.0 - c2w);
     const double E = nd * id + nw * iw;                          // E_kt = y_d m_d + y_w m_w
     const double F2 = c2d * (id * id) + c2w * (iw * iw);         // F_kt^2 = m_d^2 + m_w^2
-    const double rw = rsqrt(y2d + y2w);                          // 1 / w
+    const double rw = rsqrt13(y2d + y2w);                        // 1 / w
     const double iw2 = rw * rw;
     double R = E * iw2;                                          // curvature E_kt / w^2
     // psi = -atan2(1, sqrt(1/(R zeta) - 1)), R zeta = E^2 / (w^2 F^2):  sin|psi| = |E| / (w F), cos psi = sqrt(1 - sin^2)
-    double spsi = fabs(E) * rw * rsqrt(F2);
+    double spsi = fabs(E) * rw * rsqrt13(F2);
     spsi = spsi > 1.0 ? 1.0 : spsi;
-    double cpsi = sqrt(1.0 - spsi * spsi);
+    double cpsi = sqrt13(1.0 - spsi * spsi);
     if (!(R < 0.0)) spsi = -spsi;                                // R < 0 flips the sign of psi
     if (isnan(R)) R = 0.0;                                       // Gaussian.jl:348-351
     if (isnan(spsi) || isnan(cpsi)) { cpsi = 1.0; spsi = 0.0; }
@@ -331,13 +350,30 @@ __global__ void __launch_bounds__(PDF_TX* PDF_TY, MINB) pd_field_fast(const PdPa
             for (int k = tid; k < nw; k += PDF_TX * PDF_TY) dst[k] = src[k];
         }
         __syncthreads();
+        // Pairs that need the reference-order routine (the pixel's z falls on an earlier chief segment, degenerate geometry) are
+        // only noted here, one bit per record of the batch, and evaluated after the batch: the out-of-line call and the
+        // registers it forces the compiler to save stay out of the pair loop.  The sum then takes those pairs last, which
+        // changes its rounding at the 1e-16 level (the field is held to 1e-8 relative L2).
+        unsigned long long later[PDF_PX];
+#pragma unroll
+        for (int u = 0; u < PDF_PX; u++) later[u] = 0ull;
+        static_assert(PDF_BATCH <= 64, "one bit per record of a batch");
         for (int q = 0; q < nb; q++) {
 #pragma unroll
             for (int u = 0; u < PDF_PX; u++) {
                 bool slow;
-                Cx e = pd_pair_fast(s_rec[q], p1[u], slow);
-                if (slow) e = pd_pair_reference(P.recs[base + q], p1[u], P.R.seg_d, P.R.nsd);
-                acc[u] = acc[u] + e;
+                const Cx e = pd_pair_fast(s_rec[q], p1[u], slow);
+                if (slow) later[u] |= 1ull << q;
+                else acc[u] = acc[u] + e;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PDF_PX; u++) {
+            unsigned long long m = later[u];
+            while (m) {
+                const int q = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                acc[u] = acc[u] + pd_pair_reference(P.recs[base + q], p1[u], P.R.seg_d, P.R.nsd);
             }
         }
     }
@@ -476,7 +512,7 @@ static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t po
             dim3 grid((n + PD_TILE - 1) / PD_TILE, (n + PD_TILE - 1) / PD_TILE, n_fields), block(PD_TILE, PD_TILE);
             pd_field<<<grid, block, 0, st>>>(pp);
         } else {
-            static const int variant = getenv("BMO_PD_VARIANT") ? atoi(getenv("BMO_PD_VARIANT")) : 14;   // tuning knob: 10*PX + MINB
+            static const int variant = getenv("BMO_PD_VARIANT") ? atoi(getenv("BMO_PD_VARIANT")) : 13;   // tuning knob: 10*PX + MINB (13 = 80 registers, 3 blocks per SM: the fastest measured)
             const int px = (variant == 22 || variant == 24) ? 2 : 1;
             dim3 grid((n + PDF_TX - 1) / PDF_TX, (n + PDF_TY * px - 1) / (PDF_TY * px), n_fields), block(PDF_TX, PDF_TY);
             switch (variant) {
