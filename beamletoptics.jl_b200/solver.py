@@ -254,11 +254,33 @@ def retrace(dsys, prev, r_max=100, keep_segments=True):
     return res
 
 
+def _root_signature(beam):
+    """What a retrace starts from: the state of the first ray(s) of the beam as the host holds it now.  retrace_system!
+    re-validates the stored path starting at `first(rays(beam))` (System.jl:188-199) and a Gaussian beamlet's E0 / w0 are read
+    from the (mutable) beamlet, so a host that has changed them (`polarization!`, `electric_field!`, test/runtests.jl:2405,
+    2846-2849) expects the new values to travel down the tree."""
+    if isinstance(beam, bm.GaussianBeamlet):
+        return (tuple(np.asarray(beam.rays18(), dtype=np.float64).ravel().tolist()), float(beam.w0), complex(beam.E0), float(beam.lam))
+    if isinstance(beam, bm.Beam):
+        r = beam.rays[0]
+        return (tuple(r.pos), tuple(r.dir), float(r.lam), tuple(complex(x) for x in r.E0) if r.polarized else None)
+    if isinstance(beam, bm.BeamletBundle):
+        return (hash(np.ascontiguousarray(beam.rays).tobytes()), hash(np.ascontiguousarray(beam.w0).tobytes()), hash(np.ascontiguousarray(beam.E0).tobytes()))
+    if isinstance(beam, bm.RayBundle):
+        e = None if beam.E0 is None else hash(np.ascontiguousarray(beam.E0).tobytes())
+        return (hash(np.ascontiguousarray(beam.pos).tobytes()), hash(np.ascontiguousarray(beam.dir).tobytes()), e)
+    return None
+
+
 def _previous_solution(beam, dsys, lams):
     """The stored solution of `beam` if it can be retraced through `dsys` (same object / part structure and
-    wavelength table), else None."""
+    wavelength table, root rays as they were when it was stored), else None: the device keeps the roots of the stored
+    solution, so a beam whose first ray / E0 / w0 was changed on the host is traced afresh (same result: the reference's
+    retrace re-interacts every stored ray with the new values)."""
     prev = getattr(beam, "_solution", None)
     if prev is None or prev.h is None or not prev.keep:
+        return None
+    if getattr(prev, "_root_sig", None) != _root_signature(beam):
         return None
     pf, nf = prev.dsys.flat, dsys.flat
     if prev.dsys.device != dsys.device or len(pf.objects) != len(nf.objects) or pf.tables.n_parts != nf.tables.n_parts:
@@ -377,6 +399,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
             res = trace_rays(dsys, np.array([r0.pos]), np.array([r0.dir]), lam_id, E0, None, r_max, True)
         res.lams = lams
         beam._solution = res
+        res._root_sig = _root_signature(beam)
         _rebuild_beam(beam, res, dsys.flat)
         _collect_spots(dsys.flat, res)
         _collect_psfs(dsys, res)
@@ -391,6 +414,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
             res = trace_beamlets(dsys, np.array([beam.rays18()]), lam_id, np.array([beam.w0]), np.array([beam.E0]), None, r_max)
         res.lams = lams
         beam._solution = res
+        res._root_sig = _root_signature(beam)
         _rebuild_gauss(beam, res, dsys.flat)
         _collect_spots(dsys.flat, res)
         _accumulate_pds(dsys, res)
@@ -414,6 +438,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
             res = trace_rays(dsys, beam.pos, bdir, blam, beam.E0, None, r_max, keep_segments)
         res.lams = lams
         beam.result = beam._solution = res
+        res._root_sig = _root_signature(beam)
         _collect_spots(dsys.flat, res)
         if has_psf:
             _collect_psfs(dsys, res)
@@ -428,6 +453,7 @@ def solve_system_(system, beam, r_max=100, retrace=True, device=0, norm_zero_rul
             res = trace_beamlets(dsys, beam.rays, lam_id, beam.w0, beam.E0, None, r_max)
         res.lams = lams
         beam.result = beam._solution = res
+        res._root_sig = _root_signature(beam)
         _collect_spots(dsys.flat, res)
         _accumulate_pds(dsys, res)
         return res

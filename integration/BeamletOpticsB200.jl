@@ -63,6 +63,7 @@ const PRIM = Dict(PlanoSurfaceSDF => 0, CylinderSDF => 1, SphereSDF => 2, Convex
     ConcaveSphericalSurfaceSDF => 4, CutSphereSDF => 5, BoxSDF => 6, RingSDF => 7, RightAnglePrismSDF => 8,
     BeamletOptics.ConvexCylinderSDF => 10, BeamletOptics.ConcaveCylinderSDF => 11)
 const KEEP_SEGMENTS = UInt32(1)
+const UNIFORM_DIR = UInt32(8)
 
 check(rc) = rc == 0 || error(unsafe_string(ccall((:bmo_last_error, libbmo), Cstring, ())))
 
@@ -205,6 +206,11 @@ local_radius(s::BoxSDF) = norm((s.x, s.y, s.z)) / 2
 local_radius(s::RingSDF) = hypot(s.inner_radius + s.hwidth, s.hthickness)
 local_radius(s::RightAnglePrismSDF) = norm((s.x, s.y, s.z)) / 2
 local_radius(s::MeniscusLensSDF) = maximum(norm(position(c)) + local_radius(c) for c in (s.convex, s.cylinder, s.concave))
+# cylindric, aspheric and acylindric lens surfaces: generous radii (the flattener only needs a bound, shapes.py:local_bound is tighter)
+local_radius(s::Union{BeamletOptics.ConvexCylinderSDF,BeamletOptics.ConcaveCylinderSDF}) = hypot(s.height / 2, s.diameter / 2) + s.diameter
+local_radius(s::BeamletOptics.AbstractAsphericalSurfaceSDF) = hypot(s.diameter / 2, maximum(abs, s.max_sag)) + s.diameter / 2
+local_radius(s::BeamletOptics.AbstractAcylindricalSurfaceSDF) = hypot(s.height / 2, s.diameter / 2, maximum(abs, s.max_sag)) + s.diameter / 2
+local_radius(s::AbstractSDF) = error("BeamletOpticsB200: no bounding radius for $(typeof(s)) -- this SDF type is not supported by the GPU path")
 
 function upload(cs::CUDASystem, f)
     sys = Ref{Ptr{Cvoid}}(C_NULL)
@@ -244,9 +250,11 @@ function BeamletOptics.solve_system!(cs::CUDASystem, beams::AbstractVector{<:Bea
         ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), prev)
     else
         GC.@preserve pos dir lam E0 begin
+            # a collimated bundle ships its one direction once (BMO_UNIFORM_DIR: 24 B per ray over the bus instead of 48)
+            flags = (rebuild ? KEEP_SEGMENTS : UInt32(0)) | (all(c -> c == view(dir, :, 1), eachcol(dir)) ? UNIFORM_DIR : UInt32(0))
             check(ccall((:bmo_trace_rays, libbmo), Int32,
                 (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Float64}, Ptr{Int32}, Int32, UInt32, Ref{Ptr{Cvoid}}),
-                sys, n, pos, dir, lam, E0 === nothing ? C_NULL : pointer(E0), C_NULL, r_max, rebuild ? KEEP_SEGMENTS : UInt32(0), res))
+                sys, n, pos, dir, lam, E0 === nothing ? C_NULL : pointer(E0), C_NULL, r_max, flags, res))
         end
     end
     collect_spots!(f, res[])
@@ -335,46 +343,127 @@ function info(res)
     check(ccall((:bmo_result_get_info, libbmo), Int32, (Ptr{Cvoid}, Ref{BmoResultInfo}), res, i)); i[]
 end
 
+"""Per-beam tables of a result: parent, child slot, nseg, status, first segment row, (Gaussian) w0 and E0."""
+function beam_tables(res)
+    nfo = info(res); nb = nfo.n_beams
+    parent = Vector{Int32}(undef, nb); slot = similar(parent); nseg = similar(parent); status = similar(parent)
+    first_seg = Vector{Int64}(undef, nb); w0 = Vector{Float64}(undef, nb); E0 = Vector{ComplexF64}(undef, nb)
+    gauss = nfo.rays_per_beam == 3
+    check(ccall((:bmo_result_beams, libbmo), Int32,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Ptr{ComplexF64}, Ptr{Int32}),
+        res, parent, slot, nseg, status, first_seg, gauss ? pointer(w0) : C_NULL, gauss ? pointer(E0) : C_NULL, C_NULL))
+    return (; nfo, nb, parent, slot, nseg, status, first_seg, w0, E0)
+end
+
+"""Beam ids in the reference's processing order (System.jl:444-461): root by root, each tree level by level, children as
+[transmitted, reflected] -- the order in which `interact3d(::Spotdetector, ...)` pushes its hits (solver.py: bfs_order)."""
+function bfs_order(bt)
+    nb, nroots = bt.nb, bt.nfo.n_roots
+    nb == nroots && return collect(1:nb)
+    root = collect(1:nb); depth = zeros(Int, nb); code = zeros(Int, nb)
+    for i in nroots+1:nb                       # children always have larger ids than their parent
+        p = bt.parent[i] + 1
+        root[i], depth[i], code[i] = root[p], depth[p] + 1, 2 * code[p] + bt.slot[i]
+    end
+    return sortperm(collect(zip(root, depth, code)))
+end
+
 function collect_spots!(f, res)
-    nfo = info(res); n = nfo.n_beams * nfo.rays_per_beam
+    bt = beam_tables(res); R = bt.nfo.rays_per_beam; n = bt.nb * R
     obj = Vector{Int32}(undef, n); xz = Matrix{Float64}(undef, 2, n)
     check(ccall((:bmo_result_spots, libbmo), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Float64}), res, obj, xz))
-    for i in 1:n                                        # roots first, children in spawn order
-        obj[i] >= 0 && push!(f.leaves[obj[i] + 1], Point2(xz[1, i], xz[2, i]))
+    for b in bfs_order(bt), r in 1:R
+        i = (b - 1) * R + r
+        obj[i] >= 0 && push!(f.leaves[obj[i] + 1].data, Point2(xz[1, i], xz[2, i]))      # Spotdetector.jl:50-61
     end
 end
 
-# Beam trees from the segment table: bmo_result_beams (parent, child slot, nseg, first_seg) +
-# bmo_result_segments (pos, dir, n, t, normal, object, part); t = Inf <=> intersection === nothing.
-function rebuild_beams!(beams, f, res)
-    nfo = info(res); nb = nfo.n_beams
-    parent = Vector{Int32}(undef, nb); slot = similar(parent); nseg = similar(parent); status = similar(parent)
-    first_seg = Vector{Int64}(undef, nb)
-    check(ccall((:bmo_result_beams, libbmo), Int32,
-        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}),
-        res, parent, slot, nseg, status, first_seg, C_NULL, C_NULL, C_NULL))
-    ns = info(res).n_segments
+"""Segment table of a result as column arrays (rows = n_segments * rays_per_beam; Gaussian: chief, waist, divergence interleaved)."""
+function segment_tables(res, nfo)
+    ns = nfo.n_segments * nfo.rays_per_beam
     pos = Matrix{Float64}(undef, 3, ns); dir = similar(pos); nrm = similar(pos)
     n = Vector{Float64}(undef, ns); t = similar(n); obj = Vector{Int32}(undef, ns); part = similar(obj)
+    E0 = nfo.polarized != 0 ? Matrix{ComplexF64}(undef, 3, ns) : nothing
     check(ccall((:bmo_result_segments, libbmo), Int32,
-        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{Float64}),
-        res, pos, dir, n, t, nrm, obj, part, C_NULL))
-    made = Vector{Any}(undef, nb)
-    for b in 1:nb
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ptr{Int32}, Ptr{ComplexF64}),
+        res, pos, dir, n, t, nrm, obj, part, E0 === nothing ? C_NULL : pointer(E0)))
+    return (; pos, dir, nrm, n, t, obj, part, E0)
+end
+
+# one ray of the segment table as the reference's mutable struct (Rays.jl:14-20, PolarizedRays.jl:37-44); the stored direction
+# is the tracer's (refracted directions are not re-normalised, Lenses.jl:69), so the fields are set directly
+function make_ray(::Type{Ray{T}}, sg, s, λ, f) where {T}
+    Ray{T}(Point3{T}(sg.pos[:, s]), Point3{T}(sg.dir[:, s]), make_intersection(T, sg, s, f), T(λ), T(sg.n[s]))
+end
+function make_ray(::Type{PolarizedRay{T}}, sg, s, λ, f) where {T}
+    PolarizedRay{T}(Point3{T}(sg.pos[:, s]), Point3{T}(sg.dir[:, s]), make_intersection(T, sg, s, f), T(λ), T(sg.n[s]),
+        Point3{Complex{T}}(sg.E0[:, s]))
+end
+# t = Inf <=> intersection === nothing (AbstractRay.jl:13-18: fields object, shape, t, n)
+make_intersection(::Type{T}, sg, s, f) where {T} = isfinite(sg.t[s]) ?
+    Intersection{T}(f.leaves[sg.obj[s] + 1], shape(f.owners[sg.part[s] + 1]), T(sg.t[s]), Point3{T}(sg.nrm[:, s])) : nothing
+
+# Beam trees from the segment table (Beam.jl:13-79): roots keep their identity, children are created in id order (a child's id
+# is larger than its parent's; slot 0 = transmitted is numbered before slot 1 = reflected, which is the push! order of
+# ThinBeamsplitter.jl:150-168)
+function rebuild_beams!(beams::AbstractVector{<:Beam{T,R}}, f, res) where {T,R}
+    bt = beam_tables(res); sg = segment_tables(res, bt.nfo)
+    made = Vector{Beam{T,R}}(undef, bt.nb)
+    for b in 1:bt.nb
         root = b <= length(beams)
-        λ = wavelength(first((root ? beams[b] : made[parent[b] + 1]).rays))
-        rays = map(first_seg[b] + 1:first_seg[b] + nseg[b]) do s
-            r = Ray(Point3(pos[:, s]...), Point3(dir[:, s]...), λ); r.dir = Point3(dir[:, s]...); r.n = n[s]
-            isfinite(t[s]) && (r.intersection = Intersection(t[s], Point3(nrm[:, s]...), f.leaves[obj[s] + 1], shape(f.owners[part[s] + 1])))
-            r
-        end
+        λ = wavelength(first((root ? beams[b] : made[bt.parent[b] + 1]).rays))
+        rays = R[make_ray(R, sg, s, λ, f) for s in bt.first_seg[b] + 1:bt.first_seg[b] + bt.nseg[b]]
         if root
             beams[b].rays = rays; empty!(beams[b].children); made[b] = beams[b]
         else
-            p = made[parent[b] + 1]; made[b] = Beam(rays, p, typeof(p)[]); push!(p.children, made[b])
+            p = made[bt.parent[b] + 1]
+            made[b] = Beam{T,R}(rays, p, Vector{Beam{T,R}}())
+            push!(p.children, made[b])
         end
     end
 end
-rebuild_beamlets!(gs, f, res) = nothing   # same pattern with rays_per_beam == 3 and bmo_result_beams' w0 / E0 columns
+
+# GaussianBeamlet trees (Gaussian.jl:33-42, 96-111): three Beam{T,Ray{T}} per beamlet whose rays are rows 3k+1 (chief),
+# 3k+2 (waist), 3k+3 (divergence) of the segment table; children carry the w0 / E0 the splitter gave them
+# (ThinBeamsplitter.jl:104-148) and are linked with parent! (child.chief.parent = parent.chief, needed by length / point_on_beam)
+function rebuild_beamlets!(gs::AbstractVector{GaussianBeamlet{T}}, f, res) where {T}
+    bt = beam_tables(res); sg = segment_tables(res, bt.nfo)
+    made = Vector{GaussianBeamlet{T}}(undef, bt.nb)
+    RT = Ray{T}
+    for b in 1:bt.nb
+        root = b <= length(gs)
+        λ = root ? gs[b].λ : made[bt.parent[b] + 1].λ
+        rows = bt.first_seg[b] .+ (0:bt.nseg[b] - 1)
+        three = ntuple(k -> RT[make_ray(RT, sg, 3 * r + k, λ, f) for r in rows], 3)
+        if root
+            g = gs[b]
+            g.chief.rays, g.waist.rays, g.divergence.rays = three
+            empty!(g.children); empty!(g.chief.children); empty!(g.waist.children); empty!(g.divergence.children)
+            made[b] = g
+        else
+            p = made[bt.parent[b] + 1]
+            mk(rays) = Beam{T,RT}(rays, nothing, Vector{Beam{T,RT}}())
+            g = GaussianBeamlet(mk(three[1]), mk(three[2]), mk(three[3]), T(λ), T(bt.w0[b]), Complex{T}(bt.E0[b]))
+            BeamletOptics.parent!(g, p)
+            push!(p.children, g)
+            made[b] = g
+        end
+    end
+end
+
+# ---- multi-GPU: one process per GPU (Distributed / MPI.jl / a shared file carry the 128-byte id) -----------------------
+"""`id = comm_unique_id()` on rank 0, shipped to every rank, then `comm = comm_init(cs, n_ranks, rank, id)` on all of them."""
+function comm_unique_id()
+    id = Vector{UInt8}(undef, 128)
+    check(ccall((:bmo_comm_unique_id, libbmo), Int32, (Ptr{UInt8},), id)); id
+end
+function comm_init(cs::CUDASystem, n_ranks::Integer, rank::Integer, id::Vector{UInt8})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:bmo_comm_init, libbmo), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}, Ref{Ptr{Cvoid}}), context(cs.device), n_ranks, rank, id, h)); h[]
+end
+"""Sum the ranks' partial `pd.field`s in place (bmo_pd_allreduce: NCCL inside libbmo.so) after each rank solved its share of the beamlets."""
+allreduce_field!(comm, pd::Photodetector) = (fld = pd.field; GC.@preserve fld check(ccall((:bmo_pd_allreduce, libbmo), Int32,
+    (Ptr{Cvoid}, Ptr{ComplexF64}, Int64, UInt32), comm, fld, length(fld), UInt32(0))); pd)
+comm_free(comm) = ccall((:bmo_comm_free, libbmo), Int32, (Ptr{Cvoid},), comm)
 
 end # module

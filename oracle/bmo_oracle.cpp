@@ -874,6 +874,9 @@ int orc_eval(const char* fn, const int* ih, int ni, const double* a, int na, dou
     }
     if (k == "gauss_parameters") { Gauss* g = g_reg.at(ih[0]).gauss; gauss_parameters(*g, a[0], out[0], out[1], out[2], out[3]); return 4; }
     if (k == "gauss_electric_field") { Gauss* g = g_reg.at(ih[0]).gauss; Cx e = electric_field(*g, a[0], a[1]); out[0] = e.re; out[1] = e.im; return 2; }
+    // electric_field!(gauss, electric_field(gauss) * (a[0] + i a[1])) (Gaussian.jl: electric_field!): the E0 of the root beamlet is
+    // multiplied; a following solve_system!(...; retrace = true) carries it through the stored tree (test/runtests.jl:2846-2849)
+    if (k == "gauss_scale_E0") { Gauss* g = g_reg.at(ih[0]).gauss; g->E0 = g->E0 * Cx{a[0], a[1]}; out[0] = g->E0.re; out[1] = g->E0.im; return 2; }
     if (k == "gauss_length") { Gauss* g = g_reg.at(ih[0]).gauss; out[0] = g->length(); out[1] = g->opl(); return 2; }
     if (k == "refractive_index") { out[0] = RI(ih[0])(a[0]); return 1; }
     throw std::runtime_error("orc_eval: unknown fn " + k);

@@ -58,3 +58,49 @@ def test_gpu_matches_c1_golden(bmo):
     f = sc["pd"].field
     assert np.linalg.norm((f - g["field"]).ravel()) <= FIELD_TOL * np.linalg.norm(g["field"].ravel())
     assert abs(sc["pd"].optical_power() - float(g["power"])) <= FIELD_TOL * float(g["power"])
+
+
+# ---- fixtures of the real Julia reference (baseline/dump_fixtures.jl), used the day they exist --------------------------------
+def test_reference_fixture_reader_round_trip(tmp_path):
+    """The binary format baseline/dump_fixtures.jl writes (Int64 rank, dims, Float64 column-major data)."""
+    from tests.golden import load_reference_fixture as lf
+    a = np.arange(24, dtype=np.float64).reshape(2, 3, 4)
+    with open(tmp_path / "a.bin", "wb") as fh:
+        np.array([3, 2, 3, 4], np.int64).tofile(fh); a.ravel(order="F").tofile(fh)
+    assert np.array_equal(lf.load(str(tmp_path / "a.bin")), a)
+    z = (np.arange(6) + 1j * np.arange(6)[::-1]).reshape(2, 3)
+    with open(tmp_path / "z.bin", "wb") as fh:
+        np.array([2, 2, 3], np.int64).tofile(fh); np.stack([z.real, z.imag], -1).reshape(2, 3, 2).transpose(1, 0, 2).ravel().tofile(fh)
+    assert np.array_equal(lf.load(str(tmp_path / "z.bin"), complex=True), z)
+
+
+def _ref_c2():
+    from tests.golden import load_reference_fixture as lf
+    if not lf.available():
+        pytest.skip("no fixtures of the Julia reference (tests/golden/ref/, written by baseline/dump_fixtures.jl)")
+    seg = lf.load(os.path.join(GOLD, "ref", "c2_segments.bin"))          # (11, 8, n)
+    return np.transpose(seg, (2, 1, 0))                                    # (n, 8, 11): pos, dir, n, t, normal
+
+
+def test_oracle_matches_reference_fixture_c2(orc):
+    ref = _ref_c2()
+    n = ref.shape[0]
+    osc = scenes.doublet_spot_oracle()
+    out = orc.bulk_trace_rays(osc["system"], np.ascontiguousarray(ref[:, 0, 0:3]), np.ascontiguousarray(ref[:, 0, 3:6]), 707e-9, max_seg=8, spot=osc["spot"])
+    live = np.isfinite(ref[:, :, 0])
+    assert np.array_equal(out["nseg"], live.sum(axis=1))
+    a, b = out["seg"][:, :, 0:6][live], ref[:, :, 0:6][live]
+    assert np.abs(a - b).max() <= POS_TOL * np.abs(b).max()
+
+
+@pytest.mark.gpu
+def test_gpu_matches_reference_fixture_c2(bmo):
+    ref = _ref_c2()
+    sc = scenes.doublet_spot(bmo)
+    res = bmo.solve_system_(sc["system"], bmo.RayBundle(np.ascontiguousarray(ref[:, 0, 0:3]), np.ascontiguousarray(ref[:, 0, 3:6]), 707e-9), r_max=100)
+    beams, seg = res.beams(), res.segments()
+    for i in range(ref.shape[0]):
+        f, k = int(beams["first"][i]), int(beams["nseg"][i])
+        assert k == int(np.isfinite(ref[i, :, 0]).sum())
+        got = np.concatenate([seg["pos"][f:f + k], seg["dir"][f:f + k]], axis=1)
+        assert np.abs(got - ref[i, :k, 0:6]).max() <= POS_TOL * np.abs(ref[i, :k, 0:6]).max()
