@@ -31,12 +31,11 @@ WORKLOAD = "C2: AC254-150-AB doublet spot diagram, 2^20 collimated rays, Fibonac
 CPU_SAMPLE = 1 << 14
 # algorithmic FP64 work per unit (SURVEY 8(d) cost table): primitive SDF eval 45, triangle test 40, interaction 60
 FLOP_SDF, FLOP_TRI, FLOP_INT = 45.0, 40.0, 60.0
-# intersect_wave, 2^20 rays per launch: dram__bytes_read.sum + dram__bytes_write.sum, mean over the 4 waves of one C2 solve
-# (ncu --set full, profiles/r01s4_ncu_trace_kernels.txt): 68.1 MB read + 89.0 MB written (the excess over the algorithmic 36 MB of
-# writes is register-spill lines evicted from L1)
-K1_DRAM_BYTES_PER_LAUNCH = 157.0e6
-K1_TRAFFIC_SOURCE = ("profiles/r01s4_ncu_trace_kernels.txt (mean of the 4 waves, 2^20 rays per launch; algorithmic = 64 B ray state read "
-                     "+ 36 B hit record written per ray)")
+# intersect_wave (lean build), 2^20 rays per launch: dram__bytes_read.sum + dram__bytes_write.sum, mean over the 4 waves of one C2
+# solve (ncu --set full, profiles/r02l_ncu_k1_lean.txt).  Round 1 read 68.1 MB and wrote 89.0 MB (spill lines evicted from L1).
+K1_DRAM_BYTES_PER_LAUNCH = 91.1e6
+K1_TRAFFIC_SOURCE = ("profiles/r02l_ncu_k1_lean.txt (mean of the 4 waves, 2^20 rays per launch: 67.2 MB read + 23.9 MB written; algorithmic = 64 B ray "
+                     "state read + 36 B hit record written per ray -- part of the hit records is still in the 126 MB L2 when the kernel ends)")
 
 
 def rays_for_rank(rank, n=N_RAYS):
