@@ -312,7 +312,7 @@ BMO_D Cx pd_pair_fast(const PdFast& rc, V3 p1, bool& slow) {
     if (!(R < 0.0)) spsi = -spsi;                                // R < 0 flips the sign of psi
     if (isnan(R)) R = 0.0;                                       // Gaussian.jl:348-351
     if (isnan(spsi) || isnan(cpsi)) { cpsi = 1.0; spsi = 0.0; }
-    const double amp = rw * exp(-r2 * iw2);                      // (w0 / w) exp(-r^2/w^2) with w0 cancelled against E0
+    const double amp = rw * exp_neg(-r2 * iw2);                  // (w0 / w) exp(-r^2/w^2) with w0 cancelled against E0
     double sn, cs;
     sincos_reduced(rc.k * z + (rc.k * r2 * R) * 0.5, &sn, &cs);
     const double re = cs * cpsi - sn * spsi, im = sn * cpsi + cs * spsi;

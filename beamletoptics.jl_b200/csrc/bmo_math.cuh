@@ -166,27 +166,62 @@ BMO_HD Dual norm3_(Dual a, Dual b, Dual c, int zr) {
 // sincos of a large phase (k z is O(1e7) rad; CUDA's sincos leaves its fast path at |x| > 105615):
 // Cody-Waite reduction by pi/2 with two FMAs (n < 2^31, residual error n * 1.5e-33), then the
 // fdlibm minimax kernels on [-pi/4, pi/4] (error < 1 ulp) and the quadrant swap.
+// The coefficients sit in constant memory so that they enter the FMAs as constant-bank operands: as immediates every one of
+// them costs two uniform-register moves per evaluation (48 of the 292 instructions of the detector kernel's pair loop).
+static __constant__ double kTrigC[16] = {
+    0.6366197723675814, -1.5707963267948966, -6.123233995736766e-17,                                    // 2/pi, -pi/2 hi, -pi/2 lo
+    1.58969099521155010221e-10, -2.50507602534068634195e-08, 2.75573137070700676789e-06,                // sin: S6 .. S1
+    -1.98412698298579493134e-04, 8.33333333332248946124e-03, -1.66666666666666324348e-01,
+    -1.13596475577881948265e-11, 2.08757232129817482790e-09, -2.75573143513906633035e-07,               // cos: C6 .. C1
+    2.48015872894767294178e-05, -1.38888888888741095749e-03, 4.16666666666666019037e-02, 0.0};
 BMO_D void sincos_reduced(double x, double* sn, double* cs) {
-    const double n = rint(x * 0.6366197723675814);          // 2 / pi
-    double r = fma(n, -1.5707963267948966, x);              // pi/2 hi
-    r = fma(n, -6.123233995736766e-17, r);                  // pi/2 lo
+    const double n = rint(x * kTrigC[0]);
+    double r = fma(n, kTrigC[1], x);
+    r = fma(n, kTrigC[2], r);
     const double z = r * r;
-    double ps = fma(z, 1.58969099521155010221e-10, -2.50507602534068634195e-08);
-    ps = fma(z, ps, 2.75573137070700676789e-06);
-    ps = fma(z, ps, -1.98412698298579493134e-04);
-    ps = fma(z, ps, 8.33333333332248946124e-03);
-    ps = fma(z, ps, -1.66666666666666324348e-01);
+    double ps = fma(z, kTrigC[3], kTrigC[4]);
+    ps = fma(z, ps, kTrigC[5]);
+    ps = fma(z, ps, kTrigC[6]);
+    ps = fma(z, ps, kTrigC[7]);
+    ps = fma(z, ps, kTrigC[8]);
     const double s0 = fma(z * r, ps, r);
-    double pc = fma(z, -1.13596475577881948265e-11, 2.08757232129817482790e-09);
-    pc = fma(z, pc, -2.75573143513906633035e-07);
-    pc = fma(z, pc, 2.48015872894767294178e-05);
-    pc = fma(z, pc, -1.38888888888741095749e-03);
-    pc = fma(z, pc, 4.16666666666666019037e-02);
+    double pc = fma(z, kTrigC[9], kTrigC[10]);
+    pc = fma(z, pc, kTrigC[11]);
+    pc = fma(z, pc, kTrigC[12]);
+    pc = fma(z, pc, kTrigC[13]);
+    pc = fma(z, pc, kTrigC[14]);
     const double c0 = fma(z * z, pc, fma(z, -0.5, 1.0));
     const int q = (int)(long long)n;
     const double sv = (q & 1) ? c0 : s0, cv = (q & 1) ? s0 : c0;
     *sn = (q & 2) ? -sv : sv;
     *cs = ((q + 1) & 2) ? -cv : cv;
+}
+// exp(x) for x <= 0 (Gaussian envelopes): 2^n * P(r), r = x - n ln2 in [-ln2/2, ln2/2], Taylor polynomial of degree 11 in
+// Horner form (truncation 0.35^12 / 12! = 7e-15), coefficients from constant memory; 0 below -708 (the library returns a subnormal)
+static __constant__ double kExpC[16] = {
+    1.4426950408889634, -6.93147180369123816490e-01, -1.90821492927058770002e-10,                       // log2(e), -ln2 hi, -ln2 lo
+    2.505210838544172e-08, 2.755731922398589e-07, 2.755731922398589e-06, 2.48015873015873e-05,          // 1/11! .. 1/8!
+    1.984126984126984e-04, 1.388888888888889e-03, 8.333333333333333e-03, 4.166666666666666e-02,         // 1/7! .. 1/4!
+    1.666666666666667e-01, 0.5, 0.0, 0.0};
+BMO_D double exp_neg(double x) {
+    const double n = rint(x * kExpC[0]);
+    double r = fma(n, kExpC[1], x);
+    r = fma(n, kExpC[2], r);
+    double p = fma(r, kExpC[3], kExpC[4]);
+    p = fma(r, p, kExpC[5]);
+    p = fma(r, p, kExpC[6]);
+    p = fma(r, p, kExpC[7]);
+    p = fma(r, p, kExpC[8]);
+    p = fma(r, p, kExpC[9]);
+    p = fma(r, p, kExpC[10]);
+    p = fma(r, p, kExpC[11]);
+    p = fma(r, p, kExpC[12]);
+    p = fma(r, p, 1.0);
+    p = fma(r, p, 1.0);
+    // scale by 2^n through the exponent field (n in [-1022, 0] here, p in [0.7, 1.42])
+    const int hi = __double2hiint(p) + ((int)n << 20);
+    const double v = __hiloint2double(hi, __double2loint(p));
+    return x < -708.0 ? 0.0 : (x != x ? x : v);
 }
 
 template <class T> struct P3 { T x, y, z; };
