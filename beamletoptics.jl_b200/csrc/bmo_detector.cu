@@ -387,25 +387,53 @@ __global__ void __launch_bounds__(PDF_TX* PDF_TY, MINB) pd_field_fast(const PdPa
     }
 }
 
-// optical_power = trapz((x, y), |E|^2 / (2 Z0)) (Photodetector.jl:109-116, Trapz.jl), one block per field
-__global__ void pd_power_kernel(const double* fields, int n, double lo, double hi, double* power) {
-    extern __shared__ double s_col[];
-    const double* f = fields + (int64_t)blockIdx.x * n * n * 2;
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        double s = 0;
-        for (int i = 0; i + 1 < n; i++) {
-            const double* a = f + ((int64_t)i + (int64_t)n * j) * 2;
-            const double ia = (a[0] * a[0] + a[1] * a[1]) / (2 * kZvac), ib = (a[2] * a[2] + a[3] * a[3]) / (2 * kZvac);
-            s += (lin_coord(i + 1, n, lo, hi) - lin_coord(i, n, lo, hi)) * (ia + ib) / 2;
-        }
-        s_col[j] = s;
+// optical_power = trapz((x, y), |E|^2 / (2 Z0)) (Photodetector.jl:109-116, Trapz.jl) in two steps:
+//   pd_power_columns  one warp per pixel column j: s_j = sum_i (x_{i+1} - x_i) (I_ij + I_{i+1,j}) / 2, lanes stride over i so that
+//                     a warp reads consecutive complex values (the field is stored [i + n j]); grid = (column groups, fields)
+//   pd_power_reduce   one block per field: sum_j (y_{j+1} - y_j) (s_j + s_{j+1}) / 2
+// Deterministic (no atomics); the order of the additions differs from a serial loop at the 1e-16 level.
+constexpr int PWR_WARPS = 8;
+__global__ void __launch_bounds__(32 * PWR_WARPS) pd_power_columns(const double* fields, int n, double lo, double hi, double* s_col) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = blockIdx.x * PWR_WARPS + warp;
+    if (j >= n) return;
+    const double* f = fields + ((int64_t)blockIdx.y * n * n + (int64_t)n * j) * 2;
+    double s = 0;
+    for (int i = lane; i + 1 < n; i += 32) {
+        const double2 a = *reinterpret_cast<const double2*>(f + 2 * i), b = *reinterpret_cast<const double2*>(f + 2 * i + 2);
+        const double ia = (a.x * a.x + a.y * a.y) / (2 * kZvac), ib = (b.x * b.x + b.y * b.y) / (2 * kZvac);
+        s += (lin_coord(i + 1, n, lo, hi) - lin_coord(i, n, lo, hi)) * (ia + ib) / 2;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) s_col[(int64_t)blockIdx.y * n + j] = s;
+}
+__global__ void __launch_bounds__(256) pd_power_reduce(const double* s_col, int n, double lo, double hi, double* power) {
+    __shared__ double s_w[8];
+    const double* c = s_col + (int64_t)blockIdx.x * n;
+    double p = 0;
+    for (int j = threadIdx.x; j + 1 < n; j += 256) p += (lin_coord(j + 1, n, lo, hi) - lin_coord(j, n, lo, hi)) * (c[j] + c[j + 1]) / 2;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xffffffffu, p, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = p;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double p = 0;
-        for (int j = 0; j + 1 < n; j++) p += (lin_coord(j + 1, n, lo, hi) - lin_coord(j, n, lo, hi)) * (s_col[j] + s_col[j + 1]) / 2;
-        power[blockIdx.x] = p;
+        double t = 0;
+        for (int k = 0; k < 8; k++) t += s_w[k];
+        power[blockIdx.x] = t;
     }
+}
+// both steps on stream st; d_power: [n_fields] on the device
+static int32_t pd_power_launch(bmo_ctx* ctx, const double* d_fields, int n_fields, int n, double lo, double hi, double* d_power, cudaStream_t st) {
+    double* s_col = nullptr;
+    BMO_CUDA(dev_alloc(&s_col, (size_t)n_fields * n, st));
+    pd_power_columns<<<dim3((n + PWR_WARPS - 1) / PWR_WARPS, n_fields), 32 * PWR_WARPS, 0, st>>>(d_fields, n, lo, hi, s_col);
+    pd_power_reduce<<<n_fields, 256, 0, st>>>(s_col, n, lo, hi, d_power);
+    ctx->launches += 2;
+    cudaError_t e = cudaGetLastError();
+    dev_free(s_col, st);
+    if (e != cudaSuccess) return fail(BMO_ECUDA, std::string("pd_power: ") + cudaGetErrorString(e));
+    return BMO_OK;
 }
 
 __global__ void scan_flags(const int32_t* in, int64_t n, long long* out, long long* total);
@@ -572,8 +600,7 @@ int32_t bmo_pd_sweep(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t n_p
     if (rc) { dev_free(d_field, st); return rc; }
     if (power) {
         BMO_CUDA(dev_alloc(&d_p, (size_t)n_poses, st));
-        pd_power_kernel<<<n_poses, 256, n * sizeof(double), st>>>(d_field, n, ob.pd_lo, ob.pd_hi, d_p);
-        ctx->launches++;
+        if ((rc = pd_power_launch(ctx, d_field, n_poses, n, ob.pd_lo, ob.pd_hi, d_p, st))) { dev_free(d_field, st); dev_free(d_p, st); return rc; }
         BMO_CUDA(cudaMemcpyAsync(power, d_p, (size_t)n_poses * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     if (fields) BMO_CUDA(cudaMemcpyAsync(fields, d_field, cnt * sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -599,8 +626,7 @@ int32_t bmo_pd_power(bmo_sys* sys, int32_t pd_object, int32_t n_fields, const do
         d_f = d_tmp;
         BMO_CUDA(dev_alloc(&d_p, (size_t)n_fields, st));
     } else d_p = power;
-    pd_power_kernel<<<n_fields, 256, n * sizeof(double), st>>>(d_f, n, ob.pd_lo, ob.pd_hi, d_p);
-    ctx->launches++;
+    { int32_t rc = pd_power_launch(ctx, d_f, n_fields, n, ob.pd_lo, ob.pd_hi, d_p, st); if (rc) return rc; }
     if (!on_dev) {
         BMO_CUDA(cudaMemcpyAsync(power, d_p, (size_t)n_fields * sizeof(double), cudaMemcpyDeviceToHost, st));
         BMO_CUDA(cudaStreamSynchronize(st));
