@@ -545,21 +545,15 @@ BMO_D bool identity_gradient(const bmo_prim& pr, V3 q, V3& g) {
 
 // AbstractSDF.jl:79-95: ForwardDiff gradient of member idx; central differences (eps = 1e-8) if any
 // component of the normalised gradient is NaN.
-// FAST: unrotated lens primitives take identity_gradient instead of the generic dual evaluation (same bits)
-template <bool RK, bool FAST = true> BMO_NI V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
-    if (!(RK && is_asph(prims[idx].type))) {   // aspheric surfaces: numeric_gradient only (AsphericalLensSDF.jl:3-5)
-        V3 gf;
-        if (FAST && zr == 1 && (prims[idx].reserved & 1) && identity_gradient(prims[idx], p, gf)) {
-            st.sdf++;
-            const V3 n = normalize(gf);
-            if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
-        } else {
+// The generic evaluation, out of line: ForwardDiff's dual numbers, then central differences if a component is NaN.
+// skip_dual: the written-out gradient (same bits as the dual evaluation) has already produced a NaN.
+template <bool RK> BMO_NI V3 member_normal_generic(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st, bool skip_dual) {
+    if (!skip_dual && !(RK && is_asph(prims[idx].type))) {   // aspheric surfaces: numeric_gradient only (AsphericalLensSDF.jl:3-5)
         P3<Dual> qd;
         qd.x = mkd(p.x, 1, 0, 0); qd.y = mkd(p.y, 0, 1, 0); qd.z = mkd(p.z, 0, 0, 1);
         Dual g = member_eval<Dual, RK>(prims, idx, qd, zr, st, true);
         V3 n = normalize(mk3(g.p0, g.p1, g.p2));
         if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
-        }
     }
     const double e = 1e-8;
     P3<double> q; q.x = p.x; q.y = p.y; q.z = p.z;
@@ -572,6 +566,21 @@ template <bool RK, bool FAST = true> BMO_NI V3 member_normal(const bmo_prim* pri
     a = q; b = q; a.z = p.z + e; b.z = p.z - e;
     gr.z = member_eval<double, RK>(prims, idx, a, zr, st) - member_eval<double, RK>(prims, idx, b, zr, st);
     return normalize(gr);
+}
+// normal3d of one union member.  FAST: unrotated lens primitives take identity_gradient (inline: no call, no callee-saved
+// registers to spill) instead of the generic dual evaluation (same bits); everything else goes out of line.
+template <bool RK, bool FAST = true> BMO_D V3 member_normal(const bmo_prim* prims, int idx, V3 p, int zr, Stats& st) {
+    bool skip_dual = false;
+    if (FAST && zr == 1 && (prims[idx].reserved & 1) && !(RK && is_asph(prims[idx].type))) {
+        V3 gf;
+        if (identity_gradient(prims[idx], p, gf)) {
+            st.sdf++;
+            const V3 n = normalize(gf);
+            if (!isnan(n.x) && !isnan(n.y) && !isnan(n.z)) return n;
+            skip_dual = true;
+        }
+    }
+    return member_normal_generic<RK>(prims, idx, p, zr, st, skip_dual);
 }
 
 // intersect3d(::AbstractSDF, ray) (AbstractSDF.jl:166-181) with _raymarch_outside (:102-125) and
