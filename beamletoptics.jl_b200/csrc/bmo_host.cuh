@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -196,6 +197,7 @@ struct BigBlocks {
     struct Blk { void* p; size_t bytes; cudaStream_t stream; };
     std::vector<Blk> parked;
     std::map<void*, size_t> live;
+    std::mutex mu;   // contexts of the same device may live on different host threads
     static constexpr size_t kMin = (size_t)64 << 20;
     static BigBlocks& of_device() {
         static BigBlocks per_dev[64];
@@ -204,10 +206,15 @@ struct BigBlocks {
         return per_dev[d & 63];
     }
     void drop_parked() {
+        std::lock_guard<std::mutex> g(mu);
+        drop_parked_locked();
+    }
+    void drop_parked_locked() {
         for (auto& b : parked) cudaFree(b.p);
         parked.clear();
     }
     cudaError_t get(void** out, size_t bytes, cudaStream_t s) {
+        std::lock_guard<std::mutex> g(mu);
         size_t best = parked.size();
         for (size_t i = 0; i < parked.size(); i++)
             if (parked[i].stream == s && parked[i].bytes >= bytes && parked[i].bytes <= bytes + bytes / 4 &&
@@ -221,7 +228,7 @@ struct BigBlocks {
         cudaError_t e = cudaMalloc(out, bytes);
         if (e != cudaSuccess) {          // make room: parked blocks of other sizes, then whatever the stream-ordered pool caches
             cudaGetLastError();
-            drop_parked();
+            drop_parked_locked();
             int d = 0; cudaGetDevice(&d);
             cudaMemPool_t pool;
             if (cudaDeviceGetDefaultMemPool(&pool, d) == cudaSuccess) { cudaDeviceSynchronize(); cudaMemPoolTrimTo(pool, 0); }
@@ -231,6 +238,7 @@ struct BigBlocks {
         return e;
     }
     bool put(void* p, cudaStream_t s) {
+        std::lock_guard<std::mutex> g(mu);
         auto it = live.find(p);
         if (it == live.end()) return false;
         parked.push_back({p, it->second, s});
