@@ -759,27 +759,6 @@ BMO_NI bool mesh_intersect(const MeshTabs S, int mesh_id, int pose, V3 pos, V3 d
     return true;
 }
 
-// The same for kernels that only ever see small meshes (detector quads, cuboids, retroreflectors: at most 16 faces, no
-// BVH was built): the face loop in reference order, no traversal stack.
-BMO_NI bool mesh_intersect_small(const MeshTabs S, int mesh_id, int pose, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
-    const MeshView mv = S.meshes[mesh_id];
-    const double* verts = S.vertices + 3 * ((int64_t)pose * S.n_vertices + mv.first_vertex);
-    const int32_t* faces = S.faces + 3 * mv.first_face;
-    double t0 = INFINITY;
-    int fid = -1;
-    const int nf = (int)mv.n_faces;
-    for (int i = 0; i < nf; i++) {
-        const double tt = moeller_trumbore(load_vertex(verts, __ldg(faces + 3 * i)), load_vertex(verts, __ldg(faces + 3 * i + 1)),
-                                           load_vertex(verts, __ldg(faces + 3 * i + 2)), pos, dir, mv.f32);
-        if (tt < t0) { t0 = tt; fid = i; }
-    }
-    st.tri += nf;
-    if (fid < 0) return false;
-    t = t0;
-    n = face_normal(load_vertex(verts, __ldg(faces + 3 * fid)), load_vertex(verts, __ldg(faces + 3 * fid + 1)), load_vertex(verts, __ldg(faces + 3 * fid + 2)), mv.f32);
-    return true;
-}
-
 // ---- shapes, objects, system --------------------------------------------------------------------
 struct TraceCtx {
     MeshTabs M;
@@ -792,8 +771,7 @@ struct TraceCtx {
     unsigned lb_addr;        // LEAN kernels: shared-memory address of this thread's column of member bounds (LeanBounds)
 };
 // intersect3d(shape, ray)
-// LEAN: every SDF part of the system is a lean union (shape_eval with LeanBounds) and every mesh is small (host-side facts)
-template <bool RK, bool LEAN> BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
+template <bool RK> BMO_D bool part_intersect(const TraceCtx& C, int part, V3 pos, V3 dir, Stats& st, double& t, V3& n) {
     const bmo_part& pt = C.parts[part];
     if (pt.shape_kind == BMO_SHAPE_SDF) {
         const double* bnd = C.bounds + NBOUND * part;
@@ -808,14 +786,13 @@ template <bool RK, bool LEAN> BMO_D bool part_intersect(const TraceCtx& C, int p
             t = tm; n = nm;
             return hit;
         }
-        if (LEAN) { LeanBounds lb; lb.addr = C.lb_addr; return sdf_intersect_t<false, LeanBounds>(sh, pos, dir, st.sdf, t, n, lb); }
         return sdf_intersect_t<false, MemberBounds>(sh, pos, dir, st.sdf, t, n, MemberBounds());
     }
     // results through temporaries: the out-of-line callee takes references, and t / n of the caller (shared with the
     // SDF path) must not have their address taken or they live in local memory for every part
     Stats tmp; tmp.sdf = 0; tmp.tri = 0;
     double tm = 0.0; V3 nm = mk3(0, 0, 0);
-    const bool hit = LEAN ? mesh_intersect_small(C.M, pt.first, C.pose, pos, dir, tmp, tm, nm) : mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, tm, nm);
+    const bool hit = mesh_intersect(C.M, pt.first, C.pose, pos, dir, tmp, tm, nm);
     st.tri += tmp.tri;
     t = tm; n = nm;
     return hit;
@@ -850,7 +827,7 @@ BMO_D bool box_may_hit(const double* bx, V3 o, V3 d, V3 iv, double t_best) {
 // [lo, hi) is the range of parts that trace_all looks at: the whole system for tracing_step!, the parts
 // of one object (or one hinted shape) for retrace_system!'s `intersect3d(object(_intersection), ray)` /
 // `intersect3d(shape(_hint), ray)` (System.jl:209-218); hi < 0 means C.n_parts.
-template <bool RK, bool LEAN = false> BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st, const int lo = 0, const int hi = -1) {
+template <bool RK> BMO_D Hit tracing_step(const TraceCtx& C, V3 pos, V3 dir, int hint_part, Stats& st, const int lo = 0, const int hi = -1) {
     const V3 inv_dir = mk3(1.0 / dir.x, 1.0 / dir.y, 1.0 / dir.z);
     Hit res; res.part = -1; res.t = INFINITY; res.n = mk3(0, 0, 0);
     Hit ob; ob.part = -1; ob.t = INFINITY; ob.n = mk3(0, 0, 0);   // best of the current object
@@ -881,7 +858,7 @@ template <bool RK, bool LEAN = false> BMO_D Hit tracing_step(const TraceCtx& C, 
                 if (res.part >= 0) t_best = res.t;
                 if (ob.part >= 0 && ob.t < t_best) t_best = ob.t;
             }
-            if (box_may_hit(bx, pos, dir, inv_dir, t_best)) hit = part_intersect<RK, LEAN>(C, part, pos, dir, st, t, n);
+            if (box_may_hit(bx, pos, dir, inv_dir, t_best)) hit = part_intersect<RK>(C, part, pos, dir, st, t, n);
         }
         if (!all) {
             if (hit) { res.t = t; res.n = n; res.part = part; return res; }

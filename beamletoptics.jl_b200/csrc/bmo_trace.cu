@@ -3,9 +3,10 @@
 // One wave = one `tracing_step!` + `interact3d` of every live beam (System.jl:100-154, 274-318).
 // Kernels per wave:
 //   K1 intersect_wave     one thread per ray: trace_one / trace_all (SDF sphere tracing, Moeller-
-//                         Trumbore behind the BVH) -> hit record (t, normal, part).  Bound by the issue rate of
-//                         its non-FP64 instructions (profiles/r01s4_ncu_k1_instruction_mix.txt); 72 registers,
-//                         7 blocks per SM.
+//                         Trumbore behind the BVH) -> hit record (t, normal, part).  Two builds: LEAN (lens-stack systems:
+//                         unions of <= 4 plain primitives, no BVH mesh; tracing_step_lean of bmo_lean.cuh with its cold state
+//                         in shared-memory columns, 64 registers, 8 blocks per SM) and the general one (72-80 registers).
+//                         Bound by the issue rate of its non-FP64 instructions (profiles/r02_k1_instruction_buckets.txt).
 //   K2 interact_wave<MODE, NS> one thread per ray (Gaussian beamlets: chief/waist/divergence in adjacent
 //                         lanes, 10 triples per warp): interact3d; the continuing ray overwrites its own queue
 //                         slot, a dead one is flagged.  Systems with beamsplitters (NS = false): the children go
@@ -17,7 +18,7 @@
 //   K3 compact_fused      queue compaction in one cooperative launch once the dead slots are the majority
 //                         (compact_count + scan_counts + compact_scatter as the fallback).
 // With BMO_KEEP_SEGMENTS the segment records are written wave-major by K2 and gathered into
-// beam-major order at the end (gather_segments).
+// beam-major row records at the end (gather_segments, a warp-level transposition through shared memory).
 #include <chrono>
 #include <cstdlib>
 #include <cooperative_groups.h>
@@ -171,7 +172,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) intersect_wave(const IntersectPa
         Hit h; h.part = -1; h.t = INFINITY; h.n = mk3(0, 0, 0);
         if (budget) {   // System.jl:100-110
             if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, smem_u32(s_bounds + NBOUND * S.n_parts), pos, dir, hint, st);
-            else h = tracing_step<RK, false>(C, pos, dir, hint, st);
+            else h = tracing_step<RK>(C, pos, dir, hint, st);
         }
         const int64_t hs = P.hit.cap;
         P.hit.d[ri] = h.t; P.hit.d[hs + ri] = h.n.x; P.hit.d[2 * hs + ri] = h.n.y; P.hit.d[3 * hs + ri] = h.n.z;
@@ -762,7 +763,7 @@ __global__ void __launch_bounds__(IBLOCK, MINB) fused_wave0(const StepParams P) 
             C.lb_addr = LEAN ? smem_u32(s_lb + threadIdx.x) : 0u;
             if (budget) {
                 if (LEAN) h = tracing_step_lean(C, smem_u32(s_ls + threadIdx.x), C.lb_addr, smem_u32(s_bounds + NBOUND * S.n_parts), pos, dir, hint, st);
-                else h = tracing_step<RK, false>(C, pos, dir, hint, st);
+                else h = tracing_step<RK>(C, pos, dir, hint, st);
             }
         }
         sd += st.sdf; tr += st.tri;
