@@ -212,7 +212,7 @@ local_radius(s::BeamletOptics.AbstractAsphericalSurfaceSDF) = hypot(s.diameter /
 local_radius(s::BeamletOptics.AbstractAcylindricalSurfaceSDF) = hypot(s.height / 2, s.diameter / 2, maximum(abs, s.max_sag)) + s.diameter / 2
 local_radius(s::AbstractSDF) = error("BeamletOpticsB200: no bounding radius for $(typeof(s)) -- this SDF type is not supported by the GPU path")
 
-function upload(cs::CUDASystem, f)
+function upload_tables(cs::CUDASystem, f)
     sys = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve f begin
         t = BmoTables(length(f.prims), pointer(f.prims), length(f.parts), pointer(f.parts), length(f.objs), pointer(f.objs),
@@ -222,6 +222,27 @@ function upload(cs::CUDASystem, f)
         check(ccall((:bmo_system_upload, libbmo), Int32, (Ptr{Cvoid}, Ref{BmoTables}, Ref{Ptr{Cvoid}}), context(cs.device), t, sys))
     end
     return sys[]
+end
+
+# One uploaded copy per CUDASystem, reused while the flattened tables do not change (solver.py: cached_system): poses are static
+# during a solve and usually between the solves of a loop as well; the BVH of an STL mesh is built at upload, so re-uploading an
+# unchanged system on every solve_system! would rebuild it every time.  Moving an object changes the hash and triggers an upload.
+const UPLOADED = IdDict{Any,Tuple{UInt64,Ptr{Cvoid}}}()
+tables_hash(f) = hash((f.prims, f.parts, f.objs, f.meshes, f.verts, f.fcs, f.ntab, f.λs, f.jones, f.ext, f.norm_zero_rule))
+function upload(cs::CUDASystem, f)
+    h = tables_hash(f)
+    hit = get(UPLOADED, cs.system, nothing)
+    hit !== nothing && hit[1] == h && return hit[2]
+    hit !== nothing && ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), hit[2])
+    sys = upload_tables(cs, f)
+    UPLOADED[cs.system] = (h, sys)
+    return sys
+end
+"""Release the device copy of a system (the cache otherwise keeps it until the next upload of a changed system)."""
+function release!(cs::CUDASystem)
+    hit = pop!(UPLOADED, cs.system, nothing)
+    hit === nothing || ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), hit[2])
+    return cs
 end
 
 """
@@ -265,7 +286,6 @@ function BeamletOptics.solve_system!(cs::CUDASystem, beams::AbstractVector{<:Bea
     else
         ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), res[])
     end
-    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)      # a bmo_result does not reference its bmo_sys after the trace
     return nothing
 end
 BeamletOptics.solve_system!(cs::CUDASystem, bg::BeamletOptics.AbstractBeamGroup; kw...) = BeamletOptics.solve_system!(cs, BeamletOptics.beams(bg); kw...)
@@ -297,7 +317,6 @@ function BeamletOptics.solve_system!(cs::CUDASystem, gs::AbstractVector{<:Gaussi
     collect_spots!(f, res[])
     rebuild_beamlets!(gs, f, res[])
     ccall((:bmo_result_free, libbmo), Int32, (Ptr{Cvoid},), res[])
-    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)
     return nothing
 end
 BeamletOptics.solve_system!(cs::CUDASystem, g::GaussianBeamlet; kw...) = BeamletOptics.solve_system!(cs, [g]; kw...)
@@ -330,7 +349,6 @@ function gpu_intensity(cs::CUDASystem, psf::BeamletOptics.PSFDetector; n = 100, 
     check(ccall((:bmo_psf_intensity, libbmo), Int32,
         (Ptr{Cvoid}, Ptr{Cvoid}, Int32, Int32, Int32, Ptr{Float64}, Float64, Float64, Ptr{Float64}, UInt32),
         sys, h, oi, 0, n, lims, x0_shift, z0_shift, I, UInt32(0)))
-    ccall((:bmo_system_free, libbmo), Int32, (Ptr{Cvoid},), sys)
     return LinRange(lims[1], lims[2], n) .+ x0_shift, LinRange(lims[3], lims[4], n) .+ z0_shift, I
 end
 function Base.empty!(psf::BeamletOptics.PSFDetector, ::Type{CUDASystem})
