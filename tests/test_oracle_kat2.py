@@ -341,3 +341,92 @@ def test_double_gauss_spot_radii_gpu(bmo, orc):
         sc["det"].empty_()
         bmo.solve_system_(sc["system"], bmo.PointSource([0, -0.5, 0], [0, 1, 0], theta, 486.0e-9, num_rays=1000, num_rings=10))
         assert len(sc["det"].data) == 1000 and _radii(sc["det"].data).max() <= tol
+
+
+# ---- Gaussian beamlet through a lens against the ABCD / complex-q formalism (:1870-1931) -------------------------------------
+def test_gaussian_through_lens_vs_abcd(orc):
+    lam, w0, nl, R1, R2, y_lens = 1000e-9, 1e-3, 1.5, 1.0, 1.0, 0.1
+    zr = math.pi * w0 ** 2 / lam
+    f = 1 / ((nl - 1) * (1 / R1 + 1 / R2))                 # lensmakers_eq(R1, -R2, nl), thin lens
+    dy = 0.001
+    ys = np.arange(0, 1.5 + dy / 2, dy)
+    q = complex(0, zr)
+    w_ana, R_ana = np.zeros(len(ys)), np.zeros(len(ys))
+    for i in range(len(ys)):
+        w_ana[i] = math.sqrt(-lam / (math.pi * (1 / q).imag))
+        R_ana[i] = (1 / q).real
+        if abs((i + 1) * dy - y_lens) < 1e-12:             # the reference applies the lens in place of one propagation step
+            q = q / (-q / f + 1)
+            continue
+        q = q + dy
+    lens = orc.new("Lens", ih=[orc.new("ThinLensSDF", [R1, R2, 0.025]), orc.refindex(nl)])
+    lens.translate3d_([0, y_lens, 0])
+    g = orc.gaussian_beamlet([0, 0, 0], [0, 1, 0], lam, w0, M2=1.0, support=(1.0, 0.0, 0.0))
+    orc.solve_system_(orc.system([lens]), g)
+    num = np.array([g.eval("gauss_parameters", [y]) for y in ys])          # w, R, psi, w0 along the beam
+    assert np.abs(num[:, 0] - w_ana).max() <= 1e-6                        # beam radius within 1 um
+    assert (np.abs(num[:, 1] - R_ana) <= 1e-2).mean() > 0.95 and not np.isnan(num[:, 1]).any()
+    i_min = int(np.argmin(w_ana))
+    assert abs(num[0, 2]) <= 1e-3 and abs(num[i_min, 2]) <= 1e-3          # Gouy phase zero at both waists
+    assert abs(num[i_min, 3] - w_ana[i_min]) <= 1e-7                      # local waist after the lens
+
+
+# ---- two co-propagating beamlets through a thin lens onto a small detector: power vs start offset (:2038-2068) --------------
+def test_lambda_phase_scan_through_lens(orc):
+    w0, lam, M2, P0 = 0.01e-3, 1000e-9, 1.0, 1e-3
+    z, l, n = 0.1, 1e-2, 1000
+    R1 = R2 = d = 0.01
+    nl = 1.5
+    f = 1 / ((nl - 1) * (1 / R1 + 1 / R2))
+    pd_s = orc.new("Photodetector", [l / 10], [n // 10])
+    ln = orc.new("ThinLens", [R1, R2, d], [orc.refindex(nl)])
+    t_ln = float(ln.eval("thickness_object")[0])
+    pd_s.translate3d_([0, z, 0])
+    ln.translate3d_([0, z - f - t_ln / 2, 0])
+    system = orc.system([pd_s, ln])
+    dzs = np.linspace(0, lam, 13)                           # 50 offsets in the reference
+    for dz in dzs:
+        pd_s.pd_empty()
+        g1 = orc.gaussian_beamlet([0, 0, 0], [0, 1, 0], lam, w0, M2=M2, P0=P0)
+        g2 = orc.gaussian_beamlet([0, dz, 0], [0, 1, 0], lam, w0, M2=M2, P0=P0)
+        orc.solve_system_(system, g1)
+        orc.solve_system_(system, g2)
+        len1, opl1 = g1.eval("gauss_length")
+        len2, _ = g2.eval("gauss_length")
+        assert math.isclose(len1, z, rel_tol=1.5e-8)
+        assert math.isclose(len1, opl1 - t_ln * (nl - 1), rel_tol=1.5e-8)
+        assert math.isclose(len2, len1 - dz, rel_tol=1.5e-8)
+        p_ana = 4 * P0 * (math.cos(2 * math.pi * dz / lam) + 1) / 2
+        assert abs(pd_s.pd_power() - p_ana) <= 1e-4
+
+
+# ---- unequal-arm Michelson: real and imaginary part of the detector field against the closed form (:2122-2166) ---------------
+def test_unequal_arm_michelson_field(orc):
+    l_0, lam, w0, P0, M2 = 0.1, 635e-9, 1e-4, 1e-3, 1.0
+    pd_size, pd_n = INCH / 5, 100
+    m1, m2 = orc.new("SquarePlanoMirror2D", [INCH]), orc.new("SquarePlanoMirror2D", [INCH])
+    bs = orc.new("ThinBeamsplitter", [INCH, INCH, 0.5]); pd = orc.new("Photodetector", [pd_size], [pd_n])
+    m1.translate3d_([l_0, 0, 0]); m2.translate3d_([0, l_0, 0]); pd.translate3d_([-l_0, 0, 0])
+    bs.zrotate3d_(math.radians(45)); m1.zrotate3d_(math.radians(90)); pd.zrotate3d_(math.radians(90))
+    system = orc.system([m1, m2, bs, pd])
+    dl = 1 * l_0
+    m2.translate_to3d_([0, l_0 + dl, 0])
+    g = orc.gaussian_beamlet([0, -l_0, 0], [0, 1, 0], lam, w0, M2=M2, P0=P0)
+    orc.solve_system_(system, g)
+    field = pd.pd_field(pd_n)
+    # closed form: two Gaussians that travelled 4 l_0 and 4 l_0 + 2 dl, the longer one with a pi flip; amplitude E0 / sqrt(2)^2
+    I0 = 2 * P0 / (math.pi * w0 ** 2)
+    E0 = math.sqrt(2 * I0 * 376.730313668) / 2
+    zr = math.pi * w0 ** 2 / lam / M2
+    k = 2 * math.pi / lam
+
+    def efield(r, zz):
+        w = w0 * np.sqrt(1 + (zz / zr) ** 2)
+        R = zz / (zz ** 2 + zr ** 2)
+        psi = -math.atan(zz / zr)
+        return E0 * w0 / w * np.exp(-r ** 2 / w ** 2) * np.exp(1j * (k * zz + psi + (k * r ** 2 * R) / 2))
+    xs = np.linspace(-pd_size / 2, pd_size / 2, pd_n)
+    r = np.hypot(xs[:, None], xs[None, :])
+    screen = efield(r, 4 * l_0) + efield(r, 4 * l_0 + 2 * dl) * np.exp(1j * math.pi)
+    assert np.abs(screen.real - field.real).max() <= 5e-2 and np.abs(screen.imag - field.imag).max() <= 5e-2
+    assert np.abs(field).max() > 50.0                      # V/m: the comparison is not between two zeros
