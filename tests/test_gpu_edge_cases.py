@@ -51,6 +51,25 @@ def test_empty_bundle_and_bad_arguments_are_errors(bmo):
 
 
 @pytest.mark.gpu
+def test_ids_out_of_range_are_an_error_not_a_fault(bmo):
+    """lambda_id / pose_id index device tables (n_table, lambdas, prims per pose): a bad one must come back as BMO_EINVAL
+    (the header's promise), never as an illegal address -- and the context must stay usable afterwards."""
+    from bmo_b200 import _lib as L
+    sys_, _, _ = _lens_pair(scenes._ProductFactory(bmo))
+    dsys = bmo.upload_system(sys_, [1e-6])
+    n = 64
+    pos = np.zeros((n, 3)); pos[:, 1] = -0.1; pos[:, 0] = np.linspace(-1e-3, 1e-3, n)
+    d = np.tile(np.array([0.0, 1.0, 0.0]), (n, 1))
+    for lam_ids, pose_ids in ((np.full(n, 1, np.int32), None), (np.full(n, -1, np.int32), None),
+                              (np.zeros(n, np.int32), np.full(n, 3, np.int32)), (np.zeros(n, np.int32), np.full(n, -2, np.int32))):
+        h = C.c_void_p()
+        rc = L.lib().bmo_trace_rays(dsys.h, n, L.ptr(pos), L.ptr(d), L.ptr(lam_ids), None, L.ptr(pose_ids), 100, 0, C.byref(h))
+        assert rc == -1 and b"outside" in L.lib().bmo_last_error()
+    res = bmo.trace_rays(dsys, pos, d, np.zeros(n, np.int32), r_max=100)          # the same context still traces
+    assert res.interactions > 0
+
+
+@pytest.mark.gpu
 def test_rays_that_miss_everything(bmo, orc):
     sys_, _, _ = _lens_pair(scenes._ProductFactory(bmo))
     osys, _, _ = _lens_pair(scenes._OracleFactory())
