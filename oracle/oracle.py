@@ -12,12 +12,14 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+_LIB_PATH = os.environ.get("ORACLE_LIB") or os.path.join(_HERE, "liboracle.so")   # ORACLE_LIB: another build of the checker (the UBSan one)
 
 
 def build(force=False):
     """Compile oracle/liboracle.so with the Makefile next to this file."""
     srcs = [os.path.join(_HERE, f) for f in ("bmo_oracle.cpp", "orc_math.hpp", "orc_shapes.hpp", "orc_optics.hpp", "orc_asphere.hpp")]
+    if os.environ.get("ORACLE_LIB"):
+        return _LIB_PATH
     if (not force and os.path.exists(_LIB_PATH)
             and all(os.path.getmtime(_LIB_PATH) >= os.path.getmtime(s) for s in srcs)):
         return _LIB_PATH
