@@ -472,6 +472,7 @@ static ResView res_view(bmo_result* r) {
 
 static int32_t pd_run(bmo_sys* sys, bmo_result* r, int32_t pd_object, int32_t pose0, int32_t n_fields, double* fields, uint32_t flags,
                       bool per_pose) {
+    NvtxRange nvtx_("bmo_pd_accumulate");
     if (!sys || !r || !fields) return fail(BMO_EINVAL, "bmo_pd_accumulate: NULL argument");
     if (r->mode != 2) return fail(BMO_EINVAL, "bmo_pd_accumulate: result does not hold Gaussian beamlets (Photodetector.jl:57-60)");
     if (pd_object < 0 || pd_object >= (int)sys->objects.size() || sys->objects[pd_object].kind != BMO_OBJ_PHOTODETECTOR)

@@ -9,6 +9,7 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #include "bmo_geom.cuh"
 
 namespace bmo {
@@ -22,6 +23,14 @@ inline int32_t fail(int32_t code, const std::string& msg) { g_last_error = msg; 
         if (e_ != cudaSuccess)                                                                      \
             return fail(BMO_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_) + " @" + __FILE__ + ":" + std::to_string(__LINE__)); \
     } while (0)
+
+// NVTX range around a C-ABI call (header-only nvtx3: a no-op unless a profiler has injected itself)
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 struct DevCounters { unsigned long long interactions, sdf, tri, bad_ids; };   // bad_ids: rays whose lambda_id / pose_id was out of range (init_queue)
 

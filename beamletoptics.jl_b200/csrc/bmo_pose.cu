@@ -299,6 +299,7 @@ int32_t bmo_system_set_kinematics(bmo_sys* s, int32_t n_nodes, const bmo_kin_nod
 }
 
 int32_t bmo_system_apply_poses(bmo_sys* s, int32_t n_poses, int32_t n_ops, const bmo_kin_op* ops, int32_t n_params, const double* params) {
+    NvtxRange nvtx_("bmo_system_apply_poses");
     if (!s || n_poses < 1 || n_ops < 0 || n_params < 0 || (n_ops > 0 && !ops) || (n_params > 0 && !params))
         return fail(BMO_EINVAL, "bmo_system_apply_poses: bad arguments");
     if (s->kin_nodes.empty()) return fail(BMO_ESTATE, "bmo_system_apply_poses: call bmo_system_set_kinematics first");

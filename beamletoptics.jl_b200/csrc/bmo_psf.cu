@@ -273,6 +273,7 @@ int32_t bmo_psf_lims(bmo_sys* sys, bmo_psf* p, int32_t psf_object, int32_t pose,
 
 int32_t bmo_psf_intensity(bmo_sys* sys, bmo_psf* p, int32_t psf_object, int32_t pose, int32_t n, const double* lims, double x0_shift,
                           double z0_shift, double* intensity, uint32_t flags) {
+    NvtxRange nvtx_("bmo_psf_intensity");
     int32_t rc;
     if ((rc = psf_check(sys, psf_object, "bmo_psf_intensity"))) return rc;
     if (!p || !lims || !intensity) return fail(BMO_EINVAL, "bmo_psf_intensity: NULL argument");

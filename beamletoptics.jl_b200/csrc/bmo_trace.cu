@@ -1329,6 +1329,7 @@ template <class T> static int32_t upload(T** dptr, const T* h, size_t n) {
 }
 
 int32_t bmo_system_upload(bmo_ctx* ctx, const bmo_tables* t, bmo_sys** out) {
+    NvtxRange nvtx_("bmo_system_upload");
     if (!ctx || !out) return fail(BMO_EINVAL, "bmo_system_upload: NULL argument");
     int32_t rc = validate_tables(t);
     if (rc) return rc;
@@ -1919,6 +1920,7 @@ void SubTrace::release() {
 
 static int32_t trace_common(bmo_sys* sys, int mode, const TraceInputs& in_h, int32_t r_max, uint32_t flags, bmo_result** out,
                             int32_t* spot_obj_out = nullptr, double* spot_xz_out = nullptr, const RetraceView* prev_rt = nullptr) {
+    NvtxRange nvtx_("bmo_trace");
     if (!sys) return fail(BMO_EINVAL, "trace: NULL argument");
     if (in_h.n <= 0) return fail(BMO_EINVAL, "trace: n must be > 0");
     if (r_max < 1) return fail(BMO_EINVAL, "trace: r_max must be >= 1");
@@ -2096,6 +2098,7 @@ int32_t bmo_trace_rays_spots(bmo_sys* sys, int64_t n, const double* pos, const d
 // retrace_system!, :188-255 / :326-428): the roots restart from their stored first rays and every beam of
 // the previous tree re-validates its stored path against the previously hit objects / hinted shapes.
 int32_t bmo_retrace(bmo_sys* sys, bmo_result* prev, int32_t r_max, uint32_t flags, bmo_result** out) {
+    NvtxRange nvtx_("bmo_retrace");
     if (!sys || !prev) return fail(BMO_EINVAL, "bmo_retrace: NULL argument");
     if (!prev->keep || !prev->seg_part || !prev->seg_d) return fail(BMO_ESTATE, "bmo_retrace: the previous result has no segment table (trace it with BMO_KEEP_SEGMENTS)");
     if (sys->ctx != prev->ctx) return fail(BMO_EINVAL, "bmo_retrace: system and previous result live on different contexts");
