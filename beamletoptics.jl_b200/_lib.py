@@ -90,7 +90,7 @@ EXPORTS = [
     "bmo_result_get_info", "bmo_result_beams", "bmo_result_segments", "bmo_result_spots", "bmo_result_spots_device",
     "bmo_result_free", "bmo_pd_accumulate", "bmo_pd_accumulate_poses", "bmo_pd_power", "bmo_pd_sweep", "bmo_measure_fp64_peak",
     "bmo_system_set_kinematics", "bmo_system_apply_poses", "bmo_system_get_pose",
-    "bmo_debug_normals",
+    "bmo_debug_normals", "bmo_trim",
     "bmo_comm_unique_id", "bmo_comm_init", "bmo_comm_init_local", "bmo_comm_info", "bmo_pd_allreduce", "bmo_pd_allreduce_local", "bmo_comm_free",
 ]
 
@@ -134,6 +134,7 @@ def lib():
         L.bmo_psf_intensity.argtypes = [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp, C.c_double, C.c_double, _vp, C.c_uint32]
         L.bmo_psf_free.argtypes = [_vp]
         L.bmo_measure_fp64_peak.argtypes = [_vp, _dp]
+        L.bmo_trim.argtypes = [_vp, C.POINTER(C.c_int64)]
         L.bmo_debug_normals.argtypes = [_vp, C.c_int64, _vp, _vp, _vp, _vp]
         L.bmo_system_set_kinematics.argtypes = [_vp, C.c_int32, _vp, _vp]
         L.bmo_system_apply_poses.argtypes = [_vp, C.c_int32, C.c_int32, _vp, C.c_int32, _vp]
@@ -183,6 +184,13 @@ def counters(device=0):
 
 def counters_reset(device=0):
     check(lib().bmo_counters_reset(context(device)))
+
+
+def trim(device=0):
+    """bmo_trim: hand parked / pooled device memory back to the driver; returns the bytes released from the free list."""
+    n = C.c_int64(0)
+    check(lib().bmo_trim(context(device), C.byref(n)))
+    return int(n.value)
 
 
 def set_stream(stream_ptr, device=0):

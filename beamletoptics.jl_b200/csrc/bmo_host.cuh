@@ -214,13 +214,15 @@ struct BigBlocks {
         cudaGetDevice(&d);
         return per_dev[d & 63];
     }
-    void drop_parked() {
+    size_t drop_parked() {
         std::lock_guard<std::mutex> g(mu);
-        drop_parked_locked();
+        return drop_parked_locked();
     }
-    void drop_parked_locked() {
-        for (auto& b : parked) cudaFree(b.p);
+    size_t drop_parked_locked() {
+        size_t bytes = 0;
+        for (auto& b : parked) { bytes += b.bytes; cudaFree(b.p); }
         parked.clear();
+        return bytes;
     }
     cudaError_t get(void** out, size_t bytes, cudaStream_t s) {
         std::lock_guard<std::mutex> g(mu);

@@ -1213,6 +1213,17 @@ int32_t bmo_shutdown(bmo_ctx* c) {
     delete c;
     return BMO_OK;
 }
+int32_t bmo_trim(bmo_ctx* c, int64_t* released) {
+    if (!c) return fail(BMO_EINVAL, "ctx NULL");
+    BMO_CUDA(cudaSetDevice(c->device));
+    BMO_CUDA(cudaStreamSynchronize(c->stream));
+    const size_t bytes = BigBlocks::of_device().drop_parked();
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+    c->pool_slack = 0;        // the slack bmo_retrace grew the pool by is gone with the trim
+    if (released) *released = (int64_t)bytes;
+    return BMO_OK;
+}
 int32_t bmo_set_stream(bmo_ctx* c, void* s) { if (!c) return fail(BMO_EINVAL, "ctx NULL"); c->stream = (cudaStream_t)s; return BMO_OK; }
 int32_t bmo_counters_get(bmo_ctx* c, bmo_counters* o) {
     if (!c || !o) return fail(BMO_EINVAL, "bmo_counters_get: NULL");

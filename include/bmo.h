@@ -371,6 +371,13 @@ int32_t bmo_pd_allreduce(bmo_comm* comm, double* field, int64_t n_complex, uint3
 int32_t bmo_pd_allreduce_local(int32_t n, bmo_comm* const* comms, double* const* fields, int64_t n_complex, uint32_t flags);
 int32_t bmo_comm_free(bmo_comm* comm);
 
+/* Give device memory back: the library keeps released blocks of 64 MiB and more in a per-device free list and smaller ones in
+ * CUDA's stream-ordered pool, so that the next solve of the same shape allocates nothing ("Device memory").  A host
+ * that shares the GPU with other allocators (CUDA.jl, PyTorch) calls this after a large one-off trace; bmo_shutdown does it too.
+ * The reference has no counterpart (Julia's GC owns its arrays).  Returns the bytes released from the free list in *released
+ * (NULL ok).                                                                                                                    */
+int32_t bmo_trim(bmo_ctx* ctx, int64_t* released);
+
 /* FP64 DFMA micro-benchmark used as the roofline denominator of the FP64-bound kernels.          */
 int32_t bmo_measure_fp64_peak(bmo_ctx* ctx, double* tflops);
 

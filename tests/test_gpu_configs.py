@@ -4,7 +4,7 @@ branching and PolarizedRays, C5 Mach-Zehnder pose sweep (one interferogram per p
 import numpy as np
 import pytest
 
-from tests import scenes2 as s2
+from tests import scenes, scenes2 as s2
 
 POS_TOL = 1e-9     # hit points / directions, relative (north_star)
 FIELD_TOL = 1e-8   # detector field / intensity, relative L2 (north_star)
@@ -193,3 +193,17 @@ def test_pd_tilted_detector_behind_fold_mirror(bmo, orc):
     assert np.abs(ref).max() > 0
     assert _rel_l2(slow, ref) <= FIELD_TOL
     assert _rel_l2(fast, ref) <= FIELD_TOL
+
+
+@pytest.mark.gpu
+def test_trim_releases_parked_blocks_and_the_next_trace_still_works(bmo):
+    """bmo_trim: blocks >= 64 MiB that a large trace parked go back to the driver; tracing afterwards allocates afresh."""
+    from bmo_b200 import _lib as L
+    sc = scenes.doublet_spot(bmo)
+    n = 1 << 20                                            # queue planes of 2^20 rays are 8 MiB each, the wave buffers of a kept table 92 MiB
+    pos, d = scenes.fibonacci_disc(n)
+    bmo.solve_system_(sc["system"], bmo.RayBundle(pos, d, 707e-9), keep_segments=True).free()
+    assert L.trim() >= 64 << 20
+    assert L.trim() == 0
+    res = bmo.solve_system_(sc["system"], bmo.RayBundle(pos[:1000], d[:1000], 707e-9))
+    assert res.interactions == 4000
