@@ -238,6 +238,9 @@ function upload(cs::CUDASystem, f)
     UPLOADED[cs.system] = (h, sys)
     return sys
 end
+"""Hand the device memory the library keeps for reuse (parked blocks, its share of the stream-ordered pool) back to the driver."""
+trim!(device::Integer = 0) = (n = Ref{Int64}(0); check(ccall((:bmo_trim, libbmo), Int32, (Ptr{Cvoid}, Ref{Int64}), context(device), n)); n[])
+
 """Release the device copy of a system (the cache otherwise keeps it until the next upload of a changed system)."""
 function release!(cs::CUDASystem)
     hit = pop!(UPLOADED, cs.system, nothing)
